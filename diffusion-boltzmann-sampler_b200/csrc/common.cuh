@@ -1,0 +1,65 @@
+// common.cuh — error plumbing, launch accounting and small device helpers shared by
+// every translation unit of libdbs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/dbs_b200.h"
+
+namespace dbs {
+
+// Thread-local error text behind dbs_last_error().
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define DBS_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::dbs::set_error(__VA_ARGS__);           \
+      return DBS_ERR_INVALID;                  \
+    }                                          \
+  } while (0)
+
+#define DBS_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      ::dbs::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),      \
+                       __FILE__, __LINE__);                                         \
+      return DBS_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+// Call after every <<<>>>: counts the launch and surfaces launch-time errors.
+#define DBS_LAUNCHED()                                                              \
+  do {                                                                              \
+    ::dbs::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
+    cudaError_t e_ = cudaGetLastError();                                            \
+    if (e_ != cudaSuccess) {                                                        \
+      ::dbs::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_),  \
+                       __FILE__, __LINE__);                                         \
+      return DBS_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace dbs

@@ -1,0 +1,144 @@
+// em.cu — fused Euler–Maruyama reverse-SDE update and Gaussian fill.
+//
+// Replaces the inner step of DiffusionSampler.sample (samplers/diffusion.py:232-243; the same
+// expression at :279-287, :375-383, :431-437) and the torch.randn start (:216).
+// HBM-bound: 12 B per element (x in, score in, x out); noise is generated in-register from
+// Philox4x32-10 + Box–Muller unless the caller injects a noise tensor (parity port).
+// Evaluation order is the reference's, with explicit _rn intrinsics so nvcc cannot contract
+// mul+add into FMA:  (x + (c1*s)*dt) + ((c2*z)*temperature).
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace dbs {
+namespace {
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-8f;  // (0,1), 24 bits
+  const float u2 = ((float)(b >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  z0 = rad * cs;
+  z1 = rad * sn;
+}
+
+__device__ __forceinline__ void normal4(uint32_t seed_lo, uint32_t seed_hi, uint32_t sample, uint32_t quad,
+                                        uint32_t step, float z[4]) {
+  u32x4 c;
+  c.x = sample; c.y = quad; c.z = step; c.w = DBS_STREAM_NOISE;
+  const u32x4 o = philox4x32_10(c, seed_lo, seed_hi);
+  box_muller(o.x, o.y, z[0], z[1]);
+  box_muller(o.z, o.w, z[2], z[3]);
+}
+
+struct EmArgs {
+  float* x;
+  const float* score;
+  const float* noise;
+  int64_t n_samples, elems, quads_per_sample;
+  float c1, dt, c2, temperature;
+  int add_noise;
+  uint32_t seed_lo, seed_hi;
+  int64_t sample_offset;
+  uint32_t step;
+};
+
+template <bool kVec, bool kFill>
+__global__ void __launch_bounds__(256) em_kernel(EmArgs a) {
+  const int64_t total = a.n_samples * a.quads_per_sample;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = g / a.quads_per_sample;
+    const int64_t q = g - n * a.quads_per_sample;
+    const int64_t e0 = n * a.elems + 4 * q;
+    const int cnt = (int)((a.elems - 4 * q) < 4 ? (a.elems - 4 * q) : 4);
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    float xv[4], sv[4];
+    if (kFill || (a.add_noise && !a.noise))
+      normal4(a.seed_lo, a.seed_hi, (uint32_t)(a.sample_offset + n), (uint32_t)q, a.step, z);
+    if (kFill) {
+      if (kVec) {
+        *reinterpret_cast<float4*>(a.x + e0) = make_float4(z[0], z[1], z[2], z[3]);
+      } else {
+        for (int k = 0; k < cnt; ++k) a.x[e0 + k] = z[k];
+      }
+      continue;
+    }
+    if (kVec) {
+      const float4 X = *reinterpret_cast<const float4*>(a.x + e0);
+      const float4 S = __ldg(reinterpret_cast<const float4*>(a.score + e0));
+      xv[0] = X.x; xv[1] = X.y; xv[2] = X.z; xv[3] = X.w;
+      sv[0] = S.x; sv[1] = S.y; sv[2] = S.z; sv[3] = S.w;
+      if (a.add_noise && a.noise) {
+        const float4 Z = __ldg(reinterpret_cast<const float4*>(a.noise + e0));
+        z[0] = Z.x; z[1] = Z.y; z[2] = Z.z; z[3] = Z.w;
+      }
+    } else {
+      for (int k = 0; k < 4; ++k) {
+        xv[k] = k < cnt ? a.x[e0 + k] : 0.f;
+        sv[k] = k < cnt ? a.score[e0 + k] : 0.f;
+        if (a.add_noise && a.noise) z[k] = k < cnt ? a.noise[e0 + k] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = __fadd_rn(xv[k], __fmul_rn(__fmul_rn(a.c1, sv[k]), a.dt));
+      if (a.add_noise) v = __fadd_rn(v, __fmul_rn(__fmul_rn(a.c2, z[k]), a.temperature));
+      xv[k] = v;
+    }
+    if (kVec) {
+      *reinterpret_cast<float4*>(a.x + e0) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    } else {
+      for (int k = 0; k < cnt; ++k) a.x[e0 + k] = xv[k];
+    }
+  }
+}
+
+template <bool kFill>
+int launch_em(const EmArgs& a, cudaStream_t st) {
+  const int64_t total = a.n_samples * a.quads_per_sample;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = 148LL * 8 * 4;  // persistent-ish grid: multiples of the SM count
+  if (blocks > cap) blocks = cap;
+  const bool vec = (a.elems % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) &&
+                   (kFill || ((reinterpret_cast<uintptr_t>(a.score) & 15) == 0 &&
+                              (!a.noise || (reinterpret_cast<uintptr_t>(a.noise) & 15) == 0)));
+  if (vec) em_kernel<true, kFill><<<(unsigned)blocks, 256, 0, st>>>(a);
+  else em_kernel<false, kFill><<<(unsigned)blocks, 256, 0, st>>>(a);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+}  // namespace
+}  // namespace dbs
+
+using namespace dbs;
+
+extern "C" int dbs_em_step(float* x, const float* score, const float* noise, int64_t n_samples,
+                           int64_t elems_per_sample, float c1, float dt, float c2, float temperature,
+                           int add_noise, uint64_t seed, int64_t sample_offset, int64_t step, void* stream) {
+  DBS_REQUIRE(x && score, "em_step: null x or score");
+  DBS_REQUIRE(n_samples >= 0 && elems_per_sample >= 0, "em_step: negative size");
+  if (n_samples == 0 || elems_per_sample == 0) return DBS_OK;
+  EmArgs a;
+  a.x = x; a.score = score; a.noise = noise; a.n_samples = n_samples; a.elems = elems_per_sample;
+  a.quads_per_sample = (elems_per_sample + 3) / 4;
+  a.c1 = c1; a.dt = dt; a.c2 = c2; a.temperature = temperature; a.add_noise = add_noise ? 1 : 0;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.sample_offset = sample_offset; a.step = (uint32_t)step;
+  return launch_em<false>(a, as_stream(stream));
+}
+
+extern "C" int dbs_gaussian_fill(float* x, int64_t n_samples, int64_t elems_per_sample, uint64_t seed,
+                                 int64_t sample_offset, int64_t step, void* stream) {
+  DBS_REQUIRE(x, "gaussian_fill: null x");
+  DBS_REQUIRE(n_samples >= 0 && elems_per_sample >= 0, "gaussian_fill: negative size");
+  if (n_samples == 0 || elems_per_sample == 0) return DBS_OK;
+  EmArgs a{};
+  a.x = x; a.n_samples = n_samples; a.elems = elems_per_sample;
+  a.quads_per_sample = (elems_per_sample + 3) / 4;
+  a.add_noise = 1;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.sample_offset = sample_offset; a.step = (uint32_t)step;
+  return launch_em<true>(a, as_stream(stream));
+}

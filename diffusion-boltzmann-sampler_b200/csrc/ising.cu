@@ -1,0 +1,492 @@
+// ising.cu — bit-packed checkerboard Metropolis and lattice observables for sm_100a.
+//
+// Replaces (reference file:line, /root/reference/backend/ml):
+//   MetropolisHastings.step / sweep            samplers/mcmc.py:26-60
+//   IsingModel.local_energy_diff               systems/ising.py:68-91
+//   IsingModel.energy / magnetization          systems/ising.py:47-66, 93-102
+//   IsingModel.random_configuration            systems/ising.py:36-45
+//   pair_correlation                           analysis/correlation.py:8-47
+//
+// State layout in HBM: uint32 words[n_chains][L][W], W = ceil(L/32), 1 bit per spin.
+// One thread owns one word (32 columns of one row) for the whole multi-sweep launch; the
+// lattice lives in shared memory (double-buffered, one __syncthreads per half-sweep) and
+// touches HBM exactly twice per launch.  Per active site the work is one Philox draw
+// (2.5 rounds amortised), a 4-bit class extract, one 8-byte table LDS and two compares.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace dbs {
+namespace {
+
+constexpr int kMaxL = 128;
+
+__host__ __device__ inline bool supported_L(int L) { return L >= 4 && L <= kMaxL && (L & 1) == 0; }
+
+struct SweepArgs {
+  uint32_t* bits;
+  const uint32_t* thr;          // [n_tables][16][2]
+  const int32_t* table_index;   // [n_chains] or null
+  const uint32_t* uniforms;     // [n_sweeps][n_chains][L][L] or null
+  int64_t n_chains;
+  int64_t chain_offset;
+  int64_t sweep_offset;
+  uint32_t seed_lo, seed_hi;
+  int L;
+  int n_sweeps;
+  int cpb;                      // chains per block
+};
+
+// valid-bit mask of word w in a row of L bits
+__device__ __forceinline__ int valid_bits(int L, int w) {
+  int vb = L - 32 * w;
+  return vb > 32 ? 32 : vb;
+}
+__device__ __forceinline__ uint32_t low_mask(int vb) { return vb >= 32 ? 0xffffffffu : ((1u << vb) - 1u); }
+
+template <int LT, bool kInject>
+__global__ void __launch_bounds__(512) ising_sweep_kernel(SweepArgs a) {
+  const int L = LT ? LT : a.L;
+  const int W = (L + 31) >> 5;
+  const int tpc = L * W;
+  const int cpb = a.cpb;
+  extern __shared__ uint32_t smem[];
+  uint32_t* buf0 = smem;
+  uint32_t* buf1 = smem + cpb * tpc;
+  uint2* tbl = reinterpret_cast<uint2*>(smem + 2 * cpb * tpc + ((2 * cpb * tpc) & 1));
+
+  const int tid = threadIdx.x;
+  const int lc = tid / tpc;
+  const int r = tid - lc * tpc;
+  const int i = r / W;
+  const int w = r - i * W;
+  const int64_t chain = (int64_t)blockIdx.x * cpb + lc;
+  const bool live = (lc < cpb) && (chain < a.n_chains);
+
+  if (tid < cpb * 16) {
+    const int lc2 = tid >> 4, k = tid & 15;
+    const int64_t c2 = (int64_t)blockIdx.x * cpb + lc2;
+    uint2 e = make_uint2(0u, 0u);
+    if (c2 < a.n_chains) {
+      const int ti = a.table_index ? a.table_index[c2] : 0;
+      e.x = a.thr[(ti * 16 + k) * 2 + 0];
+      e.y = a.thr[(ti * 16 + k) * 2 + 1];
+    }
+    tbl[tid] = e;
+  }
+
+  uint32_t self = 0;
+  if (live) {
+    self = a.bits[chain * tpc + r];
+    buf0[lc * tpc + r] = self;
+  }
+  __syncthreads();
+
+  const int vb = valid_bits(L, w);
+  const uint32_t vmask = low_mask(vb);
+  const int base = lc * tpc;
+  const int row_up = (i == 0 ? L - 1 : i - 1) * W + w;
+  const int row_dn = (i == L - 1 ? 0 : i + 1) * W + w;
+  const int wl = (w == 0 ? W - 1 : w - 1);
+  const int wr = (w == W - 1 ? 0 : w + 1);
+  const int top_prev = valid_bits(L, wl) - 1;  // bit index of the last column of the left word
+  const int gpr = (L + 7) >> 3;                // Philox calls per row and colour
+  const uint2* mytbl = tbl + lc * 16;
+  const uint32_t chain_ctr = (uint32_t)(a.chain_offset + chain);
+
+  uint32_t hs = 0;  // half-sweep counter inside this launch
+  for (int s = 0; s < a.n_sweeps; ++s) {
+#pragma unroll 1
+    for (int colour = 0; colour < 2; ++colour, ++hs) {
+      const uint32_t* cur = (hs & 1) ? buf1 : buf0;
+      uint32_t* nxt = (hs & 1) ? buf0 : buf1;
+      if (live) {
+        const uint32_t up = cur[base + row_up];
+        const uint32_t dn = cur[base + row_dn];
+        const uint32_t lw = (W == 1) ? self : cur[base + i * W + wl];
+        const uint32_t rw = (W == 1) ? self : cur[base + i * W + wr];
+        const uint32_t lf = ((self << 1) | ((lw >> top_prev) & 1u)) & vmask;
+        const uint32_t rt = ((self >> 1) | ((rw & 1u) << (vb - 1))) & vmask;
+        const int par = (i + colour) & 1;  // column parity of the active sites of this row
+
+        // class nibbles k = 8*s + (#up neighbours), active sites moved to even bit positions
+        const uint32_t m1 = 0x11111111u;
+        const uint32_t s_ = self >> par, u_ = up >> par, d_ = dn >> par, l_ = lf >> par, r_ = rt >> par;
+        const uint32_t KA = (u_ & m1) + (d_ & m1) + (l_ & m1) + (r_ & m1) + ((s_ & m1) << 3);
+        const uint32_t KB = ((u_ >> 2) & m1) + ((d_ >> 2) & m1) + ((l_ >> 2) & m1) + ((r_ >> 2) & m1) +
+                            (((s_ >> 2) & m1) << 3);
+
+        uint32_t flips = 0;  // bit 2m = flip of active site m
+        const uint32_t ctr_y = 2u * (uint32_t)(a.sweep_offset + s) + (uint32_t)colour;
+#pragma unroll
+        for (int call = 0; call < 4; ++call) {
+          if (8 * call < vb) {
+            uint32_t rr[4];
+            if (kInject) {
+#pragma unroll
+              for (int d = 0; d < 4; ++d) {
+                const int j = 32 * w + par + 2 * (4 * call + d);
+                rr[d] = (j < L) ? a.uniforms[(((int64_t)s * a.n_chains + chain) * L + i) * L + j] : 0u;
+              }
+            } else {
+              u32x4 c;
+              c.x = chain_ctr;
+              c.y = ctr_y;
+              c.z = (uint32_t)(i * gpr + w * 4 + call);
+              c.w = DBS_STREAM_SWEEP;
+              const u32x4 o = philox4x32_10(c, a.seed_lo, a.seed_hi);
+              rr[0] = o.x; rr[1] = o.y; rr[2] = o.z; rr[3] = o.w;
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              const int m = 4 * call + d;
+              const uint32_t K = (m & 1) ? KB : KA;
+              const uint32_t k = (K >> (4 * (m >> 1))) & 15u;
+              const uint2 e = mytbl[k];
+              if ((rr[d] < e.x) || e.y) flips |= (1u << (2 * m));
+            }
+          }
+        }
+        const uint32_t amask = (par ? 0xAAAAAAAAu : 0x55555555u) & vmask;
+        self ^= (flips << par) & amask;
+        nxt[base + r] = self;
+      }
+      __syncthreads();
+    }
+  }
+  if (live) a.bits[chain * tpc + r] = self;
+}
+
+template <int LT, bool kInject>
+int launch_sweep_t(const SweepArgs& a, cudaStream_t st) {
+  const int L = a.L, W = (L + 31) / 32, tpc = L * W;
+  const int cpb = a.cpb;
+  int threads = cpb * tpc;
+  threads = (threads + 31) / 32 * 32;
+  if (threads < cpb * 16) threads = cpb * 16;
+  const size_t smem = (size_t)(2 * cpb * tpc + 2) * 4 + (size_t)cpb * 16 * 8;
+  const int64_t blocks = (a.n_chains + cpb - 1) / cpb;
+  ising_sweep_kernel<LT, kInject><<<(unsigned)blocks, threads, smem, st>>>(a);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+template <bool kInject>
+int launch_sweep(const SweepArgs& a, cudaStream_t st) {
+  switch (a.L) {
+    case 8: return launch_sweep_t<8, kInject>(a, st);
+    case 16: return launch_sweep_t<16, kInject>(a, st);
+    case 32: return launch_sweep_t<32, kInject>(a, st);
+    case 64: return launch_sweep_t<64, kInject>(a, st);
+    case 128: return launch_sweep_t<128, kInject>(a, st);
+    default: return launch_sweep_t<0, kInject>(a, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot start: one thread per word
+__global__ void ising_init_kernel(uint32_t* bits, int L, int64_t n_words, uint32_t seed_lo,
+                                  uint32_t seed_hi, int64_t chain_offset) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_words) return;
+  const int W = (L + 31) >> 5, tpc = L * W;
+  const int64_t chain = g / tpc;
+  const int r = (int)(g - chain * tpc);
+  const int i = r / W, w = r - i * W;
+  u32x4 c;
+  c.x = (uint32_t)(chain_offset + chain);
+  c.y = (uint32_t)i;
+  c.z = (uint32_t)w;
+  c.w = DBS_STREAM_INIT;
+  const u32x4 o = philox4x32_10(c, seed_lo, seed_hi);
+  bits[g] = o.x & low_mask(valid_bits(L, w));
+}
+
+// fp32 -> bits: one warp per word, coalesced 128 B reads, ballot builds the word
+__global__ void ising_pack_kernel(const float* __restrict__ spins, uint32_t* __restrict__ bits, int L,
+                                  int64_t n_words) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_words) return;
+  const int W = (L + 31) >> 5, tpc = L * W;
+  const int64_t chain = g / tpc;
+  const int r = (int)(g - chain * tpc);
+  const int i = r / W, w = r - i * W;
+  const int j = 32 * w + lane;
+  float v = 0.f;
+  if (j < L) v = spins[(chain * L + i) * L + j];
+  const uint32_t word = __ballot_sync(0xffffffffu, v > 0.f);
+  if (lane == 0) bits[g] = word;
+}
+
+__global__ void ising_unpack_kernel(const uint32_t* __restrict__ bits, float* __restrict__ spins, int L,
+                                    int64_t n_words) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_words) return;
+  const int W = (L + 31) >> 5, tpc = L * W;
+  const int64_t chain = g / tpc;
+  const int r = (int)(g - chain * tpc);
+  const int i = r / W, w = r - i * W;
+  const int j = 32 * w + lane;
+  const uint32_t word = bits[g];
+  if (j < L) spins[(chain * L + i) * L + j] = ((word >> lane) & 1u) ? 1.0f : -1.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// E, M from packed state: one warp per chain, popcount on word-parallel agreement masks.
+__global__ void ising_obs_packed_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chains,
+                                        float negJ, float negh, float* __restrict__ energy,
+                                        float* __restrict__ mag) {
+  const int64_t chain = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (chain >= n_chains) return;
+  const int W = (L + 31) >> 5, tpc = L * W;
+  const uint32_t* b = bits + chain * tpc;
+  int agree = 0, up = 0;
+  for (int r = lane; r < tpc; r += 32) {
+    const int i = r / W, w = r - i * W;
+    const int vb = valid_bits(L, w);
+    const uint32_t vmask = low_mask(vb);
+    const uint32_t self = b[r];
+    const uint32_t rw = b[i * W + (w == W - 1 ? 0 : w + 1)];
+    const uint32_t dn = b[(i == L - 1 ? 0 : i + 1) * W + w];
+    const uint32_t rt = ((self >> 1) | ((rw & 1u) << (vb - 1))) & vmask;
+    agree += __popc(~(self ^ rt) & vmask) + __popc(~(self ^ dn) & vmask);
+    up += __popc(self);
+  }
+  agree = warp_sum(agree);
+  up = warp_sum(up);
+  if (lane == 0) {
+    const int N = L * L;
+    const float s_bond = (float)(2 * agree - 2 * N);  // sum of s*right + s*down  (exact integer)
+    const float s_spin = (float)(2 * up - N);
+    if (energy) energy[chain] = __fadd_rn(__fmul_rn(negJ, s_bond), __fmul_rn(negh, s_spin));
+    if (mag) mag[chain] = __fdiv_rn(s_spin, (float)N);
+  }
+}
+
+// E, M from an fp32 lattice of arbitrary reals: one block per lattice, fp64 accumulation.
+__global__ void ising_obs_f32_kernel(const float* __restrict__ spins, int L, float negJ, float negh,
+                                     float* __restrict__ energy, float* __restrict__ mag) {
+  const float* x = spins + (int64_t)blockIdx.x * L * L;
+  double bond = 0.0, sum = 0.0;
+  for (int idx = threadIdx.x; idx < L * L; idx += blockDim.x) {
+    const int i = idx / L, j = idx - i * L;
+    const float s = x[idx];
+    const float rt = x[i * L + (j == L - 1 ? 0 : j + 1)];
+    const float dn = x[(i == L - 1 ? 0 : i + 1) * L + j];
+    bond += (double)__fadd_rn(__fmul_rn(s, rt), __fmul_rn(s, dn));
+    sum += (double)s;
+  }
+  __shared__ double sb[32], ss[32];
+  bond = warp_sum(bond);
+  sum = warp_sum(sum);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sb[wid] = bond; ss[wid] = sum; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    bond = lane < nw ? sb[lane] : 0.0;
+    sum = lane < nw ? ss[lane] : 0.0;
+    bond = warp_sum(bond);
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      const float fb = (float)bond, fs = (float)sum;
+      if (energy) energy[blockIdx.x] = __fadd_rn(__fmul_rn(negJ, fb), __fmul_rn(negh, fs));
+      if (mag) mag[blockIdx.x] = __fdiv_rn(fs, (float)(L * L));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C(r) sums: one block per chain.  Rows are kept twice-unrolled (bit b of D = s[b mod L]) so a
+// periodic column shift is one funnel shift; a displacement costs L*W (xor, and, popc).
+constexpr int kCorrThreads = 128;
+constexpr int kCorrDW = 2 * ((kMaxL + 31) / 32) + 2;  // words of a doubled row
+
+__global__ void __launch_bounds__(kCorrThreads)
+ising_corr_kernel(const uint32_t* __restrict__ bits, int L, const uint32_t* __restrict__ ref_mask,
+                  const int32_t* __restrict__ group, long long* __restrict__ acc) {
+  const int W = (L + 31) >> 5, tpc = L * W, R = L / 2;
+  const int DW = 2 * W + 2;
+  extern __shared__ uint32_t sm[];
+  uint32_t* S = sm;                 // [L][W]   lattice
+  uint32_t* M = S + tpc;            // [L][W]   reference-site mask
+  uint32_t* D = M + tpc;            // [L][DW]  doubled rows
+  int* sbin = reinterpret_cast<int*>(D + L * DW);  // [R]
+  __shared__ int s_refcount;
+  const int64_t chain = blockIdx.x;
+  const uint32_t* b = bits + chain * tpc;
+  if (threadIdx.x == 0) s_refcount = 0;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) sbin[r] = 0;
+  __syncthreads();
+  int myref = 0;
+  for (int r = threadIdx.x; r < tpc; r += blockDim.x) {
+    const int w = r % W;
+    const uint32_t vm = low_mask(valid_bits(L, w));
+    S[r] = b[r];
+    const uint32_t m = (ref_mask ? ref_mask[r] : 0xffffffffu) & vm;
+    M[r] = m;
+    myref += __popc(m);
+  }
+  atomicAdd(&s_refcount, myref);
+  __syncthreads();
+  for (int q = threadIdx.x; q < L * DW; q += blockDim.x) {
+    const int i = q / DW, v = q - i * DW;
+    uint32_t word = 0;
+    int src = (32 * v) % L;
+    for (int bb = 0; bb < 32; ++bb) {
+      word |= ((S[i * W + (src >> 5)] >> (src & 31)) & 1u) << bb;
+      if (++src == L) src = 0;
+    }
+    D[q] = word;
+  }
+  __syncthreads();
+  const int side = 2 * R + 1;
+  const int refcount = s_refcount;
+  for (int d = threadIdx.x; d < side * side; d += blockDim.x) {
+    const int di = d / side - R, dj = d % side - R;
+    const int x = di * di + dj * dj;
+    int rr = (int)sqrtf((float)x);
+    while (rr * rr > x) --rr;
+    while ((rr + 1) * (rr + 1) <= x) ++rr;
+    if (rr <= 0 || rr >= R) continue;
+    const int djm = ((dj % L) + L) % L;
+    int pc = 0;
+    for (int i = 0; i < L; ++i) {
+      int i2 = i + di;
+      i2 = i2 < 0 ? i2 + L : (i2 >= L ? i2 - L : i2);
+      const uint32_t* drow = D + i2 * DW;
+      for (int w = 0; w < W; ++w) {
+        const int t = 32 * w + djm;
+        const uint32_t sh = __funnelshift_r(drow[t >> 5], drow[(t >> 5) + 1], t & 31);
+        pc += __popc((S[i * W + w] ^ sh) & M[i * W + w]);
+      }
+    }
+    atomicAdd(&sbin[rr], refcount - 2 * pc);
+  }
+  __syncthreads();
+  const int g = group ? group[chain] : 0;
+  for (int r = threadIdx.x; r < R; r += blockDim.x)
+    if (sbin[r] != 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc + (int64_t)g * R + r),
+                                (unsigned long long)(long long)sbin[r]);
+}
+
+__global__ void obs_accumulate_kernel(const float* __restrict__ energy, const float* __restrict__ mag,
+                                      double N, int64_t n, const int32_t* __restrict__ group,
+                                      double* __restrict__ acc) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int g = group ? group[c] : 0;
+  const double e = (double)energy[c] / N;
+  const double m = (double)mag[c];
+  const double m2 = m * m;
+  double* a = acc + (int64_t)g * 5;
+  atomicAdd(a + 0, 1.0);
+  atomicAdd(a + 1, e);
+  atomicAdd(a + 2, fabs(m));
+  atomicAdd(a + 3, m2);
+  atomicAdd(a + 4, m2 * m2);
+}
+
+}  // namespace
+}  // namespace dbs
+
+using namespace dbs;
+
+extern "C" int dbs_ising_words_per_chain(int L) {
+  if (!supported_L(L)) return -1;
+  return L * ((L + 31) / 32);
+}
+
+extern "C" int dbs_ising_init_packed(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
+                                     int64_t chain_offset, void* stream) {
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(bits && n_chains >= 0, "ising_init: null state or negative chain count");
+  if (n_chains == 0) return DBS_OK;
+  const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
+  ising_init_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, as_stream(stream)>>>(
+      bits, L, n_words, (uint32_t)seed, (uint32_t)(seed >> 32), chain_offset);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t n_chains, void* stream) {
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(spins && bits && n_chains >= 0, "ising_pack: null pointer");
+  if (n_chains == 0) return DBS_OK;
+  const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
+  ising_pack_kernel<<<(unsigned)((n_words * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(spins, bits, L, n_words);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64_t n_chains, void* stream) {
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(spins && bits && n_chains >= 0, "ising_unpack: null pointer");
+  if (n_chains == 0) return DBS_OK;
+  const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
+  ising_unpack_kernel<<<(unsigned)((n_words * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(bits, spins, L, n_words);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_sweeps, const uint32_t* thr,
+                                int n_tables, const int32_t* table_index, uint64_t seed, int64_t chain_offset,
+                                int64_t sweep_offset, const uint32_t* uniforms, void* stream) {
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(bits && thr && n_tables >= 1, "ising_sweeps: null state or threshold table");
+  DBS_REQUIRE(n_chains >= 0 && n_sweeps >= 0, "ising_sweeps: negative chain or sweep count");
+  if (n_chains == 0 || n_sweeps == 0) return DBS_OK;
+  SweepArgs a;
+  a.bits = bits; a.thr = thr; a.table_index = table_index; a.uniforms = uniforms;
+  a.n_chains = n_chains; a.chain_offset = chain_offset; a.sweep_offset = sweep_offset;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.L = L; a.n_sweeps = n_sweeps;
+  const int tpc = dbs_ising_words_per_chain(L);
+  a.cpb = tpc >= 128 ? 1 : 128 / tpc;
+  return uniforms ? launch_sweep<true>(a, as_stream(stream)) : launch_sweep<false>(a, as_stream(stream));
+}
+
+extern "C" int dbs_ising_observables(const uint32_t* bits, int L, int64_t n_chains, float J, float h,
+                                     float* energy, float* magnetization, void* stream) {
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(bits && n_chains >= 0, "ising_observables: null state");
+  if (n_chains == 0) return DBS_OK;
+  ising_obs_packed_kernel<<<(unsigned)((n_chains * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      bits, L, n_chains, -J, -h, energy, magnetization);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_ising_observables_f32(const float* spins, int L, int64_t n, float J, float h, float* energy,
+                                         float* magnetization, void* stream) {
+  DBS_REQUIRE(L >= 1 && spins && n >= 0, "ising_observables_f32: bad arguments");
+  if (n == 0) return DBS_OK;
+  const int threads = L * L >= 1024 ? 256 : (L * L >= 128 ? 128 : 32);
+  ising_obs_f32_kernel<<<(unsigned)n, threads, 0, as_stream(stream)>>>(spins, L, -J, -h, energy, magnetization);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chains, const uint32_t* ref_mask,
+                                     const int32_t* group, long long* acc, void* stream) {
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(bits && acc && n_chains >= 0, "ising_correlation: null pointer");
+  if (n_chains == 0) return DBS_OK;
+  const int W = (L + 31) / 32, tpc = L * W;
+  const size_t smem = (size_t)(2 * tpc + L * (2 * W + 2)) * 4 + (size_t)(L / 2) * 4;
+  ising_corr_kernel<<<(unsigned)n_chains, kCorrThreads, smem, as_stream(stream)>>>(bits, L, ref_mask, group, acc);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_observable_accumulate(const float* energy, const float* magnetization, int L, int64_t n_chains,
+                                         const int32_t* group, double* acc, void* stream) {
+  DBS_REQUIRE(energy && magnetization && acc && L >= 1 && n_chains >= 0, "observable_accumulate: bad arguments");
+  if (n_chains == 0) return DBS_OK;
+  obs_accumulate_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, as_stream(stream)>>>(
+      energy, magnetization, (double)(L * L), n_chains, group, acc);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}

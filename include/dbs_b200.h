@@ -1,0 +1,220 @@
+/*
+ * dbs_b200.h — C ABI of libdbs_b200.so, the sm_100a sampling engine behind the
+ * Python API of Sakeeb91/diffusion-boltzmann-sampler's hot path.
+ *
+ * The reference has no FFI seam: its boundary is the Python class API of five
+ * modules.  Each entry point below names the reference symbol
+ * (file:line under /root/reference) whose arithmetic it replaces; the Python
+ * modules under diffusion-boltzmann-sampler_b200/backend/ml/ bind these through
+ * ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the ABI.
+ *   - every function returns int: 0 = ok, <0 = dbs_status; dbs_last_error()
+ *     returns a thread-local message.  No exception crosses the boundary.
+ *   - all buffers are CALLER-OWNED DEVICE pointers (torch.Tensor.data_ptr()).
+ *     The library allocates nothing except the opaque dbs_unet_plan (repacked
+ *     weights + TMA descriptors); workspaces are passed in by the caller.
+ *   - every launch takes a cudaStream_t as `void* stream` and is asynchronous;
+ *     no hidden device synchronisation, no global mutable state.
+ */
+#ifndef DBS_B200_H
+#define DBS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dbs_status {
+  DBS_OK = 0,
+  DBS_ERR_INVALID = -1,     /* bad argument (odd L, unsupported shape, null ptr) */
+  DBS_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed             */
+  DBS_ERR_UNSUPPORTED = -3, /* valid in the reference, not built here (documented) */
+  DBS_ERR_NO_DEVICE = -4    /* no sm_100 device visible                        */
+} dbs_status;
+
+/* Thread-local text of the last failure on this thread ("" if none). */
+const char* dbs_last_error(void);
+/* ABI version (major*1000+minor) and the SM architecture the kernels were built for (100). */
+int dbs_abi_version(void);
+int dbs_built_sm(void);
+/* Number of kernels this library has launched since load (monotonic; for bench.py's gpu_launches). */
+uint64_t dbs_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Ising lattice state: bit-packed, 1 bit per spin (1 = +1, 0 = -1).
+ * Layout: uint32 words[n_chains][L][W], W = ceil(L/32); bit (j%32) of word
+ * (j/32) of row i is spin (i,j); unused high bits are zero.  L even, 4<=L<=128.
+ * ------------------------------------------------------------------------- */
+
+/* words per chain for lattice size L (L*ceil(L/32)); <0 if L unsupported. */
+int dbs_ising_words_per_chain(int L);
+
+/* Hot start.  Replaces IsingModel.random_configuration (systems/ising.py:36-45):
+ * spin(i,j) of chain c = bit (j%32) of Philox4x32-10(key=seed,
+ * ctr={chain_offset+c, i, j/32, DBS_STREAM_INIT}).x */
+int dbs_ising_init_packed(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
+                          int64_t chain_offset, void* stream);
+
+/* fp32 (+/-1, sign test x>0) <-> bits.  Replaces the float lattice representation
+ * of systems/ising.py:36-45 / samplers/mcmc.py:82-97 at the API boundary. */
+int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t n_chains, void* stream);
+int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64_t n_chains, void* stream);
+
+/* Checkerboard Metropolis sweeps.  Replaces MetropolisHastings.step/sweep
+ * (samplers/mcmc.py:26-60) + IsingModel.local_energy_diff (systems/ising.py:68-91).
+ *
+ * One sweep = colour-0 half-sweep then colour-1 half-sweep, colour = (i+j)&1.
+ * Site class k = 8*s + u, s = spin bit, u = number of +1 neighbours (0..4).
+ * accept  <=>  (r < thr[k].lo) || thr[k].hi   with r the site's 32-bit draw, i.e.
+ * the reference's  dE<=0 || u < exp(-beta*dE)  with u = r*2^-32
+ * (thr[k].lo = ceil(exp(-beta*dE_k)*2^32), thr[k].hi = 1 iff dE_k <= 0).
+ *
+ *   thr          uint32 [n_tables][16][2]  ({lo,hi} pairs), built on the host
+ *   table_index  int32 [n_chains] or NULL (all chains use table 0): per-chain temperature
+ *   draw source  uniforms == NULL: Philox4x32-10(key=seed, ctr={chain_offset+c,
+ *                2*(sweep_offset+s)+colour, i*GPR + q/4, DBS_STREAM_SWEEP}).v[q%4],
+ *                q = rank of the site among its colour in row i, GPR = ceil(L/8);
+ *                uniforms != NULL (test-mode injection port): uint32
+ *                [n_sweeps][n_chains][L][L], r of site (i,j) in sweep s.
+ */
+int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_sweeps,
+                     const uint32_t* thr, int n_tables, const int32_t* table_index,
+                     uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
+                     const uint32_t* uniforms, void* stream);
+
+/* Per-chain energy and magnetisation from packed state.  Replaces
+ * IsingModel.energy / magnetization (systems/ising.py:47-66, 93-102):
+ * E = fl32(fl32(-J)*S_bond) + fl32(fl32(-h)*S_spin), M = fl32(S_spin)/fl32(L*L). */
+int dbs_ising_observables(const uint32_t* bits, int L, int64_t n_chains, float J, float h,
+                          float* energy, float* magnetization, void* stream);
+
+/* Same observables from an fp32 (n, L, L) tensor of arbitrary real values
+ * (the reference API accepts continuous samples: samplers/diffusion.py:571-575).
+ * Any L >= 1 here (no packing). */
+int dbs_ising_observables_f32(const float* spins, int L, int64_t n, float J, float h,
+                              float* energy, float* magnetization, void* stream);
+
+/* Spin-spin correlation sums.  Replaces pair_correlation (analysis/correlation.py:8-47).
+ * For every chain c and displacement (di,dj) in [-R,R]^2, R = L/2, with
+ * r = floor(sqrt(di^2+dj^2)), 0 < r < R:
+ *   acc[group(c)][r] += sum over reference sites (i,j) of s(i,j)*s(i+di,j+dj)
+ * ref_mask: uint32 [L][W] bit mask of reference sites (NULL = all sites);
+ * group: int32 [n_chains] or NULL (all 0).  acc: int64 [n_groups][R], accumulated
+ * atomically (caller zeroes it).  Counts are data-independent: host computes them. */
+int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chains,
+                          const uint32_t* ref_mask, const int32_t* group,
+                          long long* acc, void* stream);
+
+/* Block accumulation of per-chain observables into the fp64 all-reduce block
+ * (SURVEY.md §8e): acc[group][0..4] += {1, E/N, |M|, M^2, M^4}. */
+int dbs_observable_accumulate(const float* energy, const float* magnetization, int L,
+                              int64_t n_chains, const int32_t* group, double* acc,
+                              void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Reverse-SDE Euler–Maruyama update.  Replaces the inner step of
+ * DiffusionSampler.sample (samplers/diffusion.py:232-243):
+ *   x <- (x + (c1*score)*dt) + ((c2*z)*temperature)      (fp32, no FMA contraction)
+ * c1 = fl32(sigma^2), c2 = fl32(sigma*sqrt(dt)); add_noise=0 on the last step.
+ * noise != NULL: z read from the tensor (test-mode injection port);
+ * noise == NULL: z = Box–Muller of Philox4x32-10(key=seed, ctr={sample_offset+n,
+ *                e/4, step, DBS_STREAM_NOISE}), e = element index inside the sample.
+ * ------------------------------------------------------------------------- */
+int dbs_em_step(float* x, const float* score, const float* noise, int64_t n_samples,
+                int64_t elems_per_sample, float c1, float dt, float c2, float temperature,
+                int add_noise, uint64_t seed, int64_t sample_offset, int64_t step,
+                void* stream);
+
+/* x ~ N(0,1) start of the reverse process (torch.randn at samplers/diffusion.py:216)
+ * from the same Philox stream with step = DBS_STEP_X0. */
+int dbs_gaussian_fill(float* x, int64_t n_samples, int64_t elems_per_sample, uint64_t seed,
+                      int64_t sample_offset, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Lennard-Jones pair energy / forces.  Replaces LennardJonesSystem.energy /
+ * forces / pairwise_distances / minimum_image (systems/lennard_jones.py:58-155).
+ * pos fp32 [B][N][2]; energy fp32 [B] (may be NULL); forces fp32 [B][N][2] (may be NULL).
+ * Same masks and epsilons as the reference: d = sqrt(dx^2+dy^2+1e-10),
+ * pair counted iff 0.1 < d < cutoff, unit = dr/(d+1e-10), E = 0.5*sum_ij.
+ * ------------------------------------------------------------------------- */
+int dbs_lj_energy_forces(const float* pos, int64_t B, int N, float box, float epsilon,
+                         float sigma, float cutoff, float energy_shift, float* energy,
+                         float* forces, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Score U-Net (models/score_network.py:154-268).
+ * A plan owns device copies of the weights repacked for the kernels
+ * ([tap][C_out][C_in], fp32 and bf16) and the layer schedule.
+ * ------------------------------------------------------------------------- */
+typedef struct dbs_unet_plan dbs_unet_plan;
+
+typedef struct dbs_unet_config {
+  int in_channels;      /* only 1 is built (Ising)                         */
+  int base_channels;    /* ScoreNetwork(base_channels=...)                  */
+  int time_embed_dim;
+  int num_blocks;
+  float output_scale;
+  int normalize_output; /* 0/1                                              */
+} dbs_unet_config;
+
+/* One named parameter of the reference state_dict: fp32, contiguous, DEVICE or
+ * HOST pointer (is_device says which); name as in ScoreNetwork.state_dict(). */
+typedef struct dbs_param {
+  const char* name;
+  const float* data;
+  int64_t numel;
+  int is_device;
+} dbs_param;
+
+/* precision: 0 = fp32 CUDA-core path (parity mode), 1 = bf16 tcgen05 path. */
+int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param* params, int n_params,
+                         const float* freqs_host, dbs_unet_plan** out);
+void dbs_unet_plan_destroy(dbs_unet_plan* plan);
+
+/* Bytes of caller-provided workspace needed for a forward of (B,1,H,W). */
+int64_t dbs_unet_workspace_bytes(const dbs_unet_plan* plan, int64_t B, int H, int W,
+                                 int precision);
+
+/* score = ScoreNetwork.forward(x, t)  (score_network.py:224-268).
+ * x, score: fp32 [B][1][H][W]; t: fp32 [n_t], n_t = 1 (all samples share t, the
+ * sampler's case: samplers/diffusion.py:223) or n_t = B. */
+int dbs_unet_forward(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_t,
+                     float* score, int64_t B, int H, int W, int precision, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
+/* Debug/parity port: after a forward, copy the named intermediate
+ * ("init", "enc0", "down0", ..., "mid", "up0", "dec0", ..., see unet_plan.cu) as
+ * fp32 NCHW into out (numel must match).  Returns DBS_ERR_INVALID if unknown. */
+int dbs_unet_debug_fetch(dbs_unet_plan* plan, const char* name, float* out, int64_t numel,
+                         void* workspace, int64_t B, int H, int W, int precision, void* stream);
+
+/* Stand-alone implicit-GEMM convolution on the tensor cores (tcgen05/TMEM/TMA);
+ * parity port for the kernel itself.  Replaces nn.Conv2d / nn.ConvTranspose2d as
+ * used at score_network.py:122-131, 201, 216, 243-259.
+ *   kind: 0 = conv kxk stride 1 pad k/2 (k = 1 or 3); 1 = conv 3x3 stride 2 pad 1;
+ *         2 = conv-transpose 4x4 stride 2 pad 1.
+ *   in0/in1: bf16 NHWC sources, channels C0 + C1 (in1 may be NULL, C1 = 0): the
+ *            skip concat of score_network.py:256 read as one K range.
+ *   weight:  bf16 [taps][C_out][C0+C1]; bias fp32 [C_out].
+ *   out:     bf16 NHWC [B][Ho][Wo][C_out]; stats (may be NULL): fp32 [B][8][2]
+ *            per-(sample, group) sum / sum of squares of the fp32 outputs
+ *            (GroupNorm(8) statistics, score_network.py:124-125), accumulated atomically.
+ */
+int dbs_conv_tc(const void* in0, int C0, const void* in1, int C1, const void* weight,
+                const float* bias, void* out, float* stats, int64_t B, int H, int W,
+                int C_out, int kind, int ksize, void* stream);
+
+/* Philox stream tags (ctr.w) and the x0 step tag. */
+#define DBS_STREAM_SWEEP 0x53574550u /* 'SWEP' */
+#define DBS_STREAM_INIT  0x494e4954u /* 'INIT' */
+#define DBS_STREAM_NOISE 0x4e4f4953u /* 'NOIS' */
+#define DBS_STEP_X0 (-1)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBS_B200_H */
