@@ -302,7 +302,6 @@ __global__ void ising_obs_f32_kernel(const float* __restrict__ spins, int L, flo
 // C(r) sums: one block per chain.  Rows are kept twice-unrolled (bit b of D = s[b mod L]) so a
 // periodic column shift is one funnel shift; a displacement costs L*W (xor, and, popc).
 constexpr int kCorrThreads = 128;
-constexpr int kCorrDW = 2 * ((kMaxL + 31) / 32) + 2;  // words of a doubled row
 
 __global__ void __launch_bounds__(kCorrThreads)
 ising_corr_kernel(const uint32_t* __restrict__ bits, int L, const uint32_t* __restrict__ ref_mask,
@@ -387,6 +386,21 @@ __global__ void obs_accumulate_kernel(const float* __restrict__ energy, const fl
   atomicAdd(a + 2, fabs(m));
   atomicAdd(a + 3, m2);
   atomicAdd(a + 4, m2 * m2);
+}
+
+// Single random-site attempt on an fp32 lattice (the reference's step(), samplers/mcmc.py:26-50):
+// same class/threshold arithmetic as the sweep, one thread per lattice of the batch.
+__global__ void ising_site_update_kernel(float* __restrict__ spins, int L, int64_t n, int i, int j,
+                                         const uint32_t* __restrict__ thr, uint32_t r) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  float* x = spins + b * L * L;
+  const int iu = (i == 0 ? L - 1 : i - 1), id = (i == L - 1 ? 0 : i + 1);
+  const int jl = (j == 0 ? L - 1 : j - 1), jr = (j == L - 1 ? 0 : j + 1);
+  const int s = x[i * L + j] > 0.f;
+  const int u = (x[iu * L + j] > 0.f) + (x[id * L + j] > 0.f) + (x[i * L + jl] > 0.f) + (x[i * L + jr] > 0.f);
+  const int k = 8 * s + u;
+  if ((r < thr[2 * k]) || thr[2 * k + 1]) x[i * L + j] = -x[i * L + j];
 }
 
 }  // namespace
@@ -487,6 +501,16 @@ extern "C" int dbs_observable_accumulate(const float* energy, const float* magne
   if (n_chains == 0) return DBS_OK;
   obs_accumulate_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, as_stream(stream)>>>(
       energy, magnetization, (double)(L * L), n_chains, group, acc);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_ising_site_update(float* spins, int L, int64_t n, int i, int j, const uint32_t* thr, uint32_t r,
+                                     void* stream) {
+  DBS_REQUIRE(spins && thr && L >= 1 && n >= 0, "ising_site_update: bad arguments");
+  DBS_REQUIRE(i >= 0 && i < L && j >= 0 && j < L, "ising_site_update: site (%d,%d) outside a %dx%d lattice", i, j, L, L);
+  if (n == 0) return DBS_OK;
+  ising_site_update_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(spins, L, n, i, j, thr, r);
   DBS_LAUNCHED();
   return DBS_OK;
 }

@@ -1,0 +1,920 @@
+// unet.cu — score U-Net executor: plan (repacked weights), layer schedule, and the CUDA-core
+// kernels (fp32 parity path; also the fallback for shapes the tcgen05 kernel does not take).
+//
+// Replaces (reference file:line, /root/reference/backend/ml/models/score_network.py):
+//   SinusoidalTimeEmbedding.forward :20-41, ScoreNetwork.time_mlp :185-189,235
+//   ConvBlock.forward :133-151 (conv3x3 -> GroupNorm(8) -> SiLU -> +time bias -> conv3x3 ->
+//                               GroupNorm -> SiLU -> + residual_scale * (conv1x1(x) | x))
+//   ScoreNetwork.forward :224-268 (init conv, encoder/downsample, middle, upsample/concat/decoder,
+//                                  final conv, optional std-normalise, output_scale)
+//
+// Activations are NHWC (channels innermost) so that a pixel's channel vector is one contiguous
+// run: fp32 in precision 0, bf16 in precision 1.  With in_channels == 1 the API's NCHW input and
+// output tensors are already NHWC.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "unet.cuh"
+
+namespace dbs {
+
+// ------------------------------------------------------------------------------------------------
+// geometry builders
+ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int stride) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  const int pad = ksize / 2;
+  g.B = B; g.Hin = H; g.Win = W;
+  g.Hout = (H + 2 * pad - ksize) / stride + 1;
+  g.Wout = (W + 2 * pad - ksize) / stride + 1;
+  g.Hm = g.Hout; g.Wm = g.Wout;
+  g.C0 = C0; g.C1 = C1; g.Cout = Cout;
+  g.in_stride = stride; g.out_stride = 1; g.oph = 0; g.opw = 0;
+  g.n_taps = ksize * ksize;
+  for (int kh = 0; kh < ksize; ++kh)
+    for (int kw = 0; kw < ksize; ++kw) {
+      const int t = kh * ksize + kw;
+      g.dh[t] = (signed char)(kh - pad);
+      g.dw[t] = (signed char)(kw - pad);
+      g.widx[t] = (unsigned char)t;
+    }
+  return g;
+}
+
+// ConvTranspose2d(k=4, s=2, p=1): out[2a+ph] gathers in[a + dh] with kh = ph + 1 - 2*dh, i.e.
+// ph=0: (dh,kh) in {(0,1), (-1,3)};  ph=1: (dh,kh) in {(+1,0), (0,2)}.
+ConvGeom geom_convT_phase(int B, int H, int W, int Cin, int Cout, int ph, int pw) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.Hin = H; g.Win = W; g.Hm = H; g.Wm = W; g.Hout = 2 * H; g.Wout = 2 * W;
+  g.C0 = Cin; g.C1 = 0; g.Cout = Cout;
+  g.in_stride = 1; g.out_stride = 2; g.oph = ph; g.opw = pw;
+  g.n_taps = 4;
+  const int dhs[2][2] = {{0, -1}, {1, 0}};
+  const int khs[2][2] = {{1, 3}, {0, 2}};
+  int t = 0;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j, ++t) {
+      g.dh[t] = (signed char)dhs[ph][i];
+      g.dw[t] = (signed char)dhs[pw][j];
+      g.widx[t] = (unsigned char)(khs[ph][i] * 4 + khs[pw][j]);
+    }
+  return g;
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// element helpers
+template <typename T> struct Quad;
+template <> struct Quad<float> {
+  static __device__ __forceinline__ void load(const float* p, float v[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float v[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Quad<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[4]) {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float v[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 q;
+    q.x = *reinterpret_cast<const uint32_t*>(&a);
+    q.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = q;
+  }
+};
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// generic implicit-GEMM convolution on the CUDA cores: 64 pixels x 64 couts per CTA, K chunk 16
+constexpr int kGT = 64, kGK = 16, kGPad = 68;
+
+template <typename T, typename TW>
+__global__ void __launch_bounds__(256)
+conv_generic_kernel(ConvGeom g, const T* __restrict__ in0, const T* __restrict__ in1,
+                    const TW* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out) {
+  __shared__ __align__(16) float As[kGK][kGPad];
+  __shared__ __align__(16) float Bs[kGK][kGPad];
+  const int tid = threadIdx.x;
+  const int Cin = g.C0 + g.C1;
+  const int64_t M = (int64_t)g.B * g.Hm * g.Wm;
+  const int64_t m0 = (int64_t)blockIdx.x * kGT;
+  const int co0 = blockIdx.y * kGT;
+
+  // loader role: one pixel (resp. one cout) and one channel quad
+  const int lp = tid >> 2, lc = (tid & 3) * 4;
+  const int64_t lm = m0 + lp;
+  const bool lvalid = lm < M;
+  int ln = 0, la = 0, lb = 0;
+  if (lvalid) {
+    ln = (int)(lm / ((int64_t)g.Hm * g.Wm));
+    const int rem = (int)(lm - (int64_t)ln * g.Hm * g.Wm);
+    la = rem / g.Wm;
+    lb = rem - la * g.Wm;
+  }
+  const int lco = co0 + lp;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < g.n_taps; ++t) {
+    const int ih = la * g.in_stride + g.dh[t];
+    const int iw = lb * g.in_stride + g.dw[t];
+    const bool pix_ok = lvalid && ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win;
+    const int64_t pix = ((int64_t)ln * g.Hin + ih) * g.Win + iw;
+    const TW* wt = w + (int64_t)g.widx[t] * g.Cout * Cin;
+    for (int c0 = 0; c0 < Cin; c0 += kGK) {
+      const int c = c0 + lc;
+      float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pix_ok && c < Cin) {
+        if (c < g.C0) Quad<T>::load(in0 + pix * g.C0 + c, av);
+        else Quad<T>::load(in1 + pix * g.C1 + (c - g.C0), av);
+      }
+      if (lco < g.Cout && c < Cin) Quad<TW>::load(wt + (int64_t)lco * Cin + c, bv);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        As[lc + q][lp] = av[q];
+        Bs[lc + q][lp] = bv[q];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kGK; ++kk) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+  const int co = co0 + tx * 4;
+  if (co >= g.Cout) return;
+  float bq[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bq[j] = bias ? bias[co + j] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int n = (int)(m / ((int64_t)g.Hm * g.Wm));
+    const int rem = (int)(m - (int64_t)n * g.Hm * g.Wm);
+    const int a = rem / g.Wm, b = rem - a * g.Wm;
+    const int oh = a * g.out_stride + g.oph, ow = b * g.out_stride + g.opw;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bq[j];
+    Quad<T>::store(out + (((int64_t)n * g.Hout + oh) * g.Wout + ow) * g.Cout + co, v);
+  }
+}
+
+// init conv: 1 -> C, 3x3 pad 1 (score_network.py:192, 238).  x fp32 [B][H][W]; w [9][C].
+template <typename T>
+__global__ void __launch_bounds__(256)
+init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 T* __restrict__ out, int64_t n_pix, int H, int W, int C) {
+  const int cq = C >> 2;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_pix * cq) return;
+  const int64_t p = g / cq;
+  const int c = (int)(g - p * cq) * 4;
+  const int ww = (int)(p % W);
+  const int hh = (int)((p / W) % H);
+  float v[4] = {bias[c], bias[c + 1], bias[c + 2], bias[c + 3]};
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ih = hh + kh - 1, iw = ww + kw - 1;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const float xv = __ldg(x + p + (int64_t)(kh - 1) * W + (kw - 1));
+      const float4 wq = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C + c));
+      v[0] = fmaf(xv, wq.x, v[0]); v[1] = fmaf(xv, wq.y, v[1]);
+      v[2] = fmaf(xv, wq.z, v[2]); v[3] = fmaf(xv, wq.w, v[3]);
+    }
+  Quad<T>::store(out + p * C + c, v);
+}
+
+// final conv: C -> 1, 3x3 pad 1, then * output_scale (score_network.py:219, 259, 268).
+template <typename T>
+__global__ void __launch_bounds__(128)
+final_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int64_t n_pix, int H, int W, int C, float scale) {
+  extern __shared__ float sw[];  // [9][C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  const int ww = (int)(p % W);
+  const int hh = (int)((p / W) % H);
+  float acc = 0.f;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ih = hh + kh - 1, iw = ww + kw - 1;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const T* src = in + (p + (int64_t)(kh - 1) * W + (kw - 1)) * C;
+      const float* wk = sw + (kh * 3 + kw) * C;
+      for (int c = 0; c < C; c += 4) {
+        float v[4];
+        Quad<T>::load(src + c, v);
+        acc = fmaf(v[0], wk[c], acc); acc = fmaf(v[1], wk[c + 1], acc);
+        acc = fmaf(v[2], wk[c + 2], acc); acc = fmaf(v[3], wk[c + 3], acc);
+      }
+    }
+  out[p] = scale * (acc + bias[0]);
+}
+
+// optional per-sample std normalisation (score_network.py:262-265): score / (std + 1e-8),
+// unbiased std over H*W, applied before output_scale (so undo/redo the scale here).
+__global__ void normalize_output_kernel(float* __restrict__ score, int HW, float scale) {
+  float* s = score + (int64_t)blockIdx.x * HW;
+  __shared__ double red[2][32];
+  double sum = 0.0, sq = 0.0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const double v = (double)s[i] / (double)scale;
+    sum += v; sq += v * v;
+  }
+  sum = warp_sum(sum); sq = warp_sum(sq);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = sum; red[1][wid] = sq; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    sum = lane < nw ? red[0][lane] : 0.0;
+    sq = lane < nw ? red[1][lane] : 0.0;
+    sum = warp_sum(sum); sq = warp_sum(sq);
+    if (lane == 0) {
+      const double mean = sum / HW;
+      double var = (sq - HW * mean * mean) / (HW > 1 ? HW - 1 : 1);
+      if (var < 0) var = 0;
+      red[0][0] = sqrt(var) + 1e-8;
+    }
+  }
+  __syncthreads();
+  const float inv = (float)(1.0 / red[0][0]);
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) s[i] = scale * ((s[i] / scale) * inv);
+}
+
+// GroupNorm statistics, two passes, fp64 accumulation: one CTA per (sample, group) -> (mean, rstd)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const T* __restrict__ y, float* __restrict__ stats, int HW, int C, int G, float eps) {
+  const int n = blockIdx.x / G, gi = blockIdx.x - n * G;
+  const int Cg = C / G;
+  const T* base = y + (int64_t)n * HW * C + gi * Cg;
+  const int64_t cnt = (int64_t)HW * Cg;
+  __shared__ double red[32];
+  __shared__ double s_mean;
+  double sum = 0.0;
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int64_t p = i / Cg;
+    const int c = (int)(i - p * Cg);
+    sum += (double)to_f<T>(base[p * C + c]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  sum = warp_sum(sum);
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  if (wid == 0) {
+    sum = lane < nw ? red[lane] : 0.0;
+    sum = warp_sum(sum);
+    if (lane == 0) s_mean = sum / (double)cnt;
+  }
+  __syncthreads();
+  const double mean = s_mean;
+  double sq = 0.0;
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int64_t p = i / Cg;
+    const int c = (int)(i - p * Cg);
+    const double d = (double)to_f<T>(base[p * C + c]) - mean;
+    sq += d * d;
+  }
+  sq = warp_sum(sq);
+  __syncthreads();
+  if (lane == 0) red[wid] = sq;
+  __syncthreads();
+  if (wid == 0) {
+    sq = lane < nw ? red[lane] : 0.0;
+    sq = warp_sum(sq);
+    if (lane == 0) {
+      const float var = (float)(sq / (double)cnt);
+      stats[(int64_t)blockIdx.x * 2 + 0] = (float)mean;
+      stats[(int64_t)blockIdx.x * 2 + 1] = 1.0f / sqrtf(var + eps);
+    }
+  }
+}
+
+// normalise * gamma + beta -> SiLU -> (+ time bias) -> (+ residual_scale * residual)
+// stats: (mean, rstd) per (n, g), or raw (sum, sumsq) from the tcgen05 epilogue when raw != 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __restrict__ stats, int raw,
+                float inv_cnt, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ tbias, int t_stride, const T* __restrict__ res, float res_scale,
+                int64_t n_quads, int HW, int C, int G) {
+  const int cq = C >> 2, Cg = C / G;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = q / cq;
+    const int c = (int)(q - p * cq) * 4;
+    const int n = (int)(p / HW);
+    float v[4];
+    Quad<T>::load(y + p * C + c, v);
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (res) Quad<T>::load(res + p * C + c, r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int gi = (c + k) / Cg;
+      const float s0 = stats[((int64_t)n * G + gi) * 2 + 0];
+      const float s1 = stats[((int64_t)n * G + gi) * 2 + 1];
+      float mean, rstd;
+      if (raw) {
+        mean = s0 * inv_cnt;
+        const float var = fmaxf(s1 * inv_cnt - mean * mean, 0.f);
+        rstd = rsqrtf(var + eps);
+      } else {
+        mean = s0; rstd = s1;
+      }
+      float h = (v[k] - mean) * rstd * gamma[c + k] + beta[c + k];
+      h = silu(h);
+      if (tbias) h += tbias[(int64_t)n * t_stride + c + k];
+      if (res) h += res_scale * r[k];
+      v[k] = h;
+    }
+    Quad<T>::store(out + p * C + c, v);
+  }
+}
+
+// time path (score_network.py:20-41, 185-189, 126/146): one CTA per distinct t.
+__global__ void __launch_bounds__(128)
+time_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int T,
+            const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
+            const float* __restrict__ b2, const float* __restrict__ wt, const float* __restrict__ bt, int sumC,
+            float* __restrict__ tbias) {
+  extern __shared__ float sm[];
+  float* emb = sm;           // [T]
+  float* hid = sm + T;       // [2T]
+  float* temb = sm + 3 * T;  // [T]
+  const int half = T / 2;
+  const float tv = t[blockIdx.x];
+  for (int k = threadIdx.x; k < T; k += blockDim.x) {
+    const int f = k < half ? k : k - half;
+    const float arg = __fmul_rn(__fmul_rn(tv, freqs[f]), 1000.0f);
+    emb[k] = k < half ? sinf(arg) : cosf(arg);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * T; j += blockDim.x) {
+    float a = b0[j];
+    for (int k = 0; k < T; ++k) a = fmaf(w0[j * T + k], emb[k], a);
+    hid[j] = silu(a);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    float a = b2[i];
+    for (int j = 0; j < 2 * T; ++j) a = fmaf(w2[i * 2 * T + j], hid[j], a);
+    temb[i] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < sumC; c += blockDim.x) {
+    float a = bt[c];
+    for (int i = 0; i < T; ++i) a = fmaf(wt[c * T + i], temb[i], a);
+    tbias[(int64_t)blockIdx.x * sumC + c] = a;
+  }
+}
+
+// weight repack: Conv2d [co][ci][kh][kw] (transposed = 0) or ConvTranspose2d [ci][co][kh][kw]
+// (transposed = 1)  ->  [tap][co][ci] in fp32 and bf16
+__global__ void repack_kernel(const float* __restrict__ src, float* __restrict__ w32, __nv_bfloat16* __restrict__ w16,
+                              int co_n, int ci_n, int taps, int transposed) {
+  const int64_t total = (int64_t)taps * co_n * ci_n;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = (int)(i % ci_n);
+  const int co = (int)((i / ci_n) % co_n);
+  const int t = (int)(i / ((int64_t)ci_n * co_n));
+  const int64_t s = transposed ? (((int64_t)ci * co_n + co) * taps + t) : (((int64_t)co * ci_n + ci) * taps + t);
+  const float v = src[s];
+  w32[i] = v;
+  w16[i] = __float2bfloat16_rn(v);
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t total, int HW, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into NCHW output
+  if (i >= total) return;
+  const int64_t n = i / ((int64_t)C * HW);
+  const int c = (int)((i / HW) % C);
+  const int p = (int)(i % HW);
+  out[i] = to_f<T>(in[(n * HW + p) * C + c]);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// plan
+struct BlockW {
+  int cin = 0, cout = 0, tb_off = 0;
+  bool has_res = false;
+  ConvWeights conv1, conv2, res;
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+};
+
+}  // namespace dbs
+
+struct dbs_unet_plan {
+  dbs_unet_config cfg;
+  std::vector<void*> allocs;
+  float *freqs = nullptr, *tw0 = nullptr, *tb0 = nullptr, *tw2 = nullptr, *tb2 = nullptr;
+  float *twt = nullptr, *tbt = nullptr;  // concatenated per-block time Linear [sumC][T], [sumC]
+  int sumC = 0;
+  float *init_w = nullptr, *init_b = nullptr, *final_w = nullptr, *final_b = nullptr;
+  std::vector<dbs::BlockW> enc, dec;
+  dbs::BlockW mid;
+  std::vector<dbs::ConvWeights> down, up;
+};
+
+namespace dbs {
+namespace {
+
+struct ParamTable {
+  const dbs_param* p;
+  int n;
+  const dbs_param* find(const std::string& name) const {
+    for (int i = 0; i < n; ++i)
+      if (name == p[i].name) return &p[i];
+    return nullptr;
+  }
+};
+
+int dev_alloc(dbs_unet_plan* plan, size_t bytes, void** out) {
+  DBS_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+  plan->allocs.push_back(*out);
+  return DBS_OK;
+}
+
+// copy a named fp32 parameter to a fresh device buffer
+int upload(dbs_unet_plan* plan, const ParamTable& pt, const std::string& name, int64_t numel, float** out) {
+  const dbs_param* q = pt.find(name);
+  DBS_REQUIRE(q != nullptr, "unet plan: parameter '%s' missing from state_dict", name.c_str());
+  DBS_REQUIRE(q->numel == numel, "unet plan: parameter '%s' has %lld elements, expected %lld", name.c_str(),
+              (long long)q->numel, (long long)numel);
+  void* d = nullptr;
+  int rc = dev_alloc(plan, (size_t)numel * 4, &d);
+  if (rc) return rc;
+  DBS_CUDA(cudaMemcpy(d, q->data, (size_t)numel * 4, q->is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  *out = (float*)d;
+  return DBS_OK;
+}
+
+int make_conv(dbs_unet_plan* plan, const ParamTable& pt, const std::string& prefix, int cin, int cout, int ks,
+              bool transposed, ConvWeights* cw) {
+  cw->cin = cin; cw->cout = cout; cw->taps = ks * ks;
+  const int64_t numel = (int64_t)cin * cout * ks * ks;
+  float* raw = nullptr;
+  int rc = upload(plan, pt, prefix + ".weight", numel, &raw);
+  if (rc) return rc;
+  rc = upload(plan, pt, prefix + ".bias", cout, &cw->bias);
+  if (rc) return rc;
+  void *w32 = nullptr, *w16 = nullptr;
+  if ((rc = dev_alloc(plan, (size_t)numel * 4, &w32))) return rc;
+  if ((rc = dev_alloc(plan, (size_t)numel * 2, &w16))) return rc;
+  cw->w32 = (float*)w32; cw->w16 = (__nv_bfloat16*)w16;
+  repack_kernel<<<(unsigned)((numel + 255) / 256), 256>>>(raw, cw->w32, cw->w16, cout, cin, ks * ks, transposed ? 1 : 0);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+int make_block(dbs_unet_plan* plan, const ParamTable& pt, const std::string& prefix, int cin, int cout, BlockW* b) {
+  b->cin = cin; b->cout = cout; b->has_res = cin != cout;
+  int rc;
+  if ((rc = make_conv(plan, pt, prefix + "conv1", cin, cout, 3, false, &b->conv1))) return rc;
+  if ((rc = make_conv(plan, pt, prefix + "conv2", cout, cout, 3, false, &b->conv2))) return rc;
+  if (b->has_res && (rc = make_conv(plan, pt, prefix + "residual", cin, cout, 1, false, &b->res))) return rc;
+  if ((rc = upload(plan, pt, prefix + "norm1.weight", cout, &b->g1))) return rc;
+  if ((rc = upload(plan, pt, prefix + "norm1.bias", cout, &b->b1))) return rc;
+  if ((rc = upload(plan, pt, prefix + "norm2.weight", cout, &b->g2))) return rc;
+  if ((rc = upload(plan, pt, prefix + "norm2.bias", cout, &b->b2))) return rc;
+  return DBS_OK;
+}
+
+struct Bump {
+  char* base; int64_t cap; int64_t off = 0;
+  void* take(int64_t bytes) {
+    const int64_t a = (off + 1023) & ~(int64_t)1023;
+    off = a + bytes;
+    return (base && off <= cap) ? base + a : nullptr;
+  }
+};
+
+template <typename T> struct WSel;
+template <> struct WSel<float> { using type = float; static const float* get(const ConvWeights& w) { return w.w32; } };
+template <> struct WSel<__nv_bfloat16> { using type = __nv_bfloat16; static const __nv_bfloat16* get(const ConvWeights& w) { return w.w16; } };
+
+struct Ctx {
+  dbs_unet_plan* plan;
+  cudaStream_t st;
+  int64_t B;
+  int n_t;            // 1 or B
+  float* tbias;       // [n_t][sumC]
+  float* stats;       // [B][8][2]
+  bool use_tc;
+  const char* tap; float* tap_out; int64_t tap_numel; bool tapped = false;
+};
+
+template <typename T>
+int run_conv(Ctx& c, const ConvGeom& g, const T* in0, const T* in1, const ConvWeights& w, T* out, float* raw_stats,
+             int groups, bool* stats_done) {
+  if (stats_done) *stats_done = false;
+  if (c.use_tc && sizeof(T) == 2) {
+    const int rc = conv_tc_launch(g, (const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, w.w16, w.bias,
+                                  (__nv_bfloat16*)out, raw_stats, groups, c.st);
+    if (rc == DBS_OK) { if (stats_done) *stats_done = raw_stats != nullptr; return rc; }
+    if (rc != DBS_ERR_UNSUPPORTED) return rc;
+  }
+  const int Cin = g.C0 + g.C1;
+  DBS_REQUIRE(g.C0 % 4 == 0 && g.C1 % 4 == 0 && g.Cout % 4 == 0 && Cin > 0,
+              "unet: channel counts must be multiples of 4 (got %d+%d -> %d)", g.C0, g.C1, g.Cout);
+  const int64_t M = (int64_t)g.B * g.Hm * g.Wm;
+  dim3 grid((unsigned)((M + kGT - 1) / kGT), (unsigned)((g.Cout + kGT - 1) / kGT));
+  conv_generic_kernel<T, typename WSel<T>::type><<<grid, 256, 0, c.st>>>(g, in0, in1, WSel<T>::get(w), w.bias, out);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+template <typename T>
+int maybe_tap(Ctx& c, const char* name, const T* buf, int64_t B, int H, int W, int C) {
+  if (!c.tap || c.tapped || strcmp(c.tap, name) != 0) return DBS_OK;
+  const int64_t total = B * H * W * C;
+  DBS_REQUIRE(total == c.tap_numel, "unet tap '%s': buffer has %lld elements, caller passed %lld", name,
+              (long long)total, (long long)c.tap_numel);
+  nhwc_to_nchw_f32_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(buf, c.tap_out, total, H * W, C);
+  DBS_LAUNCHED();
+  c.tapped = true;
+  return DBS_OK;
+}
+
+// GroupNorm(min(8,C)) + SiLU (+time bias) (+residual) on y -> out
+template <typename T>
+int run_gn(Ctx& c, const T* y, T* out, bool have_raw_stats, const float* gamma, const float* beta, int tb_off,
+           bool add_time, const T* res, int H, int W, int C) {
+  const int G = C < 8 ? C : 8;
+  const int HW = H * W;
+  if (!have_raw_stats) {
+    gn_stats_kernel<T><<<(unsigned)(c.B * G), 256, 0, c.st>>>(y, c.stats, HW, C, G, 1e-5f);
+    DBS_LAUNCHED();
+  }
+  const int64_t nq = c.B * HW * (C / 4);
+  int64_t blocks = (nq + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const float inv_cnt = 1.0f / (float)((int64_t)HW * (C / G));
+  gn_apply_kernel<T><<<(unsigned)blocks, 256, 0, c.st>>>(
+      y, out, c.stats, have_raw_stats ? 1 : 0, inv_cnt, 1e-5f, gamma, beta,
+      add_time ? c.tbias + tb_off : nullptr, c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, nq, HW, C, G);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+// ConvBlock.forward (score_network.py:133-151)
+template <typename T>
+int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, const T* in1, int C1, int H, int W,
+              T* ty, T* th, T* tr, T* out) {
+  int rc;
+  const int G = bw.cout < 8 ? bw.cout : 8;
+  bool sd = false;
+  const size_t stat_bytes = (size_t)c.B * G * 2 * sizeof(float);
+  ConvGeom g1 = geom_conv((int)c.B, H, W, C0, C1, bw.cout, 3, 1);
+  if (c.use_tc) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+  if ((rc = run_conv<T>(c, g1, in0, in1, bw.conv1, ty, c.stats, G, &sd))) return rc;
+  {
+    std::string nm = std::string(name) + ".conv1";
+    if ((rc = maybe_tap<T>(c, nm.c_str(), ty, c.B, H, W, bw.cout))) return rc;
+  }
+  if ((rc = run_gn<T>(c, ty, th, sd, bw.g1, bw.b1, bw.tb_off, true, (const T*)nullptr, H, W, bw.cout))) return rc;
+  ConvGeom g2 = geom_conv((int)c.B, H, W, bw.cout, 0, bw.cout, 3, 1);
+  if (c.use_tc) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+  if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
+  const T* res = in0;
+  if (bw.has_res) {
+    ConvGeom gr = geom_conv((int)c.B, H, W, C0, C1, bw.cout, 1, 1);
+    if ((rc = run_conv<T>(c, gr, in0, in1, bw.res, tr, nullptr, G, nullptr))) return rc;
+    res = tr;
+  } else {
+    DBS_REQUIRE(C1 == 0, "unet: identity residual with a concatenated input");
+  }
+  if ((rc = run_gn<T>(c, ty, out, sd, bw.g2, bw.b2, 0, false, res, H, W, bw.cout))) return rc;
+  return maybe_tap<T>(c, name, out, c.B, H, W, bw.cout);
+}
+
+struct Sizes {
+  int64_t max_act = 0;   // elements of the largest activation tensor
+  int64_t total = 0;     // workspace bytes
+};
+
+template <typename T>
+int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_t, float* score, int64_t B, int H,
+                 int W, bool use_tc, void* workspace, int64_t ws_bytes, const char* tap, float* tap_out,
+                 int64_t tap_numel, cudaStream_t st, int64_t* need_bytes) {
+  const dbs_unet_config& cfg = plan->cfg;
+  const int nb = cfg.num_blocks, C = cfg.base_channels, Td = cfg.time_embed_dim;
+  Bump ws{(char*)workspace, ws_bytes};
+  const bool dry = need_bytes != nullptr;
+
+  // ---- workspace carve-up (identical in the dry run that sizes it)
+  float* tbias = (float*)ws.take((int64_t)n_t * plan->sumC * 4);
+  float* stats = (float*)ws.take(B * 8 * 2 * 4);
+  int64_t max_act = (int64_t)B * H * W * C * 2;  // enc0 output has 2C channels at full resolution
+  {
+    int h = H, w = W, ch = C;
+    for (int i = 0; i < nb; ++i) {
+      const int co = C << (i + 1);
+      max_act = std::max(max_act, (int64_t)B * h * w * co);
+      h = (h - 1) / 2 + 1; w = (w - 1) / 2 + 1; ch = co;
+    }
+    (void)ch;
+  }
+  T* a0 = (T*)ws.take(B * H * W * C * (int64_t)sizeof(T));
+  T* ty = (T*)ws.take(max_act * (int64_t)sizeof(T));
+  T* th = (T*)ws.take(max_act * (int64_t)sizeof(T));
+  T* tr = (T*)ws.take(max_act * (int64_t)sizeof(T));
+  T* pp[2] = {(T*)ws.take(max_act * (int64_t)sizeof(T)), (T*)ws.take(max_act * (int64_t)sizeof(T))};
+  std::vector<T*> skip(nb);
+  std::vector<int> sh(nb), sw_(nb), sc(nb);
+  {
+    int h = H, w = W;
+    for (int i = 0; i < nb; ++i) {
+      sc[i] = C << (i + 1); sh[i] = h; sw_[i] = w;
+      skip[i] = (T*)ws.take((int64_t)B * h * w * sc[i] * (int64_t)sizeof(T));
+      h = (h - 1) / 2 + 1; w = (w - 1) / 2 + 1;
+    }
+  }
+  if (dry) { *need_bytes = ws.off + 1024; return DBS_OK; }
+  DBS_REQUIRE(workspace != nullptr && ws.off <= ws_bytes, "unet_forward: workspace too small (%lld < %lld bytes)",
+              (long long)ws_bytes, (long long)ws.off);
+
+  Ctx c{plan, st, B, (int)n_t, tbias, stats, use_tc, tap, tap_out, tap_numel};
+  int rc;
+
+  // ---- time path
+  time_kernel<<<(unsigned)n_t, 128, (size_t)4 * Td * 4, st>>>(t, plan->freqs, Td, plan->tw0, plan->tb0, plan->tw2,
+                                                             plan->tb2, plan->twt, plan->tbt, plan->sumC, tbias);
+  DBS_LAUNCHED();
+
+  // ---- init conv
+  {
+    const int64_t n_pix = B * H * W;
+    const int64_t nthr = n_pix * (C / 4);
+    init_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(x, plan->init_w, plan->init_b, a0, n_pix, H, W, C);
+    DBS_LAUNCHED();
+    if ((rc = maybe_tap<T>(c, "init", a0, B, H, W, C))) return rc;
+  }
+
+  // ---- encoder
+  const T* cur = a0;
+  int ch = C, h = H, w = W, flip = 0;
+  char name[32];
+  for (int i = 0; i < nb; ++i) {
+    snprintf(name, sizeof(name), "enc%d", i);
+    if ((rc = run_block<T>(c, plan->enc[i], name, cur, ch, (const T*)nullptr, 0, h, w, ty, th, tr, skip[i]))) return rc;
+    ch = sc[i];
+    ConvGeom gd = geom_conv((int)B, h, w, ch, 0, ch, 3, 2);
+    T* dst = pp[flip]; flip ^= 1;
+    if ((rc = run_conv<T>(c, gd, skip[i], (const T*)nullptr, plan->down[i], dst, nullptr, 8, nullptr))) return rc;
+    h = gd.Hout; w = gd.Wout;
+    snprintf(name, sizeof(name), "down%d", i);
+    if ((rc = maybe_tap<T>(c, name, dst, B, h, w, ch))) return rc;
+    cur = dst;
+  }
+  // ---- middle
+  {
+    T* dst = pp[flip]; flip ^= 1;
+    if ((rc = run_block<T>(c, plan->mid, "mid", cur, ch, (const T*)nullptr, 0, h, w, ty, th, tr, dst))) return rc;
+    cur = dst;
+  }
+  // ---- decoder
+  for (int i = 0; i < nb; ++i) {
+    const int si = nb - 1 - i;
+    DBS_REQUIRE(2 * h == sh[si] && 2 * w == sw_[si],
+                "unet: lattice %dx%d is not divisible by 2^%d; the bilinear fix-up of score_network.py:254-255 is not built",
+                H, W, nb);
+    T* up = pp[flip]; flip ^= 1;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        ConvGeom gu = geom_convT_phase((int)B, h, w, ch, ch, ph, pw);
+        if ((rc = run_conv<T>(c, gu, cur, (const T*)nullptr, plan->up[i], up, nullptr, 8, nullptr))) return rc;
+      }
+    h *= 2; w *= 2;
+    snprintf(name, sizeof(name), "up%d", i);
+    if ((rc = maybe_tap<T>(c, name, up, B, h, w, ch))) return rc;
+    T* dst = pp[flip]; flip ^= 1;
+    snprintf(name, sizeof(name), "dec%d", i);
+    if ((rc = run_block<T>(c, plan->dec[i], name, up, ch, skip[si], sc[si], h, w, ty, th, tr, dst))) return rc;
+    ch = plan->dec[i].cout;
+    cur = dst;
+  }
+  // ---- final conv (+ optional normalisation, output scale)
+  {
+    const int64_t n_pix = B * H * W;
+    final_conv_kernel<T><<<(unsigned)((n_pix + 127) / 128), 128, (size_t)9 * C * 4, st>>>(
+        cur, plan->final_w, plan->final_b, score, n_pix, H, W, C, cfg.output_scale);
+    DBS_LAUNCHED();
+    if (cfg.normalize_output) {
+      normalize_output_kernel<<<(unsigned)B, 256, 0, st>>>(score, H * W, cfg.output_scale);
+      DBS_LAUNCHED();
+    }
+  }
+  if (tap && !c.tapped) {
+    set_error("unet tap '%s' not found", tap);
+    return DBS_ERR_INVALID;
+  }
+  return DBS_OK;
+}
+
+int check_forward_args(const dbs_unet_plan* plan, int64_t B, int H, int W, int precision) {
+  DBS_REQUIRE(plan != nullptr, "unet: null plan");
+  DBS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "unet: bad shape B=%lld H=%d W=%d", (long long)B, H, W);
+  DBS_REQUIRE(precision == 0 || precision == 1, "unet: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
+  const int div = 1 << plan->cfg.num_blocks;
+  DBS_REQUIRE(H % div == 0 && W % div == 0,
+              "unet: lattice %dx%d is not divisible by 2^num_blocks=%d; the bilinear fix-up of score_network.py:254-255 is not built",
+              H, W, div);
+  return DBS_OK;
+}
+
+}  // namespace
+}  // namespace dbs
+
+using namespace dbs;
+
+extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param* params, int n_params,
+                                    const float* freqs_host, dbs_unet_plan** out) {
+  DBS_REQUIRE(cfg && params && out && freqs_host, "unet_plan_create: null argument");
+  DBS_REQUIRE(cfg->in_channels == 1, "unet: only in_channels == 1 (Ising lattices) is built, got %d", cfg->in_channels);
+  DBS_REQUIRE(cfg->base_channels >= 4 && cfg->base_channels % 4 == 0, "unet: base_channels must be a multiple of 4");
+  DBS_REQUIRE(cfg->time_embed_dim >= 4 && cfg->time_embed_dim % 2 == 0 && cfg->time_embed_dim <= 1024,
+              "unet: time_embed_dim must be even, 4..1024");
+  DBS_REQUIRE(cfg->num_blocks >= 1 && cfg->num_blocks <= 6, "unet: num_blocks must be 1..6");
+  dbs_unet_plan* plan = new dbs_unet_plan();
+  plan->cfg = *cfg;
+  const ParamTable pt{params, n_params};
+  const int C = cfg->base_channels, T = cfg->time_embed_dim, nb = cfg->num_blocks;
+  int rc = DBS_OK;
+  auto fail = [&](int code) { dbs_unet_plan_destroy(plan); return code; };
+
+  void* f = nullptr;
+  if ((rc = dev_alloc(plan, (size_t)(T / 2) * 4, &f))) return fail(rc);
+  plan->freqs = (float*)f;
+  if (cudaMemcpy(plan->freqs, freqs_host, (size_t)(T / 2) * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("unet_plan_create: freqs upload failed");
+    return fail(DBS_ERR_CUDA);
+  }
+  if ((rc = upload(plan, pt, "time_mlp.0.weight", (int64_t)2 * T * T, &plan->tw0))) return fail(rc);
+  if ((rc = upload(plan, pt, "time_mlp.0.bias", 2 * T, &plan->tb0))) return fail(rc);
+  if ((rc = upload(plan, pt, "time_mlp.2.weight", (int64_t)2 * T * T, &plan->tw2))) return fail(rc);
+  if ((rc = upload(plan, pt, "time_mlp.2.bias", T, &plan->tb2))) return fail(rc);
+
+  // init / final conv: [co][ci][3][3] -> [tap][C]
+  {
+    float *raw = nullptr, *rawf = nullptr;
+    if ((rc = upload(plan, pt, "init_conv.weight", (int64_t)C * 9, &raw))) return fail(rc);
+    if ((rc = upload(plan, pt, "init_conv.bias", C, &plan->init_b))) return fail(rc);
+    if ((rc = upload(plan, pt, "final.weight", (int64_t)C * 9, &rawf))) return fail(rc);
+    if ((rc = upload(plan, pt, "final.bias", 1, &plan->final_b))) return fail(rc);
+    void *iw = nullptr, *fw = nullptr, *scratch = nullptr;
+    if ((rc = dev_alloc(plan, (size_t)C * 9 * 4, &iw))) return fail(rc);
+    if ((rc = dev_alloc(plan, (size_t)C * 9 * 4, &fw))) return fail(rc);
+    if ((rc = dev_alloc(plan, (size_t)C * 9 * 2, &scratch))) return fail(rc);
+    plan->init_w = (float*)iw; plan->final_w = (float*)fw;
+    // init: co = C, ci = 1 -> [tap][C][1]; final: co = 1, ci = C -> [tap][1][C]
+    repack_kernel<<<(unsigned)((C * 9 + 255) / 256), 256>>>(raw, plan->init_w, (__nv_bfloat16*)scratch, C, 1, 9, 0);
+    repack_kernel<<<(unsigned)((C * 9 + 255) / 256), 256>>>(rawf, plan->final_w, (__nv_bfloat16*)scratch, 1, C, 9, 0);
+    if (cudaGetLastError() != cudaSuccess) { set_error("unet_plan_create: repack launch failed"); return fail(DBS_ERR_CUDA); }
+  }
+
+  // blocks, with the per-block time Linear layers concatenated into one [sumC][T] matrix
+  struct TL { std::string prefix; int cout; };
+  std::vector<TL> tls;
+  plan->enc.resize(nb); plan->dec.resize(nb); plan->down.resize(nb); plan->up.resize(nb);
+  int ch = C, off = 0;
+  std::vector<int> enc_ch;
+  for (int i = 0; i < nb; ++i) {
+    const int co = C << (i + 1);
+    const std::string p = "encoder." + std::to_string(i) + ".";
+    if ((rc = make_block(plan, pt, p, ch, co, &plan->enc[i]))) return fail(rc);
+    plan->enc[i].tb_off = off; off += co; tls.push_back({p, co});
+    if ((rc = make_conv(plan, pt, "downsample." + std::to_string(i), co, co, 3, false, &plan->down[i]))) return fail(rc);
+    ch = co; enc_ch.push_back(co);
+  }
+  if ((rc = make_block(plan, pt, "middle.", ch, ch, &plan->mid))) return fail(rc);
+  plan->mid.tb_off = off; off += ch; tls.push_back({"middle.", ch});
+  for (int k = 0; k < nb; ++k) {
+    const int i = nb - 1 - k;
+    const int co = i > 0 ? (C << i) : C;
+    const std::string p = "decoder." + std::to_string(k) + ".";
+    if ((rc = make_conv(plan, pt, "upsample." + std::to_string(k), ch, ch, 4, true, &plan->up[k]))) return fail(rc);
+    if ((rc = make_block(plan, pt, p, ch + enc_ch[i], co, &plan->dec[k]))) return fail(rc);
+    plan->dec[k].tb_off = off; off += co; tls.push_back({p, co});
+    ch = co;
+  }
+  plan->sumC = off;
+  {
+    void *wt = nullptr, *bt = nullptr;
+    if ((rc = dev_alloc(plan, (size_t)off * T * 4, &wt))) return fail(rc);
+    if ((rc = dev_alloc(plan, (size_t)off * 4, &bt))) return fail(rc);
+    plan->twt = (float*)wt; plan->tbt = (float*)bt;
+    int o = 0;
+    for (const TL& tl : tls) {
+      const dbs_param* w = pt.find(tl.prefix + "time_mlp.weight");
+      const dbs_param* b = pt.find(tl.prefix + "time_mlp.bias");
+      if (!w || !b || w->numel != (int64_t)tl.cout * T || b->numel != tl.cout) {
+        set_error("unet plan: parameter '%stime_mlp.*' missing or mis-sized", tl.prefix.c_str());
+        return fail(DBS_ERR_INVALID);
+      }
+      const cudaMemcpyKind kw = w->is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+      const cudaMemcpyKind kb = b->is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+      if (cudaMemcpy(plan->twt + (size_t)o * T, w->data, (size_t)tl.cout * T * 4, kw) != cudaSuccess ||
+          cudaMemcpy(plan->tbt + o, b->data, (size_t)tl.cout * 4, kb) != cudaSuccess) {
+        set_error("unet plan: time_mlp upload failed");
+        return fail(DBS_ERR_CUDA);
+      }
+      o += tl.cout;
+    }
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("unet_plan_create: device error after repack"); return fail(DBS_ERR_CUDA); }
+  *out = plan;
+  return DBS_OK;
+}
+
+extern "C" void dbs_unet_plan_destroy(dbs_unet_plan* plan) {
+  if (!plan) return;
+  for (void* p : plan->allocs) cudaFree(p);
+  delete plan;
+}
+
+extern "C" int64_t dbs_unet_workspace_bytes(const dbs_unet_plan* plan, int64_t B, int H, int W, int precision) {
+  if (check_forward_args(plan, B, H, W, precision)) return -1;
+  int64_t need = 0;
+  // n_t = B sizes the time-bias block for the general per-sample-t call
+  int rc = precision == 0
+               ? forward_impl<float>(const_cast<dbs_unet_plan*>(plan), nullptr, nullptr, B, nullptr, B, H, W, false,
+                                     nullptr, 0, nullptr, nullptr, 0, nullptr, &need)
+               : forward_impl<__nv_bfloat16>(const_cast<dbs_unet_plan*>(plan), nullptr, nullptr, B, nullptr, B, H, W,
+                                             true, nullptr, 0, nullptr, nullptr, 0, nullptr, &need);
+  return rc ? -1 : need;
+}
+
+static int unet_forward_common(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
+                               int64_t B, int H, int W, int precision, void* workspace, int64_t workspace_bytes,
+                               const char* tap, float* tap_out, int64_t tap_numel, void* stream) {
+  int rc = check_forward_args(plan, B, H, W, precision);
+  if (rc) return rc;
+  DBS_REQUIRE(x && t && score, "unet_forward: null tensor");
+  DBS_REQUIRE(n_t == 1 || n_t == B, "unet_forward: n_t must be 1 or B");
+  // carve the workspace exactly as dbs_unet_workspace_bytes did (time-bias block sized for B rows)
+  if (precision == 0)
+    return forward_impl<float>(plan, x, t, n_t, score, B, H, W, false, workspace, workspace_bytes, tap, tap_out,
+                               tap_numel, as_stream(stream), nullptr);
+  return forward_impl<__nv_bfloat16>(plan, x, t, n_t, score, B, H, W, true, workspace, workspace_bytes, tap, tap_out,
+                                     tap_numel, as_stream(stream), nullptr);
+}
+
+extern "C" int dbs_unet_forward(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
+                                int64_t B, int H, int W, int precision, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+  return unet_forward_common(plan, x, t, n_t, score, B, H, W, precision, workspace, workspace_bytes, nullptr, nullptr,
+                             0, stream);
+}
+
+extern "C" int dbs_unet_forward_tap(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
+                                    int64_t B, int H, int W, int precision, void* workspace, int64_t workspace_bytes,
+                                    const char* tap, float* tap_out, int64_t tap_numel, void* stream) {
+  DBS_REQUIRE(tap && tap_out, "unet_forward_tap: null tap");
+  return unet_forward_common(plan, x, t, n_t, score, B, H, W, precision, workspace, workspace_bytes, tap, tap_out,
+                             tap_numel, stream);
+}

@@ -1,0 +1,45 @@
+// unet.cuh — shared declarations of the score U-Net executor (unet.cu) and the tcgen05
+// implicit-GEMM convolution (conv_tc.cu).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dbs {
+
+// One convolution as an implicit GEMM over a "pixel grid" (Hm x Wm per sample):
+//   out[n, a*os+oph, b*os+opw, co] = bias[co] +
+//       sum_t sum_c in[n, a*is+dh[t], b*is+dw[t], c] * w[widx[t]][co][c]      (zero outside the image)
+// which covers Conv2d k in {1,3} stride {1,2} and, phase by phase, ConvTranspose2d(4, 2, 1).
+// The input is the channel concat [in0 (C0) | in1 (C1)] (score_network.py:256), NHWC.
+struct ConvGeom {
+  int B, Hin, Win;    // input spatial size
+  int Hm, Wm;         // GEMM pixel grid
+  int Hout, Wout;     // output spatial size
+  int C0, C1, Cout;
+  int in_stride;      // 1 or 2
+  int out_stride;     // 1 or 2 (transposed conv)
+  int oph, opw;       // output phase
+  int n_taps;
+  signed char dh[16], dw[16];
+  unsigned char widx[16];
+};
+
+struct ConvWeights {
+  int cin = 0, cout = 0, taps = 0;
+  float* w32 = nullptr;           // [taps][cout][cin]
+  __nv_bfloat16* w16 = nullptr;   // same layout
+  float* bias = nullptr;          // [cout]
+};
+
+// tcgen05 path.  Returns DBS_OK, or DBS_ERR_UNSUPPORTED if this geometry is not eligible
+// (caller then uses the CUDA-core kernel).  stats: fp32 [B][G][2] raw (sum, sumsq) or null.
+int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1,
+                   const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, float* stats,
+                   int groups, cudaStream_t st);
+
+// geometry builders
+ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
+ConvGeom geom_convT_phase(int B, int H, int W, int Cin, int Cout, int ph, int pw);
+
+}  // namespace dbs

@@ -86,6 +86,12 @@ int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_sweeps,
                      uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
                      const uint32_t* uniforms, void* stream);
 
+/* One random-site Metropolis attempt at (i,j) on fp32 lattices [n][L][L] in place, with draw r:
+ * the reference's step() (samplers/mcmc.py:26-50) for API parity (flips at most one spin per
+ * lattice).  Any L >= 1. */
+int dbs_ising_site_update(float* spins, int L, int64_t n, int i, int j, const uint32_t* thr,
+                          uint32_t r, void* stream);
+
 /* Per-chain energy and magnetisation from packed state.  Replaces
  * IsingModel.energy / magnetization (systems/ising.py:47-66, 93-102):
  * E = fl32(fl32(-J)*S_bond) + fl32(fl32(-h)*S_spin), M = fl32(S_spin)/fl32(L*L). */
@@ -186,11 +192,13 @@ int dbs_unet_forward(dbs_unet_plan* plan, const float* x, const float* t, int64_
                      float* score, int64_t B, int H, int W, int precision, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
-/* Debug/parity port: after a forward, copy the named intermediate
- * ("init", "enc0", "down0", ..., "mid", "up0", "dec0", ..., see unet_plan.cu) as
- * fp32 NCHW into out (numel must match).  Returns DBS_ERR_INVALID if unknown. */
-int dbs_unet_debug_fetch(dbs_unet_plan* plan, const char* name, float* out, int64_t numel,
-                         void* workspace, int64_t B, int H, int W, int precision, void* stream);
+/* Debug/parity port: the same forward, additionally copying one named intermediate as fp32
+ * NCHW into tap_out (tap_numel must match).  Names: "init", "enc<i>", "enc<i>.conv1", "down<i>",
+ * "mid", "mid.conv1", "up<i>", "dec<i>", "dec<i>.conv1".  DBS_ERR_INVALID if unknown. */
+int dbs_unet_forward_tap(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_t,
+                         float* score, int64_t B, int H, int W, int precision, void* workspace,
+                         int64_t workspace_bytes, const char* tap, float* tap_out,
+                         int64_t tap_numel, void* stream);
 
 /* Stand-alone implicit-GEMM convolution on the tensor cores (tcgen05/TMEM/TMA);
  * parity port for the kernel itself.  Replaces nn.Conv2d / nn.ConvTranspose2d as

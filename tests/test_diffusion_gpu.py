@@ -1,0 +1,243 @@
+"""GPU parity of the diffusion path (U-Net forward, Euler–Maruyama, samplers) through the C ABI.
+
+Floating point: tolerances are stated per test.  fp32 path: <= 1e-4 relative (north_star) against
+the reference's own outputs (tests/golden/unet_tiny.npz) and the pinned torch-fp32 oracle.
+bf16 tcgen05 path: stated bound 5e-2 of the output rms per forward (measured ~1e-2).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import em as o_em
+from oracle import unet as o_unet
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(base=32, tdim=64, nb=3, seed=0, **kw):
+    from backend.ml.models.score_network import ScoreNetwork
+    torch.manual_seed(seed)
+    return ScoreNetwork(1, base, tdim, nb, **kw).eval()
+
+
+def _sd(net):
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def _tiny_from_golden():
+    from backend.ml.models.score_network import ScoreNetwork
+    g = load_golden("unet_tiny.npz")
+    net = ScoreNetwork(1, 8, 16, 2).eval()
+    net.load_state_dict({k[4:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd::")})
+    return net, g
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+# ----------------------------------------------------------------------------- EM / Gaussian
+def test_em_step_bit_exact_vs_reference_golden():
+    from dbs_b200 import abi, runtime
+    g = load_golden("diffusion_scalar.npz")
+    for out, (i, N, temp, sigma) in zip(g["em_out"], g["em_meta"]):
+        x = torch.tensor(g["em_x"]).cuda()
+        s = torch.tensor(g["em_score"]).cuda()
+        z = torch.tensor(g["em_z"]).cuda()
+        c1, dt, c2 = o_em.step_coefficients(float(sigma), int(N))
+        abi.check(abi.lib.dbs_em_step(x.data_ptr(), s.data_ptr(), z.data_ptr(), x.shape[0], x[0].numel(), float(c1),
+                                      float(dt), float(c2), float(np.float32(temp)), int(i > 1), 0, 0, int(i),
+                                      runtime.current_stream()))
+        assert np.array_equal(x.cpu().numpy(), out)
+
+
+@pytest.mark.parametrize("elems", [64, 1024, 4096, 6])
+def test_gaussian_stream_matches_oracle(elems):
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    x = DiffusionSampler._gaussian((5, elems), seed=77, step=13, sample_offset=2).cpu().numpy()
+    want = o_em.gaussian(77, np.arange(2, 7), elems, 13)
+    np.testing.assert_allclose(x, want, rtol=0, atol=2e-6)
+    big = DiffusionSampler._gaussian((64, 4096), seed=1, step=-1).cpu().numpy()
+    assert abs(big.mean()) < 0.01 and abs(big.std() - 1.0) < 0.01 and np.abs(big).max() < 6.5
+
+
+def test_em_in_kernel_noise_equals_injected_noise():
+    from dbs_b200 import abi, runtime
+    x0 = torch.randn(3, 1, 16, 16).cuda()
+    s = torch.randn(3, 1, 16, 16).cuda()
+    z = torch.tensor(o_em.gaussian(5, np.arange(3), 256, 40)).reshape(3, 1, 16, 16)
+    a, b = x0.clone(), x0.clone()
+    args = (3, 256, 0.5, 0.01, 0.07, 1.0, 1)
+    abi.check(abi.lib.dbs_em_step(a.data_ptr(), s.data_ptr(), 0, *args, 5, 0, 40, runtime.current_stream()))
+    zc = z.cuda()
+    abi.check(abi.lib.dbs_em_step(b.data_ptr(), s.data_ptr(), zc.data_ptr(), *args, 5, 0, 40, runtime.current_stream()))
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=0, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- U-Net forward
+def test_unet_fp32_vs_reference_golden():
+    net, g = _tiny_from_golden()
+    with torch.no_grad():
+        out = net(torch.tensor(g["fwd_x"]), torch.tensor(g["fwd_t"]))
+        assert not out.is_cuda and out.shape == (3, 1, 16, 16)
+        assert _rel(out.numpy(), g["fwd_out"]) <= 1e-4
+        out = net(torch.tensor(g["fwd_ns_x"]), torch.tensor(g["fwd_ns_t"]))      # non-square 8x16
+        assert _rel(out.numpy(), g["fwd_ns_out"]) <= 1e-4
+
+
+TAPS = ["init", "enc0.conv1", "enc0", "down0", "enc1", "down1", "enc2", "down2", "mid.conv1", "mid", "up0", "dec0",
+        "up1", "dec1", "up2", "dec2.conv1", "dec2"]
+
+
+@pytest.mark.parametrize("H,W,B", [(16, 16, 3), (32, 32, 2), (8, 8, 5), (16, 32, 2)])
+def test_unet_fp32_default_net_every_layer_vs_oracle(H, W, B):
+    """Default ScoreNetwork(1,32,64,3): every named intermediate and the score against the pinned
+    torch-fp32 oracle, <= 1e-4 relative to the tensor's max."""
+    net = _net()
+    sd = _sd(net)
+    x = torch.randn(B, 1, H, W)
+    t = torch.tensor([1.0, 0.4, 0.05, 0.77, 0.3][:B])
+    taps = {}
+    want = o_unet.unet_forward(sd, x, t, taps=taps)
+    taps = {k.replace("encoder.", "enc").replace("decoder.", "dec").replace("middle.", "mid.").rstrip("."): v
+            for k, v in taps.items()}
+    for name in TAPS:
+        ref = taps[name]
+        got_score, got = net.engine_forward(x, t, precision="fp32", tap=(name, tuple(ref.shape)))
+        assert _rel(got.cpu().numpy(), ref.numpy()) <= 1e-4, name
+    assert _rel(got_score.cpu().numpy(), want.numpy()) <= 1e-4
+    # shared-t fast path (n_t = 1) equals per-sample t
+    t1 = torch.full((B,), 0.62)
+    a = net.engine_forward(x, t1, precision="fp32").cpu()
+    assert _rel(a.numpy(), o_unet.unet_forward(sd, x, t1).numpy()) <= 1e-4
+
+
+def test_unet_options_output_scale_and_normalize():
+    net = _net(16, 32, 2, seed=3, output_scale=2.5, normalize_output=True)
+    x, t = torch.randn(4, 1, 16, 16), torch.rand(4)
+    want = o_unet.unet_forward(_sd(net), x, t, output_scale=2.5, normalize_output=True)
+    with torch.no_grad():
+        got = net(x, t)
+    assert _rel(got.numpy(), want.numpy()) <= 1e-4
+
+
+def test_unet_plan_follows_parameter_updates():
+    net = _net(16, 32, 2, seed=4)
+    x, t = torch.randn(2, 1, 8, 8), torch.rand(2)
+    with torch.no_grad():
+        a = net(x, t)
+        net.final.bias.add_(1.0)
+        b = net(x, t)
+    assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+
+
+@pytest.mark.parametrize("H,B", [(16, 4), (32, 3), (64, 2)])
+def test_unet_bf16_default_net_vs_oracle(H, B):
+    """bf16 tcgen05 path, stated bound: max error <= 5e-2 of the output's max, rms error <= 2e-2 of rms."""
+    net = _net()
+    x, t = torch.randn(B, 1, H, H), torch.full((B,), 0.5)
+    want = o_unet.unet_forward(_sd(net), x, t).numpy()
+    got = net.engine_forward(x, t, precision="bf16").cpu().numpy()
+    assert np.isfinite(got).all()
+    assert _rel(got, want) <= 5e-2
+    assert np.sqrt(((got - want) ** 2).mean()) <= 2e-2 * np.sqrt((want ** 2).mean())
+
+
+def test_unet_rejects_unsupported_shapes_loudly():
+    net = _net(16, 32, 2, seed=1)
+    with pytest.raises(ValueError, match="not divisible"):
+        with torch.no_grad():
+            net(torch.randn(1, 1, 10, 10), torch.rand(1))
+
+
+# ----------------------------------------------------------------------------- samplers
+def test_sampler_fp32_vs_reference_golden_injected_noise():
+    """The reference's own DiffusionSampler.sample output (tiny net, 12 steps, its recorded
+    torch.randn draws) reproduced through the engine: <= 1e-4 relative."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net, g = _tiny_from_golden()
+    N, temp = int(g["smp_meta"][0]), float(g["smp_meta"][1])
+    smp = DiffusionSampler(net, num_steps=N, precision="fp32")
+    out = smp.sample(tuple(g["smp_x0"].shape), temperature=temp, x0=torch.tensor(g["smp_x0"]),
+                     noises=torch.tensor(g["smp_noises"]))
+    assert not out.is_cuda
+    assert _rel(out.numpy(), g["smp_out"]) <= 1e-4
+
+
+def test_sampler_default_net_vs_oracle_and_bf16_bound():
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net()
+    N, shape = 20, (4, 1, 32, 32)
+    x0 = torch.randn(shape)
+    noises = torch.randn(N, *shape)
+    want = o_unet.sample(_sd(net), shape, N, x0, noises).numpy()
+    got = DiffusionSampler(net, num_steps=N, precision="fp32").sample(shape, x0=x0, noises=noises).numpy()
+    assert _rel(got, want) <= 1e-4
+    got16 = DiffusionSampler(net, num_steps=N, precision="bf16").sample(shape, x0=x0, noises=noises).numpy()
+    # stated bf16 bound on the final state: rms error <= 1e-2 of rms, sign agreement >= 99.5 %
+    assert np.sqrt(((got16 - want) ** 2).mean()) <= 1e-2 * np.sqrt((want ** 2).mean())
+    assert (np.sign(got16) == np.sign(want)).mean() >= 0.995
+
+
+def test_sampler_api_surface():
+    """Shapes / types / contracts of backend/tests/test_diffusion_sampler.py (reference)."""
+    from backend.ml.samplers.diffusion import DiffusionSampler, PretrainedDiffusionSampler
+    from backend.ml.systems.ising import IsingModel
+    net = _net(16, 32, 2, seed=2)
+    smp = DiffusionSampler(net, num_steps=6)
+    assert smp.model is net and smp.num_steps == 6 and smp.device == "cpu"
+    shape = (3, 1, 16, 16)
+    assert smp.sample(shape).shape == shape
+    for m in ("euler", "heun", "rk4"):
+        assert smp.sample_ode(shape, method=m).shape == shape
+    assert smp.sample_predictor_corrector(shape).shape == shape
+    traj = list(smp.sample_with_trajectory(shape, yield_every=2))
+    assert isinstance(traj[0][0], torch.Tensor) and traj[0][1] == 1.0 and traj[-1][1] == 0.0 and len(traj) == 1 + 3
+    frames = list(smp.sample_trajectory_with_metadata(shape, n_frames=3, include_statistics=True,
+                                                      ising_model=IsingModel(16)))
+    assert set(frames[0]) >= {"x", "t", "step", "progress", "sigma", "statistics"} and frames[0]["t"] == 1.0
+    assert frames[-1]["step"] == 0
+    for method in ("sde", "ode", "pc"):
+        out = smp.generate_batch(5, lattice_size=16, batch_size=2, sampling_method=method)
+        assert out.shape == (5, 16, 16) and set(out.unique().tolist()) <= {-1.0, 0.0, 1.0}
+    assert smp.sample_ising(2, 16).shape == (2, 16, 16)
+    torch.manual_seed(11)
+    a = smp.sample_ode(shape)
+    torch.manual_seed(11)
+    b = smp.sample_ode(shape)
+    torch.manual_seed(12)
+    c = smp.sample_ode(shape)
+    assert torch.allclose(a, b, atol=1e-6) and not torch.allclose(a, c, atol=1e-3)
+    smp.training_temperature = 2.0
+    assert smp.compute_temperature_scale(3.0) == 1.5 and abs(smp.compute_temperature_scale(8.0, "sqrt") - 2.0) < 1e-12
+    h = PretrainedDiffusionSampler(lattice_size=16, num_steps=10).sample_heuristic(batch_size=3)
+    assert h.shape == (3, 1, 16, 16) and set(h.unique().tolist()) <= {-1.0, 1.0}
+    st = smp.compute_sample_statistics(smp.sample(shape), IsingModel(16))
+    assert {"mean", "std", "magnetization_mean", "energy_mean", "sample_diversity"} <= set(st)
+
+
+def test_sampler_checkpoint_round_trip(tmp_path):
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net(16, 32, 2, seed=5)
+    smp = DiffusionSampler(net, num_steps=4)
+    p = str(tmp_path / "ckpt.pt")
+    smp.save_checkpoint(p, model_config=dict(in_channels=1, base_channels=16, time_embed_dim=32, num_blocks=2),
+                        training_temperature=2.3)
+    back = DiffusionSampler.from_checkpoint(p, num_steps=4)
+    assert back.training_temperature == 2.3
+    a = smp.sample((2, 1, 8, 8), seed=3)
+    b = back.sample((2, 1, 8, 8), seed=3)
+    assert torch.equal(a, b)
+
+
+def test_sample_sharding_invariance():
+    """Samples carry global indices in the Philox counters: a shard equals the same rows of the
+    unsharded run (multi-GPU batch sharding)."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net(16, 32, 2, seed=6)
+    smp = DiffusionSampler(net, num_steps=5, device="cuda")
+    full = smp.sample((8, 1, 16, 16), seed=9)
+    part = smp.sample((4, 1, 16, 16), seed=9, sample_offset=4)
+    assert torch.allclose(part, full[4:], atol=1e-5)

@@ -1,0 +1,217 @@
+"""GPU parity of the Ising path (through the C ABI) against the pinned oracle and the golden
+vectors of the unmodified reference.  Integer/bit work: everything here is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ising as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from backend.ml.systems.ising import IsingModel
+    from backend.ml.samplers.mcmc import MetropolisHastings
+    return IsingModel, MetropolisHastings
+
+
+def _words(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def _sweep_cases():
+    g = load_golden("ising_sweeps.npz")
+    keys = ["L", "J", "h", "T", "n_sweeps", "seed", "start", "r", "final"]
+    return [{k: g[f"c{i}_{k}"] for k in keys} for i in range(int(g["n_cases"]))]
+
+
+@pytest.mark.parametrize("L", [4, 8, 12, 16, 32, 48, 64, 96, 128])
+def test_hot_start_pack_unpack_bit_exact(L):
+    IsingModel, _ = _mods()
+    m = IsingModel(L)
+    bits = m.random_packed(5, seed=99, chain_offset=3)
+    want = o.init_bits_words(99, np.arange(3, 8), L)
+    assert np.array_equal(_words(bits), want)
+    spins = m.unpack(bits)
+    assert np.array_equal(spins.cpu().numpy(), o.unpack(want, L).astype(np.float32))
+    assert np.array_equal(_words(m.pack(spins)), want)
+
+
+@pytest.mark.parametrize("case", _sweep_cases(), ids=lambda c: f"L{int(c['L'])}_J{float(c['J'])}_h{float(c['h'])}_T{float(c['T'])}")
+def test_sweeps_bit_exact_vs_reference_golden(case):
+    """Both draw sources — the reference's uniforms injected, and in-kernel Philox — must land on
+    the lattice the reference's own step() produced (tests/golden/ising_sweeps.npz)."""
+    IsingModel, MetropolisHastings = _mods()
+    L, seed, ns = int(case["L"]), int(case["seed"]), int(case["n_sweeps"])
+    m = IsingModel(L, J=float(case["J"]), h=float(case["h"]))
+    start = torch.tensor(case["start"].astype(np.float32))
+    n = start.shape[0]
+    # (a) injection port
+    mh = MetropolisHastings(m, float(case["T"]), seed=seed)
+    bits = m.pack(start)
+    uni = torch.from_numpy(case["r"].view(np.int32).copy()).cuda()
+    mh.sweeps_packed(bits, ns, uniforms=uni, sweep_offset=0)
+    assert np.array_equal(m.unpack(bits).cpu().numpy(), case["final"].astype(np.float32))
+    # (b) Philox in the kernel, all sweeps in one launch
+    bits = m.pack(start)
+    mh.sweeps_packed(bits, ns, sweep_offset=0)
+    assert np.array_equal(m.unpack(bits).cpu().numpy(), case["final"].astype(np.float32))
+    # (c) one launch per sweep continues the same stream
+    mh2 = MetropolisHastings(m, float(case["T"]), seed=seed)
+    bits = m.pack(start)
+    for _ in range(ns):
+        mh2.sweeps_packed(bits, 1)
+    assert np.array_equal(m.unpack(bits).cpu().numpy(), case["final"].astype(np.float32))
+    assert n == 2
+
+
+@pytest.mark.parametrize("L,n_chains,n_sweeps", [(16, 64, 20), (64, 33, 6), (128, 3, 3), (24, 7, 5), (40, 5, 4), (8, 130, 9)])
+def test_sweeps_vs_oracle_many_chains_per_chain_temperature(L, n_chains, n_sweeps):
+    IsingModel, MetropolisHastings = _mods()
+    m = IsingModel(L, J=1.0, h=0.05)
+    temps = np.linspace(1.5, 3.5, n_chains)
+    mh = MetropolisHastings(m, temps, seed=4242)
+    bits = m.random_packed(n_chains, seed=4242, chain_offset=10)
+    start = o.unpack(_words(bits), L)
+    mh.sweeps_packed(bits, n_sweeps, chain_offset=10, sweep_offset=7)
+    want = o.run_sweeps(start.copy(), 1.0, 0.05, temps, n_sweeps, seed=4242, chain_ids=np.arange(10, 10 + n_chains),
+                        sweep_offset=7)
+    assert np.array_equal(o.unpack(_words(bits), L), want)
+    assert not np.array_equal(start, want)
+
+
+@pytest.mark.parametrize("L", [8, 16, 64])
+def test_observables_bit_exact_vs_reference_golden(L):
+    IsingModel, _ = _mods()
+    g = load_golden("ising_static.npz")
+    for tag, (J, h) in {"a": (1.0, 0.0), "b": (0.7, -0.45)}.items():
+        m = IsingModel(L, J=J, h=h)
+        s = torch.tensor(g[f"obs_L{L}_{tag}_spins"])
+        assert np.array_equal(m.energy(s).numpy(), g[f"obs_L{L}_{tag}_E"])
+        assert np.array_equal(m.magnetization(s).numpy(), g[f"obs_L{L}_{tag}_M"])
+        assert np.array_equal(m.energy_per_spin(s).numpy(), g[f"obs_L{L}_{tag}_Eps"])
+        e, mag = m.packed_observables(m.pack(s))
+        assert np.array_equal(e.cpu().numpy(), g[f"obs_L{L}_{tag}_E"])
+        assert np.array_equal(mag.cpu().numpy(), g[f"obs_L{L}_{tag}_M"])
+
+
+def test_observables_known_answers_and_shapes():
+    """backend/tests/test_ising.py:11-36, 55-79 of the reference."""
+    IsingModel, _ = _mods()
+    m = IsingModel(8)
+    up = torch.ones(8, 8)
+    cb = torch.tensor([[1.0 if (i + j) % 2 == 0 else -1.0 for j in range(8)] for i in range(8)])
+    assert m.energy(up).item() == -128.0 and m.energy(-up).item() == -128.0 and m.energy(cb).item() == 128.0
+    assert m.magnetization(up).item() == 1.0 and m.magnetization(-up).item() == -1.0 and m.magnetization(cb).item() == 0.0
+    assert m.local_energy_diff(up, 0, 0).item() == 8.0
+    batch = torch.stack([up, cb, -up])
+    assert m.energy(batch).shape == (3,) and m.energy(batch).tolist() == [-128.0, 128.0, -128.0]
+    assert m.energy(batch.cuda()).is_cuda
+    r = m.random_configuration(4)
+    assert r.shape == (4, 8, 8) and not r.is_cuda and set(r.unique().tolist()) <= {-1.0, 1.0}
+    g = load_golden("ising_static.npz")
+    mc = IsingModel(16, J=1.0, h=0.2)
+    np.testing.assert_allclose(mc.energy(torch.tensor(g["obs_cont_spins"])).numpy(), g["obs_cont_E"], rtol=2e-6, atol=1e-4)
+    np.testing.assert_allclose(mc.magnetization(torch.tensor(g["obs_cont_spins"])).numpy(), g["obs_cont_M"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("L", [8, 16])
+def test_pair_correlation_equals_reference(L):
+    from backend.ml.analysis.correlation import pair_correlation
+    g = load_golden("correlation.npz")
+    s = torch.tensor(g[f"corr_L{L}_samples"])
+    res = pair_correlation(s, ref_indices=g[f"corr_L{L}_ref_indices"])
+    assert res["r"] == list(g[f"corr_L{L}_r"])
+    assert np.array_equal(np.array(res["C_r"]), g[f"corr_L{L}_C"])
+    # same numpy seed -> same reference sites as the reference draws (analysis/correlation.py:25-26)
+    np.random.seed(100 + L)
+    assert np.array_equal(np.array(pair_correlation(s)["C_r"]), g[f"corr_L{L}_C"])
+
+
+@pytest.mark.parametrize("L", [12, 32, 64, 128])
+def test_pair_correlation_all_sites_vs_oracle(L):
+    from backend.ml.analysis.correlation import pair_correlation
+    rng = np.random.RandomState(L)
+    s = rng.choice([-1.0, 1.0], size=(3, L, L)).astype(np.float32)
+    s[0] = 1.0
+    got = pair_correlation(torch.tensor(s), ref_indices="all")
+    want = o.pair_correlation(s, None)
+    assert np.array_equal(np.array(got["C_r"]), np.array(want["C_r"]))
+    idx = rng.choice(L * L, 37, replace=False)
+    assert np.array_equal(np.array(pair_correlation(torch.tensor(s), ref_indices=idx)["C_r"]),
+                          np.array(o.pair_correlation(s, idx)["C_r"]))
+
+
+def test_mcmc_api_contract():
+    """Reference contract tests (backend/tests/test_mcmc.py:22-71, 256-349): beta, step flips at
+    most one spin and mutates/returns its argument, sample/trajectory shapes."""
+    IsingModel, MetropolisHastings = _mods()
+    np.random.seed(42)
+    m = IsingModel(8)
+    assert MetropolisHastings(m, 2.0).beta == 0.5 and MetropolisHastings(m, 0.0).beta == float("inf")
+    mh = MetropolisHastings(m, 2.27)
+    x = m.random_configuration(1).squeeze(0)
+    for _ in range(50):
+        before = x.clone()
+        y = mh.step(x)
+        assert y is x and y.shape == (8, 8) and int((y != before).sum()) <= 1
+        assert set(y.unique().tolist()) <= {-1.0, 1.0}
+    cold = MetropolisHastings(m, 0.01)
+    z = m.random_configuration(1).squeeze(0)
+    e_prev = m.energy(z).item()
+    for _ in range(300):
+        z = cold.step(z)
+        e = m.energy(z).item()
+        assert e <= e_prev + 1e-6
+        e_prev = e
+    s = mh.sample(n_samples=5, n_sweeps=2, burn_in=10)
+    assert s.shape == (5, 8, 8) and not s.is_cuda and set(s.unique().tolist()) <= {-1.0, 1.0}
+    init = torch.ones(8, 8)
+    s0 = mh.sample(n_samples=1, n_sweeps=0, initial=init, burn_in=0)
+    assert torch.equal(s0[0], init) and torch.equal(init, torch.ones(8, 8))
+    frames = list(mh.sample_with_trajectory(6, initial=init))
+    assert len(frames) == 7 and torch.equal(frames[0], init) and all(f.shape == (8, 8) for f in frames)
+    sw = mh.sweep(init.clone())
+    assert sw.shape == (8, 8)
+    many = mh.sample(n_samples=3, n_sweeps=1, burn_in=5, n_chains=16)
+    assert many.shape == (16, 3, 8, 8)
+
+
+def test_mcmc_physics_envelopes():
+    """Statistical envelopes of backend/tests/test_mcmc.py:95-108, 355-488 at 16x16, 256 chains."""
+    IsingModel, MetropolisHastings = _mods()
+    m = IsingModel(16)
+    def run(T, init=None):
+        mh = MetropolisHastings(m, T, seed=7)
+        x = mh.sample(n_samples=4, n_sweeps=10, burn_in=400, n_chains=256, initial=init, return_device=True)
+        flat = x.reshape(-1, 16, 16)
+        return m.magnetization(flat).abs().mean().item(), m.energy_per_spin(flat).mean().item()
+    mlow, elow = run(1.0, torch.ones(16, 16))
+    assert mlow > 0.95 and elow < -1.9
+    mhigh, ehigh = run(5.0)
+    assert mhigh < 0.2 and -0.6 < ehigh < 0.0
+    mc, ec = run(2.269)
+    assert 0.3 < mc < 0.9 and -1.6 < ec < -1.2
+    # exact 2-D Ising energy per spin at T=2.0 (Onsager): -1.7455...; finite-size + MC error < 1%
+    _, e2 = run(2.0, torch.ones(16, 16))
+    assert abs(e2 - (-1.7456)) < 0.02
+
+
+def test_full_size_sharding_invariance():
+    """BASELINE config-3 shape (64x64, per-chain temperatures): chains carry global indices, so a
+    rank's shard equals the same rows of the single-GPU run for any world size."""
+    IsingModel, MetropolisHastings = _mods()
+    L, n = 64, 4096
+    m = IsingModel(L)
+    temps = np.repeat(np.linspace(1.5, 3.5, 64), n // 64)
+    full = m.random_packed(n, seed=5)
+    MetropolisHastings(m, temps, seed=5).sweeps_packed(full, 10, sweep_offset=0)
+    for rank, world in [(1, 2), (5, 8)]:
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        part = m.random_packed(hi - lo, seed=5, chain_offset=lo)
+        MetropolisHastings(m, temps[lo:hi], seed=5).sweeps_packed(part, 10, chain_offset=lo, sweep_offset=0)
+        assert torch.equal(part, full[lo:hi])
+    e, mag = m.packed_observables(full)
+    spins = m.unpack(full)
+    assert torch.equal(e.cpu(), m.energy(spins).cpu()) and torch.equal(mag.cpu(), m.magnetization(spins).cpu())
