@@ -1,13 +1,546 @@
-// conv_tc.cu — placeholder until the tcgen05 kernel lands in this file (next commit).
+// conv_tc.cu — implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a):
+// tcgen05.mma with the accumulator in TMEM, operands staged in shared memory by TMA.
+//
+// Replaces nn.Conv2d / nn.ConvTranspose2d of the score U-Net (reference
+// models/score_network.py:122-131 ConvBlock convs + 1x1 residual, :201 stride-2 downsample,
+// :216 ConvTranspose 4x4 stride 2, with the skip concat of :256 read as one K range) and fuses the
+// GroupNorm(8) sum / sum-of-squares (:124-125) into the epilogue.
+//
+// GEMM view (one launch = one ConvGeom):
+//   D[128 pixels x Nb couts] += A[128 pixels x KC channels] * B[Nb couts x KC channels]^T
+//   summed over k-blocks = (tap, channel chunk).  A is a TMA box {KC, Wt, 1, Ht, Nt} of the NHWC
+//   activation shifted by the tap offset — out-of-image rows/columns are zero-filled by TMA, which
+//   is the convolution's zero padding — and lands in shared memory as 128 rows of KC bf16, K-major,
+//   in the 128/64/32-byte swizzle the UMMA descriptor names.  B is a box {KC, Nb, 1} of the
+//   repacked weights [tap][Cout][Cin].  A stride-2 conv reads the same NHWC memory through a
+//   space-to-depth view {2C, W/2, 2, H/2, N}; a transposed conv is four stride-1 phase convs whose
+//   epilogue scatters to the odd/even output pixels.
+//
+// CTA = 6 warps, persistent over tiles (static round-robin):
+//   warp 0   TMA producer (one lane)   — kStages-deep full/empty mbarrier ring
+//   warp 1   MMA issuer  (one lane)    — tcgen05.mma cta_group::1, M=128, N=Nb, K=16 per instruction
+//   warps 2-5 epilogue                 — tcgen05.ld 32x32b -> +bias -> GN partial sums -> bf16 -> HBM
+// Two TMEM accumulator stages (2*Nb columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "unet.cuh"
+
 namespace dbs {
-int conv_tc_launch(const ConvGeom&, const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const float*,
-                   __nv_bfloat16*, float*, int, cudaStream_t) {
-  return DBS_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kSmemBudget = 200 * 1024;
+
+struct TcParams {
+  int Wt, Ht, Nt;
+  int tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n;
+  int Nb, KC, chunks0, chunks1, n_taps, stages;
+  int B, Hout, Wout, Cout, out_stride, oph, opw;
+  int groups, Cg;
+  int tap_dw[16], tap_dh[16], tap_p[16], tap_c0[16], tap_c1[16], tap_w[16];
+  const float* bias;
+  __nv_bfloat16* out;
+  float* stats;
+  uint32_t idesc;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  uint32_t tmem_cols;
+  uint64_t desc_hi;  // descriptor bits above the start address (LBO, SBO, version, swizzle)
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins == (1u << 14)) t0 = global_timer_ns();
+    if (spins > (1u << 14) && (spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_acc[2][kTileM * 8 * 2];  // GroupNorm partial sums, double-buffered by tile parity
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_in0);
+    tma_prefetch_desc(&map_in1);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols);
+  for (int i = threadIdx.x; i < 2 * kTileM * 8 * 2; i += kThreads) (&s_acc[0][0])[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int kblocks_per_tap = p.chunks0 + p.chunks1;
+  const int n_kblocks = p.n_taps * kblocks_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / p.n_tiles_m, mt = tile - nt * p.n_tiles_m;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Nb;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const int cw = w0 + p.tap_dw[t], chh = h0 + p.tap_dh[t], cp = p.tap_p[t];
+          for (int ch = 0; ch < kblocks_per_tap; ++ch) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t a_dst = smem_base + stage * p.stage_bytes;
+            const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
+            if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, p.tap_c0[t] + ch * p.KC, cw, cp, chh, n0);
+            else tma_load_5d(a_dst, &map_in1, fb, p.tap_c1[t] + (ch - p.chunks0) * p.KC, cw, cp, chh, n0);
+            tma_load_3d(b_dst, &map_w, fb, ch * p.KC, co0, p.tap_w[t]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const int mmas = p.KC / 16;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.Nb;
+        for (int kb = 0; kb < n_kblocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * p.stage_bytes;
+          const uint32_t b_addr = a_addr + ((p.a_bytes + 1023u) & ~1023u);
+          for (int k = 0; k < mmas; ++k) {
+            const uint64_t adesc = p.desc_hi | (uint64_t)(((a_addr + 32 * k) & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = p.desc_hi | (uint64_t)(((b_addr + 32 * k) & 0x3FFFFu) >> 4);
+            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * as);       // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                 // TMEM lane quarter accessible to this warp
+    const int row = q * 32 + lane;          // tile-local GEMM row = pixel
+    const int ppi = p.Ht * p.Wt;            // pixels per image inside a tile
+    const int nl = row / ppi, hl = (row / p.Wt) % p.Ht, wl = row % p.Wt;
+    const int etid = threadIdx.x - 64;      // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nt = tile / p.n_tiles_m, mt = tile - nt * p.n_tiles_m;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      const int n = tn * p.Nt + nl, a = th * p.Ht + hl, b = tw * p.Wt + wl, co0 = nt * p.Nb;
+      const bool valid = n < p.B;
+      __nv_bfloat16* optr =
+          p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (b * p.out_stride + p.opw)) * p.Cout + co0;
+      float* acc = &s_acc[it & 1][0];
+
+      mbar_wait(bar_tfull + 8 * as, aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.Nb;
+      float run_s = 0.f, run_ss = 0.f;
+      for (int c = 0; c < p.Nb; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) + __ldg(p.bias + co0 + c + j) : 0.f;
+        if (p.stats) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            run_s += f[j];
+            run_ss = fmaf(f[j], f[j], run_ss);
+            const int co = co0 + c + j;
+            if ((co + 1) % p.Cg == 0) {  // end of a GroupNorm group: flush this run
+              const int gi = co / p.Cg;
+              if (ppi >= 32) {
+                const float s = warp_sum(run_s), ss = warp_sum(run_ss);
+                if (lane == 0) {
+                  atomicAdd(&acc[(nl * 8 + gi) * 2 + 0], s);
+                  atomicAdd(&acc[(nl * 8 + gi) * 2 + 1], ss);
+                }
+              } else {
+                atomicAdd(&acc[(nl * 8 + gi) * 2 + 0], run_s);
+                atomicAdd(&acc[(nl * 8 + gi) * 2 + 1], run_ss);
+              }
+              run_s = 0.f; run_ss = 0.f;
+            }
+          }
+        }
+        if (valid) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(optr + c);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      // TMEM stage drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (p.stats) {
+        epi_bar_sync();
+        const int n_img = p.Nt;
+        for (int i = etid; i < n_img * 8 * 2; i += 128) {
+          const int img = i >> 4, rest = i & 15, gi = rest >> 1, k = rest & 1;
+          const float vsum = acc[i];
+          acc[i] = 0.f;
+          const int ng = tn * p.Nt + img;
+          if (ng < p.B && gi < p.groups && vsum != 0.f) atomicAdd(p.stats + ((int64_t)ng * p.groups + gi) * 2 + k, vsum);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// activation map: stride 1 -> {C, W, 1, H, N}; stride 2 -> space-to-depth view {2C, W/2, 2, H/2, N}
+int encode_act(EncodeTiledFn enc, CUtensorMap* m, const void* ptr, int C, int H, int W, int B, int stride, int KC, int Wt,
+               int Ht, int Nt, CUtensorMapSwizzle sw) {
+  cuuint64_t dims[5], strides[4];
+  const cuuint64_t e = 2;
+  if (stride == 1) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
+    strides[0] = C * e; strides[1] = (cuuint64_t)W * C * e; strides[2] = (cuuint64_t)W * C * e;
+    strides[3] = (cuuint64_t)H * W * C * e;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides[0] = 2 * C * e; strides[1] = (cuuint64_t)W * C * e; strides[2] = (cuuint64_t)2 * W * C * e;
+    strides[3] = (cuuint64_t)H * W * C * e;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)Wt, 1u, (cuuint32_t)Ht, (cuuint32_t)Nt};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled(activation C=%d H=%d W=%d B=%d stride=%d) failed with %d", C, H, W, B,
+              stride, (int)r);
+    return DBS_ERR_CUDA;
+  }
+  return DBS_OK;
+}
+
+int encode_w(EncodeTiledFn enc, CUtensorMap* m, const void* ptr, int Cin, int Cout, int taps, int KC, int Nb,
+             CUtensorMapSwizzle sw) {
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+  cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)Nb, 1u};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled(weights Cin=%d Cout=%d taps=%d) failed with %d", Cin, Cout, taps, (int)r);
+    return DBS_ERR_CUDA;
+  }
+  return DBS_OK;
+}
+
+}  // namespace
+
+int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1, const __nv_bfloat16* w,
+                   const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st) {
+  // ---- eligibility
+  const int Cin = g.C0 + g.C1;
+  int KC = 0;
+  for (int k : {64, 32, 16})
+    if (g.C0 % k == 0 && g.C1 % k == 0) { KC = k; break; }
+  if (!KC || g.C0 == 0) return DBS_ERR_UNSUPPORTED;
+  if (g.Cout % 16 != 0) return DBS_ERR_UNSUPPORTED;
+  const int n_tiles_n = (g.Cout + 255) / 256;
+  if (g.Cout % n_tiles_n != 0 || (g.Cout / n_tiles_n) % 16 != 0) return DBS_ERR_UNSUPPORTED;
+  const int Nb = g.Cout / n_tiles_n;
+  if (g.in_stride == 2 && ((g.Hin & 1) || (g.Win & 1) || g.out_stride != 1)) return DBS_ERR_UNSUPPORTED;
+  if (g.in_stride != 1 && g.in_stride != 2) return DBS_ERR_UNSUPPORTED;
+  // pixel box {Wt, Ht, Nt} with Wt*Ht*Nt == 128
+  int Wt, Ht, Nt;
+  if (g.Wm >= kTileM) {
+    if (g.Wm % kTileM) return DBS_ERR_UNSUPPORTED;
+    Wt = kTileM; Ht = 1; Nt = 1;
+  } else {
+    if (!is_pow2(g.Wm)) return DBS_ERR_UNSUPPORTED;
+    Wt = g.Wm;
+    const int rows = kTileM / Wt;
+    if (g.Hm >= rows) {
+      if (g.Hm % rows) return DBS_ERR_UNSUPPORTED;
+      Ht = rows; Nt = 1;
+    } else {
+      if (!is_pow2(g.Hm)) return DBS_ERR_UNSUPPORTED;
+      Ht = g.Hm; Nt = rows / Ht;
+    }
+  }
+  if (groups > 8 || (stats && (groups < 1 || g.Cout % groups))) return DBS_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return DBS_ERR_UNSUPPORTED;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DBS_ERR_CUDA; }
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.Wt = Wt; p.Ht = Ht; p.Nt = Nt;
+  p.tiles_w = g.Wm / Wt; p.tiles_h = g.Hm / Ht; p.tiles_n = (g.B + Nt - 1) / Nt;
+  p.n_tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.n_tiles_n = n_tiles_n;
+  p.Nb = Nb; p.KC = KC; p.chunks0 = g.C0 / KC; p.chunks1 = g.C1 / KC; p.n_taps = g.n_taps;
+  p.B = g.B; p.Hout = g.Hout; p.Wout = g.Wout; p.Cout = g.Cout;
+  p.out_stride = g.out_stride; p.oph = g.oph; p.opw = g.opw;
+  p.groups = groups; p.Cg = stats ? g.Cout / groups : g.Cout;
+  for (int t = 0; t < g.n_taps; ++t) {
+    if (g.in_stride == 1) {
+      p.tap_dw[t] = g.dw[t]; p.tap_dh[t] = g.dh[t]; p.tap_p[t] = 0; p.tap_c0[t] = 0; p.tap_c1[t] = 0;
+    } else {
+      // input row 2a+dh, dh in {-1,0,1}: (row pair, parity) = (a-1, 1) | (a, 0) | (a, 1); same for columns,
+      // where the column parity selects the upper or lower C channels of the 2C-wide inner dimension
+      p.tap_dh[t] = g.dh[t] < 0 ? -1 : 0;
+      p.tap_p[t] = g.dh[t] < 0 ? 1 : g.dh[t];
+      p.tap_dw[t] = g.dw[t] < 0 ? -1 : 0;
+      const int pw = g.dw[t] < 0 ? 1 : g.dw[t];
+      p.tap_c0[t] = pw * g.C0; p.tap_c1[t] = pw * g.C1;
+    }
+    p.tap_w[t] = g.widx[t];
+  }
+  p.bias = bias; p.out = out; p.stats = stats;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  p.a_bytes = (uint32_t)kTileM * KC * 2;
+  p.b_bytes = (uint32_t)Nb * KC * 2;
+  p.stage_bytes = ((p.a_bytes + 1023u) & ~1023u) + ((p.b_bytes + 1023u) & ~1023u);
+  int stages = (int)(kSmemBudget / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return DBS_ERR_UNSUPPORTED;
+  p.stages = stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * Nb)) cols <<= 1;
+  p.tmem_cols = cols;
+  const uint32_t row_bytes = (uint32_t)KC * 2;
+  const uint64_t layout = KC == 64 ? 2ull : (KC == 32 ? 4ull : 6ull);  // SWIZZLE_128B / 64B / 32B
+  p.desc_hi = (1ull << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+
+  CUtensorMap m0, m1, mw;
+  int rc;
+  if ((rc = encode_act(enc, &m0, in0, g.C0, g.Hin, g.Win, g.B, g.in_stride, KC, Wt, Ht, Nt, sw))) return rc;
+  if (g.C1 > 0) {
+    if ((rc = encode_act(enc, &m1, in1, g.C1, g.Hin, g.Win, g.B, g.in_stride, KC, Wt, Ht, Nt, sw))) return rc;
+  } else {
+    m1 = m0;
+  }
+  // weights [taps_total][Cout][Cin]: the tap dimension is addressed by widx, so size it generously
+  int taps_total = 0;
+  for (int t = 0; t < g.n_taps; ++t) taps_total = g.widx[t] + 1 > taps_total ? g.widx[t] + 1 : taps_total;
+  if (g.out_stride == 2) taps_total = 16;
+  if ((rc = encode_w(enc, &mw, w, Cin, g.Cout, taps_total, KC, Nb, sw))) return rc;
+
+  const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+  });
+  DBS_CUDA(attr_err);
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  conv_tc_kernel<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
 }  // namespace dbs
-extern "C" int dbs_conv_tc(const void*, int, const void*, int, const void*, const float*, void*, float*, int64_t, int,
-                           int, int, int, int, void*) {
-  dbs::set_error("dbs_conv_tc: tcgen05 kernel not built yet");
-  return DBS_ERR_UNSUPPORTED;
+
+using namespace dbs;
+
+extern "C" int dbs_conv_tc(const void* in0, int C0, const void* in1, int C1, const void* weight, const float* bias,
+                           void* out, float* stats, int64_t B, int H, int W, int C_out, int kind, int ksize,
+                           void* stream) {
+  DBS_REQUIRE(in0 && weight && bias && out && B >= 1 && H >= 1 && W >= 1, "conv_tc: bad arguments");
+  DBS_REQUIRE(kind >= 0 && kind <= 2, "conv_tc: kind must be 0 (stride 1), 1 (3x3 stride 2) or 2 (transposed 4x4)");
+  const int groups = C_out < 8 ? C_out : 8;
+  int rc = DBS_OK;
+  if (kind == 0) {
+    DBS_REQUIRE(ksize == 1 || ksize == 3, "conv_tc: ksize must be 1 or 3");
+    rc = conv_tc_launch(geom_conv((int)B, H, W, C0, C1, C_out, ksize, 1), (const __nv_bfloat16*)in0,
+                        (const __nv_bfloat16*)in1, (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups,
+                        as_stream(stream));
+  } else if (kind == 1) {
+    rc = conv_tc_launch(geom_conv((int)B, H, W, C0, C1, C_out, 3, 2), (const __nv_bfloat16*)in0,
+                        (const __nv_bfloat16*)in1, (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups,
+                        as_stream(stream));
+  } else {
+    DBS_REQUIRE(C1 == 0, "conv_tc: transposed conv takes a single source");
+    for (int ph = 0; ph < 2 && rc == DBS_OK; ++ph)
+      for (int pw = 0; pw < 2 && rc == DBS_OK; ++pw)
+        rc = conv_tc_launch(geom_convT_phase((int)B, H, W, C0, C_out, ph, pw), (const __nv_bfloat16*)in0, nullptr,
+                            (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups, as_stream(stream));
+  }
+  if (rc == DBS_ERR_UNSUPPORTED) set_error("conv_tc: this geometry is not eligible for the tcgen05 kernel");
+  return rc;
 }

@@ -194,7 +194,7 @@ def test_sampler_api_surface():
         assert smp.sample_ode(shape, method=m).shape == shape
     assert smp.sample_predictor_corrector(shape).shape == shape
     traj = list(smp.sample_with_trajectory(shape, yield_every=2))
-    assert isinstance(traj[0][0], torch.Tensor) and traj[0][1] == 1.0 and traj[-1][1] == 0.0 and len(traj) == 1 + 3
+    assert isinstance(traj[0][0], torch.Tensor) and traj[0][1] == 1.0 and traj[-1][1] == 0.0 and len(traj) == 1 + 3 + 1
     frames = list(smp.sample_trajectory_with_metadata(shape, n_frames=3, include_statistics=True,
                                                       ising_model=IsingModel(16)))
     assert set(frames[0]) >= {"x", "t", "step", "progress", "sigma", "statistics"} and frames[0]["t"] == 1.0
