@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 sampling engine (contract: see DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1], the single-B200 configuration): score U-Net reverse-SDE
+sampling of 32x32 Ising lattices, 100 Euler–Maruyama steps, batch 1024 per GPU, random-init default
+ScoreNetwork(1,32,64,3), default VP-SDE.  One "step" = one full sampling pass over one batch.
+  value  : samples/s with everything resident in HBM (x0 drawn on the device by Philox)
+  e2e    : samples/s through the reference-facing API DiffusionSampler.sample(...) with HOST tensors:
+           pinned x0 copied host->device and the samples copied device->host inside the timed region
+  roofline: tcgen05 conv kernel, algorithmic FLOPs / its summed launch durations (CUDA events on
+           the launching stream, recorded inside the library), against MEASURED_PEAKS.json
+  cpu_baseline: the oracle port (plain torch fp32 on the host cores) on a bounded sample
+Secondary blocks in the same line: "ising" (bit-packed checkerboard Metropolis, config-3 shape per
+GPU) and "diffusion_64" (config-4 lattice size on a bounded batch/step count).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "diffusion-boltzmann-sampler_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+L_MAIN, STEPS_MAIN, BATCH_MAIN = 32, 100, 1024
+NET_CFG = dict(in_channels=1, base_channels=32, time_embed_dim=64, num_blocks=3)
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def unet_flops_per_sample(L, base=32, nb=3, tdim=64):
+    """Algorithmic FLOPs (2*MACs) of one ScoreNetwork forward on an LxL lattice."""
+    f = 2 * 9 * 1 * base * L * L            # init conv
+    ch, res, skips = base, L, []
+    for i in range(nb):
+        co = base << (i + 1)
+        f += 2 * res * res * (9 * ch * co + 9 * co * co + ch * co)
+        skips.append(co)
+        res //= 2
+        f += 2 * res * res * 9 * co * co      # stride-2 downsample
+        ch = co
+    f += 2 * res * res * (2 * 9 * ch * ch)    # middle (identity residual)
+    for i in reversed(range(nb)):
+        co = base << i
+        f += 2 * res * res * 16 * ch * ch     # ConvTranspose 4x4 s2: 2*Cin*Hin*Win*Cout*16
+        res *= 2
+        cin = ch + skips[i]
+        f += 2 * res * res * (9 * cin * co + 9 * co * co + cin * co)
+        ch = co
+    f += 2 * 9 * base * 1 * L * L             # final conv
+    f += 2 * (tdim * 2 * tdim * 2 + sum(tdim * c for c in
+                                         [base << (i + 1) for i in range(nb)] + [base << nb] +
+                                         [base << i for i in reversed(range(nb))]))
+    return float(f)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.tmp = None
+
+    def start(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(",") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed(fn, steps, world):
+    """K calls of fn bracketed by barrier + synchronize, CUDA events on the current stream; max over ranks."""
+    torch.cuda.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        fn(k)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def make_sampler(L, steps, precision, device):
+    from backend.ml.models.score_network import ScoreNetwork
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    torch.manual_seed(0)
+    net = ScoreNetwork(**NET_CFG).eval()
+    return DiffusionSampler(net, num_steps=steps, device=device, precision=precision)
+
+
+def observable_block(model, x, world):
+    """Final observables of one batch: {count, sum E/N, sum |M|, sum M^2, sum M^4} in fp64, all-reduced
+    over NCCL when sharded (the only collective on this path)."""
+    from dbs_b200 import abi, runtime
+    spins = torch.sign(x).reshape(-1, model.size, model.size)
+    bits = model.pack(spins)
+    e, m = model.packed_observables(bits)
+    acc = torch.zeros(5, dtype=torch.float64, device=x.device)
+    abi.check(abi.lib.dbs_observable_accumulate(e.data_ptr(), m.data_ptr(), model.size, e.numel(), 0, acc.data_ptr(),
+                                                runtime.current_stream()))
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(acc)
+    return acc
+
+
+def bench_ours(args, world, rank, local):
+    from backend.ml.samplers.mcmc import MetropolisHastings
+    from backend.ml.systems.ising import IsingModel
+    from dbs_b200 import abi
+    from oracle import unet as o_unet  # cpu_baseline leg only
+
+    peaks = measured_peaks()
+    B, L, NS = args.batch, L_MAIN, STEPS_MAIN
+    shape = (B, 1, L, L)
+    prec = args.precision
+    smp = make_sampler(L, NS, prec, "cuda")
+    model = IsingModel(L)
+    flops_step = unet_flops_per_sample(L) * B * NS
+    last = {}
+
+    def step_device(k):
+        x = smp.sample(shape, seed=1000 + k, sample_offset=rank * B)
+        last["acc"] = observable_block(model, x, world)
+
+    for k in range(args.warmup):
+        step_device(-1 - k)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = abi.launch_count()
+    ms = timed(step_device, args.steps, world)
+    launches = abi.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else {}
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: reference-facing API with HOST tensors (pinned x0 in, samples out), copies inside the timed region
+    smp_host = make_sampler(L, NS, prec, "cpu")
+    smp_host.model = smp.model  # same plan / weights
+    x0_host = torch.randn(shape).pin_memory()
+    out_bytes = {}
+
+    def step_e2e(k):
+        out = smp_host.sample(shape, x0=x0_host, seed=2000 + k, sample_offset=rank * B)   # returns a host tensor
+        out_bytes["n"] = out.numel() * 4
+        m = float(out.mean())  # host read of the result
+        last["e2e_mean"] = m
+
+    step_e2e(-1)
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e = timed(step_e2e, e2e_steps, world)
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel-class breakdown of one step (events inside the library, on the launching stream)
+    abi.profile_read(reset=True)
+    abi.profile(True)
+    step_device(0)
+    torch.cuda.synchronize()
+    prof = abi.profile_read(reset=True)
+    abi.profile(False)
+    conv_ms, conv_n = prof["conv_tc"]
+    breakdown = {k: round(v[0], 3) for k, v in prof.items() if v[1]}
+    tot_ms = sum(v[0] for v in prof.values())
+    achieved = flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)",
+        "achieved": round(achieved, 2), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": round(achieved / peaks["bf16_sustained"], 4), "frac_of_burst": round(achieved / peaks["bf16_burst"], 4),
+        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "traffic": None,
+        "algorithmic_flops_per_step": flops_step, "flops_per_sample_step": unet_flops_per_sample(L),
+        "conv_launches_per_step": conv_n, "conv_ms_per_step": round(conv_ms, 3),
+        "conv_share_of_kernel_time": round(conv_ms / tot_ms, 4) if tot_ms else None,
+        "whole_step_tflops": round(flops_step * args.steps / (ms * 1e-3) / 1e12, 2),
+    }
+
+    line = {
+        "metric": "diffusion_samples_per_s", "value": round(value, 2), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == "bf16" else "f32",
+        "data": "synthetic (Philox N(0,1) start, random-init weights torch.manual_seed(0))",
+        "config": {"workload": f"C2: score U-Net reverse-SDE sampling, {L}x{L} Ising lattices, {NS} Euler-Maruyama steps, "
+                               f"batch {B} per GPU, ScoreNetwork(1,32,64,3) random-init, default VP-SDE",
+                   "lattice": L, "em_steps": NS, "batch_per_gpu": B, "global_batch": B * world,
+                   "precision": prec, "parallelism": f"batch-sharded x{world}, one final observable all-reduce",
+                   "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no flush needed"},
+        "sample_steps_per_s": round(value * NS, 1),
+        "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(x0_host.numel() * 4),
+                "d2h_bytes_per_step": int(out_bytes.get("n", 0)), "steps": e2e_steps,
+                "api": "backend.ml.samplers.diffusion.DiffusionSampler.sample(shape, x0=<pinned host tensor>) -> host tensor"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "breakdown_ms_per_step": breakdown,
+        "clocks": clk,
+        "observables": {"count": float(last["acc"][0]), "mean_abs_M": float(last["acc"][2] / max(float(last["acc"][0]), 1))},
+    }
+
+    if rank == 0 and world == 1:
+        # ---- CPU baseline: oracle port (torch fp32, all host threads) on a bounded sample of the same workload
+        sd = {k: v.detach().clone() for k, v in smp.model.state_dict().items()}
+        nthr = torch.get_num_threads()
+        xb = torch.randn(8, 1, L, L)
+        t0 = time.time()
+        o_unet.unet_forward(sd, xb, torch.full((8,), 0.5))
+        o_unet.unet_forward(sd, xb, torch.full((8,), 0.5))
+        per_ss = (time.time() - t0) / 16
+        Bc = int(max(1, min(64, 20.0 / (per_ss * NS))))
+        x0c = torch.randn(Bc, 1, L, L)
+        nz = torch.randn(NS, Bc, 1, L, L)
+        t0 = time.time()
+        o_unet.sample(sd, (Bc, 1, L, L), NS, x0c, nz)
+        dtc = time.time() - t0
+        line["cpu_baseline"] = {"value": round(Bc / dtc, 4), "unit": "samples/s", "cores": nthr, "kind": "port",
+                                "host_cpus": os.cpu_count(),
+                                "sample": f"{Bc} samples x {NS} EM steps of the same {L}x{L} workload, torch fp32 on the host"}
+        # ---- secondary blocks
+        line["ising"] = bench_ising(peaks)
+        line["diffusion_64"] = bench_diffusion64(peaks, prec)
+        line["lj"] = bench_lj()
+    return line
+
+
+def bench_ising(peaks):
+    """Config-3 per-GPU shape: 64x64, 8192 chains at 64 temperatures in [1.5, 3.5]; resident mode
+    (100 sweeps per launch) and streaming mode (1 sweep per launch, state round-trips HBM)."""
+    from backend.ml.samplers.mcmc import MetropolisHastings
+    from backend.ml.systems.ising import IsingModel
+    from dbs_b200 import abi
+    L, n = 64, 8192
+    m = IsingModel(L)
+    temps = np.repeat(np.linspace(1.5, 3.5, 64), n // 64)
+    mh = MetropolisHastings(m, temps, seed=1234)
+    bits = m.random_packed(n, seed=1234)
+    out = {}
+    for mode, sweeps, reps in (("resident", 100, 5), ("streaming", 1, 200)):
+        for _ in range(3):
+            mh.sweeps_packed(bits, sweeps)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            mh.sweeps_packed(bits, sweeps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        flips = n * L * L * sweeps * reps / (ms * 1e-3)
+        out[mode] = {"flips_per_s": float(f"{flips:.4e}"), "ms_per_launch": round(ms / reps, 4), "sweeps_per_launch": sweeps}
+    # streaming mode: 0.25 B per attempt (1 bit read + 1 bit written), HBM roofline
+    ach = out["streaming"]["flips_per_s"] * 0.25 / 1e9
+    out["roofline_streaming"] = {"bound": "hbm", "achieved": round(ach, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": round(ach / peaks["hbm_gbs"], 5), "bytes_per_attempt": 0.25,
+                                 "note": "512 B lattices: launch/ALU bound by design, see DESIGN.md"}
+    out["metric"] = "ising_spin_flips_per_s"
+    out["value"] = out["resident"]["flips_per_s"]
+    out["config"] = {"workload": "C3 per-GPU shape: 2D Ising 64x64 checkerboard Metropolis, 8192 chains, 64 temperatures in [1.5,3.5]"}
+    e, mg = m.packed_observables(bits)
+    out["mean_abs_M_T1.5"] = round(float(mg[: n // 64].abs().mean()), 4)
+    out["mean_abs_M_T3.5"] = round(float(mg[-n // 64:].abs().mean()), 4)
+    return out
+
+
+def bench_diffusion64(peaks, prec):
+    """Config-4 lattice size (64x64) on a bounded sample: batch 256, 20 EM steps."""
+    B, L, NS = 256, 64, 20
+    smp = make_sampler(L, NS, prec, "cuda")
+    for _ in range(2):
+        smp.sample((B, 1, L, L), seed=1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 3
+    for r in range(reps):
+        smp.sample((B, 1, L, L), seed=2 + r)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    sss = B * NS * reps / (ms * 1e-3)
+    tf = sss * unet_flops_per_sample(L) / 1e12
+    return {"metric": "diffusion_sample_steps_per_s_64x64", "value": round(sss, 1),
+            "samples_per_s_at_1000_steps": round(sss / 1000, 3), "whole_step_tflops": round(tf, 2),
+            "frac_of_sustained_bf16": round(tf / peaks["bf16_sustained"], 4),
+            "sample": f"batch {B}, {NS} of 1000 EM steps, 64x64 (C4 shape, bounded)"}
+
+
+def bench_lj():
+    """Config-5 kernel shape: N = 256 at rho* = 0.8, 4096 configurations, energy + forces in one pass."""
+    from backend.ml.systems.lennard_jones import LennardJonesSystem
+    N, B = 256, 4096
+    box = float((N / 0.8) ** 0.5)
+    s = LennardJonesSystem(N, box)
+    torch.manual_seed(0)
+    pos = ((s.lattice_configuration(B) + 0.05 * torch.randn(B, N, 2)) % box).cuda()
+    for _ in range(3):
+        s.energy_and_forces(pos)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 20
+    for _ in range(reps):
+        s.energy_and_forces(pos)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"metric": "lj_configs_per_s", "value": round(B / (ms * 1e-3), 1), "pairs_per_s": float(f"{B * N * N / (ms * 1e-3):.4e}"),
+            "ms_per_launch": round(ms, 4), "config": {"workload": "C5 kernel: N=256, 4096 configurations, energy+forces"}}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def bench_reference(args, world, rank):
+    """The reference's CPU implementation of the path (plain PyTorch fp32 on the host cores).  The
+    reference is Python and does not exist on the GPU box, so this runs the oracle port
+    (oracle/unet.py, pinned to the reference by tests/golden) with all host threads.  Each step is
+    a bounded sample of the workload: Bc samples x 100 EM steps."""
+    if rank != 0:
+        return None
+    from backend.ml.models.score_network import ScoreNetwork
+    from oracle import unet as o_unet
+    L, NS = L_MAIN, STEPS_MAIN
+    torch.manual_seed(0)
+    net = ScoreNetwork(**NET_CFG).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    nthr = torch.get_num_threads()
+    xb = torch.randn(8, 1, L, L)
+    o_unet.unet_forward(sd, xb, torch.full((8,), 0.5))
+    t0 = time.time()
+    o_unet.unet_forward(sd, xb, torch.full((8,), 0.5))
+    per_ss = (time.time() - t0) / 8
+    budget = 150.0 / max(1, args.steps + args.warmup)       # seconds per step
+    Bc = int(max(1, min(64, budget / (per_ss * NS))))
+    shape = (Bc, 1, L, L)
+    x0, nz = torch.randn(shape), torch.randn(NS, *shape)
+    for _ in range(args.warmup):
+        o_unet.sample(sd, shape, NS, x0, nz)
+    t0 = time.time()
+    for _ in range(args.steps):
+        o_unet.sample(sd, shape, NS, x0, nz)
+    dt = time.time() - t0
+    value = Bc * args.steps / dt
+    return {
+        "impl": "reference", "metric": "diffusion_samples_per_s", "value": round(value, 4), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: score U-Net reverse-SDE sampling, {L}x{L} Ising lattices, {NS} Euler-Maruyama steps, "
+                               f"bounded sample of {Bc} samples per step, ScoreNetwork(1,32,64,3) random-init",
+                   "lattice": L, "em_steps": NS, "batch_per_step": Bc},
+        "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": nthr, "kind": "port",
+                         "host_cpus": os.cpu_count(),
+                         "sample": f"{Bc} samples x {NS} EM steps per step, torch fp32 CPU (oracle port of the reference path)"},
+        "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_MAIN)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        line = bench_reference(args, world, rank)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+
+    world, rank, local = dist_setup(args.gpus)
+    line = bench_ours(args, world, rank, local)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

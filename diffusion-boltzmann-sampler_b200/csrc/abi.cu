@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace dbs {
@@ -15,6 +18,63 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 }  // namespace dbs
+
+namespace dbs {
+bool g_prof_on = false;
+namespace {
+struct ProfPair { cudaEvent_t a, b; int cls; };
+std::vector<ProfPair> g_pairs;       // recorded pairs awaiting dbs_profile_read
+std::vector<cudaEvent_t> g_pool;     // recycled events
+std::mutex g_prof_mu;
+cudaEvent_t g_open[kProfNumClasses];
+double g_ms[kProfNumClasses];
+uint64_t g_cnt[kProfNumClasses];
+const char* kProfNames[kProfNumClasses] = {"conv_tc", "conv_generic", "gn_stats", "gn_apply", "em_step", "unet_misc",
+                                           "ising_sweep", "ising_observables", "ising_misc", "lj_pair"};
+cudaEvent_t take_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void prof_begin(ProfClass c, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_open[c] = take_event();
+  cudaEventRecord(g_open[c], st);
+}
+void prof_end(ProfClass c, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t b = take_event();
+  cudaEventRecord(b, st);
+  g_pairs.push_back({g_open[c], b, (int)c});
+}
+}  // namespace dbs
+
+extern "C" int dbs_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(dbs::g_prof_mu);
+  dbs::g_prof_on = on != 0;
+  return DBS_OK;
+}
+extern "C" int dbs_profile_num_classes(void) { return dbs::kProfNumClasses; }
+extern "C" const char* dbs_profile_class_name(int c) {
+  return (c >= 0 && c < dbs::kProfNumClasses) ? dbs::kProfNames[c] : "";
+}
+extern "C" int dbs_profile_read(double* ms, uint64_t* launches, int n, int reset) {
+  using namespace dbs;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (const ProfPair& pr : g_pairs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(pr.b) != cudaSuccess || cudaEventElapsedTime(&t, pr.a, pr.b) != cudaSuccess) {
+      set_error("profile_read: event query failed");
+      return DBS_ERR_CUDA;
+    }
+    g_ms[pr.cls] += t; g_cnt[pr.cls] += 1;
+    g_pool.push_back(pr.a); g_pool.push_back(pr.b);
+  }
+  g_pairs.clear();
+  for (int c = 0; c < n && c < kProfNumClasses; ++c) { if (ms) ms[c] = g_ms[c]; if (launches) launches[c] = g_cnt[c]; }
+  if (reset) for (int c = 0; c < kProfNumClasses; ++c) { g_ms[c] = 0; g_cnt[c] = 0; }
+  return DBS_OK;
+}
 
 extern "C" const char* dbs_last_error(void) { return dbs::t_error; }
 extern "C" int dbs_abi_version(void) { return 1000; }

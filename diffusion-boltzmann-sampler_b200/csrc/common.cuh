@@ -16,6 +16,21 @@ extern std::atomic<uint64_t> g_launches;
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Optional per-kernel-class timing (dbs_profile_enable): CUDA events recorded on the launching
+// stream around each launch, summed at dbs_profile_read.  Off by default: zero cost.
+enum ProfClass {
+  kProfConvTC = 0, kProfConvGeneric, kProfGnStats, kProfGnApply, kProfEm, kProfUnetMisc,
+  kProfIsingSweep, kProfIsingObs, kProfIsingMisc, kProfLj, kProfNumClasses
+};
+extern bool g_prof_on;
+void prof_begin(ProfClass c, cudaStream_t st);
+void prof_end(ProfClass c, cudaStream_t st);
+struct ProfScope {
+  ProfClass c; cudaStream_t st; bool on;
+  ProfScope(ProfClass c_, cudaStream_t st_) : c(c_), st(st_), on(g_prof_on) { if (on) prof_begin(c, st); }
+  ~ProfScope() { if (on) prof_end(c, st); }
+};
+
 #define DBS_REQUIRE(cond, ...)                 \
   do {                                         \
     if (!(cond)) {                             \

@@ -509,6 +509,7 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   DBS_CUDA(attr_err);
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  ProfScope prof(kProfConvTC, st);
   conv_tc_kernel<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
   DBS_LAUNCHED();
   return DBS_OK;

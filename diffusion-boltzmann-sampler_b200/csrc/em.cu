@@ -103,6 +103,7 @@ int launch_em(const EmArgs& a, cudaStream_t st) {
   const bool vec = (a.elems % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) &&
                    (kFill || ((reinterpret_cast<uintptr_t>(a.score) & 15) == 0 &&
                               (!a.noise || (reinterpret_cast<uintptr_t>(a.noise) & 15) == 0)));
+  ProfScope prof(kProfEm, st);
   if (vec) em_kernel<true, kFill><<<(unsigned)blocks, 256, 0, st>>>(a);
   else em_kernel<false, kFill><<<(unsigned)blocks, 256, 0, st>>>(a);
   DBS_LAUNCHED();

@@ -165,6 +165,7 @@ int launch_sweep_t(const SweepArgs& a, cudaStream_t st) {
   if (threads < cpb * 16) threads = cpb * 16;
   const size_t smem = (size_t)(2 * cpb * tpc + 2) * 4 + (size_t)cpb * 16 * 8;
   const int64_t blocks = (a.n_chains + cpb - 1) / cpb;
+  ProfScope prof(kProfIsingSweep, st);
   ising_sweep_kernel<LT, kInject><<<(unsigned)blocks, threads, smem, st>>>(a);
   DBS_LAUNCHED();
   return DBS_OK;
@@ -467,6 +468,7 @@ extern "C" int dbs_ising_observables(const uint32_t* bits, int L, int64_t n_chai
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
   DBS_REQUIRE(bits && n_chains >= 0, "ising_observables: null state");
   if (n_chains == 0) return DBS_OK;
+  ProfScope prof(kProfIsingObs, as_stream(stream));
   ising_obs_packed_kernel<<<(unsigned)((n_chains * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(
       bits, L, n_chains, -J, -h, energy, magnetization);
   DBS_LAUNCHED();
@@ -490,6 +492,7 @@ extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chai
   if (n_chains == 0) return DBS_OK;
   const int W = (L + 31) / 32, tpc = L * W;
   const size_t smem = (size_t)(2 * tpc + L * (2 * W + 2)) * 4 + (size_t)(L / 2) * 4;
+  ProfScope prof(kProfIsingObs, as_stream(stream));
   ising_corr_kernel<<<(unsigned)n_chains, kCorrThreads, smem, as_stream(stream)>>>(bits, L, ref_mask, group, acc);
   DBS_LAUNCHED();
   return DBS_OK;

@@ -95,6 +95,7 @@ extern "C" int dbs_lj_energy_forces(const float* pos, int64_t B, int N, float bo
   const size_t smem = (size_t)N * 2 * sizeof(float);
   if (smem > 48 * 1024)
     DBS_CUDA(cudaFuncSetAttribute(lj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(kProfLj, as_stream(stream));
   lj_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(a);
   DBS_LAUNCHED();
   return DBS_OK;

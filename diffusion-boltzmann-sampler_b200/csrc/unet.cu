@@ -563,6 +563,7 @@ int run_conv(Ctx& c, const ConvGeom& g, const T* in0, const T* in1, const ConvWe
               "unet: channel counts must be multiples of 4 (got %d+%d -> %d)", g.C0, g.C1, g.Cout);
   const int64_t M = (int64_t)g.B * g.Hm * g.Wm;
   dim3 grid((unsigned)((M + kGT - 1) / kGT), (unsigned)((g.Cout + kGT - 1) / kGT));
+  ProfScope prof(kProfConvGeneric, c.st);
   conv_generic_kernel<T, typename WSel<T>::type><<<grid, 256, 0, c.st>>>(g, in0, in1, WSel<T>::get(w), w.bias, out);
   DBS_LAUNCHED();
   return DBS_OK;
@@ -587,6 +588,7 @@ int run_gn(Ctx& c, const T* y, T* out, bool have_raw_stats, const float* gamma, 
   const int G = C < 8 ? C : 8;
   const int HW = H * W;
   if (!have_raw_stats) {
+    ProfScope prof(kProfGnStats, c.st);
     gn_stats_kernel<T><<<(unsigned)(c.B * G), 256, 0, c.st>>>(y, c.stats, HW, C, G, 1e-5f);
     DBS_LAUNCHED();
   }
@@ -594,6 +596,7 @@ int run_gn(Ctx& c, const T* y, T* out, bool have_raw_stats, const float* gamma, 
   int64_t blocks = (nq + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   const float inv_cnt = 1.0f / (float)((int64_t)HW * (C / G));
+  ProfScope prof(kProfGnApply, c.st);
   gn_apply_kernel<T><<<(unsigned)blocks, 256, 0, c.st>>>(
       y, out, c.stats, have_raw_stats ? 1 : 0, inv_cnt, 1e-5f, gamma, beta,
       add_time ? c.tbias + tb_off : nullptr, c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, nq, HW, C, G);
@@ -682,14 +685,18 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   int rc;
 
   // ---- time path
-  time_kernel<<<(unsigned)n_t, 128, (size_t)4 * Td * 4, st>>>(t, plan->freqs, Td, plan->tw0, plan->tb0, plan->tw2,
-                                                             plan->tb2, plan->twt, plan->tbt, plan->sumC, tbias);
-  DBS_LAUNCHED();
+  {
+    ProfScope prof(kProfUnetMisc, st);
+    time_kernel<<<(unsigned)n_t, 128, (size_t)4 * Td * 4, st>>>(t, plan->freqs, Td, plan->tw0, plan->tb0, plan->tw2,
+                                                               plan->tb2, plan->twt, plan->tbt, plan->sumC, tbias);
+    DBS_LAUNCHED();
+  }
 
   // ---- init conv
   {
     const int64_t n_pix = B * H * W;
     const int64_t nthr = n_pix * (C / 4);
+    ProfScope prof(kProfUnetMisc, st);
     init_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(x, plan->init_w, plan->init_b, a0, n_pix, H, W, C);
     DBS_LAUNCHED();
     if ((rc = maybe_tap<T>(c, "init", a0, B, H, W, C))) return rc;
@@ -741,6 +748,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- final conv (+ optional normalisation, output scale)
   {
     const int64_t n_pix = B * H * W;
+    ProfScope prof(kProfUnetMisc, st);
     final_conv_kernel<T><<<(unsigned)((n_pix + 127) / 128), 128, (size_t)9 * C * 4, st>>>(
         cur, plan->final_w, plan->final_b, score, n_pix, H, W, C, cfg.output_scale);
     DBS_LAUNCHED();
