@@ -41,6 +41,10 @@ PROTOTYPES = {
     "dbs_abi_version": (i32, []),
     "dbs_built_sm": (i32, []),
     "dbs_launch_count": (u64, []),
+    "dbs_profile_enable": (i32, [i32]),
+    "dbs_profile_num_classes": (i32, []),
+    "dbs_profile_class_name": (C.c_char_p, [i32]),
+    "dbs_profile_read": (i32, [vp, vp, i32, i32]),
     "dbs_ising_words_per_chain": (i32, [i32]),
     "dbs_ising_init_packed": (i32, [vp, i32, i64, u64, i64, vp]),
     "dbs_ising_pack": (i32, [vp, vp, i32, i64, vp]),
@@ -85,3 +89,16 @@ def check(rc, what=""):
 
 def launch_count():
     return int(lib.dbs_launch_count())
+
+
+def profile(on):
+    check(lib.dbs_profile_enable(1 if on else 0))
+
+
+def profile_read(reset=True):
+    """{class name: (milliseconds, launches)} accumulated since the last reset."""
+    n = lib.dbs_profile_num_classes()
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    check(lib.dbs_profile_read(ms, cnt, n, 1 if reset else 0), "profile_read")
+    return {lib.dbs_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

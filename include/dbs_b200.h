@@ -44,6 +44,14 @@ int dbs_built_sm(void);
 /* Number of kernels this library has launched since load (monotonic; for bench.py's gpu_launches). */
 uint64_t dbs_launch_count(void);
 
+/* Optional per-kernel-class device timing for bench.py's roofline: when enabled, every launch is
+ * bracketed by CUDA events on its own stream (no synchronisation); dbs_profile_read waits for the
+ * recorded events and returns accumulated milliseconds and launch counts per class. */
+int dbs_profile_enable(int on);
+int dbs_profile_num_classes(void);
+const char* dbs_profile_class_name(int cls);
+int dbs_profile_read(double* ms, uint64_t* launches, int n, int reset);
+
 /* ------------------------------------------------------------------------- *
  * Ising lattice state: bit-packed, 1 bit per spin (1 = +1, 0 = -1).
  * Layout: uint32 words[n_chains][L][W], W = ceil(L/32); bit (j%32) of word
