@@ -34,13 +34,14 @@ constexpr int kTileM = 128;
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemBudget = 200 * 1024;
+constexpr int kMaxCout = 512;
 
 struct TcParams {
   int Wt, Ht, Nt;
   int tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n;
   int Nb, KC, chunks0, chunks1, n_taps, stages;
   int B, Hout, Wout, Cout, out_stride, oph, opw;
-  int groups, Cg;
+  int groups, Cg, cg_log2;
   int tap_dw[16], tap_dh[16], tap_p[16], tap_c0[16], tap_c1[16], tap_w[16];
   const float* bias;
   __nv_bfloat16* out;
@@ -140,6 +141,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// kRun: 0 = no GroupNorm statistics, else min(channels per group, 16) in {2, 4, 8, 16}
+template <int kRun>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p) {
@@ -149,6 +152,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t s_tmem_base;
   __shared__ float s_acc[2][kTileM * 8 * 2];  // GroupNorm partial sums, double-buffered by tile parity
+  __shared__ __align__(16) float s_bias[kMaxCout];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
@@ -175,6 +179,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   }
   if (warp == 2) tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols);
   for (int i = threadIdx.x; i < 2 * kTileM * 8 * 2; i += kThreads) (&s_acc[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < p.Cout; i += kThreads) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -247,6 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
     const int ppi = p.Ht * p.Wt;            // pixels per image inside a tile
     const int nl = row / ppi, hl = (row / p.Wt) % p.Ht, wl = row % p.Wt;
     const int etid = threadIdx.x - 64;      // 0..127
+    const bool warp_uniform_image = ppi >= 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -257,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       const bool valid = n < p.B;
       __nv_bfloat16* optr =
           p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (b * p.out_stride + p.opw)) * p.Cout + co0;
-      float* acc = &s_acc[it & 1][0];
+      float* acc = &s_acc[it & 1][nl * 16];
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
@@ -268,27 +274,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
         float f[16];
+        const float4* bq = reinterpret_cast<const float4*>(s_bias + co0 + c);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) + __ldg(p.bias + co0 + c + j) : 0.f;
-        if (p.stats) {
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = bq[j4];
+          f[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b4.x;
+          f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+          f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b4.z;
+          f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b4.w;
+        }
+        if (kRun > 0) {
+          if (!valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            run_s += f[j];
-            run_ss = fmaf(f[j], f[j], run_ss);
-            const int co = co0 + c + j;
-            if ((co + 1) % p.Cg == 0) {  // end of a GroupNorm group: flush this run
-              const int gi = co / p.Cg;
-              if (ppi >= 32) {
-                const float s = warp_sum(run_s), ss = warp_sum(run_ss);
-                if (lane == 0) {
-                  atomicAdd(&acc[(nl * 8 + gi) * 2 + 0], s);
-                  atomicAdd(&acc[(nl * 8 + gi) * 2 + 1], ss);
-                }
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
+          }
+          // GroupNorm partial sums: a run = the columns of this chunk that share a group
+          constexpr int R = kRun > 0 ? kRun : 16;
+#pragma unroll
+          for (int r = 0; r < 16 / R; ++r) {
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              s += f[r * R + j];
+              ss = fmaf(f[r * R + j], f[r * R + j], ss);
+            }
+            bool flush = true;
+            if (R == 16) {
+              run_s += s; run_ss += ss;
+              s = run_s; ss = run_ss;
+              flush = ((c + 16) & (p.Cg - 1)) == 0;   // warp-uniform: end of a group of >= 16 channels
+              if (flush) { run_s = 0.f; run_ss = 0.f; }
+            }
+            if (flush) {
+              const int gi = ((co0 + c) >> p.cg_log2) + (R == 16 ? 0 : r);
+              if (warp_uniform_image) {
+                s = warp_sum(s); ss = warp_sum(ss);
+                if (lane == 0) { atomicAdd(&acc[gi * 2 + 0], s); atomicAdd(&acc[gi * 2 + 1], ss); }
               } else {
-                atomicAdd(&acc[(nl * 8 + gi) * 2 + 0], run_s);
-                atomicAdd(&acc[(nl * 8 + gi) * 2 + 1], run_ss);
+                atomicAdd(&acc[gi * 2 + 0], s); atomicAdd(&acc[gi * 2 + 1], ss);
               }
-              run_s = 0.f; run_ss = 0.f;
             }
           }
         }
@@ -308,13 +332,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-      if (p.stats) {
+      if (kRun > 0) {
         epi_bar_sync();
-        const int n_img = p.Nt;
-        for (int i = etid; i < n_img * 8 * 2; i += 128) {
+        float* accb = &s_acc[it & 1][0];
+        for (int i = etid; i < p.Nt * 16; i += 128) {
           const int img = i >> 4, rest = i & 15, gi = rest >> 1, k = rest & 1;
-          const float vsum = acc[i];
-          acc[i] = 0.f;
+          const float vsum = accb[i];
+          accb[i] = 0.f;
           const int ng = tn * p.Nt + img;
           if (ng < p.B && gi < p.groups && vsum != 0.f) atomicAdd(p.stats + ((int64_t)ng * p.groups + gi) * 2 + k, vsum);
         }
@@ -438,6 +462,8 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
     }
   }
   if (groups > 8 || (stats && (groups < 1 || g.Cout % groups))) return DBS_ERR_UNSUPPORTED;
+  if (g.Cout > kMaxCout) return DBS_ERR_UNSUPPORTED;
+  if (stats && (!is_pow2(g.Cout / groups) || g.Cout / groups < 2)) return DBS_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w) |
        reinterpret_cast<uintptr_t>(out)) & 15)
     return DBS_ERR_UNSUPPORTED;
@@ -454,6 +480,8 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   p.B = g.B; p.Hout = g.Hout; p.Wout = g.Wout; p.Cout = g.Cout;
   p.out_stride = g.out_stride; p.oph = g.oph; p.opw = g.opw;
   p.groups = groups; p.Cg = stats ? g.Cout / groups : g.Cout;
+  p.cg_log2 = 0;
+  while ((1 << p.cg_log2) < p.Cg) ++p.cg_log2;
   for (int t = 0; t < g.n_taps; ++t) {
     if (g.in_stride == 1) {
       p.tap_dw[t] = g.dw[t]; p.tap_dh[t] = g.dh[t]; p.tap_p[t] = 0; p.tap_c0[t] = 0; p.tap_c1[t] = 0;
@@ -501,16 +529,25 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   if ((rc = encode_w(enc, &mw, w, Cin, g.Cout, taps_total, KC, Nb, sw))) return rc;
 
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+  const int run = !stats ? 0 : (p.Cg >= 16 ? 16 : p.Cg);
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
+      run == 0 ? conv_tc_kernel<0> : run == 2 ? conv_tc_kernel<2> : run == 4 ? conv_tc_kernel<4>
+               : run == 8 ? conv_tc_kernel<8> : conv_tc_kernel<16>;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+    void (*ks[5])(CUtensorMap, CUtensorMap, CUtensorMap, TcParams) = {conv_tc_kernel<0>, conv_tc_kernel<2>, conv_tc_kernel<4>,
+                                                                      conv_tc_kernel<8>, conv_tc_kernel<16>};
+    for (auto k : ks) {
+      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+      if (e != cudaSuccess) attr_err = e;
+    }
   });
   DBS_CUDA(attr_err);
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   ProfScope prof(kProfConvTC, st);
-  conv_tc_kernel<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
+  kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
   DBS_LAUNCHED();
   return DBS_OK;
 }

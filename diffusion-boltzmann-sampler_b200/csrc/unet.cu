@@ -333,42 +333,85 @@ gn_stats_kernel(const T* __restrict__ y, float* __restrict__ stats, int HW, int 
 
 // normalise * gamma + beta -> SiLU -> (+ time bias) -> (+ residual_scale * residual)
 // stats: (mean, rstd) per (n, g), or raw (sum, sumsq) from the tcgen05 epilogue when raw != 0.
+// Grid = (chunks, B): a CTA works on one sample, folds the statistics into per-channel
+// scale/shift once (shared memory), then streams 16-byte vectors: HBM-bound, 2 B read + 2 B
+// written per element in bf16 (+2 B for the residual).
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float v[4]) { Quad<float>::load(p, v); }
+  static __device__ __forceinline__ void store(float* p, const float v[4]) { Quad<float>::store(p, v); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float v[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __restrict__ stats, int raw,
                 float inv_cnt, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ tbias, int t_stride, const T* __restrict__ res, float res_scale,
-                int64_t n_quads, int HW, int C, int G) {
-  const int cq = C >> 2, Cg = C / G;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = q / cq;
-    const int c = (int)(q - p * cq) * 4;
-    const int n = (int)(p / HW);
-    float v[4];
-    Quad<T>::load(y + p * C + c, v);
-    float r[4] = {0.f, 0.f, 0.f, 0.f};
-    if (res) Quad<T>::load(res + p * C + c, r);
+                int HW, int C, int G) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sm_gn[];  // scale[C], shift[C], tb[C]
+  float* sc = sm_gn;
+  float* sh = sm_gn + C;
+  float* tb = sm_gn + 2 * C;
+  const int n = blockIdx.y;
+  const int Cg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int gi = c / Cg;
+    const float s0 = stats[((int64_t)n * G + gi) * 2 + 0];
+    const float s1 = stats[((int64_t)n * G + gi) * 2 + 1];
+    float mean, rstd;
+    if (raw) {
+      mean = s0 * inv_cnt;
+      rstd = rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps);
+    } else {
+      mean = s0; rstd = s1;
+    }
+    const float a = rstd * gamma[c];
+    sc[c] = a;
+    sh[c] = beta[c] - mean * a;
+    tb[c] = tbias ? tbias[(int64_t)n * t_stride + c] : 0.f;
+  }
+  __syncthreads();
+  const int cv = C / V;                       // vectors per pixel
+  const int items = HW * cv;
+  const T* yb = y + (int64_t)n * HW * C;
+  const T* rb = res ? res + (int64_t)n * HW * C : nullptr;
+  T* ob = out + (int64_t)n * HW * C;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    const int c = (it % cv) * V;
+    float v[V], r[V];
+    Vec16<T>::load(yb + (int64_t)it * V, v);
+    if (rb) Vec16<T>::load(rb + (int64_t)it * V, r);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int gi = (c + k) / Cg;
-      const float s0 = stats[((int64_t)n * G + gi) * 2 + 0];
-      const float s1 = stats[((int64_t)n * G + gi) * 2 + 1];
-      float mean, rstd;
-      if (raw) {
-        mean = s0 * inv_cnt;
-        const float var = fmaxf(s1 * inv_cnt - mean * mean, 0.f);
-        rstd = rsqrtf(var + eps);
-      } else {
-        mean = s0; rstd = s1;
-      }
-      float h = (v[k] - mean) * rstd * gamma[c + k] + beta[c + k];
-      h = silu(h);
-      if (tbias) h += tbias[(int64_t)n * t_stride + c + k];
-      if (res) h += res_scale * r[k];
+    for (int k = 0; k < V; ++k) {
+      float h = fmaf(v[k], sc[c + k], sh[c + k]);
+      h = silu(h) + tb[c + k];
+      if (rb) h = fmaf(res_scale, r[k], h);
       v[k] = h;
     }
-    Quad<T>::store(out + p * C + c, v);
+    Vec16<T>::store(ob + (int64_t)it * V, v);
   }
 }
 
@@ -592,14 +635,17 @@ int run_gn(Ctx& c, const T* y, T* out, bool have_raw_stats, const float* gamma, 
     gn_stats_kernel<T><<<(unsigned)(c.B * G), 256, 0, c.st>>>(y, c.stats, HW, C, G, 1e-5f);
     DBS_LAUNCHED();
   }
-  const int64_t nq = c.B * HW * (C / 4);
-  int64_t blocks = (nq + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int V = 16 / (int)sizeof(T);
+  DBS_REQUIRE(C % V == 0, "unet: channel count %d is not a multiple of %d", C, V);
+  const int items = HW * (C / V);
+  int bx = (items + 255) / 256;
+  const int cap = (int)std::max<int64_t>(1, (148 * 8) / c.B);   // ~8 CTAs per SM across the batch
+  if (bx > cap) bx = cap;
   const float inv_cnt = 1.0f / (float)((int64_t)HW * (C / G));
   ProfScope prof(kProfGnApply, c.st);
-  gn_apply_kernel<T><<<(unsigned)blocks, 256, 0, c.st>>>(
+  gn_apply_kernel<T><<<dim3((unsigned)bx, (unsigned)c.B), 256, (size_t)3 * C * sizeof(float), c.st>>>(
       y, out, c.stats, have_raw_stats ? 1 : 0, inv_cnt, 1e-5f, gamma, beta,
-      add_time ? c.tbias + tb_off : nullptr, c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, nq, HW, C, G);
+      add_time ? c.tbias + tb_off : nullptr, c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, HW, C, G);
   DBS_LAUNCHED();
   return DBS_OK;
 }
