@@ -1,0 +1,436 @@
+// conv_strip.cu — "strip" variant of the tcgen05 implicit-GEMM convolution for the full-resolution,
+// small-channel layers of the score U-Net (stride-1 convs and transposed-conv phases, Cout <= 64).
+//
+// Why a second kernel: conv_tc.cu re-fetches the activation tile once per tap and the weights once
+// per tile; ncu shows those layers bound by L2->SM request rate (~4 cycles per TMA row, tensor pipe
+// < 20 %).  Here a tile is Ht full-width image rows (Ht*W = 128 pixels) and, per channel chunk, ONE
+// TMA box brings the rows h0+dh_min .. h0+Ht-1+dh_max (zero-filled outside the image).  Every tap
+// then reads the same strip:
+//   * a vertical tap offset dh is a start-address offset of dh*W rows in the UMMA descriptor
+//     (a multiple of the 8-row swizzle atom because W % 8 == 0, so no descriptor base offset);
+//   * a horizontal offset dw in {-1,0,+1} is NOT applied to the operand.  Taps are accumulated
+//     into one TMEM accumulator per dw, P_dw[m] = sum_{dh,c} X[m + dh*W][c] * Wt[dh,dw][c], and the
+//     epilogue combines  out[m] = P_0[m] + P_{+1}[m+1]*[w<W-1] + P_{-1}[m-1]*[w>0]  with a lane
+//     shuffle (rows of the TMEM tile are pixels, so pixel m+-1 is lane m+-1; the mask is the
+//     convolution's zero padding at the left/right image border).
+// The layer's weights ([chunk][tap] slabs of Nb x KC, K-major, swizzled) are loaded once per CTA and
+// stay in shared memory when they fit; otherwise a chunk's slabs travel with its strip.
+// Activation traffic drops from 9 tiles to (Ht+2)/Ht strips per chunk; weight traffic to ~zero.
+//
+// Warp roles, barriers, TMEM double buffering and the GroupNorm epilogue are those of conv_tc.cu.
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
+#include "unet.cuh"
+
+namespace dbs {
+namespace {
+
+using namespace tc;
+using namespace tch;
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+constexpr uint32_t kSmemBudget = 200 * 1024;
+constexpr int kMaxCout = 64;
+
+struct StripParams {
+  int W, Ht, tiles_h, n_tiles;
+  int Nb, KC, chunks0, chunks1, n_taps, stages, resident;
+  int B, Hout, Wout, Cout, out_stride, oph, opw;
+  int groups, Cg, cg_log2;
+  int dh_min;
+  int tap_row[16];    // (dh - dh_min): strip row offset of the tap
+  int tap_slot[16];   // accumulator slot of the tap's dw
+  int tap_first[16];  // 1 if this tap is the first (in issue order) to touch its slot
+  int tap_w[16];      // weight tap index
+  int slot_c, slot_p, slot_m, nacc;  // accumulator slots of dw = 0, +1, -1 (-1 = unused)
+  const float* bias;
+  __nv_bfloat16* out;
+  float* stats;
+  uint32_t idesc;
+  uint32_t a_bytes, slab_bytes, stage_bytes, w_region_bytes;
+  uint32_t tmem_cols;
+  uint64_t desc_hi;
+};
+
+template <int kRun>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StripParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_acc[2][8 * 2];               // GroupNorm partial sums of the tile's image
+  __shared__ __align__(16) float s_bias[kMaxCout];
+  __shared__ float s_x[2][4][2][16];              // cross-warp neighbour exchange (W > 32)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_region = smem_u32(smem);                       // resident weights (may be empty)
+  const uint32_t ring = w_region + p.w_region_bytes;              // strip (+ streamed weight) stages
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+  const uint32_t bar_w = smem_u32(&bars[2 * kMaxStages + 4]);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull + 8 * s, 1);
+      mbar_init(bar_tempty + 8 * s, 4);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_in0);
+    tma_prefetch_desc(&map_in1);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols);
+  if (threadIdx.x < 32) (&s_acc[0][0])[threadIdx.x] = 0.f;
+  for (int i = threadIdx.x; i < p.Cout; i += kThreads) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int chunks = p.chunks0 + p.chunks1;
+  const uint32_t row_bytes = (uint32_t)p.KC * 2;
+  const uint32_t chunk_w_bytes = p.slab_bytes * p.n_taps;
+  const int acc_cols = p.nacc * p.Nb;   // TMEM columns of one accumulator stage
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      if (p.resident) {
+        mbar_expect_tx(bar_w, chunk_w_bytes * chunks);
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int t = 0; t < p.n_taps; ++t)
+            tma_load_3d(w_region + (ch * p.n_taps + t) * p.slab_bytes, &map_w, bar_w, ch * p.KC, 0, p.tap_w[t]);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int n = tile / p.tiles_h, h0 = (tile - n * p.tiles_h) * p.Ht;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t a_dst = ring + stage * p.stage_bytes;
+          const uint32_t fb = bar_full + 8 * stage;
+          mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : chunk_w_bytes));
+          if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, ch * p.KC, 0, 0, h0 + p.dh_min, n);
+          else tma_load_5d(a_dst, &map_in1, fb, (ch - p.chunks0) * p.KC, 0, 0, h0 + p.dh_min, n);
+          if (!p.resident) {
+            const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
+            for (int t = 0; t < p.n_taps; ++t)
+              tma_load_3d(b_dst + t * p.slab_bytes, &map_w, fb, ch * p.KC, 0, p.tap_w[t]);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      if (p.resident) {
+        mbar_wait(bar_w, 0);
+        tc_fence_after();
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const int mmas = p.KC / 16;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + as * acc_cols;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_base = ring + stage * p.stage_bytes;
+          const uint32_t b_base = p.resident ? w_region + ch * chunk_w_bytes : a_base + ((p.a_bytes + 1023u) & ~1023u);
+          for (int t = 0; t < p.n_taps; ++t) {
+            const uint32_t a_addr = a_base + (uint32_t)(p.tap_row[t] * p.W) * row_bytes;
+            const uint32_t b_addr = b_base + t * p.slab_bytes;
+            const uint32_t d_tmem = d_base + p.tap_slot[t] * p.Nb;
+            const bool fresh = ch == 0 && p.tap_first[t];
+            for (int k = 0; k < mmas; ++k) {
+              const uint64_t adesc = p.desc_hi | (uint64_t)(((a_addr + 32 * k) & 0x3FFFFu) >> 4);
+              const uint64_t bdesc = p.desc_hi | (uint64_t)(((b_addr + 32 * k) & 0x3FFFFu) >> 4);
+              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (fresh && k == 0) ? 0u : 1u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * as);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;          // tile-local pixel
+    const int hl = row / p.W, wl = row - hl * p.W;
+    const bool has_right = wl < p.W - 1;    // pixel m+1 is in the same image row
+    const bool has_left = wl > 0;
+    const bool xchg = p.W > 32;             // an image row spans several warps
+    const int etid = threadIdx.x - 64;
+    int it = 0;
+    int xb = 0;  // exchange-buffer parity, toggled per chunk across tiles (one barrier per chunk suffices)
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n = tile / p.tiles_h, a = (tile - n * p.tiles_h) * p.Ht + hl;
+      __nv_bfloat16* optr =
+          p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout;
+      float* acc = &s_acc[it & 1][0];
+
+      mbar_wait(bar_tfull + 8 * as, aphase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
+      float run_s = 0.f, run_ss = 0.f;
+      for (int c = 0; c < p.Nb; c += 16, xb ^= 1) {
+        uint32_t v0[16], vp[16], vm[16];
+        tmem_ld16(tbase + p.slot_c * p.Nb + c, v0);
+        if (p.slot_p >= 0) tmem_ld16(tbase + p.slot_p * p.Nb + c, vp);
+        if (p.slot_m >= 0) tmem_ld16(tbase + p.slot_m * p.Nb + c, vm);
+        tmem_ld_wait();
+        if (xchg) {
+          // publish the edge lanes: my lane 0's P_{+1} is pixel m+1 of the previous warp's lane 31,
+          // my lane 31's P_{-1} is pixel m-1 of the next warp's lane 0
+          if (lane == 0 && p.slot_p >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s_x[xb][q][0][j] = __uint_as_float(vp[j]);
+          }
+          if (lane == 31 && p.slot_m >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s_x[xb][q][1][j] = __uint_as_float(vm[j]);
+          }
+          epi_bar_sync();
+        }
+        float f[16];
+        const float4* bq = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = bq[j4];
+          f[4 * j4 + 0] = __uint_as_float(v0[4 * j4 + 0]) + b4.x;
+          f[4 * j4 + 1] = __uint_as_float(v0[4 * j4 + 1]) + b4.y;
+          f[4 * j4 + 2] = __uint_as_float(v0[4 * j4 + 2]) + b4.z;
+          f[4 * j4 + 3] = __uint_as_float(v0[4 * j4 + 3]) + b4.w;
+        }
+        if (p.slot_p >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[j]), 1);
+            if (lane == 31) nb = (xchg && has_right) ? s_x[xb][(q + 1) & 3][0][j] : 0.f;
+            f[j] += has_right ? nb : 0.f;
+          }
+        }
+        if (p.slot_m >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float nb = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j]), 1);
+            if (lane == 0) nb = (xchg && has_left) ? s_x[xb][(q + 3) & 3][1][j] : 0.f;
+            f[j] += has_left ? nb : 0.f;
+          }
+        }
+        if (kRun > 0) {
+          constexpr int R = kRun > 0 ? kRun : 16;
+#pragma unroll
+          for (int r = 0; r < 16 / R; ++r) {
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              s += f[r * R + j];
+              ss = fmaf(f[r * R + j], f[r * R + j], ss);
+            }
+            bool flush = true;
+            if (R == 16) {
+              run_s += s; run_ss += ss;
+              s = run_s; ss = run_ss;
+              flush = ((c + 16) & (p.Cg - 1)) == 0;
+              if (flush) { run_s = 0.f; run_ss = 0.f; }
+            }
+            if (flush) {
+              const int gi = (c >> p.cg_log2) + (R == 16 ? 0 : r);
+              s = warp_sum(s); ss = warp_sum(ss);
+              if (lane == 0) { atomicAdd(&acc[gi * 2 + 0], s); atomicAdd(&acc[gi * 2 + 1], ss); }
+            }
+          }
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(optr + c);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (kRun > 0) {
+        epi_bar_sync();
+        if (etid < 16) {
+          const float vsum = acc[etid];
+          acc[etid] = 0.f;
+          const int gi = etid >> 1, k = etid & 1;
+          if (gi < p.groups && vsum != 0.f) atomicAdd(p.stats + ((int64_t)n * p.groups + gi) * 2 + k, vsum);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace
+
+int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1, const __nv_bfloat16* w,
+                      const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st) {
+  static const bool disabled = [] { const char* e = getenv("DBS_CONV_STRIP"); return e && e[0] == '0'; }();
+  if (disabled) return DBS_ERR_UNSUPPORTED;
+  // ---- eligibility
+  if (g.in_stride != 1 || g.Wm != g.Win || g.Hm != g.Hin) return DBS_ERR_UNSUPPORTED;
+  const int W = g.Win, H = g.Hin;
+  if (!(W == 8 || W == 16 || W == 32 || W == 64 || W == 128)) return DBS_ERR_UNSUPPORTED;
+  const int Ht = kTileM / W;
+  if (H < Ht || H % Ht) return DBS_ERR_UNSUPPORTED;
+  if (g.Cout > kMaxCout || g.Cout % 16 || g.C0 == 0) return DBS_ERR_UNSUPPORTED;
+  int KC = 0;
+  for (int k : {64, 32, 16})
+    if (g.C0 % k == 0 && g.C1 % k == 0) { KC = k; break; }
+  if (!KC) return DBS_ERR_UNSUPPORTED;
+  if (groups > 8 || (stats && (groups < 1 || g.Cout % groups))) return DBS_ERR_UNSUPPORTED;
+  if (stats && (!is_pow2(g.Cout / groups) || g.Cout / groups < 2)) return DBS_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return DBS_ERR_UNSUPPORTED;
+  int dh_min = 0, dh_max = 0;
+  for (int t = 0; t < g.n_taps; ++t) {
+    if (g.dw[t] < -1 || g.dw[t] > 1) return DBS_ERR_UNSUPPORTED;
+    dh_min = g.dh[t] < dh_min ? g.dh[t] : dh_min;
+    dh_max = g.dh[t] > dh_max ? g.dh[t] : dh_max;
+  }
+  const int rows = Ht + dh_max - dh_min;
+  if (rows > 256) return DBS_ERR_UNSUPPORTED;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("conv_strip: cuTensorMapEncodeTiled entry point unavailable"); return DBS_ERR_CUDA; }
+
+  StripParams p;
+  memset(&p, 0, sizeof(p));
+  const int Cin = g.C0 + g.C1, Nb = g.Cout;
+  p.W = W; p.Ht = Ht; p.tiles_h = H / Ht; p.n_tiles = g.B * p.tiles_h;
+  p.Nb = Nb; p.KC = KC; p.chunks0 = g.C0 / KC; p.chunks1 = g.C1 / KC; p.n_taps = g.n_taps;
+  p.B = g.B; p.Hout = g.Hout; p.Wout = g.Wout; p.Cout = g.Cout;
+  p.out_stride = g.out_stride; p.oph = g.oph; p.opw = g.opw;
+  p.groups = groups; p.Cg = stats ? g.Cout / groups : g.Cout;
+  while ((1 << p.cg_log2) < p.Cg) ++p.cg_log2;
+  p.dh_min = dh_min;
+  // accumulator slots by dw: the dw = 0 slot must exist (the epilogue starts from it)
+  int slot_of[3] = {-1, -1, -1};  // index dw + 1
+  int nacc = 0;
+  bool has_c = false;
+  for (int t = 0; t < g.n_taps; ++t) has_c |= g.dw[t] == 0;
+  if (!has_c) return DBS_ERR_UNSUPPORTED;
+  slot_of[1] = nacc++;
+  for (int t = 0; t < g.n_taps; ++t)
+    if (slot_of[g.dw[t] + 1] < 0) slot_of[g.dw[t] + 1] = nacc++;
+  bool seen[3] = {false, false, false};
+  for (int t = 0; t < g.n_taps; ++t) {
+    p.tap_row[t] = g.dh[t] - dh_min;
+    p.tap_slot[t] = slot_of[g.dw[t] + 1];
+    p.tap_first[t] = seen[p.tap_slot[t]] ? 0 : 1;
+    seen[p.tap_slot[t]] = true;
+    p.tap_w[t] = g.widx[t];
+  }
+  p.slot_c = slot_of[1]; p.slot_p = slot_of[2]; p.slot_m = slot_of[0]; p.nacc = nacc;
+  p.bias = bias; p.out = out; p.stats = stats;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  p.a_bytes = (uint32_t)rows * W * KC * 2;
+  p.slab_bytes = (uint32_t)Nb * KC * 2;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * nacc * Nb)) cols <<= 1;
+  if (cols > 512) return DBS_ERR_UNSUPPORTED;
+  p.tmem_cols = cols;
+  const uint32_t a_pad = (p.a_bytes + 1023u) & ~1023u;
+  const uint32_t chunk_w = p.slab_bytes * g.n_taps;
+  const uint32_t all_w = chunk_w * (uint32_t)(p.chunks0 + p.chunks1);
+  if (p.slab_bytes % 1024u && KC == 64) return DBS_ERR_UNSUPPORTED;   // slab bases must stay atom-aligned
+  if (p.slab_bytes % (8u * KC * 2u)) return DBS_ERR_UNSUPPORTED;
+  // resident weights if they leave room for >= 3 strip stages
+  if (all_w + 3 * a_pad <= kSmemBudget) {
+    p.resident = 1;
+    p.w_region_bytes = (all_w + 1023u) & ~1023u;
+    p.stage_bytes = a_pad;
+  } else {
+    p.resident = 0;
+    p.w_region_bytes = 0;
+    p.stage_bytes = a_pad + ((chunk_w + 1023u) & ~1023u);
+  }
+  int stages = (int)((kSmemBudget - p.w_region_bytes) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return DBS_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const uint32_t row_bytes = (uint32_t)KC * 2;
+  const uint64_t layout = KC == 64 ? 2ull : (KC == 32 ? 4ull : 6ull);
+  p.desc_hi = (1ull << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap m0, m1, mw;
+  int rc;
+  if ((rc = encode_act(enc, &m0, in0, g.C0, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
+  if (g.C1 > 0) {
+    if ((rc = encode_act(enc, &m1, in1, g.C1, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
+  } else {
+    m1 = m0;
+  }
+  int taps_total = 0;
+  for (int t = 0; t < g.n_taps; ++t) taps_total = g.widx[t] + 1 > taps_total ? g.widx[t] + 1 : taps_total;
+  if (g.out_stride == 2) taps_total = 16;
+  if ((rc = encode_w(enc, &mw, w, Cin, g.Cout, taps_total, KC, Nb, sw))) return rc;
+
+  const size_t smem = (size_t)p.w_region_bytes + (size_t)stages * p.stage_bytes + 1024;
+  const int run = !stats ? 0 : (p.Cg >= 16 ? 16 : p.Cg);
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, StripParams) =
+      run == 0 ? conv_strip_kernel<0> : run == 2 ? conv_strip_kernel<2> : run == 4 ? conv_strip_kernel<4>
+               : run == 8 ? conv_strip_kernel<8> : conv_strip_kernel<16>;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    void (*ks[5])(CUtensorMap, CUtensorMap, CUtensorMap, StripParams) = {conv_strip_kernel<0>, conv_strip_kernel<2>,
+                                                                         conv_strip_kernel<4>, conv_strip_kernel<8>,
+                                                                         conv_strip_kernel<16>};
+    for (auto k : ks) {
+      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+      if (e != cudaSuccess) attr_err = e;
+    }
+  });
+  DBS_CUDA(attr_err);
+  const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  ProfScope prof(kProfConvTC, st);
+  kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+}  // namespace dbs

@@ -104,6 +104,16 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// bf16 path: x*sigmoid(x) with sigmoid = 0.5*tanh(x/2)+0.5, one MUFU.TANH per element (rel. error
+// ~2^-11, below bf16 resolution).  The accurate form above costs two MUFU ops + an IEEE division.
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+template <typename T> __device__ __forceinline__ float silu_t(float x);
+template <> __device__ __forceinline__ float silu_t<float>(float x) { return silu(x); }
+template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) { return silu_fast(x); }
 
 // ------------------------------------------------------------------------------------------------
 // generic implicit-GEMM convolution on the CUDA cores: 64 pixels x 64 couts per CTA, K chunk 16
@@ -195,31 +205,69 @@ conv_generic_kernel(ConvGeom g, const T* __restrict__ in0, const T* __restrict__
   }
 }
 
+// 16-byte vectors of the activation type
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float v[4]) { Quad<float>::load(p, v); }
+  static __device__ __forceinline__ void store(float* p, const float v[4]) { Quad<float>::store(p, v); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float v[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 // init conv: 1 -> C, 3x3 pad 1 (score_network.py:192, 238).  x fp32 [B][H][W]; w [9][C].
+// One thread per pixel: 9 input taps in registers, weights broadcast from shared memory, the
+// pixel's C outputs leave as contiguous 16-byte stores.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  T* __restrict__ out, int64_t n_pix, int H, int W, int C) {
-  const int cq = C >> 2;
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_pix * cq) return;
-  const int64_t p = g / cq;
-  const int c = (int)(g - p * cq) * 4;
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ __align__(16) float sw_init[];  // [9][C] weights, then [C] bias
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw_init[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw_init[9 * C + i] = bias[i];
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
   const int ww = (int)(p % W);
   const int hh = (int)((p / W) % H);
-  float v[4] = {bias[c], bias[c + 1], bias[c + 2], bias[c + 3]};
+  float xs[9];
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
       const int ih = hh + kh - 1, iw = ww + kw - 1;
-      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-      const float xv = __ldg(x + p + (int64_t)(kh - 1) * W + (kw - 1));
-      const float4 wq = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C + c));
-      v[0] = fmaf(xv, wq.x, v[0]); v[1] = fmaf(xv, wq.y, v[1]);
-      v[2] = fmaf(xv, wq.z, v[2]); v[3] = fmaf(xv, wq.w, v[3]);
+      xs[kh * 3 + kw] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + p + (int64_t)(kh - 1) * W + (kw - 1)) : 0.f;
     }
-  Quad<T>::store(out + p * C + c, v);
+  for (int c = 0; c < C; c += V) {
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = sw_init[9 * C + c + k];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = fmaf(xs[t], sw_init[t * C + c + k], v[k]);
+    Vec16<T>::store(out + p * C + c, v);
+  }
 }
 
 // final conv: C -> 1, 3x3 pad 1, then * output_scale (score_network.py:219, 259, 268).
@@ -227,28 +275,31 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 final_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ out, int64_t n_pix, int H, int W, int C, float scale) {
-  extern __shared__ float sw[];  // [9][C]
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ __align__(16) float sw[];  // [9][C]
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pix) return;
   const int ww = (int)(p % W);
   const int hh = (int)((p / W) % H);
-  float acc = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
   for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
       const int ih = hh + kh - 1, iw = ww + kw - 1;
       if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
       const T* src = in + (p + (int64_t)(kh - 1) * W + (kw - 1)) * C;
       const float* wk = sw + (kh * 3 + kw) * C;
-      for (int c = 0; c < C; c += 4) {
-        float v[4];
-        Quad<T>::load(src + c, v);
-        acc = fmaf(v[0], wk[c], acc); acc = fmaf(v[1], wk[c + 1], acc);
-        acc = fmaf(v[2], wk[c + 2], acc); acc = fmaf(v[3], wk[c + 3], acc);
+      for (int c = 0; c < C; c += V) {
+        float v[V];
+        Vec16<T>::load(src + c, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k & 3] = fmaf(v[k], wk[c + k], acc[k & 3]);
       }
     }
-  out[p] = scale * (acc + bias[0]);
+  out[p] = scale * (((acc[0] + acc[1]) + (acc[2] + acc[3])) + bias[0]);
 }
 
 // optional per-sample std normalisation (score_network.py:262-265): score / (std + 1e-8),
@@ -336,34 +387,6 @@ gn_stats_kernel(const T* __restrict__ y, float* __restrict__ stats, int HW, int 
 // Grid = (chunks, B): a CTA works on one sample, folds the statistics into per-channel
 // scale/shift once (shared memory), then streams 16-byte vectors: HBM-bound, 2 B read + 2 B
 // written per element in bf16 (+2 B for the residual).
-template <typename T> struct Vec16;
-template <> struct Vec16<float> {
-  static constexpr int N = 4;
-  static __device__ __forceinline__ void load(const float* p, float v[4]) { Quad<float>::load(p, v); }
-  static __device__ __forceinline__ void store(float* p, const float v[4]) { Quad<float>::store(p, v); }
-};
-template <> struct Vec16<__nv_bfloat16> {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[8]) {
-    const uint4 q = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-      v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
-    }
-  }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float v[8]) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __restrict__ stats, int raw,
@@ -407,7 +430,7 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float h = fmaf(v[k], sc[c + k], sh[c + k]);
-      h = silu(h) + tb[c + k];
+      h = silu_t<T>(h) + tb[c + k];
       if (rb) h = fmaf(res_scale, r[k], h);
       v[k] = h;
     }
@@ -415,8 +438,10 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
   }
 }
 
-// time path (score_network.py:20-41, 185-189, 126/146): one CTA per distinct t.
-__global__ void __launch_bounds__(128)
+// time path (score_network.py:20-41, 185-189, 126/146): gridDim.x = distinct t values; the small
+// embedding MLP is recomputed by each of the gridDim.y CTAs, which then split the concatenated
+// per-block Linear layers (sumC outputs) between them.
+__global__ void __launch_bounds__(256)
 time_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int T,
             const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
             const float* __restrict__ b2, const float* __restrict__ wt, const float* __restrict__ bt, int sumC,
@@ -427,28 +452,34 @@ time_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int T,
   float* temb = sm + 3 * T;  // [T]
   const int half = T / 2;
   const float tv = t[blockIdx.x];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int k = threadIdx.x; k < T; k += blockDim.x) {
     const int f = k < half ? k : k - half;
     const float arg = __fmul_rn(__fmul_rn(tv, freqs[f]), 1000.0f);
     emb[k] = k < half ? sinf(arg) : cosf(arg);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < 2 * T; j += blockDim.x) {
-    float a = b0[j];
-    for (int k = 0; k < T; ++k) a = fmaf(w0[j * T + k], emb[k], a);
-    hid[j] = silu(a);
+  for (int j = wid; j < 2 * T; j += nw) {   // one warp per output row: coalesced weight reads
+    float a = 0.f;
+    for (int k = lane; k < T; k += 32) a = fmaf(w0[j * T + k], emb[k], a);
+    a = warp_sum(a);
+    if (lane == 0) hid[j] = silu(a + b0[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T; i += blockDim.x) {
-    float a = b2[i];
-    for (int j = 0; j < 2 * T; ++j) a = fmaf(w2[i * 2 * T + j], hid[j], a);
-    temb[i] = a;
+  for (int i = wid; i < T; i += nw) {
+    float a = 0.f;
+    for (int j = lane; j < 2 * T; j += 32) a = fmaf(w2[i * 2 * T + j], hid[j], a);
+    a = warp_sum(a);
+    if (lane == 0) temb[i] = a + b2[i];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < sumC; c += blockDim.x) {
-    float a = bt[c];
-    for (int i = 0; i < T; ++i) a = fmaf(wt[c * T + i], temb[i], a);
-    tbias[(int64_t)blockIdx.x * sumC + c] = a;
+  const int per = (sumC + gridDim.y - 1) / gridDim.y;
+  const int c_lo = blockIdx.y * per, c_hi = min(sumC, c_lo + per);
+  for (int c = c_lo + wid; c < c_hi; c += nw) {
+    float a = 0.f;
+    for (int i = lane; i < T; i += 32) a = fmaf(wt[c * T + i], temb[i], a);
+    a = warp_sum(a);
+    if (lane == 0) tbias[(int64_t)blockIdx.x * sumC + c] = a + bt[c];
   }
 }
 
@@ -733,7 +764,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- time path
   {
     ProfScope prof(kProfUnetMisc, st);
-    time_kernel<<<(unsigned)n_t, 128, (size_t)4 * Td * 4, st>>>(t, plan->freqs, Td, plan->tw0, plan->tb0, plan->tw2,
+    time_kernel<<<dim3((unsigned)n_t, n_t == 1 ? 16u : 2u), 256, (size_t)4 * Td * 4, st>>>(t, plan->freqs, Td, plan->tw0, plan->tb0, plan->tw2,
                                                                plan->tb2, plan->twt, plan->tbt, plan->sumC, tbias);
     DBS_LAUNCHED();
   }
@@ -741,9 +772,9 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- init conv
   {
     const int64_t n_pix = B * H * W;
-    const int64_t nthr = n_pix * (C / 4);
     ProfScope prof(kProfUnetMisc, st);
-    init_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(x, plan->init_w, plan->init_b, a0, n_pix, H, W, C);
+    init_conv_kernel<T><<<(unsigned)((n_pix + 127) / 128), 128, (size_t)10 * C * 4, st>>>(x, plan->init_w, plan->init_b, a0,
+                                                                                       n_pix, H, W, C);
     DBS_LAUNCHED();
     if ((rc = maybe_tap<T>(c, "init", a0, B, H, W, C))) return rc;
   }
@@ -814,6 +845,8 @@ int check_forward_args(const dbs_unet_plan* plan, int64_t B, int H, int W, int p
   DBS_REQUIRE(plan != nullptr, "unet: null plan");
   DBS_REQUIRE(B >= 1 && H >= 1 && W >= 1, "unet: bad shape B=%lld H=%d W=%d", (long long)B, H, W);
   DBS_REQUIRE(precision == 0 || precision == 1, "unet: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
+  DBS_REQUIRE(precision == 0 || plan->cfg.base_channels % 8 == 0,
+              "unet: the bf16 path needs base_channels to be a multiple of 8 (got %d)", plan->cfg.base_channels);
   const int div = 1 << plan->cfg.num_blocks;
   DBS_REQUIRE(H % div == 0 && W % div == 0,
               "unet: lattice %dx%d is not divisible by 2^num_blocks=%d; the bilinear fix-up of score_network.py:254-255 is not built",

@@ -38,6 +38,13 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
                    const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, float* stats,
                    int groups, cudaStream_t st);
 
+// Strip variant of the tcgen05 path for stride-1 convs with Cout <= 64 on full-width row tiles: one
+// halo strip of the input per channel chunk serves every tap, weights stay resident in shared memory
+// when they fit.  Same contract as conv_tc_launch (DBS_ERR_UNSUPPORTED if not eligible).
+int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1,
+                      const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, float* stats,
+                      int groups, cudaStream_t st);
+
 // geometry builders
 ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 ConvGeom geom_convT_phase(int B, int H, int W, int Cin, int Cout, int ph, int pw);

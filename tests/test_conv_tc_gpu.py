@@ -72,6 +72,15 @@ CASES = [
     (0, 3, 1, 128, 128, 32, 0, 32),   # API maximum lattice (W = tile width)
     (0, 3, 2, 16, 32, 64, 0, 64),     # non-square
     (0, 3, 300, 8, 8, 64, 0, 64),     # more tiles than SMs: persistent loop + TMEM double buffering
+    # strip kernel (conv_strip.cu) specifics
+    (0, 3, 3, 16, 16, 256, 0, 64),    # decoder.1.conv1-like: weights too large to stay resident (streamed slabs)
+    (0, 3, 2, 16, 16, 128, 128, 64),  # decoder.1.conv1 over the concat, streamed
+    (0, 3, 5, 16, 8, 64, 0, 32),      # W = 8: 16 rows per tile
+    (0, 3, 3, 64, 64, 64, 0, 16),     # Nb = 16, rows span two warps (cross-warp neighbour exchange)
+    (2, 4, 2, 64, 64, 32, 0, 32),     # transposed-conv phases with W = 64
+    (0, 3, 2, 128, 128, 64, 0, 64),   # one image row per tile, rows span four warps
+    (0, 3, 150, 32, 32, 32, 0, 32),   # 1200 tiles: persistent loop, stats double buffering
+    (0, 1, 3, 32, 32, 128, 0, 32),    # decoder.2.residual 1x1
 ]
 
 
