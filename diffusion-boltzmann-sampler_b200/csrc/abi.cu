@@ -3,6 +3,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -22,7 +24,9 @@ void set_error(const char* fmt, ...) {
 namespace dbs {
 bool g_prof_on = false;
 namespace {
-struct ProfPair { cudaEvent_t a, b; int cls; };
+struct ProfPair { cudaEvent_t a, b; int cls; std::string label; };
+std::vector<std::pair<std::string, float>> g_detail;
+thread_local char t_label[96] = "";
 std::vector<ProfPair> g_pairs;       // recorded pairs awaiting dbs_profile_read
 std::vector<cudaEvent_t> g_pool;     // recycled events
 std::mutex g_prof_mu;
@@ -36,6 +40,13 @@ cudaEvent_t take_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 }  // namespace
+void prof_set_label(const char* fmt, ...) {
+  if (!g_prof_on) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_label, sizeof(t_label), fmt, ap);
+  va_end(ap);
+}
 void prof_begin(ProfClass c, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_open[c] = take_event();
@@ -45,7 +56,8 @@ void prof_end(ProfClass c, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   cudaEvent_t b = take_event();
   cudaEventRecord(b, st);
-  g_pairs.push_back({g_open[c], b, (int)c});
+  g_pairs.push_back({g_open[c], b, (int)c, std::string(t_label)});
+  t_label[0] = 0;
 }
 }  // namespace dbs
 
@@ -68,11 +80,25 @@ extern "C" int dbs_profile_read(double* ms, uint64_t* launches, int n, int reset
       return DBS_ERR_CUDA;
     }
     g_ms[pr.cls] += t; g_cnt[pr.cls] += 1;
+    if (!pr.label.empty()) g_detail.push_back({std::string(kProfNames[pr.cls]) + " " + pr.label, t});
     g_pool.push_back(pr.a); g_pool.push_back(pr.b);
   }
   g_pairs.clear();
   for (int c = 0; c < n && c < kProfNumClasses; ++c) { if (ms) ms[c] = g_ms[c]; if (launches) launches[c] = g_cnt[c]; }
   if (reset) for (int c = 0; c < kProfNumClasses; ++c) { g_ms[c] = 0; g_cnt[c] = 0; }
+  return DBS_OK;
+}
+
+// Writes "class label<TAB>ms" lines for every labelled launch seen by dbs_profile_read since the
+// last dump, then clears the list.
+extern "C" int dbs_profile_dump(const char* path) {
+  using namespace dbs;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  FILE* f = fopen(path, "w");
+  if (!f) { set_error("profile_dump: cannot open %s", path); return DBS_ERR_INVALID; }
+  for (auto& d : g_detail) fprintf(f, "%s\t%.4f\n", d.first.c_str(), d.second);
+  fclose(f);
+  g_detail.clear();
   return DBS_OK;
 }
 

@@ -23,6 +23,8 @@ enum ProfClass {
   kProfIsingSweep, kProfIsingObs, kProfIsingMisc, kProfLj, kProfNumClasses
 };
 extern bool g_prof_on;
+// free-form label attached to the next recorded launch (per-layer dumps: dbs_profile_dump)
+void prof_set_label(const char* fmt, ...);
 void prof_begin(ProfClass c, cudaStream_t st);
 void prof_end(ProfClass c, cudaStream_t st);
 struct ProfScope {

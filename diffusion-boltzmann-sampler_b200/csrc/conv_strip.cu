@@ -33,7 +33,8 @@ using namespace tc;
 using namespace tch;
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;               // two warps per TMEM lane quadrant, splitting the column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kSmemBudget = 200 * 1024;
 constexpr int kMaxCout = 64;
@@ -56,9 +57,85 @@ struct StripParams {
   uint32_t a_bytes, slab_bytes, stage_bytes, w_region_bytes;
   uint32_t tmem_cols;
   uint64_t desc_hi;
+  int dbg;  // diagnostics (env DBS_STRIP_DBG): 1 no MMA, 2 no epilogue body, 4 no stores, 8 no strip loads
 };
 
-template <int kRun>
+
+// MMA issuer role, unrolled over NT taps x MM (= KC/16) MMAs so that per-tap offsets live in registers
+// and one MMA costs a handful of scalar instructions (the generic NT = 0 form measured ~130 cycles
+// of issue overhead per tcgen05.mma, 4-8x the MMA's own duration at N <= 64).
+template <int NT, int MM>
+__device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ring, uint32_t w_region, uint32_t tmem_base,
+                                               uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tfull,
+                                               uint32_t bar_tempty, uint32_t bar_w, int tile_lo, int tile_hi) {
+  const int chunks = p.chunks0 + p.chunks1;
+  const uint32_t row_bytes = (uint32_t)p.KC * 2;
+  const uint32_t chunk_w_bytes = p.slab_bytes * p.n_taps;
+  const int acc_cols = p.nacc * p.Nb;
+  const uint32_t lo_bits = (uint32_t)p.desc_hi;            // LBO field
+  const uint32_t hi32 = (uint32_t)(p.desc_hi >> 32);       // SBO, version, swizzle mode
+  const uint32_t slab_lo = p.slab_bytes >> 4;
+  constexpr int NTR = NT > 0 ? NT : 1;
+  uint32_t aoff[NTR], dcol[NTR];
+  uint32_t first_mask = 0;
+  if (NT > 0) {
+#pragma unroll
+    for (int t = 0; t < NTR; ++t) {
+      aoff[t] = ((uint32_t)(p.tap_row[t] * p.W) * row_bytes) >> 4;
+      dcol[t] = (uint32_t)(p.tap_slot[t] * p.Nb);
+      first_mask |= (uint32_t)(p.tap_first[t] ? 1 : 0) << t;
+    }
+  }
+  if (p.resident) {
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+  }
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+    tc_fence_after();
+    const uint32_t d_base = tmem_base + as * acc_cols;
+    for (int ch = 0; ch < chunks; ++ch) {
+      mbar_wait(bar_full + 8 * stage, phase);
+      tc_fence_after();
+      const uint32_t a_base = ring + stage * p.stage_bytes;
+      const uint32_t b_base = p.resident ? w_region + ch * chunk_w_bytes : a_base + ((p.a_bytes + 1023u) & ~1023u);
+      const uint32_t a_lo = lo_bits | ((a_base & 0x3FFFFu) >> 4);
+      const uint32_t b_lo = lo_bits | ((b_base & 0x3FFFFu) >> 4);
+      if (!(p.dbg & 1)) {
+        if (NT > 0) {
+#pragma unroll
+          for (int t = 0; t < NTR; ++t) {
+            const uint32_t acc0 = (ch == 0 && ((first_mask >> t) & 1u)) ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < MM; ++k)
+              umma_bf16_lohi(d_base + dcol[t], a_lo + aoff[t] + 2 * k, b_lo + t * slab_lo + 2 * k, hi32, p.idesc,
+                             k == 0 ? acc0 : 1u);
+          }
+        } else {
+          for (int t = 0; t < p.n_taps; ++t) {
+            const uint32_t al = a_lo + (((uint32_t)(p.tap_row[t] * p.W) * row_bytes) >> 4);
+            const uint32_t bl = b_lo + t * slab_lo;
+            const uint32_t d_tmem = d_base + p.tap_slot[t] * p.Nb;
+            const bool fresh = ch == 0 && p.tap_first[t];
+            for (int k = 0; k < p.KC / 16; ++k)
+              umma_bf16_lohi(d_tmem, al + 2 * k, bl + 2 * k, hi32, p.idesc, (fresh && k == 0) ? 0u : 1u);
+          }
+        }
+      }
+      umma_commit(bar_empty + 8 * stage);
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(bar_tfull + 8 * as);
+  }
+}
+
+// kStats: accumulate GroupNorm(8) sums; NCH = Cout / 16 column chunks (group width Cg = 2 * NCH)
+template <bool kStats, int NCH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StripParams p) {
@@ -66,9 +143,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_acc[2][8 * 2];               // GroupNorm partial sums of the tile's image
   __shared__ __align__(16) float s_bias[kMaxCout];
-  __shared__ float s_x[2][4][2][16];              // cross-warp neighbour exchange (W > 32)
+  __shared__ float s_x[2][2][4][2][16];           // [parity][half][quadrant][side][col]: cross-warp neighbours (W > 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_region = smem_u32(smem);                       // resident weights (may be empty)
@@ -86,7 +162,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);
+      mbar_init(bar_tempty + 8 * s, kEpiWarps);
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -97,13 +173,16 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     tma_prefetch_desc(&map_w);
   }
   if (warp == 2) tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols);
-  if (threadIdx.x < 32) (&s_acc[0][0])[threadIdx.x] = 0.f;
   for (int i = threadIdx.x; i < p.Cout; i += kThreads) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
+  // contiguous tile range per CTA: consecutive tiles are rows of the same image, which lets the
+  // epilogue keep GroupNorm partial sums in registers until the image changes
+  const int tile_lo = (int)(((int64_t)p.n_tiles * blockIdx.x) / gridDim.x);
+  const int tile_hi = (int)(((int64_t)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
   const int chunks = p.chunks0 + p.chunks1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2;
   const uint32_t chunk_w_bytes = p.slab_bytes * p.n_taps;
@@ -120,12 +199,17 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
         const int n = tile / p.tiles_h, h0 = (tile - n * p.tiles_h) * p.Ht;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t a_dst = ring + stage * p.stage_bytes;
           const uint32_t fb = bar_full + 8 * stage;
+          if (p.dbg & 8) {
+            mbar_arrive(fb);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : chunk_w_bytes));
           if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, ch * p.KC, 0, 0, h0 + p.dh_min, n);
           else tma_load_5d(a_dst, &map_in1, fb, (ch - p.chunks0) * p.KC, 0, 0, h0 + p.dh_min, n);
@@ -142,67 +226,72 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      if (p.resident) {
-        mbar_wait(bar_w, 0);
-        tc_fence_after();
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      const int mmas = p.KC / 16;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + as * acc_cols;
-        for (int ch = 0; ch < chunks; ++ch) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t a_base = ring + stage * p.stage_bytes;
-          const uint32_t b_base = p.resident ? w_region + ch * chunk_w_bytes : a_base + ((p.a_bytes + 1023u) & ~1023u);
-          for (int t = 0; t < p.n_taps; ++t) {
-            const uint32_t a_addr = a_base + (uint32_t)(p.tap_row[t] * p.W) * row_bytes;
-            const uint32_t b_addr = b_base + t * p.slab_bytes;
-            const uint32_t d_tmem = d_base + p.tap_slot[t] * p.Nb;
-            const bool fresh = ch == 0 && p.tap_first[t];
-            for (int k = 0; k < mmas; ++k) {
-              const uint64_t adesc = p.desc_hi | (uint64_t)(((a_addr + 32 * k) & 0x3FFFFu) >> 4);
-              const uint64_t bdesc = p.desc_hi | (uint64_t)(((b_addr + 32 * k) & 0x3FFFFu) >> 4);
-              umma_bf16(d_tmem, adesc, bdesc, p.idesc, (fresh && k == 0) ? 0u : 1u);
-            }
-          }
-          umma_commit(bar_empty + 8 * stage);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(bar_tfull + 8 * as);
-      }
+#define DBS_STRIP_ROLE(NT, MM) \
+  strip_mma_role<NT, MM>(p, ring, w_region, tmem_base, bar_full, bar_empty, bar_tfull, bar_tempty, bar_w, tile_lo, tile_hi)
+      const int mm = p.KC / 16;
+      if (p.n_taps == 9 && mm == 4) DBS_STRIP_ROLE(9, 4);
+      else if (p.n_taps == 9 && mm == 2) DBS_STRIP_ROLE(9, 2);
+      else if (p.n_taps == 9 && mm == 1) DBS_STRIP_ROLE(9, 1);
+      else if (p.n_taps == 4 && mm == 4) DBS_STRIP_ROLE(4, 4);
+      else if (p.n_taps == 4 && mm == 2) DBS_STRIP_ROLE(4, 2);
+      else if (p.n_taps == 1 && mm == 4) DBS_STRIP_ROLE(1, 4);
+      else if (p.n_taps == 1 && mm == 2) DBS_STRIP_ROLE(1, 2);
+      else DBS_STRIP_ROLE(0, 0);
+#undef DBS_STRIP_ROLE
     }
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;       // which of the quadrant's two warps: takes chunks half, half+2
     const int row = q * 32 + lane;          // tile-local pixel
     const int hl = row / p.W, wl = row - hl * p.W;
-    const bool has_right = wl < p.W - 1;    // pixel m+1 is in the same image row
-    const bool has_left = wl > 0;
+    const float m_right = wl < p.W - 1 ? 1.f : 0.f;   // pixel m+1 is in the same image row
+    const float m_left = wl > 0 ? 1.f : 0.f;
     const bool xchg = p.W > 32;             // an image row spans several warps
-    const int etid = threadIdx.x - 64;
+    constexpr int CG = 2 * NCH;             // channels per GroupNorm group (8 groups)
+    constexpr int GPC = 16 / CG;            // groups per 16-column chunk
+    constexpr int MYCH = (NCH + 1) / 2;     // chunks this warp may own
+    float st_s[MYCH * GPC], st_ss[MYCH * GPC];
+#pragma unroll
+    for (int i = 0; i < MYCH * GPC; ++i) { st_s[i] = 0.f; st_ss[i] = 0.f; }
+    int cur_n = -1;
+    auto flush_stats = [&](int n_img) {
+#pragma unroll
+      for (int i = 0; i < MYCH * GPC; ++i) {
+        const int chunk = half + 2 * (i / GPC);
+        if (chunk < NCH) {
+          const float s_ = warp_sum(st_s[i]), ss_ = warp_sum(st_ss[i]);
+          const int gi = chunk * GPC + (i % GPC);
+          if (lane == 0) {
+            atomicAdd(p.stats + ((int64_t)n_img * 8 + gi) * 2 + 0, s_);
+            atomicAdd(p.stats + ((int64_t)n_img * 8 + gi) * 2 + 1, ss_);
+          }
+        }
+        st_s[i] = 0.f; st_ss[i] = 0.f;
+      }
+    };
     int it = 0;
-    int xb = 0;  // exchange-buffer parity, toggled per chunk across tiles (one barrier per chunk suffices)
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    int xb = 0;  // exchange-buffer parity, toggled per chunk (one named barrier per chunk suffices)
+    for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int n = tile / p.tiles_h, a = (tile - n * p.tiles_h) * p.Ht + hl;
+      if (kStats && n != cur_n) {
+        if (cur_n >= 0) flush_stats(cur_n);
+        cur_n = n;
+      }
       __nv_bfloat16* optr =
           p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout;
-      float* acc = &s_acc[it & 1][0];
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
-      float run_s = 0.f, run_ss = 0.f;
-      for (int c = 0; c < p.Nb; c += 16, xb ^= 1) {
+#pragma unroll
+      for (int mc = 0; mc < MYCH; ++mc) {
+        const int chunk = half + 2 * mc;
+        if (chunk >= NCH || (p.dbg & 2)) break;
+        const int c = chunk * 16;
         uint32_t v0[16], vp[16], vm[16];
         tmem_ld16(tbase + p.slot_c * p.Nb + c, v0);
         if (p.slot_p >= 0) tmem_ld16(tbase + p.slot_p * p.Nb + c, vp);
@@ -213,13 +302,13 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           // my lane 31's P_{-1} is pixel m-1 of the next warp's lane 0
           if (lane == 0 && p.slot_p >= 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s_x[xb][q][0][j] = __uint_as_float(vp[j]);
+            for (int j = 0; j < 16; ++j) s_x[xb][half][q][0][j] = __uint_as_float(vp[j]);
           }
           if (lane == 31 && p.slot_m >= 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s_x[xb][q][1][j] = __uint_as_float(vm[j]);
+            for (int j = 0; j < 16; ++j) s_x[xb][half][q][1][j] = __uint_as_float(vm[j]);
           }
-          epi_bar_sync();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         }
         float f[16];
         const float4* bq = reinterpret_cast<const float4*>(s_bias + c);
@@ -235,39 +324,25 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[j]), 1);
-            if (lane == 31) nb = (xchg && has_right) ? s_x[xb][(q + 1) & 3][0][j] : 0.f;
-            f[j] += has_right ? nb : 0.f;
+            if (xchg && lane == 31) nb = s_x[xb][half][(q + 1) & 3][0][j];
+            f[j] = fmaf(m_right, nb, f[j]);
           }
         }
         if (p.slot_m >= 0) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float nb = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j]), 1);
-            if (lane == 0) nb = (xchg && has_left) ? s_x[xb][(q + 3) & 3][1][j] : 0.f;
-            f[j] += has_left ? nb : 0.f;
+            if (xchg && lane == 0) nb = s_x[xb][half][(q + 3) & 3][1][j];
+            f[j] = fmaf(m_left, nb, f[j]);
           }
         }
-        if (kRun > 0) {
-          constexpr int R = kRun > 0 ? kRun : 16;
+        if (kStats) {
 #pragma unroll
-          for (int r = 0; r < 16 / R; ++r) {
-            float s = 0.f, ss = 0.f;
+          for (int r = 0; r < GPC; ++r) {
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-              s += f[r * R + j];
-              ss = fmaf(f[r * R + j], f[r * R + j], ss);
-            }
-            bool flush = true;
-            if (R == 16) {
-              run_s += s; run_ss += ss;
-              s = run_s; ss = run_ss;
-              flush = ((c + 16) & (p.Cg - 1)) == 0;
-              if (flush) { run_s = 0.f; run_ss = 0.f; }
-            }
-            if (flush) {
-              const int gi = (c >> p.cg_log2) + (R == 16 ? 0 : r);
-              s = warp_sum(s); ss = warp_sum(ss);
-              if (lane == 0) { atomicAdd(&acc[gi * 2 + 0], s); atomicAdd(&acc[gi * 2 + 1], ss); }
+            for (int j = 0; j < CG; ++j) {
+              st_s[mc * GPC + r] += f[r * CG + j];
+              st_ss[mc * GPC + r] = fmaf(f[r * CG + j], f[r * CG + j], st_ss[mc * GPC + r]);
             }
           }
         }
@@ -278,22 +353,17 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         uint4* dst = reinterpret_cast<uint4*>(optr + c);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (!(p.dbg & 4)) {
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        xb ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-      if (kRun > 0) {
-        epi_bar_sync();
-        if (etid < 16) {
-          const float vsum = acc[etid];
-          acc[etid] = 0.f;
-          const int gi = etid >> 1, k = etid & 1;
-          if (gi < p.groups && vsum != 0.f) atomicAdd(p.stats + ((int64_t)n * p.groups + gi) * 2 + k, vsum);
-        }
-      }
     }
+    if (kStats && cur_n >= 0) flush_stats(cur_n);
   }
   tc_fence_before();
   __syncthreads();
@@ -320,8 +390,8 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   for (int k : {64, 32, 16})
     if (g.C0 % k == 0 && g.C1 % k == 0) { KC = k; break; }
   if (!KC) return DBS_ERR_UNSUPPORTED;
-  if (groups > 8 || (stats && (groups < 1 || g.Cout % groups))) return DBS_ERR_UNSUPPORTED;
-  if (stats && (!is_pow2(g.Cout / groups) || g.Cout / groups < 2)) return DBS_ERR_UNSUPPORTED;
+  if (stats && groups != 8) return DBS_ERR_UNSUPPORTED;     // GroupNorm(8): Cg = Cout / 8 = 2 * (Cout / 16)
+  if (g.Cout == 48) return DBS_ERR_UNSUPPORTED;             // 3 chunks: group width 6 straddles no chunk, not built
   if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w) |
        reinterpret_cast<uintptr_t>(out)) & 15)
     return DBS_ERR_UNSUPPORTED;
@@ -365,6 +435,7 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   }
   p.slot_c = slot_of[1]; p.slot_p = slot_of[2]; p.slot_m = slot_of[0]; p.nacc = nacc;
   p.bias = bias; p.out = out; p.stats = stats;
+  { const char* e = getenv("DBS_STRIP_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   p.a_bytes = (uint32_t)rows * W * KC * 2;
   p.slab_bytes = (uint32_t)Nb * KC * 2;
@@ -410,23 +481,26 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   if ((rc = encode_w(enc, &mw, w, Cin, g.Cout, taps_total, KC, Nb, sw))) return rc;
 
   const size_t smem = (size_t)p.w_region_bytes + (size_t)stages * p.stage_bytes + 1024;
-  const int run = !stats ? 0 : (p.Cg >= 16 ? 16 : p.Cg);
-  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, StripParams) =
-      run == 0 ? conv_strip_kernel<0> : run == 2 ? conv_strip_kernel<2> : run == 4 ? conv_strip_kernel<4>
-               : run == 8 ? conv_strip_kernel<8> : conv_strip_kernel<16>;
+  typedef void (*Kern)(CUtensorMap, CUtensorMap, CUtensorMap, StripParams);
+  static const Kern table[2][3] = {
+      {conv_strip_kernel<false, 1>, conv_strip_kernel<false, 2>, conv_strip_kernel<false, 4>},
+      {conv_strip_kernel<true, 1>, conv_strip_kernel<true, 2>, conv_strip_kernel<true, 4>}};
+  const int nch = Nb / 16;
+  Kern kern = table[stats ? 1 : 0][nch == 1 ? 0 : (nch == 2 ? 1 : 2)];
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    void (*ks[5])(CUtensorMap, CUtensorMap, CUtensorMap, StripParams) = {conv_strip_kernel<0>, conv_strip_kernel<2>,
-                                                                         conv_strip_kernel<4>, conv_strip_kernel<8>,
-                                                                         conv_strip_kernel<16>};
-    for (auto k : ks) {
-      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
-      if (e != cudaSuccess) attr_err = e;
-    }
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 3; ++b) {
+        const cudaError_t e = cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(kSmemBudget + 2048));
+        if (e != cudaSuccess) attr_err = e;
+      }
   });
   DBS_CUDA(attr_err);
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  prof_set_label("strip H%d W%d C%d+%d->%d taps%d os%d KC%d B%d res%d st%d", H, W, g.C0, g.C1, g.Cout, g.n_taps, g.out_stride,
+                 KC, g.B, p.resident, p.stages);
   ProfScope prof(kProfConvTC, st);
   kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
   DBS_LAUNCHED();

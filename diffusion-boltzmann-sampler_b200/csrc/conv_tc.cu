@@ -138,6 +138,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       uint32_t phase = 0;
       int it = 0;
       const int mmas = p.KC / 16;
+      const uint32_t lo_bits = (uint32_t)p.desc_hi, hi32 = (uint32_t)(p.desc_hi >> 32), idesc = p.idesc;
+      const uint32_t b_off = (p.a_bytes + 1023u) & ~1023u;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -148,11 +150,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-          const uint32_t b_addr = a_addr + ((p.a_bytes + 1023u) & ~1023u);
-          for (int k = 0; k < mmas; ++k) {
-            const uint64_t adesc = p.desc_hi | (uint64_t)(((a_addr + 32 * k) & 0x3FFFFu) >> 4);
-            const uint64_t bdesc = p.desc_hi | (uint64_t)(((b_addr + 32 * k) & 0x3FFFFu) >> 4);
-            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (kb | k) ? 1u : 0u);
+          const uint32_t b_addr = a_addr + b_off;
+          const uint32_t a_lo = lo_bits | ((a_addr & 0x3FFFFu) >> 4);
+          const uint32_t b_lo = lo_bits | ((b_addr & 0x3FFFFu) >> 4);
+          const uint32_t acc0 = kb ? 1u : 0u;
+          if (mmas == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
+          } else if (mmas == 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
+          } else {
+            umma_bf16_lohi(d_tmem, a_lo, b_lo, hi32, idesc, acc0);
           }
           umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -469,6 +478,8 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   DBS_CUDA(attr_err);
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  prof_set_label("tile H%d W%d C%d+%d->%d taps%d s%d os%d KC%d B%d", g.Hin, g.Win, g.C0, g.C1, g.Cout, g.n_taps, g.in_stride,
+                 g.out_stride, KC, g.B);
   ProfScope prof(kProfConvTC, st);
   kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
   DBS_LAUNCHED();

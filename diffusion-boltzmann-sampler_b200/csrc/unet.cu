@@ -394,14 +394,17 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
                 const float* __restrict__ tbias, int t_stride, const T* __restrict__ res, float res_scale,
                 int HW, int C, int G) {
   constexpr int V = Vec16<T>::N;
-  extern __shared__ float sm_gn[];  // scale[C], shift[C], tb[C]
-  float* sc = sm_gn;
-  float* sh = sm_gn + C;
-  float* tb = sm_gn + 2 * C;
   const int n = blockIdx.y;
   const int Cg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int gi = c / Cg;
+  const int cv = C / V;                       // 16-byte vectors per pixel (divides blockDim.x, see launch)
+  // a thread keeps one channel vector for its whole life: scale/shift/time-bias stay in registers
+  const int c = (threadIdx.x % cv) * V;
+  const int prow = threadIdx.x / cv;          // pixel offset of this thread inside a block-row
+  const int ppb = blockDim.x / cv;            // pixels per block iteration
+  float sc[V], sh[V], tb[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int gi = (c + k) / Cg;
     const float s0 = stats[((int64_t)n * G + gi) * 2 + 0];
     const float s1 = stats[((int64_t)n * G + gi) * 2 + 1];
     float mean, rstd;
@@ -411,30 +414,46 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
     } else {
       mean = s0; rstd = s1;
     }
-    const float a = rstd * gamma[c];
-    sc[c] = a;
-    sh[c] = beta[c] - mean * a;
-    tb[c] = tbias ? tbias[(int64_t)n * t_stride + c] : 0.f;
+    const float a = rstd * gamma[c + k];
+    sc[k] = a;
+    sh[k] = beta[c + k] - mean * a;
+    tb[k] = tbias ? tbias[(int64_t)n * t_stride + c + k] : 0.f;
   }
-  __syncthreads();
-  const int cv = C / V;                       // vectors per pixel
-  const int items = HW * cv;
-  const T* yb = y + (int64_t)n * HW * C;
-  const T* rb = res ? res + (int64_t)n * HW * C : nullptr;
-  T* ob = out + (int64_t)n * HW * C;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    const int c = (it % cv) * V;
-    float v[V], r[V];
-    Vec16<T>::load(yb + (int64_t)it * V, v);
-    if (rb) Vec16<T>::load(rb + (int64_t)it * V, r);
+  const T* yb = y + (int64_t)n * HW * C + c;
+  const T* rb = res ? res + (int64_t)n * HW * C + c : nullptr;
+  T* ob = out + (int64_t)n * HW * C + c;
+  const int stride = gridDim.x * ppb;
+  int p0 = blockIdx.x * ppb + prow;
+  // two pixels per iteration: two independent 16-byte loads in flight per thread
+  for (; p0 + stride < HW; p0 += 2 * stride) {
+    float v0[V], v1[V], r0[V], r1[V];
+    Vec16<T>::load(yb + (int64_t)p0 * C, v0);
+    Vec16<T>::load(yb + (int64_t)(p0 + stride) * C, v1);
+    if (rb) {
+      Vec16<T>::load(rb + (int64_t)p0 * C, r0);
+      Vec16<T>::load(rb + (int64_t)(p0 + stride) * C, r1);
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      float h = fmaf(v[k], sc[c + k], sh[c + k]);
-      h = silu_t<T>(h) + tb[c + k];
-      if (rb) h = fmaf(res_scale, r[k], h);
-      v[k] = h;
+      float h0 = silu_t<T>(fmaf(v0[k], sc[k], sh[k])) + tb[k];
+      float h1 = silu_t<T>(fmaf(v1[k], sc[k], sh[k])) + tb[k];
+      if (rb) { h0 = fmaf(res_scale, r0[k], h0); h1 = fmaf(res_scale, r1[k], h1); }
+      v0[k] = h0; v1[k] = h1;
     }
-    Vec16<T>::store(ob + (int64_t)it * V, v);
+    Vec16<T>::store(ob + (int64_t)p0 * C, v0);
+    Vec16<T>::store(ob + (int64_t)(p0 + stride) * C, v1);
+  }
+  if (p0 < HW) {
+    float v0[V], r0[V];
+    Vec16<T>::load(yb + (int64_t)p0 * C, v0);
+    if (rb) Vec16<T>::load(rb + (int64_t)p0 * C, r0);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float h0 = silu_t<T>(fmaf(v0[k], sc[k], sh[k])) + tb[k];
+      if (rb) h0 = fmaf(res_scale, r0[k], h0);
+      v0[k] = h0;
+    }
+    Vec16<T>::store(ob + (int64_t)p0 * C, v0);
   }
 }
 
@@ -668,13 +687,17 @@ int run_gn(Ctx& c, const T* y, T* out, bool have_raw_stats, const float* gamma, 
   }
   const int V = 16 / (int)sizeof(T);
   DBS_REQUIRE(C % V == 0, "unet: channel count %d is not a multiple of %d", C, V);
-  const int items = HW * (C / V);
-  int bx = (items + 255) / 256;
+  const int cv = C / V;
+  DBS_REQUIRE(cv <= 256, "unet: %d channels exceed the GroupNorm kernel's limit", C);
+  const int threads = (256 / cv) * cv;          // a whole number of pixels per block iteration
+  const int ppb = threads / cv;
+  int bx = (HW + 2 * ppb - 1) / (2 * ppb);
   const int cap = (int)std::max<int64_t>(1, (148 * 8) / c.B);   // ~8 CTAs per SM across the batch
   if (bx > cap) bx = cap;
   const float inv_cnt = 1.0f / (float)((int64_t)HW * (C / G));
+  prof_set_label("HW%d C%d res%d", HW, C, res ? 1 : 0);
   ProfScope prof(kProfGnApply, c.st);
-  gn_apply_kernel<T><<<dim3((unsigned)bx, (unsigned)c.B), 256, (size_t)3 * C * sizeof(float), c.st>>>(
+  gn_apply_kernel<T><<<dim3((unsigned)bx, (unsigned)c.B), threads, 0, c.st>>>(
       y, out, c.stats, have_raw_stats ? 1 : 0, inv_cnt, 1e-5f, gamma, beta,
       add_time ? c.tbias + tb_off : nullptr, c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, HW, C, G);
   DBS_LAUNCHED();

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "dbs_profile_num_classes": (i32, []),
     "dbs_profile_class_name": (C.c_char_p, [i32]),
     "dbs_profile_read": (i32, [vp, vp, i32, i32]),
+    "dbs_profile_dump": (i32, [C.c_char_p]),
     "dbs_ising_words_per_chain": (i32, [i32]),
     "dbs_ising_init_packed": (i32, [vp, i32, i64, u64, i64, vp]),
     "dbs_ising_pack": (i32, [vp, vp, i32, i64, vp]),

@@ -51,6 +51,8 @@ int dbs_profile_enable(int on);
 int dbs_profile_num_classes(void);
 const char* dbs_profile_class_name(int cls);
 int dbs_profile_read(double* ms, uint64_t* launches, int n, int reset);
+/* Per-launch detail ("class label<TAB>ms" per line) of the labelled launches read so far. */
+int dbs_profile_dump(const char* path);
 
 /* ------------------------------------------------------------------------- *
  * Ising lattice state: bit-packed, 1 bit per spin (1 = +1, 0 = -1).
