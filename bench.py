@@ -280,6 +280,7 @@ def bench_ours(args, world, rank, local):
     if rank == 0 and world == 1:
         # ---- CPU baseline: oracle port (torch fp32, all host threads) on a bounded sample of the same workload
         sd = {k: v.detach().clone() for k, v in smp.model.state_dict().items()}
+        torch.set_num_threads(os.cpu_count() or 1)
         nthr = torch.get_num_threads()
         xb = torch.randn(8, 1, L, L)
         t0 = time.time()
@@ -395,6 +396,7 @@ def bench_reference(args, world, rank):
     a bounded sample of the workload: Bc samples x 100 EM steps."""
     if rank != 0:
         return None
+    torch.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; use every host core
     from backend.ml.models.score_network import ScoreNetwork
     from oracle import unet as o_unet
     L, NS = L_MAIN, STEPS_MAIN

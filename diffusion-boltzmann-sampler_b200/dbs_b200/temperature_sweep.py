@@ -1,0 +1,83 @@
+"""Driver for BASELINE config 3: a 2-D Ising temperature sweep with many chains per temperature,
+sharded over the GPUs of one box, observables accumulated on the device and all-reduced once.
+
+The serial loop this replaces is the reference's /analysis/phase_diagram handler
+(backend/api/routes/analysis.py:198-207: one MetropolisHastings.sample per temperature)."""
+import numpy as np
+import torch
+
+from . import abi, runtime
+from .distributed import allreduce_block, finalize_observables, striped_temperatures, world
+
+
+def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_temperature=1024, burn_in=1000,
+                          n_measure=1000, measure_every=10, seed=1234, J=1.0, h=0.0, with_correlation=True):
+    """Returns a dict of per-temperature observables (identical on every rank)."""
+    from backend.ml.samplers.mcmc import MetropolisHastings
+    from backend.ml.systems.ising import IsingModel
+
+    rank, ws = world()
+    temps = np.linspace(1.5, 3.5, 64) if temperatures is None else np.asarray(temperatures, dtype=np.float64)
+    ids, t_chain, t_idx = striped_temperatures(temps, chains_per_temperature, rank, ws)
+    # chains of one rank are not a contiguous global range: give each its global id through a
+    # contiguous block [rank_lo, rank_lo + n) of the permuted numbering (still world-size invariant
+    # per (temperature, stripe) pair) by sorting ids and launching one block per contiguous run
+    model = IsingModel(lattice_size, J=J, h=h)
+    L = lattice_size
+    n = len(ids)
+    dev = runtime.require_cuda()
+    group = torch.from_numpy(t_idx).to(dev)
+    mh = MetropolisHastings(model, t_chain, seed=seed)
+    # global chain ids are carried by remapping: chain k of this rank uses offset ids[k]; runs of
+    # consecutive ids are launched together
+    runs = np.split(np.arange(n), np.where(np.diff(ids) != 1)[0] + 1) if n else []
+    bits = torch.empty((n, L, (L + 31) // 32), dtype=torch.int32, device=dev)
+    for r in runs:
+        sub = model.random_packed(len(r), seed, chain_offset=int(ids[r[0]]))
+        bits[r[0]:r[0] + len(r)] = sub
+
+    tables, _ = mh._tables()
+    index = torch.from_numpy(mh._table_index_host).to(dev)
+
+    def sweeps(k, offset):
+        for r in runs:
+            view = bits[r[0]:r[0] + len(r)]
+            abi.check(abi.lib.dbs_ising_sweeps(view.data_ptr(), L, len(r), k, tables.data_ptr(), tables.shape[0],
+                                               index[r[0]:].data_ptr(), seed, int(ids[r[0]]), offset, 0,
+                                               runtime.current_stream()), "ising_sweeps")
+
+    nT = len(temps)
+    acc = torch.zeros((nT, 5), dtype=torch.float64, device=dev)
+    R = L // 2
+    corr = torch.zeros((nT, R), dtype=torch.int64, device=dev)
+    e = torch.empty(n, dtype=torch.float32, device=dev)
+    m = torch.empty(n, dtype=torch.float32, device=dev)
+    done = 0
+    if burn_in:
+        sweeps(burn_in, done)
+        done += burn_in
+    n_meas = 0
+    for _ in range(n_measure // measure_every):
+        sweeps(measure_every, done)
+        done += measure_every
+        abi.check(abi.lib.dbs_ising_observables(bits.data_ptr(), L, n, float(J), float(h), e.data_ptr(), m.data_ptr(),
+                                                runtime.current_stream()))
+        abi.check(abi.lib.dbs_observable_accumulate(e.data_ptr(), m.data_ptr(), L, n, group.data_ptr(), acc.data_ptr(),
+                                                    runtime.current_stream()))
+        if with_correlation:
+            abi.check(abi.lib.dbs_ising_correlation(bits.data_ptr(), L, n, 0, group.data_ptr(), corr.data_ptr(),
+                                                    runtime.current_stream()))
+        n_meas += 1
+    allreduce_block(acc)
+    corr_f = corr.to(torch.float64)
+    allreduce_block(corr_f)
+    out = finalize_observables(acc)
+    out["temperatures"] = temps
+    out["sweeps"] = done
+    out["flip_attempts_this_rank"] = float(n) * L * L * done
+    if with_correlation:
+        from backend.ml.analysis.correlation import _displacement_counts
+        cnt = _displacement_counts(L).astype(np.float64) * (L * L) * chains_per_temperature * max(n_meas, 1)
+        c = corr_f.cpu().numpy()
+        out["C_r"] = np.divide(c, cnt[None, :], where=cnt[None, :] > 0, out=np.zeros_like(c))
+    return out
