@@ -45,10 +45,9 @@ struct StripParams {
   int B, Hout, Wout, Cout, out_stride, oph, opw;
   int groups, Cg, cg_log2;
   int dh_min;
-  int tap_row[16];    // (dh - dh_min): strip row offset of the tap
-  int tap_slot[16];   // accumulator slot of the tap's dw
-  int tap_first[16];  // 1 if this tap is the first (in issue order) to touch its slot
-  int tap_w[16];      // weight tap index
+  int n_groups;       // distinct vertical offsets dh; every group holds the same nacc horizontal offsets
+  int grp_row[4];     // (dh - dh_min): strip row offset of the group
+  int tap_w[16];      // weight tap index of slab (group g, slot s) at position g * nacc + s
   int slot_c, slot_p, slot_m, nacc;  // accumulator slots of dw = 0, +1, -1 (-1 = unused)
   const float* bias;
   __nv_bfloat16* out;
@@ -61,10 +60,13 @@ struct StripParams {
 };
 
 
-// MMA issuer role, unrolled over NT taps x MM (= KC/16) MMAs so that per-tap offsets live in registers
-// and one MMA costs a handful of scalar instructions (the generic NT = 0 form measured ~130 cycles
-// of issue overhead per tcgen05.mma, 4-8x the MMA's own duration at N <= 64).
-template <int NT, int MM>
+// MMA issuer role.  The taps of one vertical offset dh share their A rows, so their weight slabs
+// are stacked along N in shared memory ([dw = -1 | 0 | +1] x Nb couts) and ONE tcgen05.mma with
+// N = nacc * Nb feeds all horizontal-offset accumulators (contiguous TMEM column ranges): the A
+// operand is read from shared memory once per (dh, K-slice) instead of once per tap.  Unrolled over
+// G groups x MM (= KC/16) MMAs with the per-group offsets in registers (the first generic loop
+// measured ~130 cycles of scalar issue overhead per MMA).
+template <int G, int MM>
 __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ring, uint32_t w_region, uint32_t tmem_base,
                                                uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tfull,
                                                uint32_t bar_tempty, uint32_t bar_w, int tile_lo, int tile_hi) {
@@ -74,18 +76,11 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
   const int acc_cols = p.nacc * p.Nb;
   const uint32_t lo_bits = (uint32_t)p.desc_hi;            // LBO field
   const uint32_t hi32 = (uint32_t)(p.desc_hi >> 32);       // SBO, version, swizzle mode
-  const uint32_t slab_lo = p.slab_bytes >> 4;
-  constexpr int NTR = NT > 0 ? NT : 1;
-  uint32_t aoff[NTR], dcol[NTR];
-  uint32_t first_mask = 0;
-  if (NT > 0) {
+  const uint32_t grp_lo = (p.slab_bytes * p.nacc) >> 4;    // descriptor step between groups' stacked slabs
+  uint32_t aoff[G];
 #pragma unroll
-    for (int t = 0; t < NTR; ++t) {
-      aoff[t] = ((uint32_t)(p.tap_row[t] * p.W) * row_bytes) >> 4;
-      dcol[t] = (uint32_t)(p.tap_slot[t] * p.Nb);
-      first_mask |= (uint32_t)(p.tap_first[t] ? 1 : 0) << t;
-    }
-  }
+  for (int g = 0; g < G; ++g) aoff[g] = ((uint32_t)(p.grp_row[g] * p.W) * row_bytes) >> 4;
+  const uint32_t idesc = p.idesc;
   if (p.resident) {
     mbar_wait(bar_w, 0);
     tc_fence_after();
@@ -98,7 +93,7 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
     const uint32_t aphase = (it >> 1) & 1;
     mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
     tc_fence_after();
-    const uint32_t d_base = tmem_base + as * acc_cols;
+    const uint32_t d_tmem = tmem_base + as * acc_cols;
     for (int ch = 0; ch < chunks; ++ch) {
       mbar_wait(bar_full + 8 * stage, phase);
       tc_fence_after();
@@ -107,24 +102,12 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
       const uint32_t a_lo = lo_bits | ((a_base & 0x3FFFFu) >> 4);
       const uint32_t b_lo = lo_bits | ((b_base & 0x3FFFFu) >> 4);
       if (!(p.dbg & 1)) {
-        if (NT > 0) {
 #pragma unroll
-          for (int t = 0; t < NTR; ++t) {
-            const uint32_t acc0 = (ch == 0 && ((first_mask >> t) & 1u)) ? 0u : 1u;
+        for (int g = 0; g < G; ++g) {
 #pragma unroll
-            for (int k = 0; k < MM; ++k)
-              umma_bf16_lohi(d_base + dcol[t], a_lo + aoff[t] + 2 * k, b_lo + t * slab_lo + 2 * k, hi32, p.idesc,
-                             k == 0 ? acc0 : 1u);
-          }
-        } else {
-          for (int t = 0; t < p.n_taps; ++t) {
-            const uint32_t al = a_lo + (((uint32_t)(p.tap_row[t] * p.W) * row_bytes) >> 4);
-            const uint32_t bl = b_lo + t * slab_lo;
-            const uint32_t d_tmem = d_base + p.tap_slot[t] * p.Nb;
-            const bool fresh = ch == 0 && p.tap_first[t];
-            for (int k = 0; k < p.KC / 16; ++k)
-              umma_bf16_lohi(d_tmem, al + 2 * k, bl + 2 * k, hi32, p.idesc, (fresh && k == 0) ? 0u : 1u);
-          }
+          for (int k = 0; k < MM; ++k)
+            umma_bf16_lohi(d_tmem, a_lo + aoff[g] + 2 * k, b_lo + g * grp_lo + 2 * k, hi32, idesc,
+                           (ch == 0 && g == 0 && k == 0) ? 0u : 1u);
         }
       }
       umma_commit(bar_empty + 8 * stage);
@@ -226,17 +209,18 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-#define DBS_STRIP_ROLE(NT, MM) \
-  strip_mma_role<NT, MM>(p, ring, w_region, tmem_base, bar_full, bar_empty, bar_tfull, bar_tempty, bar_w, tile_lo, tile_hi)
+#define DBS_STRIP_ROLE(G, MM) \
+  strip_mma_role<G, MM>(p, ring, w_region, tmem_base, bar_full, bar_empty, bar_tfull, bar_tempty, bar_w, tile_lo, tile_hi)
       const int mm = p.KC / 16;
-      if (p.n_taps == 9 && mm == 4) DBS_STRIP_ROLE(9, 4);
-      else if (p.n_taps == 9 && mm == 2) DBS_STRIP_ROLE(9, 2);
-      else if (p.n_taps == 9 && mm == 1) DBS_STRIP_ROLE(9, 1);
-      else if (p.n_taps == 4 && mm == 4) DBS_STRIP_ROLE(4, 4);
-      else if (p.n_taps == 4 && mm == 2) DBS_STRIP_ROLE(4, 2);
-      else if (p.n_taps == 1 && mm == 4) DBS_STRIP_ROLE(1, 4);
-      else if (p.n_taps == 1 && mm == 2) DBS_STRIP_ROLE(1, 2);
-      else DBS_STRIP_ROLE(0, 0);
+      if (p.n_groups == 3 && mm == 4) DBS_STRIP_ROLE(3, 4);
+      else if (p.n_groups == 3 && mm == 2) DBS_STRIP_ROLE(3, 2);
+      else if (p.n_groups == 3) DBS_STRIP_ROLE(3, 1);
+      else if (p.n_groups == 2 && mm == 4) DBS_STRIP_ROLE(2, 4);
+      else if (p.n_groups == 2 && mm == 2) DBS_STRIP_ROLE(2, 2);
+      else if (p.n_groups == 2) DBS_STRIP_ROLE(2, 1);
+      else if (mm == 4) DBS_STRIP_ROLE(1, 4);
+      else if (mm == 2) DBS_STRIP_ROLE(1, 2);
+      else DBS_STRIP_ROLE(1, 1);
 #undef DBS_STRIP_ROLE
     }
     __syncwarp();
@@ -416,27 +400,37 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   p.groups = groups; p.Cg = stats ? g.Cout / groups : g.Cout;
   while ((1 << p.cg_log2) < p.Cg) ++p.cg_log2;
   p.dh_min = dh_min;
-  // accumulator slots by dw: the dw = 0 slot must exist (the epilogue starts from it)
-  int slot_of[3] = {-1, -1, -1};  // index dw + 1
-  int nacc = 0;
-  bool has_c = false;
-  for (int t = 0; t < g.n_taps; ++t) has_c |= g.dw[t] == 0;
-  if (!has_c) return DBS_ERR_UNSUPPORTED;
-  slot_of[1] = nacc++;
-  for (int t = 0; t < g.n_taps; ++t)
-    if (slot_of[g.dw[t] + 1] < 0) slot_of[g.dw[t] + 1] = nacc++;
-  bool seen[3] = {false, false, false};
-  for (int t = 0; t < g.n_taps; ++t) {
-    p.tap_row[t] = g.dh[t] - dh_min;
-    p.tap_slot[t] = slot_of[g.dw[t] + 1];
-    p.tap_first[t] = seen[p.tap_slot[t]] ? 0 : 1;
-    seen[p.tap_slot[t]] = true;
-    p.tap_w[t] = g.widx[t];
+  // taps must form a full (dh x dw) grid: groups = distinct dh, slots = distinct dw (ascending), and
+  // the dw = 0 slot must exist (the epilogue starts from it)
+  int dhs[4], dws[3], G = 0, nacc = 0;
+  for (int v = dh_min; v <= dh_max; ++v) {
+    bool present = false;
+    for (int t = 0; t < g.n_taps; ++t) present |= g.dh[t] == v;
+    if (present) { if (G == 4) return DBS_ERR_UNSUPPORTED; dhs[G++] = v; }
   }
+  int slot_of[3] = {-1, -1, -1};  // index dw + 1
+  for (int v = -1; v <= 1; ++v) {
+    bool present = false;
+    for (int t = 0; t < g.n_taps; ++t) present |= g.dw[t] == v;
+    if (present) { slot_of[v + 1] = nacc; dws[nacc++] = v; }
+  }
+  if (slot_of[1] < 0 || G > 3 || G * nacc != g.n_taps) return DBS_ERR_UNSUPPORTED;
+  if (nacc * Nb > 256) return DBS_ERR_UNSUPPORTED;
+  for (int gi = 0; gi < G; ++gi) {
+    p.grp_row[gi] = dhs[gi] - dh_min;
+    for (int si = 0; si < nacc; ++si) {
+      int found = -1;
+      for (int t = 0; t < g.n_taps; ++t)
+        if (g.dh[t] == dhs[gi] && g.dw[t] == dws[si]) { if (found >= 0) return DBS_ERR_UNSUPPORTED; found = t; }
+      if (found < 0) return DBS_ERR_UNSUPPORTED;
+      p.tap_w[gi * nacc + si] = g.widx[found];
+    }
+  }
+  p.n_groups = G;
   p.slot_c = slot_of[1]; p.slot_p = slot_of[2]; p.slot_m = slot_of[0]; p.nacc = nacc;
   p.bias = bias; p.out = out; p.stats = stats;
   { const char* e = getenv("DBS_STRIP_DBG"); p.dbg = e ? atoi(e) : 0; }
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((nacc * Nb) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   p.a_bytes = (uint32_t)rows * W * KC * 2;
   p.slab_bytes = (uint32_t)Nb * KC * 2;
   uint32_t cols = 32;
