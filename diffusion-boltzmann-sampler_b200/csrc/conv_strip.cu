@@ -33,7 +33,7 @@ using namespace tc;
 using namespace tch;
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 8;               // two warps per TMEM lane quadrant, splitting the column chunks
+constexpr int kEpiWarps = 16;              // four warps per TMEM lane quadrant, one 16-column chunk each
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kSmemBudget = 200 * 1024;
@@ -127,7 +127,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_bias[kMaxCout];
-  __shared__ float s_x[2][2][4][2][16];           // [parity][half][quadrant][side][col]: cross-warp neighbours (W > 32)
+  __shared__ float s_x[2][4][4][2][16];           // [parity][sub][quadrant][side][col]: cross-warp neighbours (W > 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_region = smem_u32(smem);                       // resident weights (may be empty)
@@ -227,7 +227,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                 // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;       // which of the quadrant's two warps: takes chunks half, half+2
+    const int half = (warp - 2) >> 2;       // which of the quadrant's four warps: takes chunks half, half+4, ...
     const int row = q * 32 + lane;          // tile-local pixel
     const int hl = row / p.W, wl = row - hl * p.W;
     const float m_right = wl < p.W - 1 ? 1.f : 0.f;   // pixel m+1 is in the same image row
@@ -235,7 +235,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     const bool xchg = p.W > 32;             // an image row spans several warps
     constexpr int CG = 2 * NCH;             // channels per GroupNorm group (8 groups)
     constexpr int GPC = 16 / CG;            // groups per 16-column chunk
-    constexpr int MYCH = (NCH + 1) / 2;     // chunks this warp may own
+    constexpr int MYCH = (NCH + 3) / 4;     // chunks this warp may own
     float st_s[MYCH * GPC], st_ss[MYCH * GPC];
 #pragma unroll
     for (int i = 0; i < MYCH * GPC; ++i) { st_s[i] = 0.f; st_ss[i] = 0.f; }
@@ -243,7 +243,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     auto flush_stats = [&](int n_img) {
 #pragma unroll
       for (int i = 0; i < MYCH * GPC; ++i) {
-        const int chunk = half + 2 * (i / GPC);
+        const int chunk = half + 4 * (i / GPC);
         if (chunk < NCH) {
           const float s_ = warp_sum(st_s[i]), ss_ = warp_sum(st_ss[i]);
           const int gi = chunk * GPC + (i % GPC);
@@ -273,13 +273,13 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
 #pragma unroll
       for (int mc = 0; mc < MYCH; ++mc) {
-        const int chunk = half + 2 * mc;
+        const int chunk = half + 4 * mc;
         if (chunk >= NCH || (p.dbg & 2)) break;
         const int c = chunk * 16;
         uint32_t v0[16], vp[16], vm[16];
         tmem_ld16(tbase + p.slot_c * p.Nb + c, v0);
-        if (p.slot_p >= 0) tmem_ld16(tbase + p.slot_p * p.Nb + c, vp);
-        if (p.slot_m >= 0) tmem_ld16(tbase + p.slot_m * p.Nb + c, vm);
+        if (p.slot_p >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + p.slot_p * p.Nb + c, vp);
+        if (p.slot_m >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + p.slot_m * p.Nb + c, vm);
         tmem_ld_wait();
         if (xchg) {
           // publish the edge lanes: my lane 0's P_{+1} is pixel m+1 of the previous warp's lane 31,
@@ -304,7 +304,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           f[4 * j4 + 2] = __uint_as_float(v0[4 * j4 + 2]) + b4.z;
           f[4 * j4 + 3] = __uint_as_float(v0[4 * j4 + 3]) + b4.w;
         }
-        if (p.slot_p >= 0) {
+        if (p.slot_p >= 0 && !(p.dbg & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[j]), 1);
@@ -312,7 +312,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             f[j] = fmaf(m_right, nb, f[j]);
           }
         }
-        if (p.slot_m >= 0) {
+        if (p.slot_m >= 0 && !(p.dbg & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float nb = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j]), 1);
@@ -320,7 +320,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             f[j] = fmaf(m_left, nb, f[j]);
           }
         }
-        if (kStats) {
+        if (kStats && !(p.dbg & 32)) {
 #pragma unroll
           for (int r = 0; r < GPC; ++r) {
 #pragma unroll

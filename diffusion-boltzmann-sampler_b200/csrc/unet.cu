@@ -12,6 +12,7 @@
 // run: fp32 in precision 0, bf16 in precision 1.  With in_channels == 1 the API's NCHW input and
 // output tensors are already NHWC.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -235,71 +236,76 @@ template <> struct Vec16<__nv_bfloat16> {
 };
 
 // init conv: 1 -> C, 3x3 pad 1 (score_network.py:192, 238).  x fp32 [B][H][W]; w [9][C].
-// One thread per pixel: 9 input taps in registers, weights broadcast from shared memory, the
-// pixel's C outputs leave as contiguous 16-byte stores.
+// C/V threads per pixel, one 16-byte channel vector each: a warp's store covers contiguous memory.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  T* __restrict__ out, int64_t n_pix, int H, int W, int C) {
   constexpr int V = Vec16<T>::N;
-  extern __shared__ __align__(16) float sw_init[];  // [9][C] weights, then [C] bias
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw_init[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sw_init[9 * C + i] = bias[i];
-  __syncthreads();
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pix) return;
+  const int cv = C / V;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_pix * cv) return;
+  const int64_t p = g / cv;
+  const int c = (int)(g - p * cv) * V;
   const int ww = (int)(p % W);
   const int hh = (int)((p / W) % H);
-  float xs[9];
+  float v[V];
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int ih = hh + kh - 1, iw = ww + kw - 1;
-      xs[kh * 3 + kw] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + p + (int64_t)(kh - 1) * W + (kw - 1)) : 0.f;
-    }
-  for (int c = 0; c < C; c += V) {
-    float v[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) v[k] = sw_init[9 * C + c + k];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int k = 0; k < V; ++k) v[k] = fmaf(xs[t], sw_init[t * C + c + k], v[k]);
-    Vec16<T>::store(out + p * C + c, v);
-  }
-}
-
-// final conv: C -> 1, 3x3 pad 1, then * output_scale (score_network.py:219, 259, 268).
-template <typename T>
-__global__ void __launch_bounds__(128)
-final_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ out, int64_t n_pix, int H, int W, int C, float scale) {
-  constexpr int V = Vec16<T>::N;
-  extern __shared__ __align__(16) float sw[];  // [9][C]
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pix) return;
-  const int ww = (int)(p % W);
-  const int hh = (int)((p / W) % H);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < V; ++k) v[k] = __ldg(bias + c + k);
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
       const int ih = hh + kh - 1, iw = ww + kw - 1;
       if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-      const T* src = in + (p + (int64_t)(kh - 1) * W + (kw - 1)) * C;
-      const float* wk = sw + (kh * 3 + kw) * C;
-      for (int c = 0; c < C; c += V) {
-        float v[V];
-        Vec16<T>::load(src + c, v);
+      const float xv = __ldg(x + p + (int64_t)(kh - 1) * W + (kw - 1));
+      const float* wk = w + (kh * 3 + kw) * C + c;
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k & 3] = fmaf(v[k], wk[c + k], acc[k & 3]);
+      for (int k = 0; k < V; k += 4) {
+        const float4 wq = __ldg(reinterpret_cast<const float4*>(wk + k));
+        v[k] = fmaf(xv, wq.x, v[k]); v[k + 1] = fmaf(xv, wq.y, v[k + 1]);
+        v[k + 2] = fmaf(xv, wq.z, v[k + 2]); v[k + 3] = fmaf(xv, wq.w, v[k + 3]);
       }
     }
-  out[p] = scale * (((acc[0] + acc[1]) + (acc[2] + acc[3])) + bias[0]);
+  Vec16<T>::store(out + p * C + c, v);
+}
+
+// final conv: C -> 1, 3x3 pad 1, then * output_scale (score_network.py:219, 259, 268).
+// C/V threads per pixel (a warp's load of one tap is contiguous), partial dot products combined
+// with shuffles inside the pixel's thread group.  Requires C/V to be a power of two <= 32.
+template <typename T>
+__global__ void __launch_bounds__(256)
+final_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int64_t n_pix, int H, int W, int C, float scale) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = g / cv;
+  const int c = (int)(g - p * cv) * V;
+  const bool live = p < n_pix;
+  const int ww = (int)(p % W);
+  const int hh = (int)((p / W) % H);
+  float acc = 0.f;
+  if (live) {
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = hh + kh - 1, iw = ww + kw - 1;
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+        float v[V];
+        Vec16<T>::load(in + (p + (int64_t)(kh - 1) * W + (kw - 1)) * C + c, v);
+        const float* wk = w + (kh * 3 + kw) * C + c;
+#pragma unroll
+        for (int k = 0; k < V; k += 4) {
+          const float4 wq = __ldg(reinterpret_cast<const float4*>(wk + k));
+          acc = fmaf(v[k], wq.x, acc); acc = fmaf(v[k + 1], wq.y, acc);
+          acc = fmaf(v[k + 2], wq.z, acc); acc = fmaf(v[k + 3], wq.w, acc);
+        }
+      }
+  }
+  for (int o = cv >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (live && c == 0) out[p] = scale * (acc + bias[0]);
 }
 
 // optional per-sample std normalisation (score_network.py:262-265): score / (std + 1e-8),
@@ -387,7 +393,7 @@ gn_stats_kernel(const T* __restrict__ y, float* __restrict__ stats, int HW, int 
 // Grid = (chunks, B): a CTA works on one sample, folds the statistics into per-channel
 // scale/shift once (shared memory), then streams 16-byte vectors: HBM-bound, 2 B read + 2 B
 // written per element in bf16 (+2 B for the residual).
-template <typename T>
+template <typename T, int UN>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __restrict__ stats, int raw,
                 float inv_cnt, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -424,26 +430,27 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
   T* ob = out + (int64_t)n * HW * C + c;
   const int stride = gridDim.x * ppb;
   int p0 = blockIdx.x * ppb + prow;
-  // two pixels per iteration: two independent 16-byte loads in flight per thread
-  for (; p0 + stride < HW; p0 += 2 * stride) {
-    float v0[V], v1[V], r0[V], r1[V];
-    Vec16<T>::load(yb + (int64_t)p0 * C, v0);
-    Vec16<T>::load(yb + (int64_t)(p0 + stride) * C, v1);
+  // UN pixels per iteration: UN (2*UN with a residual) independent 16-byte loads in flight per thread
+  for (; p0 + (UN - 1) * stride < HW; p0 += UN * stride) {
+    float v[UN][V], r[UN][V];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) Vec16<T>::load(yb + (int64_t)(p0 + u * stride) * C, v[u]);
     if (rb) {
-      Vec16<T>::load(rb + (int64_t)p0 * C, r0);
-      Vec16<T>::load(rb + (int64_t)(p0 + stride) * C, r1);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) Vec16<T>::load(rb + (int64_t)(p0 + u * stride) * C, r[u]);
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float h0 = silu_t<T>(fmaf(v0[k], sc[k], sh[k])) + tb[k];
-      float h1 = silu_t<T>(fmaf(v1[k], sc[k], sh[k])) + tb[k];
-      if (rb) { h0 = fmaf(res_scale, r0[k], h0); h1 = fmaf(res_scale, r1[k], h1); }
-      v0[k] = h0; v1[k] = h1;
+    for (int u = 0; u < UN; ++u) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float h = silu_t<T>(fmaf(v[u][k], sc[k], sh[k])) + tb[k];
+        if (rb) h = fmaf(res_scale, r[u][k], h);
+        v[u][k] = h;
+      }
+      Vec16<T>::store(ob + (int64_t)(p0 + u * stride) * C, v[u]);
     }
-    Vec16<T>::store(ob + (int64_t)p0 * C, v0);
-    Vec16<T>::store(ob + (int64_t)(p0 + stride) * C, v1);
   }
-  if (p0 < HW) {
+  for (; p0 < HW; p0 += stride) {
     float v0[V], r0[V];
     Vec16<T>::load(yb + (int64_t)p0 * C, v0);
     if (rb) Vec16<T>::load(rb + (int64_t)p0 * C, r0);
@@ -459,7 +466,18 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
 
 // time path (score_network.py:20-41, 185-189, 126/146): gridDim.x = distinct t values; the small
 // embedding MLP is recomputed by each of the gridDim.y CTAs, which then split the concatenated
-// per-block Linear layers (sumC outputs) between them.
+// per-block Linear layers (sumC outputs) between them.  One thread per output row, float4 weight
+// loads issued back to back: three dependent stages of ~L2 latency each.
+__device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const float* __restrict__ v, int n) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int k = 0; k < n; k += 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(wrow + k));
+    a0 = fmaf(q.x, v[k], a0); a1 = fmaf(q.y, v[k + 1], a1);
+    a2 = fmaf(q.z, v[k + 2], a2); a3 = fmaf(q.w, v[k + 3], a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
 __global__ void __launch_bounds__(256)
 time_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int T,
             const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
@@ -471,35 +489,20 @@ time_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int T,
   float* temb = sm + 3 * T;  // [T]
   const int half = T / 2;
   const float tv = t[blockIdx.x];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int k = threadIdx.x; k < T; k += blockDim.x) {
     const int f = k < half ? k : k - half;
     const float arg = __fmul_rn(__fmul_rn(tv, freqs[f]), 1000.0f);
     emb[k] = k < half ? sinf(arg) : cosf(arg);
   }
   __syncthreads();
-  for (int j = wid; j < 2 * T; j += nw) {   // one warp per output row: coalesced weight reads
-    float a = 0.f;
-    for (int k = lane; k < T; k += 32) a = fmaf(w0[j * T + k], emb[k], a);
-    a = warp_sum(a);
-    if (lane == 0) hid[j] = silu(a + b0[j]);
-  }
+  for (int j = threadIdx.x; j < 2 * T; j += blockDim.x) hid[j] = silu(dot_row(w0 + (int64_t)j * T, emb, T) + b0[j]);
   __syncthreads();
-  for (int i = wid; i < T; i += nw) {
-    float a = 0.f;
-    for (int j = lane; j < 2 * T; j += 32) a = fmaf(w2[i * 2 * T + j], hid[j], a);
-    a = warp_sum(a);
-    if (lane == 0) temb[i] = a + b2[i];
-  }
+  for (int i = threadIdx.x; i < T; i += blockDim.x) temb[i] = dot_row(w2 + (int64_t)i * 2 * T, hid, 2 * T) + b2[i];
   __syncthreads();
   const int per = (sumC + gridDim.y - 1) / gridDim.y;
   const int c_lo = blockIdx.y * per, c_hi = min(sumC, c_lo + per);
-  for (int c = c_lo + wid; c < c_hi; c += nw) {
-    float a = 0.f;
-    for (int i = lane; i < T; i += 32) a = fmaf(wt[c * T + i], temb[i], a);
-    a = warp_sum(a);
-    if (lane == 0) tbias[(int64_t)blockIdx.x * sumC + c] = a + bt[c];
-  }
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x)
+    tbias[(int64_t)blockIdx.x * sumC + c] = dot_row(wt + (int64_t)c * T, temb, T) + bt[c];
 }
 
 // weight repack: Conv2d [co][ci][kh][kw] (transposed = 0) or ConvTranspose2d [ci][co][kh][kw]
@@ -689,17 +692,26 @@ int run_gn(Ctx& c, const T* y, T* out, bool have_raw_stats, const float* gamma, 
   DBS_REQUIRE(C % V == 0, "unet: channel count %d is not a multiple of %d", C, V);
   const int cv = C / V;
   DBS_REQUIRE(cv <= 256, "unet: %d channels exceed the GroupNorm kernel's limit", C);
-  const int threads = (256 / cv) * cv;          // a whole number of pixels per block iteration
+  static const int tune_threads = [] { const char* e = getenv("DBS_GN_THREADS"); return e ? atoi(e) : 256; }();
+  static const int tune_un = [] { const char* e = getenv("DBS_GN_UN"); return e ? atoi(e) : 2; }();
+  static const int tune_cap = [] { const char* e = getenv("DBS_GN_CAP"); return e ? atoi(e) : 8; }();
+  const int threads = (tune_threads / cv) * cv;   // a whole number of pixels per block iteration
   const int ppb = threads / cv;
-  int bx = (HW + 2 * ppb - 1) / (2 * ppb);
-  const int cap = (int)std::max<int64_t>(1, (148 * 8) / c.B);   // ~8 CTAs per SM across the batch
+  int bx = (HW + tune_un * ppb - 1) / (tune_un * ppb);
+  const int cap = (int)std::max<int64_t>(1, (148 * tune_cap) / c.B);   // ~tune_cap CTAs per SM across the batch
   if (bx > cap) bx = cap;
   const float inv_cnt = 1.0f / (float)((int64_t)HW * (C / G));
   prof_set_label("HW%d C%d res%d", HW, C, res ? 1 : 0);
   ProfScope prof(kProfGnApply, c.st);
-  gn_apply_kernel<T><<<dim3((unsigned)bx, (unsigned)c.B), threads, 0, c.st>>>(
-      y, out, c.stats, have_raw_stats ? 1 : 0, inv_cnt, 1e-5f, gamma, beta,
-      add_time ? c.tbias + tb_off : nullptr, c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, HW, C, G);
+  const dim3 grid((unsigned)bx, (unsigned)c.B);
+#define DBS_GN_LAUNCH(UN)                                                                                   \
+  gn_apply_kernel<T, UN><<<grid, threads, 0, c.st>>>(y, out, c.stats, have_raw_stats ? 1 : 0, inv_cnt, 1e-5f, gamma, beta, \
+                                                     add_time ? c.tbias + tb_off : nullptr,                 \
+                                                     c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, HW, C, G)
+  if (tune_un >= 4) DBS_GN_LAUNCH(4);
+  else if (tune_un == 2) DBS_GN_LAUNCH(2);
+  else DBS_GN_LAUNCH(1);
+#undef DBS_GN_LAUNCH
   DBS_LAUNCHED();
   return DBS_OK;
 }
@@ -786,6 +798,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
 
   // ---- time path
   {
+    prof_set_label("time");
     ProfScope prof(kProfUnetMisc, st);
     time_kernel<<<dim3((unsigned)n_t, n_t == 1 ? 16u : 2u), 256, (size_t)4 * Td * 4, st>>>(t, plan->freqs, Td, plan->tw0, plan->tb0, plan->tw2,
                                                                plan->tb2, plan->twt, plan->tbt, plan->sumC, tbias);
@@ -795,9 +808,10 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- init conv
   {
     const int64_t n_pix = B * H * W;
+    prof_set_label("init_conv");
     ProfScope prof(kProfUnetMisc, st);
-    init_conv_kernel<T><<<(unsigned)((n_pix + 127) / 128), 128, (size_t)10 * C * 4, st>>>(x, plan->init_w, plan->init_b, a0,
-                                                                                       n_pix, H, W, C);
+    const int64_t nthr = n_pix * (C / (16 / (int)sizeof(T)));
+    init_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(x, plan->init_w, plan->init_b, a0, n_pix, H, W, C);
     DBS_LAUNCHED();
     if ((rc = maybe_tap<T>(c, "init", a0, B, H, W, C))) return rc;
   }
@@ -848,10 +862,18 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- final conv (+ optional normalisation, output scale)
   {
     const int64_t n_pix = B * H * W;
-    ProfScope prof(kProfUnetMisc, st);
-    final_conv_kernel<T><<<(unsigned)((n_pix + 127) / 128), 128, (size_t)9 * C * 4, st>>>(
-        cur, plan->final_w, plan->final_b, score, n_pix, H, W, C, cfg.output_scale);
-    DBS_LAUNCHED();
+    prof_set_label("final_conv");
+    {
+      const int cvf = C / (16 / (int)sizeof(T));
+      DBS_REQUIRE(cvf >= 1 && cvf <= 32 && (cvf & (cvf - 1)) == 0,
+                  "unet: base_channels %d unsupported by the final conv kernel (C/%d must be a power of two <= 32)", C,
+                  16 / (int)sizeof(T));
+      ProfScope prof(kProfUnetMisc, st);
+      const int64_t nthr = n_pix * cvf;
+      final_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(cur, plan->final_w, plan->final_b, score, n_pix,
+                                                                          H, W, C, cfg.output_scale);
+      DBS_LAUNCHED();
+    }
     if (cfg.normalize_output) {
       normalize_output_kernel<<<(unsigned)B, 256, 0, st>>>(score, H * W, cfg.output_scale);
       DBS_LAUNCHED();
@@ -887,8 +909,8 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
   DBS_REQUIRE(cfg && params && out && freqs_host, "unet_plan_create: null argument");
   DBS_REQUIRE(cfg->in_channels == 1, "unet: only in_channels == 1 (Ising lattices) is built, got %d", cfg->in_channels);
   DBS_REQUIRE(cfg->base_channels >= 4 && cfg->base_channels % 4 == 0, "unet: base_channels must be a multiple of 4");
-  DBS_REQUIRE(cfg->time_embed_dim >= 4 && cfg->time_embed_dim % 2 == 0 && cfg->time_embed_dim <= 1024,
-              "unet: time_embed_dim must be even, 4..1024");
+  DBS_REQUIRE(cfg->time_embed_dim >= 4 && cfg->time_embed_dim % 4 == 0 && cfg->time_embed_dim <= 1024,
+              "unet: time_embed_dim must be a multiple of 4, 4..1024");
   DBS_REQUIRE(cfg->num_blocks >= 1 && cfg->num_blocks <= 6, "unet: num_blocks must be 1..6");
   dbs_unet_plan* plan = new dbs_unet_plan();
   plan->cfg = *cfg;
