@@ -37,10 +37,11 @@ constexpr int kEpiWarps = 16;              // four warps per TMEM lane quadrant,
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kSmemBudget = 200 * 1024;
-constexpr int kMaxCout = 64;
+constexpr int kMaxCout = 512;             // Cout > 64 is processed as N tiles of 64 couts
 
 struct StripParams {
   int W, Ht, tiles_h, n_tiles;
+  int n_tiles_n;      // N tiles of Nb couts; a CTA's tile order is (image, n-tile, row block)
   int Nb, KC, chunks0, chunks1, n_taps, stages, resident;
   int B, Hout, Wout, Cout, out_stride, oph, opw;
   int groups, Cg, cg_log2;
@@ -117,8 +118,10 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
   }
 }
 
-// kStats: accumulate GroupNorm(8) sums; NCH = Cout / 16 column chunks (group width Cg = 2 * NCH)
-template <bool kStats, int NCH>
+// kStats: accumulate GroupNorm(8) sums; NCH = Nb / 16 column chunks.  kWide = false: Cout <= 64, group
+// width Cg = 2 * NCH <= 8 (several groups per chunk); kWide = true: Cout >= 128, Cg >= 16 (a chunk lies
+// inside one group).
+template <bool kStats, int NCH, bool kWide>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StripParams p) {
@@ -178,12 +181,14 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         mbar_expect_tx(bar_w, chunk_w_bytes * chunks);
         for (int ch = 0; ch < chunks; ++ch)
           for (int t = 0; t < p.n_taps; ++t)
-            tma_load_3d(w_region + (ch * p.n_taps + t) * p.slab_bytes, &map_w, bar_w, ch * p.KC, 0, p.tap_w[t]);
+            tma_load_3d(w_region + (ch * p.n_taps + t) * p.slab_bytes, &map_w, bar_w, ch * p.KC, 0, p.tap_w[t]);  // n_tiles_n == 1
       }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        const int n = tile / p.tiles_h, h0 = (tile - n * p.tiles_h) * p.Ht;
+        const int per_img = p.n_tiles_n * p.tiles_h;
+        const int n = tile / per_img, rem = tile - n * per_img;
+        const int nt = rem / p.tiles_h, h0 = (rem - nt * p.tiles_h) * p.Ht, co0 = nt * p.Nb;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t a_dst = ring + stage * p.stage_bytes;
@@ -199,7 +204,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           if (!p.resident) {
             const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
             for (int t = 0; t < p.n_taps; ++t)
-              tma_load_3d(b_dst + t * p.slab_bytes, &map_w, fb, ch * p.KC, 0, p.tap_w[t]);
+              tma_load_3d(b_dst + t * p.slab_bytes, &map_w, fb, ch * p.KC, co0, p.tap_w[t]);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -233,20 +238,20 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     const float m_right = wl < p.W - 1 ? 1.f : 0.f;   // pixel m+1 is in the same image row
     const float m_left = wl > 0 ? 1.f : 0.f;
     const bool xchg = p.W > 32;             // an image row spans several warps
-    constexpr int CG = 2 * NCH;             // channels per GroupNorm group (8 groups)
-    constexpr int GPC = 16 / CG;            // groups per 16-column chunk
+    constexpr int CG = kWide ? 16 : 2 * NCH;  // channels of a group inside one chunk
+    constexpr int GPC = 16 / CG;              // groups per 16-column chunk (1 when kWide)
     constexpr int MYCH = (NCH + 3) / 4;     // chunks this warp may own
     float st_s[MYCH * GPC], st_ss[MYCH * GPC];
 #pragma unroll
     for (int i = 0; i < MYCH * GPC; ++i) { st_s[i] = 0.f; st_ss[i] = 0.f; }
-    int cur_n = -1;
-    auto flush_stats = [&](int n_img) {
+    int cur_n = -1, cur_nt = 0;
+    auto flush_stats = [&](int n_img, int nt_img) {
 #pragma unroll
       for (int i = 0; i < MYCH * GPC; ++i) {
         const int chunk = half + 4 * (i / GPC);
         if (chunk < NCH) {
           const float s_ = warp_sum(st_s[i]), ss_ = warp_sum(st_ss[i]);
-          const int gi = chunk * GPC + (i % GPC);
+          const int gi = kWide ? ((nt_img * p.Nb + chunk * 16) >> p.cg_log2) : chunk * GPC + (i % GPC);
           if (lane == 0) {
             atomicAdd(p.stats + ((int64_t)n_img * 8 + gi) * 2 + 0, s_);
             atomicAdd(p.stats + ((int64_t)n_img * 8 + gi) * 2 + 1, ss_);
@@ -260,13 +265,15 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int n = tile / p.tiles_h, a = (tile - n * p.tiles_h) * p.Ht + hl;
-      if (kStats && n != cur_n) {
-        if (cur_n >= 0) flush_stats(cur_n);
-        cur_n = n;
+      const int per_img = p.n_tiles_n * p.tiles_h;
+      const int n = tile / per_img, rem = tile - n * per_img;
+      const int nt = rem / p.tiles_h, a = (rem - nt * p.tiles_h) * p.Ht + hl, co0 = nt * p.Nb;
+      if (kStats && (n != cur_n || nt != cur_nt)) {
+        if (cur_n >= 0) flush_stats(cur_n, cur_nt);
+        cur_n = n; cur_nt = nt;
       }
       __nv_bfloat16* optr =
-          p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout;
+          p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout + co0;
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
@@ -295,7 +302,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         }
         float f[16];
-        const float4* bq = reinterpret_cast<const float4*>(s_bias + c);
+        const float4* bq = reinterpret_cast<const float4*>(s_bias + co0 + c);
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 b4 = bq[j4];
@@ -347,7 +354,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
     }
-    if (kStats && cur_n >= 0) flush_stats(cur_n);
+    if (kStats && cur_n >= 0) flush_stats(cur_n, cur_nt);
   }
   tc_fence_before();
   __syncthreads();
@@ -370,6 +377,7 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   const int Ht = kTileM / W;
   if (H < Ht || H % Ht) return DBS_ERR_UNSUPPORTED;
   if (g.Cout > kMaxCout || g.Cout % 16 || g.C0 == 0) return DBS_ERR_UNSUPPORTED;
+  if (g.Cout > 64 && g.Cout % 64) return DBS_ERR_UNSUPPORTED;
   int KC = 0;
   for (int k : {64, 32, 16})
     if (g.C0 % k == 0 && g.C1 % k == 0) { KC = k; break; }
@@ -392,8 +400,8 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
 
   StripParams p;
   memset(&p, 0, sizeof(p));
-  const int Cin = g.C0 + g.C1, Nb = g.Cout;
-  p.W = W; p.Ht = Ht; p.tiles_h = H / Ht; p.n_tiles = g.B * p.tiles_h;
+  const int Cin = g.C0 + g.C1, Nb = g.Cout > 64 ? 64 : g.Cout;
+  p.W = W; p.Ht = Ht; p.tiles_h = H / Ht; p.n_tiles_n = g.Cout / Nb; p.n_tiles = g.B * p.tiles_h * p.n_tiles_n;
   p.Nb = Nb; p.KC = KC; p.chunks0 = g.C0 / KC; p.chunks1 = g.C1 / KC; p.n_taps = g.n_taps;
   p.B = g.B; p.Hout = g.Hout; p.Wout = g.Wout; p.Cout = g.Cout;
   p.out_stride = g.out_stride; p.oph = g.oph; p.opw = g.opw;
@@ -443,7 +451,7 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   if (p.slab_bytes % 1024u && KC == 64) return DBS_ERR_UNSUPPORTED;   // slab bases must stay atom-aligned
   if (p.slab_bytes % (8u * KC * 2u)) return DBS_ERR_UNSUPPORTED;
   // resident weights if they leave room for >= 3 strip stages
-  if (all_w + 3 * a_pad <= kSmemBudget) {
+  if (p.n_tiles_n == 1 && all_w + 3 * a_pad <= kSmemBudget) {
     p.resident = 1;
     p.w_region_bytes = (all_w + 1023u) & ~1023u;
     p.stage_bytes = a_pad;
@@ -476,16 +484,21 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
 
   const size_t smem = (size_t)p.w_region_bytes + (size_t)stages * p.stage_bytes + 1024;
   typedef void (*Kern)(CUtensorMap, CUtensorMap, CUtensorMap, StripParams);
-  static const Kern table[2][3] = {
-      {conv_strip_kernel<false, 1>, conv_strip_kernel<false, 2>, conv_strip_kernel<false, 4>},
-      {conv_strip_kernel<true, 1>, conv_strip_kernel<true, 2>, conv_strip_kernel<true, 4>}};
+  // [stats][NCH index] for Cout <= 64, plus the wide-group pair for N-tiled layers (Nb = 64, Cg >= 16)
+  static const Kern table[2][4] = {
+      {conv_strip_kernel<false, 1, false>, conv_strip_kernel<false, 2, false>, conv_strip_kernel<false, 4, false>,
+       conv_strip_kernel<false, 4, true>},
+      {conv_strip_kernel<true, 1, false>, conv_strip_kernel<true, 2, false>, conv_strip_kernel<true, 4, false>,
+       conv_strip_kernel<true, 4, true>}};
   const int nch = Nb / 16;
-  Kern kern = table[stats ? 1 : 0][nch == 1 ? 0 : (nch == 2 ? 1 : 2)];
+  const bool wide = g.Cout > 64;
+  if (wide && stats && (!is_pow2(p.Cg) || p.Cg < 16)) return DBS_ERR_UNSUPPORTED;
+  Kern kern = table[stats ? 1 : 0][wide ? 3 : (nch == 1 ? 0 : (nch == 2 ? 1 : 2))];
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 3; ++b) {
+      for (int b = 0; b < 4; ++b) {
         const cudaError_t e = cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)(kSmemBudget + 2048));
         if (e != cudaSuccess) attr_err = e;
