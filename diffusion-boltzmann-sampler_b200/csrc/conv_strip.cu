@@ -48,12 +48,18 @@ struct StripParams {
   int dh_min;
   int n_groups;       // distinct vertical offsets dh; every group holds the same nacc horizontal offsets
   int grp_row[4];     // (dh - dh_min): strip row offset of the group
-  int tap_w[16];      // weight tap index of slab (group g, slot s) at position g * nacc + s
+  int n_slabs;        // weight slabs per chunk = n_taps (+1 with a fused 1x1 residual conv)
+  int has_res;        // fused residual: an extra slab stacked onto the dh = 0 group, own accumulator slot nacc
+  int grp_off[4];     // first slab of each group
+  int grp_nslab[4];   // slabs stacked along N in each group
+  int slab_tap[16];   // weight tap index of each slab in smem order; -1 = the residual 1x1 weights
   int slot_c, slot_p, slot_m, nacc;  // accumulator slots of dw = 0, +1, -1 (-1 = unused)
   const float* bias;
   __nv_bfloat16* out;
   float* stats;
-  uint32_t idesc;
+  const float* bias_res;
+  __nv_bfloat16* out_res;
+  uint32_t idesc_g[4];  // instruction descriptor per group (N = grp_nslab * Nb)
   uint32_t a_bytes, slab_bytes, stage_bytes, w_region_bytes;
   uint32_t tmem_cols;
   uint64_t desc_hi;
@@ -73,15 +79,21 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
                                                uint32_t bar_tempty, uint32_t bar_w, int tile_lo, int tile_hi) {
   const int chunks = p.chunks0 + p.chunks1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2;
-  const uint32_t chunk_w_bytes = p.slab_bytes * p.n_taps;
-  const int acc_cols = p.nacc * p.Nb;
+  const uint32_t chunk_w_bytes = p.slab_bytes * p.n_slabs;
+  const int acc_cols = (p.nacc + p.has_res) * p.Nb;
   const uint32_t lo_bits = (uint32_t)p.desc_hi;            // LBO field
   const uint32_t hi32 = (uint32_t)(p.desc_hi >> 32);       // SBO, version, swizzle mode
-  const uint32_t grp_lo = (p.slab_bytes * p.nacc) >> 4;    // descriptor step between groups' stacked slabs
-  uint32_t aoff[G];
+  uint32_t aoff[G], boff[G], idesc[G];
 #pragma unroll
-  for (int g = 0; g < G; ++g) aoff[g] = ((uint32_t)(p.grp_row[g] * p.W) * row_bytes) >> 4;
-  const uint32_t idesc = p.idesc;
+  for (int g = 0; g < G; ++g) {
+    aoff[g] = ((uint32_t)(p.grp_row[g] * p.W) * row_bytes) >> 4;
+    boff[g] = (p.slab_bytes * (uint32_t)p.grp_off[g]) >> 4;
+    idesc[g] = p.idesc_g[g];
+  }
+  // Zero-initialisation: the first MMA of a tile (chunk 0, group 0) overwrites the nacc tap slots.  With a
+  // fused residual the widest group (dh = 0, nacc + 1 slabs) is issued FIRST so that the same overwrite also
+  // covers the residual slot (the host orders the groups accordingly).
+  auto acc_flag = [](int ch, int g, int k) -> uint32_t { return (ch == 0 && g == 0 && k == 0) ? 0u : 1u; };
   if (p.resident) {
     mbar_wait(bar_w, 0);
     tc_fence_after();
@@ -107,8 +119,7 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
         for (int g = 0; g < G; ++g) {
 #pragma unroll
           for (int k = 0; k < MM; ++k)
-            umma_bf16_lohi(d_tmem, a_lo + aoff[g] + 2 * k, b_lo + g * grp_lo + 2 * k, hi32, idesc,
-                           (ch == 0 && g == 0 && k == 0) ? 0u : 1u);
+            umma_bf16_lohi(d_tmem, a_lo + aoff[g] + 2 * k, b_lo + boff[g] + 2 * k, hi32, idesc[g], acc_flag(ch, g, k));
         }
       }
       umma_commit(bar_empty + 8 * stage);
@@ -124,12 +135,14 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
 template <bool kStats, int NCH, bool kWide>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
-                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StripParams p) {
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wr,
+                  const __grid_constant__ StripParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_bias[kMaxCout];
+  __shared__ __align__(16) float s_bias_r[kMaxCout];
   __shared__ float s_x[2][4][4][2][16];           // [parity][sub][quadrant][side][col]: cross-warp neighbours (W > 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,9 +170,13 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     tma_prefetch_desc(&map_in0);
     tma_prefetch_desc(&map_in1);
     tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_wr);
   }
   if (warp == 2) tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols);
-  for (int i = threadIdx.x; i < p.Cout; i += kThreads) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.Cout; i += kThreads) {
+    s_bias[i] = p.bias[i];
+    s_bias_r[i] = p.has_res ? p.bias_res[i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -171,8 +188,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   const int tile_hi = (int)(((int64_t)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
   const int chunks = p.chunks0 + p.chunks1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2;
-  const uint32_t chunk_w_bytes = p.slab_bytes * p.n_taps;
-  const int acc_cols = p.nacc * p.Nb;   // TMEM columns of one accumulator stage
+  const uint32_t chunk_w_bytes = p.slab_bytes * p.n_slabs;
+  const int acc_cols = (p.nacc + p.has_res) * p.Nb;   // TMEM columns of one accumulator stage
 
   if (warp == 0) {
     if (lane == 0) {
@@ -180,8 +197,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       if (p.resident) {
         mbar_expect_tx(bar_w, chunk_w_bytes * chunks);
         for (int ch = 0; ch < chunks; ++ch)
-          for (int t = 0; t < p.n_taps; ++t)
-            tma_load_3d(w_region + (ch * p.n_taps + t) * p.slab_bytes, &map_w, bar_w, ch * p.KC, 0, p.tap_w[t]);  // n_tiles_n == 1
+          for (int t = 0; t < p.n_slabs; ++t) {  // n_tiles_n == 1 here
+            const uint32_t dst = w_region + (ch * p.n_slabs + t) * p.slab_bytes;
+            if (p.slab_tap[t] >= 0) tma_load_3d(dst, &map_w, bar_w, ch * p.KC, 0, p.slab_tap[t]);
+            else tma_load_3d(dst, &map_wr, bar_w, ch * p.KC, 0, 0);
+          }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -203,8 +223,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           else tma_load_5d(a_dst, &map_in1, fb, (ch - p.chunks0) * p.KC, 0, 0, h0 + p.dh_min, n);
           if (!p.resident) {
             const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
-            for (int t = 0; t < p.n_taps; ++t)
-              tma_load_3d(b_dst + t * p.slab_bytes, &map_w, fb, ch * p.KC, co0, p.tap_w[t]);
+            for (int t = 0; t < p.n_slabs; ++t) {
+              if (p.slab_tap[t] >= 0) tma_load_3d(b_dst + t * p.slab_bytes, &map_w, fb, ch * p.KC, co0, p.slab_tap[t]);
+              else tma_load_3d(b_dst + t * p.slab_bytes, &map_wr, fb, ch * p.KC, co0, 0);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -348,6 +370,27 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        if (p.has_res) {
+          // fused 1x1 residual conv of the same input (score_network.py:131,151): own slot, own bias, no GN
+          uint32_t vr[16];
+          tmem_ld16(tbase + p.nacc * p.Nb + c, vr);
+          tmem_ld_wait();
+          const float4* br = reinterpret_cast<const float4*>(s_bias_r + co0 + c);
+          uint32_t pr[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = br[j4];
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(vr[4 * j4 + 0]) + b4.x,
+                                                             __uint_as_float(vr[4 * j4 + 1]) + b4.y);
+            const __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(vr[4 * j4 + 2]) + b4.z,
+                                                             __uint_as_float(vr[4 * j4 + 3]) + b4.w);
+            pr[2 * j4] = *reinterpret_cast<const uint32_t*>(&h0);
+            pr[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          }
+          uint4* dr = reinterpret_cast<uint4*>(p.out_res + (optr - p.out) + c);
+          dr[0] = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+          dr[1] = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+        }
         xb ^= 1;
       }
       tc_fence_before();
@@ -367,7 +410,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
 }  // namespace
 
 int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1, const __nv_bfloat16* w,
-                      const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st) {
+                      const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st,
+                      const __nv_bfloat16* w_res, const float* bias_res, __nv_bfloat16* out_res) {
+  const bool fuse_res = w_res != nullptr;
+  if (fuse_res && (!bias_res || !out_res || g.out_stride != 1 || g.n_taps != 9)) return DBS_ERR_UNSUPPORTED;
   static const bool disabled = [] { const char* e = getenv("DBS_CONV_STRIP"); return e && e[0] == '0'; }();
   if (disabled) return DBS_ERR_UNSUPPORTED;
   // ---- eligibility
@@ -423,30 +469,46 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
     if (present) { slot_of[v + 1] = nacc; dws[nacc++] = v; }
   }
   if (slot_of[1] < 0 || G > 3 || G * nacc != g.n_taps) return DBS_ERR_UNSUPPORTED;
-  if (nacc * Nb > 256) return DBS_ERR_UNSUPPORTED;
+  if ((nacc + (fuse_res ? 1 : 0)) * Nb > 256) return DBS_ERR_UNSUPPORTED;
+  // issue order of the groups: with a fused residual the dh = 0 group (one slab wider) goes first, so the
+  // tile's zero-initialising MMA covers the residual slot too
+  if (fuse_res) {
+    int z = -1;
+    for (int gi = 0; gi < G; ++gi) if (dhs[gi] == 0) z = gi;
+    if (z < 0) return DBS_ERR_UNSUPPORTED;
+    const int tmp = dhs[0]; dhs[0] = dhs[z]; dhs[z] = tmp;
+  }
+  int slab = 0;
   for (int gi = 0; gi < G; ++gi) {
     p.grp_row[gi] = dhs[gi] - dh_min;
+    p.grp_off[gi] = slab;
     for (int si = 0; si < nacc; ++si) {
       int found = -1;
       for (int t = 0; t < g.n_taps; ++t)
         if (g.dh[t] == dhs[gi] && g.dw[t] == dws[si]) { if (found >= 0) return DBS_ERR_UNSUPPORTED; found = t; }
       if (found < 0) return DBS_ERR_UNSUPPORTED;
-      p.tap_w[gi * nacc + si] = g.widx[found];
+      p.slab_tap[slab++] = g.widx[found];
     }
+    if (fuse_res && dhs[gi] == 0) p.slab_tap[slab++] = -1;
+    p.grp_nslab[gi] = slab - p.grp_off[gi];
+    p.idesc_g[gi] = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((p.grp_nslab[gi] * Nb) >> 3) << 17) |
+                    ((uint32_t)(kTileM >> 4) << 24);
   }
+  p.n_slabs = slab;
+  p.has_res = fuse_res ? 1 : 0;
+  p.bias_res = bias_res; p.out_res = out_res;
   p.n_groups = G;
   p.slot_c = slot_of[1]; p.slot_p = slot_of[2]; p.slot_m = slot_of[0]; p.nacc = nacc;
   p.bias = bias; p.out = out; p.stats = stats;
   { const char* e = getenv("DBS_STRIP_DBG"); p.dbg = e ? atoi(e) : 0; }
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((nacc * Nb) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   p.a_bytes = (uint32_t)rows * W * KC * 2;
   p.slab_bytes = (uint32_t)Nb * KC * 2;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * nacc * Nb)) cols <<= 1;
+  while (cols < (uint32_t)(2 * (nacc + (fuse_res ? 1 : 0)) * Nb)) cols <<= 1;
   if (cols > 512) return DBS_ERR_UNSUPPORTED;
   p.tmem_cols = cols;
   const uint32_t a_pad = (p.a_bytes + 1023u) & ~1023u;
-  const uint32_t chunk_w = p.slab_bytes * g.n_taps;
+  const uint32_t chunk_w = p.slab_bytes * (uint32_t)p.n_slabs;
   const uint32_t all_w = chunk_w * (uint32_t)(p.chunks0 + p.chunks1);
   if (p.slab_bytes % 1024u && KC == 64) return DBS_ERR_UNSUPPORTED;   // slab bases must stay atom-aligned
   if (p.slab_bytes % (8u * KC * 2u)) return DBS_ERR_UNSUPPORTED;
@@ -481,9 +543,11 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   for (int t = 0; t < g.n_taps; ++t) taps_total = g.widx[t] + 1 > taps_total ? g.widx[t] + 1 : taps_total;
   if (g.out_stride == 2) taps_total = 16;
   if ((rc = encode_w(enc, &mw, w, Cin, g.Cout, taps_total, KC, Nb, sw))) return rc;
+  CUtensorMap mwr = mw;
+  if (fuse_res && (rc = encode_w(enc, &mwr, w_res, Cin, g.Cout, 1, KC, Nb, sw))) return rc;
 
   const size_t smem = (size_t)p.w_region_bytes + (size_t)stages * p.stage_bytes + 1024;
-  typedef void (*Kern)(CUtensorMap, CUtensorMap, CUtensorMap, StripParams);
+  typedef void (*Kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, StripParams);
   // [stats][NCH index] for Cout <= 64, plus the wide-group pair for N-tiled layers (Nb = 64, Cg >= 16)
   static const Kern table[2][4] = {
       {conv_strip_kernel<false, 1, false>, conv_strip_kernel<false, 2, false>, conv_strip_kernel<false, 4, false>,
@@ -506,10 +570,10 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   });
   DBS_CUDA(attr_err);
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-  prof_set_label("strip H%d W%d C%d+%d->%d taps%d os%d KC%d B%d res%d st%d", H, W, g.C0, g.C1, g.Cout, g.n_taps, g.out_stride,
-                 KC, g.B, p.resident, p.stages);
+  prof_set_label("strip H%d W%d C%d+%d->%d taps%d os%d KC%d B%d res%d st%d%s", H, W, g.C0, g.C1, g.Cout, g.n_taps,
+                 g.out_stride, KC, g.B, p.resident, p.stages, fuse_res ? " +res1x1" : "");
   ProfScope prof(kProfConvTC, st);
-  kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
+  kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, mwr, p);
   DBS_LAUNCHED();
   return DBS_OK;
 }

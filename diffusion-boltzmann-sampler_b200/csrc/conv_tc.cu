@@ -516,3 +516,16 @@ extern "C" int dbs_conv_tc(const void* in0, int C0, const void* in1, int C1, con
   if (rc == DBS_ERR_UNSUPPORTED) set_error("conv_tc: this geometry is not eligible for the tcgen05 kernel");
   return rc;
 }
+
+// Parity port for the fused (3x3 conv + 1x1 residual conv of the same input) pass of the strip kernel.
+extern "C" int dbs_conv_block_tc(const void* in0, int C0, const void* in1, int C1, const void* w3, const float* bias3,
+                                 const void* w1, const float* bias1, void* out3, void* out1, float* stats, int64_t B,
+                                 int H, int W, int C_out, void* stream) {
+  DBS_REQUIRE(in0 && w3 && bias3 && w1 && bias1 && out3 && out1 && B >= 1, "conv_block_tc: bad arguments");
+  const int groups = C_out < 8 ? C_out : 8;
+  const int rc = conv_strip_launch(geom_conv((int)B, H, W, C0, C1, C_out, 3, 1), (const __nv_bfloat16*)in0,
+                                   (const __nv_bfloat16*)in1, (const __nv_bfloat16*)w3, bias3, (__nv_bfloat16*)out3, stats,
+                                   groups, as_stream(stream), (const __nv_bfloat16*)w1, bias1, (__nv_bfloat16*)out1);
+  if (rc == DBS_ERR_UNSUPPORTED) set_error("conv_block_tc: this geometry is not eligible for the fused strip kernel");
+  return rc;
+}

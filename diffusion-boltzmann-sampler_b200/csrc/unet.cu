@@ -726,7 +726,15 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   const size_t stat_bytes = (size_t)c.B * G * 2 * sizeof(float);
   ConvGeom g1 = geom_conv((int)c.B, H, W, C0, C1, bw.cout, 3, 1);
   if (c.use_tc) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
-  if ((rc = run_conv<T>(c, g1, in0, in1, bw.conv1, ty, c.stats, G, &sd))) return rc;
+  bool res_done = false;
+  if (c.use_tc && sizeof(T) == 2 && bw.has_res) {
+    // conv1 and the 1x1 residual conv read the same input: one pass of the strip kernel does both
+    rc = conv_strip_launch(g1, (const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, bw.conv1.w16, bw.conv1.bias,
+                           (__nv_bfloat16*)ty, c.stats, G, c.st, bw.res.w16, bw.res.bias, (__nv_bfloat16*)tr);
+    if (rc == DBS_OK) { res_done = true; sd = true; }
+    else if (rc != DBS_ERR_UNSUPPORTED) return rc;
+  }
+  if (!res_done && (rc = run_conv<T>(c, g1, in0, in1, bw.conv1, ty, c.stats, G, &sd))) return rc;
   {
     std::string nm = std::string(name) + ".conv1";
     if ((rc = maybe_tap<T>(c, nm.c_str(), ty, c.B, H, W, bw.cout))) return rc;
@@ -737,8 +745,10 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
   const T* res = in0;
   if (bw.has_res) {
-    ConvGeom gr = geom_conv((int)c.B, H, W, C0, C1, bw.cout, 1, 1);
-    if ((rc = run_conv<T>(c, gr, in0, in1, bw.res, tr, nullptr, G, nullptr))) return rc;
+    if (!res_done) {
+      ConvGeom gr = geom_conv((int)c.B, H, W, C0, C1, bw.cout, 1, 1);
+      if ((rc = run_conv<T>(c, gr, in0, in1, bw.res, tr, nullptr, G, nullptr))) return rc;
+    }
     res = tr;
   } else {
     DBS_REQUIRE(C1 == 0, "unet: identity residual with a concatenated input");

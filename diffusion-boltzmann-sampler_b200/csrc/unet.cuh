@@ -41,9 +41,12 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
 // Strip variant of the tcgen05 path for stride-1 convs with Cout <= 64 on full-width row tiles: one
 // halo strip of the input per channel chunk serves every tap, weights stay resident in shared memory
 // when they fit.  Same contract as conv_tc_launch (DBS_ERR_UNSUPPORTED if not eligible).
+// With w_res != nullptr the ConvBlock's 1x1 residual conv of the SAME input (score_network.py:131,151) is
+// computed in the same pass (extra weight slab on the dh = 0 group, own accumulator, own output).
 int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1,
                       const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, float* stats,
-                      int groups, cudaStream_t st);
+                      int groups, cudaStream_t st, const __nv_bfloat16* w_res = nullptr,
+                      const float* bias_res = nullptr, __nv_bfloat16* out_res = nullptr);
 
 // geometry builders
 ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int stride);

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "dbs_unet_forward": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp]),
     "dbs_unet_forward_tap": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, C.c_char_p, vp, i64, vp]),
     "dbs_conv_tc": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
+    "dbs_conv_block_tc": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -226,6 +226,14 @@ int dbs_conv_tc(const void* in0, int C0, const void* in1, int C1, const void* we
                 const float* bias, void* out, float* stats, int64_t B, int H, int W,
                 int C_out, int kind, int ksize, void* stream);
 
+/* Fused first half of a ConvBlock on the tensor cores (parity port): out3 = conv3x3(x) + bias3 with
+ * GroupNorm(8) partial sums, out1 = conv1x1(x) + bias1 (the block's residual projection,
+ * score_network.py:131,151), both from ONE pass over x = [in0 | in1].  w3: bf16 [9][C_out][C],
+ * w1: bf16 [1][C_out][C].  DBS_ERR_UNSUPPORTED when the shape is not eligible for the strip kernel. */
+int dbs_conv_block_tc(const void* in0, int C0, const void* in1, int C1, const void* w3,
+                      const float* bias3, const void* w1, const float* bias1, void* out3, void* out1,
+                      float* stats, int64_t B, int H, int W, int C_out, void* stream);
+
 /* Philox stream tags (ctr.w) and the x0 step tag. */
 #define DBS_STREAM_SWEEP 0x53574550u /* 'SWEP' */
 #define DBS_STREAM_INIT  0x494e4954u /* 'INIT' */

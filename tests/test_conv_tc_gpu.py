@@ -102,3 +102,36 @@ def test_conv_tc_rejects_ineligible_shapes():
     rc = abi.lib.dbs_conv_tc(x.data_ptr(), 32, 0, 0, w.data_ptr(), b.data_ptr(), o.data_ptr(), 0, 1, 12, 12, 32, 0, 3,
                              runtime.current_stream())
     assert rc == abi.ERR_UNSUPPORTED and "not eligible" in abi.last_error()
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout", [(3, 32, 32, 32, 0, 64), (2, 64, 64, 32, 0, 64), (2, 32, 32, 64, 64, 32),
+                                              (2, 16, 16, 128, 128, 64), (3, 16, 16, 64, 0, 128), (2, 16, 32, 64, 0, 32)])
+def test_fused_conv3x3_plus_residual_1x1(B, H, W, C0, C1, Cout):
+    """One strip-kernel pass = ConvBlock.conv1 (+GN sums) and ConvBlock.residual on the same input."""
+    from dbs_b200 import abi, runtime
+    torch.manual_seed(1)
+    Cin = C0 + C1
+    x0 = _bf(torch.randn(B, H, W, C0))
+    x1 = _bf(torch.randn(B, H, W, C1)) if C1 else None
+    w3 = _bf(torch.randn(9, Cout, Cin) / (9 * Cin) ** 0.5)
+    w1 = _bf(torch.randn(1, Cout, Cin) / Cin ** 0.5)
+    b3, b1 = torch.randn(Cout), torch.randn(Cout)
+    xin = torch.cat([x0] + ([x1] if C1 else []), dim=-1).float().permute(0, 3, 1, 2)
+    ref3 = F.conv2d(xin, w3.float().reshape(3, 3, Cout, Cin).permute(2, 3, 0, 1).contiguous(), b3, padding=1)
+    ref1 = F.conv2d(xin, w1.float().reshape(1, 1, Cout, Cin).permute(2, 3, 0, 1).contiguous(), b1)
+    o3 = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+    o1 = torch.zeros_like(o3)
+    st = torch.zeros(B, 8, 2, device="cuda")
+    d0, d1 = x0.cuda(), (x1.cuda() if C1 else None)
+    dw3, dw1, db3, db1 = w3.cuda(), w1.cuda(), b3.cuda(), b1.cuda()
+    abi.check(abi.lib.dbs_conv_block_tc(d0.data_ptr(), C0, runtime.ptr(d1), C1, dw3.data_ptr(), db3.data_ptr(),
+                                        dw1.data_ptr(), db1.data_ptr(), o3.data_ptr(), o1.data_ptr(), st.data_ptr(), B, H, W,
+                                        Cout, runtime.current_stream()), "conv_block_tc")
+    torch.cuda.synchronize()
+    for got, ref in ((o3, ref3), (o1, ref1)):
+        g_ = got.float().cpu().permute(0, 3, 1, 2).numpy()
+        tol = 2e-3 + np.abs(ref.numpy()) * 2.0 ** -8
+        assert (np.abs(g_ - ref.numpy()) <= tol).all(), float(np.abs(g_ - ref.numpy()).max())
+    r = ref3.reshape(B, 8, -1)
+    want = torch.stack([r.sum(-1), (r * r).sum(-1)], dim=-1)
+    np.testing.assert_allclose(st.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-2)
