@@ -59,6 +59,11 @@ PROTOTYPES = {
     "dbs_em_step": (i32, [vp, vp, vp, i64, i64, f32, f32, f32, f32, i32, u64, i64, i64, vp]),
     "dbs_gaussian_fill": (i32, [vp, i64, i64, u64, i64, i64, vp]),
     "dbs_lj_energy_forces": (i32, [vp, i64, i32, f32, f32, f32, f32, f32, vp, vp, vp]),
+    "dbs_mala_propose": (i32, [vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, u64, i64, i64, vp]),
+    "dbs_mala_accept": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, f32, u64, i64, i64, vp, vp]),
+    "dbs_baoab_first": (i32, [vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, f32, u64, i64, i64, vp]),
+    "dbs_baoab_second": (i32, [vp, vp, i64, i32, f32, f32, vp]),
+    "dbs_rdf_histogram": (i32, [vp, i64, i32, f32, vp, i32, vp, vp]),
     "dbs_unet_plan_create": (i32, [C.POINTER(UnetConfig), C.POINTER(Param), i32, vp, C.POINTER(vp)]),
     "dbs_unet_plan_destroy": (None, [vp]),
     "dbs_unet_workspace_bytes": (i64, [vp, i64, i32, i32, i32]),

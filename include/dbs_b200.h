@@ -162,6 +162,40 @@ int dbs_lj_energy_forces(const float* pos, int64_t B, int N, float box, float ep
                          float* forces, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Batched Langevin samplers on the pair kernel and the RDF histogram (f-2).
+ * pos/vel/force: fp32 [B][N][2]; energy fp32 [B].  The state carries its cached force and energy,
+ * so one MALA step = propose, ONE dbs_lj_energy_forces on the proposal, accept.
+ * noise / uniforms != NULL are the test-mode injection ports; otherwise Philox streams keyed by
+ * (seed, cfg_offset + b, step).
+ * ------------------------------------------------------------------------- */
+
+/* x' = ((x + (dt*F)/T) + z*noise_scale) mod box.  Replaces samplers/langevin.py:56-63. */
+int dbs_mala_propose(const float* pos, const float* force, const float* noise, float* pos_new,
+                     int64_t B, int N, float dt, float temperature, float noise_scale, float box,
+                     uint64_t seed, int64_t cfg_offset, int64_t step, void* stream);
+
+/* Metropolis-Hastings test of the proposal, samplers/langevin.py:65-87: accept iff
+ * log(u) < -beta (E'-E) + log q(x|x') - log q(x'|x); accepted configurations take the proposal's
+ * positions, force and energy in place.  accepted: int32 [B] or NULL. */
+int dbs_mala_accept(float* pos, float* force, float* energy, const float* pos_new,
+                    const float* force_new, const float* energy_new, const float* uniforms,
+                    int64_t B, int N, float dt, float temperature, uint64_t seed, int64_t cfg_offset,
+                    int64_t step, int* accepted, void* stream);
+
+/* BAOAB (samplers/langevin.py:192-225): first = B A O A + periodic wrap (uses the cached force of
+ * the old positions), then the caller evaluates forces at the new positions, then second = B. */
+int dbs_baoab_first(float* pos, float* vel, const float* force, const float* noise, int64_t B, int N,
+                    float dt, float mass, float c1, float c2, float box, uint64_t seed,
+                    int64_t cfg_offset, int64_t step, void* stream);
+int dbs_baoab_second(float* vel, const float* force, int64_t B, int N, float dt, float mass,
+                     void* stream);
+
+/* Pair-distance histogram behind compute_rdf (analysis/rdf.py:49-68): i<j pairs, minimum image,
+ * np.histogram's bin rule on float64 edges [n_bins+1]; hist uint64 [n_bins] accumulated atomically. */
+int dbs_rdf_histogram(const float* pos, int64_t B, int N, float box, const double* edges, int n_bins,
+                      unsigned long long* hist, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Score U-Net (models/score_network.py:154-268).
  * A plan owns device copies of the weights repacked for the kernels
  * ([tap][C_out][C_in], fp32 and bf16) and the layer schedule.

@@ -258,6 +258,59 @@ def main():
     g["lj_minimg_out"] = ljp.minimum_image(torch.tensor(g["lj_minimg_in"])).numpy()
     np.savez_compressed(os.path.join(OUT, "lennard_jones.npz"), **g)
 
+    # ---- Langevin samplers (reference step() with recorded draws) and RDF -----------------------
+    from backend.ml.samplers.langevin import LangevinDynamics, UnderdampedLangevin
+    from backend.ml.analysis.rdf import compute_rdf
+    g = {}
+    lj = LennardJonesSystem(16, 5.0)
+    real_randn_like = torch.randn_like
+    rec = []
+
+    def rec_like(*a, **k):
+        v = real_randn_like(*a, **k)
+        rec.append(v.clone())
+        return v
+
+    torch.manual_seed(21)
+    np.random.seed(21)
+    pos = lj.lattice_configuration(1).squeeze(0) + 0.05 * torch.randn(16, 2)
+    smp = LangevinDynamics(lj, temperature=1.0, dt=0.002)
+    traj, us = [pos.numpy().copy()], []
+    torch.randn_like = rec_like
+    try:
+        st = np.random.get_state()
+        for _ in range(6):
+            # the reference draws its uniform only inside step(); replay the same stream to record it
+            pos = smp.step(pos)
+            traj.append(pos.numpy().copy())
+        np.random.set_state(st)
+        us = [np.random.random() for _ in range(6)]
+    finally:
+        torch.randn_like = real_randn_like
+    g["mala_traj"], g["mala_noise"], g["mala_u"] = np.stack(traj), torch.stack(rec).numpy(), np.array(us)
+    g["mala_params"] = np.array([16, 5.0, 1.0, 0.002])
+    rec.clear()
+    ud = UnderdampedLangevin(lj, temperature=1.2, dt=0.003, mass=1.5, friction=0.8)
+    p0 = lj.lattice_configuration(1).squeeze(0) + 0.05 * torch.randn(16, 2)
+    v0 = 0.3 * torch.randn(16, 2)
+    ptraj, vtraj = [p0.numpy().copy()], [v0.numpy().copy()]
+    torch.randn_like = rec_like
+    try:
+        pp, vv = p0, v0
+        for _ in range(5):
+            pp, vv = ud.step(pp, vv)
+            ptraj.append(pp.numpy().copy()); vtraj.append(vv.numpy().copy())
+    finally:
+        torch.randn_like = real_randn_like
+    g["baoab_pos"], g["baoab_vel"], g["baoab_noise"] = np.stack(ptraj), np.stack(vtraj), torch.stack(rec).numpy()
+    g["baoab_params"] = np.array([16, 5.0, 1.2, 0.003, 1.5, 0.8])
+    cfgs = (lj.lattice_configuration(4) + 0.2 * torch.randn(4, 16, 2)) % 5.0
+    r, gr = compute_rdf(cfgs, 5.0, n_bins=40)
+    g["rdf_pos"], g["rdf_r"], g["rdf_g"] = cfgs.numpy(), r, gr
+    r2, gr2 = compute_rdf(cfgs[0], 5.0, n_bins=25, r_max=2.0)
+    g["rdf2_r"], g["rdf2_g"] = r2, gr2
+    np.savez_compressed(os.path.join(OUT, "langevin_rdf.npz"), **g)
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
