@@ -249,7 +249,12 @@ def bench_ours(args, world, rank, local):
         "achieved": round(achieved, 2), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": round(achieved / peaks["bf16_sustained"], 4), "frac_of_burst": round(achieved / peaks["bf16_burst"], 4),
         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-        "traffic": None,
+        # dram__bytes_read+write summed over the conv launches of one forward (ncu --set full,
+        # profiles/r1_conv_ncu_final.csv: 1.30 GB read + 0.51 GB written at B=1024, 32x32) x EM steps,
+        # scaled by the batch; per step like `achieved`
+        "traffic": round(1.81e9 * (B / 1024.0) * (L * L / 1024.0) * NS, 0),
+        "traffic_note": "ncu capture of the same build (profiles/r1_conv_ncu_final.csv); activations of the next "
+                        "layer partly stay in the 126 MB L2, so DRAM traffic is below the sum of layer in+out bytes",
         "algorithmic_flops_per_step": flops_step, "flops_per_sample_step": unet_flops_per_sample(L),
         "conv_launches_per_step": conv_n, "conv_ms_per_step": round(conv_ms, 3),
         "conv_share_of_kernel_time": round(conv_ms / tot_ms, 4) if tot_ms else None,
@@ -333,6 +338,14 @@ def bench_ising(peaks):
     out["roofline_streaming"] = {"bound": "hbm", "achieved": round(ach, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": round(ach / peaks["hbm_gbs"], 5), "bytes_per_attempt": 0.25,
                                  "note": "512 B lattices: launch/ALU bound by design, see DESIGN.md"}
+    # resident mode is INT-pipe bound: 23.5 thread-instructions per attempt (ncu smsp__inst_executed,
+    # profiles/README.md) against the issue peak of 148 SMs x 128 lanes x SM clock
+    ipa, sm_hz = 23.5, 1.965e9
+    ach = out["resident"]["flips_per_s"] * ipa
+    out["roofline_int"] = {"bound": "int-issue", "achieved": float(f"{ach:.4e}"), "peak": float(f"{148 * 128 * sm_hz:.4e}"),
+                           "unit": "thread-instr/s", "frac": round(ach / (148 * 128 * sm_hz), 4),
+                           "instr_per_attempt": ipa, "alu_pipe_busy_pct_ncu": 71.0,
+                           "note": "HBM traffic ~0 by design (4 MB of state read once, written once per launch)"}
     out["metric"] = "ising_spin_flips_per_s"
     out["value"] = out["resident"]["flips_per_s"]
     out["config"] = {"workload": "C3 per-GPU shape: 2D Ising 64x64 checkerboard Metropolis, 8192 chains, 64 temperatures in [1.5,3.5]"}
