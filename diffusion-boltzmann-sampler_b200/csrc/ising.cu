@@ -15,6 +15,10 @@
 #include "common.cuh"
 #include "philox.cuh"
 
+#ifndef DBS_ISING_MIN_BLOCKS
+#define DBS_ISING_MIN_BLOCKS 6
+#endif
+
 namespace dbs {
 namespace {
 
@@ -44,7 +48,9 @@ __device__ __forceinline__ int valid_bits(int L, int w) {
 __device__ __forceinline__ uint32_t low_mask(int vb) { return vb >= 32 ? 0xffffffffu : ((1u << vb) - 1u); }
 
 template <int LT, bool kInject>
-__global__ void __launch_bounds__(512) ising_sweep_kernel(SweepArgs a) {
+// lattices up to 64x64 run 128- or 256-thread CTAs: cap registers at 40 so 48 warps fit on an SM
+__global__ void __launch_bounds__((LT == 0 || LT > 64) ? 512 : 256, (LT == 0 || LT > 64) ? 1 : DBS_ISING_MIN_BLOCKS)
+ising_sweep_kernel(SweepArgs a) {
   const int L = LT ? LT : a.L;
   const int W = (L + 31) >> 5;
   const int tpc = L * W;
