@@ -36,6 +36,11 @@ class DiffusionSampler:
         self.device = device
         self.precision = precision  # None -> the network's default (env DBS_PRECISION or fp32)
         self._training_temperature: Optional[float] = None
+        # One U-Net forward is ~70 kernel launches; for API-sized batches the step is launch-bound, so
+        # the forward is captured once per shape into a CUDA graph and replayed every step
+        # (True / False / "auto": graphs for B*H*W <= 2^18 elements).
+        self.use_graph = "auto"
+        self._graphs: Dict[Any, Any] = {}
 
     # ------------------------------------------------------------------ temperature scaling
     @property
@@ -103,6 +108,10 @@ class DiffusionSampler:
     def _out(self, x: torch.Tensor) -> torch.Tensor:
         return x if str(self.device).startswith("cuda") else x.cpu()
 
+    def _result(self, x: torch.Tensor) -> torch.Tensor:
+        """Detach a result from the sampler's persistent state buffer."""
+        return x.clone() if str(self.device).startswith("cuda") else x.cpu()
+
     @staticmethod
     def _fresh_seed() -> int:
         # drawn from torch's global generator: torch.manual_seed() makes sampling reproducible,
@@ -136,16 +145,60 @@ class DiffusionSampler:
                                       1 if add_noise else 0, seed, sample_offset, step, runtime.current_stream()),
                   "em_step")
 
+    def _graph_step(self, shape):
+        """Persistent (x, score, t) buffers and, when enabled, a captured graph of one forward for
+        this shape.  Returns (x, score, t_dev, graph_or_None)."""
+        dev = runtime.require_cuda()
+        want = self.use_graph
+        if want == "auto":
+            want = int(np.prod(shape)) <= (1 << 18)
+        plan_version = None
+        if hasattr(self.model, "engine_plan"):
+            self.model.engine_plan()
+            plan_version = id(self.model._plan)
+        key = (tuple(shape), self.precision, bool(want), plan_version, torch.cuda.current_device())
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs = {k: v for k, v in self._graphs.items() if k[3] == plan_version}  # drop stale plans
+            x = torch.empty(shape, dtype=torch.float32, device=dev)
+            score = torch.empty_like(x)
+            t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+            graph = None
+            if want and hasattr(self.model, "engine_forward"):
+                x.zero_()
+                for _ in range(2):          # warm-up: workspace allocation, one-time function attributes
+                    self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
+            ent = (x, score, t_dev, graph)
+            self._graphs[key] = ent
+        return ent
+
     def _reverse_sde(self, shape, temperature, seed, x0=None, noises=None, sample_offset=0):
         """Generator over the Euler–Maruyama trajectory: first (num_steps + 1, x_1) — the Gaussian
-        start — then (i, x) after step i = num_steps .. 1.  x is updated in place."""
+        start — then (i, x) after step i = num_steps .. 1.  x is a persistent buffer updated in place
+        (callers copy what they keep)."""
         runtime.require_cuda()
-        x = runtime.to_device(x0).clone() if x0 is not None else self._gaussian(shape, seed, abi.STEP_X0, sample_offset)
-        score = torch.empty_like(x)
+        shape = tuple(shape)
+        x, score, t_dev, graph = self._graph_step(shape)
+        if x0 is not None:
+            x.copy_(runtime.to_device(x0).reshape(shape))
+        else:
+            n = shape[0]
+            abi.check(abi.lib.dbs_gaussian_fill(x.data_ptr(), n, x.numel() // max(n, 1), seed, sample_offset, abi.STEP_X0,
+                                                runtime.current_stream()), "gaussian_fill")
         sig = self.diffusion.sigma_table(self.num_steps)
+        t_table = torch.tensor([i / self.num_steps for i in range(self.num_steps, 0, -1)], dtype=torch.float32,
+                               device=x.device)
         yield self.num_steps + 1, x
         for k, i in enumerate(range(self.num_steps, 0, -1)):
-            self._score(x, i / self.num_steps, out=score)
+            if graph is not None:
+                t_dev.copy_(t_table[k:k + 1])
+                graph.replay()
+            else:
+                self._score(x, i / self.num_steps, out=score)
             nz = None
             if noises is not None and i > 1:
                 nz = runtime.to_device(noises[k])
@@ -161,7 +214,7 @@ class DiffusionSampler:
         x = None
         for _, x in self._reverse_sde(tuple(shape), temperature, seed, x0, noises, sample_offset):
             pass
-        return self._out(x)
+        return self._result(x)
 
     @torch.no_grad()
     def sample_with_trajectory(self, shape: Tuple[int, ...], temperature: float = 1.0, yield_every: int = 1,
@@ -171,9 +224,9 @@ class DiffusionSampler:
         seed = self._fresh_seed() if seed is None else seed
         for i, x in self._reverse_sde(tuple(shape), temperature, seed):
             if i > self.num_steps:
-                yield self._out(x.clone()), 1.0
+                yield self._result(x), 1.0
             elif i % yield_every == 0 or i == 1:
-                yield self._out(x.clone()), (i - 1) / self.num_steps
+                yield self._result(x), (i - 1) / self.num_steps
 
     @torch.no_grad()
     def sample_trajectory_with_metadata(self, shape: Tuple[int, ...], temperature: float = 1.0, n_frames: int = 50,
@@ -196,7 +249,7 @@ class DiffusionSampler:
 
         def frame(x, step):
             t = step / N
-            d = {"x": self._out(x.clone()), "t": t, "step": step, "progress": 1.0 - t, "sigma": self._sigma(t)}
+            d = {"x": self._result(x), "t": t, "step": step, "progress": 1.0 - t, "sigma": self._sigma(t)}
             if include_statistics and ising_model:
                 d["statistics"] = self.compute_sample_statistics(d["x"], ising_model)
             return d
@@ -224,7 +277,7 @@ class DiffusionSampler:
                     step_size = (corrector_snr * noise_norm / grad_norm) ** 2 * 2
                     z = self._gaussian(shape, seed, N + 1 + (N - i) * n_corrector_steps + c)
                     x.add_(step_size * score + (2 * step_size) ** 0.5 * z * temperature)
-        return self._out(x)
+        return self._result(x)
 
     @torch.no_grad()
     def sample_ode(self, shape: Tuple[int, ...], method: str = "euler", seed: Optional[int] = None) -> torch.Tensor:
