@@ -11,12 +11,15 @@ from .distributed import allreduce_block, finalize_observables, striped_temperat
 
 
 def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_temperature=1024, burn_in=1000,
-                          n_measure=1000, measure_every=10, seed=1234, J=1.0, h=0.0, with_correlation=True):
+                          n_measure=1000, measure_every=10, seed=1234, J=1.0, h=0.0, with_correlation=True,
+                          rank=None, world_size=None, reduce=True):
     """Returns a dict of per-temperature observables (identical on every rank)."""
     from backend.ml.samplers.mcmc import MetropolisHastings
     from backend.ml.systems.ising import IsingModel
 
-    rank, ws = world()
+    rank_, ws_ = world()
+    rank = rank_ if rank is None else rank
+    ws = ws_ if world_size is None else world_size
     temps = np.linspace(1.5, 3.5, 64) if temperatures is None else np.asarray(temperatures, dtype=np.float64)
     ids, t_chain, t_idx = striped_temperatures(temps, chains_per_temperature, rank, ws)
     # chains of one rank are not a contiguous global range: give each its global id through a
@@ -68,10 +71,13 @@ def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_tempera
             abi.check(abi.lib.dbs_ising_correlation(bits.data_ptr(), L, n, 0, group.data_ptr(), corr.data_ptr(),
                                                     runtime.current_stream()))
         n_meas += 1
-    allreduce_block(acc)
     corr_f = corr.to(torch.float64)
-    allreduce_block(corr_f)
+    if reduce:
+        allreduce_block(acc)
+        allreduce_block(corr_f)
     out = finalize_observables(acc)
+    out["acc"] = acc
+    out["corr_sums"] = corr_f
     out["temperatures"] = temps
     out["sweeps"] = done
     out["flip_attempts_this_rank"] = float(n) * L * L * done
