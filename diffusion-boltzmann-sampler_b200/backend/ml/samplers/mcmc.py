@@ -40,6 +40,8 @@ class MetropolisHastings:
         # from it so np.random.seed() keeps runs reproducible
         self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
         self._sweeps_done = 0
+        # h == 0: the kernel's multi-spin path (agreement counts for 32 sites at once, two thresholds)
+        self.zero_field = 0 if (model.h != 0 or model.J == 0) else (1 if model.J > 0 else -1)
 
     # ---------------------------------------------------------------- device-side state
     def _tables(self):
@@ -62,7 +64,8 @@ class MetropolisHastings:
         off = self._sweeps_done if sweep_offset is None else sweep_offset
         abi.check(abi.lib.dbs_ising_sweeps(bits.data_ptr(), self.model.size, n, int(n_sweeps), tables.data_ptr(),
                                            tables.shape[0], runtime.ptr(index), self.seed, chain_offset, off,
-                                           runtime.ptr(uniforms), runtime.current_stream()), "ising_sweeps")
+                                           runtime.ptr(uniforms), self.zero_field, runtime.current_stream()),
+                  "ising_sweeps")
         if sweep_offset is None:
             self._sweeps_done += int(n_sweeps)
         return bits

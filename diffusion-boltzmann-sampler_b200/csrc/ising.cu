@@ -15,10 +15,6 @@
 #include "common.cuh"
 #include "philox.cuh"
 
-#ifndef DBS_ISING_MIN_BLOCKS
-#define DBS_ISING_MIN_BLOCKS 6
-#endif
-
 namespace dbs {
 namespace {
 
@@ -38,6 +34,8 @@ struct SweepArgs {
   int L;
   int n_sweeps;
   int cpb;                      // chains per block
+  uint32_t one;                 // = 1, a run-time multiplier that keeps the compares on IMAD.WIDE (FMA pipe)
+  int antiferro;                // zero-field mode: count disagreeing neighbours (J < 0)
 };
 
 // valid-bit mask of word w in a row of L bits
@@ -47,9 +45,27 @@ __device__ __forceinline__ int valid_bits(int L, int w) {
 }
 __device__ __forceinline__ uint32_t low_mask(int vb) { return vb >= 32 ? 0xffffffffu : ((1u << vb) - 1u); }
 
-template <int LT, bool kInject>
-// lattices up to 64x64 run 128- or 256-thread CTAs: cap registers at 40 so 48 warps fit on an SM
-__global__ void __launch_bounds__((LT == 0 || LT > 64) ? 512 : 256, (LT == 0 || LT > 64) ? 1 : DBS_ISING_MIN_BLOCKS)
+// accept mask of one draw: all ones iff r < thr, computed as the high word of r + (2^64 - thr) with ONE
+// IMAD.WIDE.U32 on the FMA pipe (the ALU pipe is the binding one here: ncu, profiles/README.md).
+// c = 0xFFFFFFFF00000000 encodes "always" (dE <= 0), c = 0 "never" (thr = 0).
+__device__ __forceinline__ uint32_t accept_mask(uint32_t r, uint32_t one, uint64_t c) {
+  uint64_t t;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"(r), "r"(one), "l"(c));
+  return (uint32_t)(t >> 32);
+}
+__device__ __forceinline__ uint64_t threshold_constant(uint32_t lo, uint32_t hi) {
+  return hi ? 0xFFFFFFFF00000000ull : (0ull - (uint64_t)lo);
+}
+
+// kMode 0: any (J, h): per-site class k = 8*s + #up-neighbours, 16-entry table lookup.
+// kMode 1: h == 0: the class depends only on the number of AGREEING neighbours (disagreeing for J < 0),
+//          counted for all 32 sites of a word at once with a bit-sliced adder; only the two uphill
+//          classes (3 and 4 agreeing: dE = 4|J|, 8|J|) need a draw comparison, done against two per-chain
+//          constants: no table lookup, no per-site class extraction.
+template <int LT, bool kInject, int kMode>
+// 16/32/64-wide lattices run 128-thread CTAs: cap registers at 40 so 12 CTAs (48 warps) fit on an SM
+// (A/B/C-tested on a B200: 930 vs 907 Gflips/s uncapped; a 256-thread cap was slower, 816)
+__global__ void __launch_bounds__((LT == 16 || LT == 32 || LT == 64) ? 128 : 512, (LT == 16 || LT == 32 || LT == 64) ? 12 : 1)
 ising_sweep_kernel(SweepArgs a) {
   const int L = LT ? LT : a.L;
   const int W = (L + 31) >> 5;
@@ -58,7 +74,7 @@ ising_sweep_kernel(SweepArgs a) {
   extern __shared__ uint32_t smem[];
   uint32_t* buf0 = smem;
   uint32_t* buf1 = smem + cpb * tpc;
-  uint2* tbl = reinterpret_cast<uint2*>(smem + 2 * cpb * tpc + ((2 * cpb * tpc) & 1));
+  uint64_t* tbl = reinterpret_cast<uint64_t*>(smem + 2 * cpb * tpc + ((2 * cpb * tpc) & 1));
 
   const int tid = threadIdx.x;
   const int lc = tid / tpc;
@@ -71,11 +87,10 @@ ising_sweep_kernel(SweepArgs a) {
   if (tid < cpb * 16) {
     const int lc2 = tid >> 4, k = tid & 15;
     const int64_t c2 = (int64_t)blockIdx.x * cpb + lc2;
-    uint2 e = make_uint2(0u, 0u);
+    uint64_t e = 0;
     if (c2 < a.n_chains) {
       const int ti = a.table_index ? a.table_index[c2] : 0;
-      e.x = a.thr[(ti * 16 + k) * 2 + 0];
-      e.y = a.thr[(ti * 16 + k) * 2 + 1];
+      e = threshold_constant(a.thr[(ti * 16 + k) * 2 + 0], a.thr[(ti * 16 + k) * 2 + 1]);
     }
     tbl[tid] = e;
   }
@@ -96,7 +111,19 @@ ising_sweep_kernel(SweepArgs a) {
   const int wr = (w == W - 1 ? 0 : w + 1);
   const int top_prev = valid_bits(L, wl) - 1;  // bit index of the last column of the left word
   const int gpr = (L + 7) >> 3;                // Philox calls per row and colour
-  const uint2* mytbl = tbl + lc * 16;
+  const uint64_t* mytbl = tbl + lc * 16;
+  // zero-field constants: classes (s=1, 3 or 4 up-neighbours) for J > 0, (s=1, 1 or 0) for J < 0 — same
+  // dE as their s=0 mirror images
+  uint64_t c4 = 0, c8 = 0;
+  if (kMode == 1 && lc < cpb) {
+    c4 = mytbl[a.antiferro ? 8 + 1 : 8 + 3];
+    c8 = mytbl[a.antiferro ? 8 + 0 : 8 + 4];
+  }
+  const uint32_t one = a.one;
+  // the same two thresholds as plain 32-bit compare operands (c = 2^64 - thr, or the always / never codes)
+  const bool alw4 = (c4 >> 32) == 0xFFFFFFFFull && (uint32_t)c4 == 0u, alw8 = (c8 >> 32) == 0xFFFFFFFFull && (uint32_t)c8 == 0u;
+  const uint32_t t4 = alw4 ? 0u : (uint32_t)(0ull - c4), t8 = alw8 ? 0u : (uint32_t)(0ull - c8);
+  (void)t4; (void)t8; (void)one;
   const uint32_t chain_ctr = (uint32_t)(a.chain_offset + chain);
 
   uint32_t hs = 0;  // half-sweep counter inside this launch
@@ -114,14 +141,23 @@ ising_sweep_kernel(SweepArgs a) {
         const uint32_t rt = ((self >> 1) | ((rw & 1u) << (vb - 1))) & vmask;
         const int par = (i + colour) & 1;  // column parity of the active sites of this row
 
-        // class nibbles k = 8*s + (#up neighbours), active sites moved to even bit positions
-        const uint32_t m1 = 0x11111111u;
-        const uint32_t s_ = self >> par, u_ = up >> par, d_ = dn >> par, l_ = lf >> par, r_ = rt >> par;
-        const uint32_t KA = (u_ & m1) + (d_ & m1) + (l_ & m1) + (r_ & m1) + ((s_ & m1) << 3);
-        const uint32_t KB = ((u_ >> 2) & m1) + ((d_ >> 2) & m1) + ((l_ >> 2) & m1) + ((r_ >> 2) & m1) +
-                            (((s_ >> 2) & m1) << 3);
+        uint32_t KA = 0, KB = 0, is3 = 0, is4 = 0;
+        if (kMode == 0) {
+          // class nibbles k = 8*s + (#up neighbours), active sites moved to even bit positions
+          const uint32_t m1 = 0x11111111u;
+          const uint32_t s_ = self >> par, u_ = up >> par, d_ = dn >> par, l_ = lf >> par, r_ = rt >> par;
+          KA = (u_ & m1) + (d_ & m1) + (l_ & m1) + (r_ & m1) + ((s_ & m1) << 3);
+          KB = ((u_ >> 2) & m1) + ((d_ >> 2) & m1) + ((l_ >> 2) & m1) + ((r_ >> 2) & m1) + (((s_ >> 2) & m1) << 3);
+        } else {
+          // bit-sliced count of agreeing (J > 0) / disagreeing (J < 0) neighbours for all 32 sites
+          const uint32_t fx = a.antiferro ? 0u : 0xffffffffu;
+          const uint32_t xu = (self ^ up) ^ fx, xd = (self ^ dn) ^ fx, xl = (self ^ lf) ^ fx, xr = (self ^ rt) ^ fx;
+          const uint32_t s1 = xu ^ xd, c1 = xu & xd, s2 = xl ^ xr, c2 = xl & xr;
+          is4 = c1 & c2;                               // all four
+          is3 = (s1 ^ s2) & (c1 ^ c2 ^ (s1 & s2));     // count = 0b011
+        }
 
-        uint32_t flips = 0;  // bit 2m = flip of active site m
+        uint32_t flips = 0, b4 = 0, b8 = 0;  // bit 2m = active site m (shifted domain)
         const uint32_t ctr_y = 2u * (uint32_t)(a.sweep_offset + s) + (uint32_t)colour;
 #pragma unroll
         for (int call = 0; call < 4; ++call) {
@@ -145,12 +181,27 @@ ising_sweep_kernel(SweepArgs a) {
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
               const int m = 4 * call + d;
-              const uint32_t K = (m & 1) ? KB : KA;
-              const uint32_t k = (K >> (4 * (m >> 1))) & 15u;
-              const uint2 e = mytbl[k];
-              if ((rr[d] < e.x) || e.y) flips |= (1u << (2 * m));
+              if (kMode == 0) {
+                const uint32_t K = (m & 1) ? KB : KA;
+                const uint32_t k = (K >> (4 * (m >> 1))) & 15u;
+                flips |= accept_mask(rr[d], one, mytbl[k]) & (1u << (2 * m));
+              } else {
+                // plain compares here: with Philox already filling the FMA pipe with IMAD.WIDE, two more per
+                // site measured slower (946 vs 1054 Gflips/s at 64x64) than ISETP + predicated LOP on the ALU pipe
+                if (rr[d] < t4) b4 |= (1u << (2 * m));
+                if (rr[d] < t8) b8 |= (1u << (2 * m));
+              }
             }
           }
+        }
+        if (kMode == 1) {   // thresholds that round to "always" (p == 1.0 in float64)
+          if (alw4) b4 = 0xffffffffu;
+          if (alw8) b8 = 0xffffffffu;
+        }
+        if (kMode == 1) {
+          // downhill / flat moves (count <= 2) always flip; counts 3 and 4 flip where the draw allowed it
+          const uint32_t up3 = is3 >> par, up4 = is4 >> par;
+          flips = ~(up3 | up4) | (up3 & b4) | (up4 & b8);
         }
         const uint32_t amask = (par ? 0xAAAAAAAAu : 0x55555555u) & vmask;
         self ^= (flips << par) & amask;
@@ -162,30 +213,30 @@ ising_sweep_kernel(SweepArgs a) {
   if (live) a.bits[chain * tpc + r] = self;
 }
 
-template <int LT, bool kInject>
+template <int LT, bool kInject, int kMode>
 int launch_sweep_t(const SweepArgs& a, cudaStream_t st) {
   const int L = a.L, W = (L + 31) / 32, tpc = L * W;
   const int cpb = a.cpb;
   int threads = cpb * tpc;
   threads = (threads + 31) / 32 * 32;
   if (threads < cpb * 16) threads = cpb * 16;
-  const size_t smem = (size_t)(2 * cpb * tpc + 2) * 4 + (size_t)cpb * 16 * 8;
+  const size_t smem = (size_t)(2 * cpb * tpc + 2) * 4 + (size_t)cpb * 16 * 8;  // lattices x2 + 16 x uint64 per chain
   const int64_t blocks = (a.n_chains + cpb - 1) / cpb;
   ProfScope prof(kProfIsingSweep, st);
-  ising_sweep_kernel<LT, kInject><<<(unsigned)blocks, threads, smem, st>>>(a);
+  ising_sweep_kernel<LT, kInject, kMode><<<(unsigned)blocks, threads, smem, st>>>(a);
   DBS_LAUNCHED();
   return DBS_OK;
 }
 
-template <bool kInject>
+template <bool kInject, int kMode>
 int launch_sweep(const SweepArgs& a, cudaStream_t st) {
   switch (a.L) {
-    case 8: return launch_sweep_t<8, kInject>(a, st);
-    case 16: return launch_sweep_t<16, kInject>(a, st);
-    case 32: return launch_sweep_t<32, kInject>(a, st);
-    case 64: return launch_sweep_t<64, kInject>(a, st);
-    case 128: return launch_sweep_t<128, kInject>(a, st);
-    default: return launch_sweep_t<0, kInject>(a, st);
+    case 8: return launch_sweep_t<8, kInject, kMode>(a, st);
+    case 16: return launch_sweep_t<16, kInject, kMode>(a, st);
+    case 32: return launch_sweep_t<32, kInject, kMode>(a, st);
+    case 64: return launch_sweep_t<64, kInject, kMode>(a, st);
+    case 128: return launch_sweep_t<128, kInject, kMode>(a, st);
+    default: return launch_sweep_t<0, kInject, kMode>(a, st);
   }
 }
 
@@ -454,19 +505,23 @@ extern "C" int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64
 
 extern "C" int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_sweeps, const uint32_t* thr,
                                 int n_tables, const int32_t* table_index, uint64_t seed, int64_t chain_offset,
-                                int64_t sweep_offset, const uint32_t* uniforms, void* stream) {
+                                int64_t sweep_offset, const uint32_t* uniforms, int zero_field, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
   DBS_REQUIRE(bits && thr && n_tables >= 1, "ising_sweeps: null state or threshold table");
   DBS_REQUIRE(n_chains >= 0 && n_sweeps >= 0, "ising_sweeps: negative chain or sweep count");
+  DBS_REQUIRE(zero_field >= -1 && zero_field <= 1, "ising_sweeps: zero_field must be -1, 0 or +1");
   if (n_chains == 0 || n_sweeps == 0) return DBS_OK;
   SweepArgs a;
   a.bits = bits; a.thr = thr; a.table_index = table_index; a.uniforms = uniforms;
   a.n_chains = n_chains; a.chain_offset = chain_offset; a.sweep_offset = sweep_offset;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.L = L; a.n_sweeps = n_sweeps;
+  a.one = 1u; a.antiferro = zero_field < 0 ? 1 : 0;
   const int tpc = dbs_ising_words_per_chain(L);
   a.cpb = tpc >= 128 ? 1 : 128 / tpc;
-  return uniforms ? launch_sweep<true>(a, as_stream(stream)) : launch_sweep<false>(a, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  if (zero_field != 0) return uniforms ? launch_sweep<true, 1>(a, st) : launch_sweep<false, 1>(a, st);
+  return uniforms ? launch_sweep<true, 0>(a, st) : launch_sweep<false, 0>(a, st);
 }
 
 extern "C" int dbs_ising_observables(const uint32_t* bits, int L, int64_t n_chains, float J, float h,

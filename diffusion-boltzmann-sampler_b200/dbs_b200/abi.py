@@ -50,7 +50,7 @@ PROTOTYPES = {
     "dbs_ising_init_packed": (i32, [vp, i32, i64, u64, i64, vp]),
     "dbs_ising_pack": (i32, [vp, vp, i32, i64, vp]),
     "dbs_ising_unpack": (i32, [vp, vp, i32, i64, vp]),
-    "dbs_ising_sweeps": (i32, [vp, i32, i64, i32, vp, i32, vp, u64, i64, i64, vp, vp]),
+    "dbs_ising_sweeps": (i32, [vp, i32, i64, i32, vp, i32, vp, u64, i64, i64, vp, i32, vp]),
     "dbs_ising_site_update": (i32, [vp, i32, i64, i32, i32, vp, C.c_uint32, vp]),
     "dbs_ising_observables": (i32, [vp, i32, i64, f32, f32, vp, vp, vp]),
     "dbs_ising_observables_f32": (i32, [vp, i32, i64, f32, f32, vp, vp, vp]),

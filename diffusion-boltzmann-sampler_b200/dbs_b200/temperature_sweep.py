@@ -47,7 +47,7 @@ def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_tempera
             view = bits[r[0]:r[0] + len(r)]
             abi.check(abi.lib.dbs_ising_sweeps(view.data_ptr(), L, len(r), k, tables.data_ptr(), tables.shape[0],
                                                index[r[0]:].data_ptr(), seed, int(ids[r[0]]), offset, 0,
-                                               runtime.current_stream()), "ising_sweeps")
+                                               mh.zero_field, runtime.current_stream()), "ising_sweeps")
 
     nT = len(temps)
     acc = torch.zeros((nT, 5), dtype=torch.float64, device=dev)

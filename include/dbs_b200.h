@@ -90,11 +90,15 @@ int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64_t n_chains
  *                q = rank of the site among its colour in row i, GPR = ceil(L/8);
  *                uniforms != NULL (test-mode injection port): uint32
  *                [n_sweeps][n_chains][L][L], r of site (i,j) in sweep s.
+ *   zero_field   0: general (J, h) table path.  +1 / -1: the caller guarantees h == 0 with J > 0 / J < 0;
+ *                the kernel then counts agreeing (disagreeing) neighbours for 32 sites at once and
+ *                compares draws only against the two uphill thresholds of the table — the same
+ *                decisions bit for bit, ~1.6x faster.
  */
 int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_sweeps,
                      const uint32_t* thr, int n_tables, const int32_t* table_index,
                      uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
-                     const uint32_t* uniforms, void* stream);
+                     const uint32_t* uniforms, int zero_field, void* stream);
 
 /* One random-site Metropolis attempt at (i,j) on fp32 lattices [n][L][L] in place, with draw r:
  * the reference's step() (samplers/mcmc.py:26-50) for API parity (flips at most one spin per

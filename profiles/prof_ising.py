@@ -8,7 +8,8 @@ from backend.ml.samplers.mcmc import MetropolisHastings
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-m = IsingModel(L)
+h = float(os.environ.get('ISING_H', '0'))
+m = IsingModel(L, h=h)
 temps = np.repeat(np.linspace(1.5, 3.5, 64), n // 64)
 mh = MetropolisHastings(m, temps, seed=1234)
 bits = m.random_packed(n, seed=1234)
@@ -18,4 +19,4 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); mh.sweeps_packed(bits, sweeps); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
-print(f"L={L} chains={n} sweeps={sweeps}: {ms:.3f} ms  {n*L*L*sweeps/ms/1e6:.1f} Gflips/s")
+print(f"h={h} L={L} chains={n} sweeps={sweeps}: {ms:.3f} ms  {n*L*L*sweeps/ms/1e6:.1f} Gflips/s")

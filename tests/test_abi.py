@@ -31,7 +31,7 @@ def test_argument_validation_needs_no_gpu():
     assert abi.lib.dbs_ising_words_per_chain(64) == 128
     assert abi.lib.dbs_ising_words_per_chain(16) == 16
     assert abi.lib.dbs_ising_words_per_chain(7) < 0      # odd L is not checkerboard-decomposable
-    rc = abi.lib.dbs_ising_sweeps(0, 15, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0)
+    rc = abi.lib.dbs_ising_sweeps(0, 15, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0)
     assert rc == abi.ERR_INVALID and "unsupported" in abi.last_error()
     with pytest.raises(ValueError):
         abi.check(rc, "ising_sweeps")
