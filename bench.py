@@ -210,9 +210,9 @@ def bench_ours(args, world, rank, local):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = abi.launch_count()
+    l0 = abi.launch_count() + smp.graph_kernel_launches
     ms = timed(step_device, args.steps, world)
-    launches = abi.launch_count() - l0
+    launches = abi.launch_count() + smp.graph_kernel_launches - l0   # eager launches + kernels replayed from graphs
     clk = clocks.stop() if rank == 0 else {}
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -234,12 +234,17 @@ def bench_ours(args, world, rank, local):
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel-class breakdown of one step (events inside the library, on the launching stream)
+    # (eager launches for this one step: graph replays bypass the library's launch path)
+    smp.use_graph = False
+    step_device(-100)
+    torch.cuda.synchronize()
     abi.profile_read(reset=True)
     abi.profile(True)
     step_device(0)
     torch.cuda.synchronize()
     prof = abi.profile_read(reset=True)
     abi.profile(False)
+    smp.use_graph = "auto"
     conv_ms, conv_n = prof["conv_tc"]
     breakdown = {k: round(v[0], 3) for k, v in prof.items() if v[1]}
     tot_ms = sum(v[0] for v in prof.values())
@@ -270,7 +275,8 @@ def bench_ours(args, world, rank, local):
                                f"batch {B} per GPU, ScoreNetwork(1,32,64,3) random-init, default VP-SDE",
                    "lattice": L, "em_steps": NS, "batch_per_gpu": B, "global_batch": B * world,
                    "precision": prec, "parallelism": f"batch-sharded x{world}, one final observable all-reduce",
-                   "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no flush needed"},
+                   "l2": "working set per step (>3 GB of activations) exceeds the 126 MB L2; no flush needed",
+                   "launch": "U-Net forward replayed from a CUDA graph captured once per shape; EM / observables eager"},
         "sample_steps_per_s": round(value * NS, 1),
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(x0_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_bytes.get("n", 0)), "steps": e2e_steps,

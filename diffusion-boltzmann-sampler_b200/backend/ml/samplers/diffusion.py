@@ -36,11 +36,12 @@ class DiffusionSampler:
         self.device = device
         self.precision = precision  # None -> the network's default (env DBS_PRECISION or fp32)
         self._training_temperature: Optional[float] = None
-        # One U-Net forward is ~70 kernel launches; for API-sized batches the step is launch-bound, so
-        # the forward is captured once per shape into a CUDA graph and replayed every step
-        # (True / False / "auto": graphs for B*H*W <= 2^18 elements).
+        # One U-Net forward is ~70 kernel launches: the forward is captured once per shape into a CUDA
+        # graph and replayed every step (measured +7 % at batch 1024, +10 % at batch 1-8).
+        # True / False / "auto" (= True; kept as a switch for debugging).
         self.use_graph = "auto"
         self._graphs: Dict[Any, Any] = {}
+        self.graph_kernel_launches = 0   # kernels executed through graph replays (for launch accounting)
 
     # ------------------------------------------------------------------ temperature scaling
     @property
@@ -151,7 +152,7 @@ class DiffusionSampler:
         dev = runtime.require_cuda()
         want = self.use_graph
         if want == "auto":
-            want = int(np.prod(shape)) <= (1 << 18)
+            want = True
         plan_version = None
         if hasattr(self.model, "engine_plan"):
             self.model.engine_plan()
@@ -170,8 +171,10 @@ class DiffusionSampler:
                     self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
+                before = abi.launch_count()
                 with torch.cuda.graph(graph):
                     self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
+                graph.n_kernels = abi.launch_count() - before    # kernels recorded in this graph
             ent = (x, score, t_dev, graph)
             self._graphs[key] = ent
         return ent
@@ -197,6 +200,7 @@ class DiffusionSampler:
             if graph is not None:
                 t_dev.copy_(t_table[k:k + 1])
                 graph.replay()
+                self.graph_kernel_launches += graph.n_kernels
             else:
                 self._score(x, i / self.num_steps, out=score)
             nz = None
