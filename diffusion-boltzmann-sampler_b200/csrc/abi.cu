@@ -34,7 +34,8 @@ cudaEvent_t g_open[kProfNumClasses];
 double g_ms[kProfNumClasses];
 uint64_t g_cnt[kProfNumClasses];
 const char* kProfNames[kProfNumClasses] = {"conv_tc", "conv_generic", "gn_stats", "gn_apply", "em_step", "unet_misc",
-                                           "ising_sweep", "ising_observables", "ising_misc", "lj_pair"};
+                                           "ising_sweep", "ising_observables", "ising_misc", "lj_pair",
+                                           "csn_linear", "csn_attention"};
 cudaEvent_t take_event() {
   if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;

@@ -20,7 +20,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // stream around each launch, summed at dbs_profile_read.  Off by default: zero cost.
 enum ProfClass {
   kProfConvTC = 0, kProfConvGeneric, kProfGnStats, kProfGnApply, kProfEm, kProfUnetMisc,
-  kProfIsingSweep, kProfIsingObs, kProfIsingMisc, kProfLj, kProfNumClasses
+  kProfIsingSweep, kProfIsingObs, kProfIsingMisc, kProfLj, kProfCsnLinear, kProfCsnAttention, kProfNumClasses
 };
 extern bool g_prof_on;
 // free-form label attached to the next recorded launch (per-layer dumps: dbs_profile_dump)

@@ -31,6 +31,11 @@ class UnetConfig(C.Structure):
                 ("output_scale", f32), ("normalize_output", i32)]
 
 
+class CsnConfig(C.Structure):
+    _fields_ = [("n_particles", i32), ("hidden_dim", i32), ("time_embed_dim", i32), ("pos_embed_dim", i32),
+                ("num_blocks", i32), ("num_heads", i32), ("use_attention", i32)]
+
+
 class Param(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", vp), ("numel", i64), ("is_device", i32)]
 
@@ -69,6 +74,10 @@ PROTOTYPES = {
     "dbs_unet_workspace_bytes": (i64, [vp, i64, i32, i32, i32]),
     "dbs_unet_forward": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, vp]),
     "dbs_unet_forward_tap": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, C.c_char_p, vp, i64, vp]),
+    "dbs_csn_plan_create": (i32, [C.POINTER(CsnConfig), C.POINTER(Param), i32, vp, vp, C.POINTER(vp)]),
+    "dbs_csn_plan_destroy": (None, [vp]),
+    "dbs_csn_workspace_bytes": (i64, [vp, i64, i32, i64]),
+    "dbs_csn_forward": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, i64, vp]),
     "dbs_conv_tc": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     "dbs_conv_block_tc": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
 }

@@ -272,6 +272,40 @@ int dbs_conv_block_tc(const void* in0, int C0, const void* in1, int C1, const vo
                       const float* bias3, const void* w1, const float* bias1, void* out3, void* out1,
                       float* stats, int64_t B, int H, int W, int C_out, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Particle score network for continuous systems.  Replaces
+ * ContinuousScoreNetwork.forward and its sub-modules
+ * (models/score_network_continuous.py:36-75, 85-101, 123-136, 155-180, 256-282).
+ * A plan owns device copies of the fp32 weights (names as in the module's state_dict:
+ * time_mlp.{0,2}, input_proj, blocks.i.{fc1,fc2,norm1,norm2,time_mlp},
+ * attention_layers.i.{norm,qkv,proj}, output_proj.{0,1,3}).
+ * ------------------------------------------------------------------------- */
+typedef struct dbs_csn_plan dbs_csn_plan;
+
+typedef struct dbs_csn_config {
+  int n_particles;    /* informational: forward() takes N per call, as the reference does */
+  int hidden_dim;     /* multiple of 8, <= 256                                           */
+  int time_embed_dim;
+  int pos_embed_dim;  /* = 4 * n_frequencies                                             */
+  int num_blocks;
+  int num_heads;      /* head_dim = hidden_dim / num_heads in {8, 16, 32, 64}            */
+  int use_attention;  /* 0/1                                                             */
+} dbs_csn_config;
+
+/* pos_freqs_host: the module's `pos_embed.freqs` buffer [pos_embed_dim/4];
+ * t_freqs_host: exp(-ln(1e4) * k / (half-1)), k < time_embed_dim/2 (computed by the caller with the
+ * reference's torch expression so the values are bit-identical). */
+int dbs_csn_plan_create(const dbs_csn_config* cfg, const dbs_param* params, int n_params,
+                        const float* pos_freqs_host, const float* t_freqs_host,
+                        dbs_csn_plan** out);
+void dbs_csn_plan_destroy(dbs_csn_plan* plan);
+int64_t dbs_csn_workspace_bytes(const dbs_csn_plan* plan, int64_t B, int N, int64_t n_t);
+
+/* score = ContinuousScoreNetwork.forward(x, t)  (score_network_continuous.py:256-282).
+ * x, score: fp32 [B][N][2] (positions normalised to [-1,1]); t: fp32 [n_t], n_t = 1 or B. */
+int dbs_csn_forward(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
+                    int64_t B, int N, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Philox stream tags (ctr.w) and the x0 step tag. */
 #define DBS_STREAM_SWEEP 0x53574550u /* 'SWEP' */
 #define DBS_STREAM_INIT  0x494e4954u /* 'INIT' */

@@ -25,6 +25,7 @@ from backend.ml.systems.ising import IsingModel  # noqa: E402
 from backend.ml.systems.lennard_jones import LennardJonesSystem  # noqa: E402
 from backend.ml.models.score_network import ScoreNetwork, SinusoidalTimeEmbedding  # noqa: E402
 from backend.ml.models.diffusion import DiffusionProcess  # noqa: E402
+from backend.ml.models.score_network_continuous import ContinuousScoreNetwork  # noqa: E402
 from backend.ml.samplers.diffusion import DiffusionSampler  # noqa: E402
 from backend.ml.analysis.correlation import pair_correlation  # noqa: E402
 
@@ -310,6 +311,57 @@ def main():
     r2, gr2 = compute_rdf(cfgs[0], 5.0, n_bins=25, r_max=2.0)
     g["rdf2_r"], g["rdf2_g"] = r2, gr2
     np.savez_compressed(os.path.join(OUT, "langevin_rdf.npz"), **g)
+
+    # ---- particle score network (ContinuousScoreNetwork) + sampler on particle configurations -------
+    g = {}
+    torch.manual_seed(43)
+    cnet = ContinuousScoreNetwork(n_particles=12, hidden_dim=32, time_embed_dim=16, pos_embed_dim=16, num_blocks=2,
+                                  num_heads=4).eval()
+    for k, v in cnet.state_dict().items():
+        g["sd::" + k] = v.numpy()
+    x = torch.rand(3, 12, 2) * 2 - 1
+    t = torch.tensor([1.0, 0.41, 0.03])
+    with torch.no_grad():
+        g["fwd_x"], g["fwd_t"], g["fwd_out"] = x.numpy(), t.numpy(), cnet(x, t).numpy()
+        xw = torch.randn(2, 40, 2) * 1.5     # outside [-1, 1] and N != n_particles: forward() accepts both
+        tw = torch.tensor([0.77, 0.77])
+        g["fwd_w_x"], g["fwd_w_t"], g["fwd_w_out"] = xw.numpy(), tw.numpy(), cnet(xw, tw).numpy()
+    torch.manual_seed(44)
+    cnet_na = ContinuousScoreNetwork(n_particles=8, hidden_dim=24, time_embed_dim=8, pos_embed_dim=8, num_blocks=1,
+                                     use_attention=False).eval()
+    for k, v in cnet_na.state_dict().items():
+        g["sdna::" + k] = v.numpy()
+    with torch.no_grad():
+        xa = torch.rand(2, 8, 2) * 2 - 1
+        ta = torch.tensor([0.6, 0.2])
+        g["na_x"], g["na_t"], g["na_out"] = xa.numpy(), ta.numpy(), cnet_na(xa, ta).numpy()
+    N, shape = 10, (2, 12, 2)
+    noises = []
+    real_randn, real_randn_like = torch.randn, torch.randn_like
+
+    def rec2_randn(*a, **k):
+        v = real_randn(*a, **k)
+        noises.append(v.clone())
+        return v
+
+    def rec2_randn_like(*a, **k):
+        v = real_randn_like(*a, **k)
+        noises.append(v.clone())
+        return v
+
+    sampler = DiffusionSampler(cnet, num_steps=N)
+    torch.randn, torch.randn_like = rec2_randn, rec2_randn_like
+    try:
+        torch.manual_seed(8)
+        out = sampler.sample(shape, temperature=0.9)
+    finally:
+        torch.randn, torch.randn_like = real_randn, real_randn_like
+    g["smp_x0"] = noises[0].numpy()
+    g["smp_noises"] = torch.stack(noises[1:]).numpy()
+    g["smp_out"] = out.numpy()
+    g["smp_meta"] = np.array([N, 0.9])
+    np.savez_compressed(os.path.join(OUT, "csn_tiny.npz"), **g)
+
 
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
