@@ -266,6 +266,28 @@ def bench_ours(args, world, rank, local):
         "whole_step_tflops": round(flops_step * args.steps / (ms * 1e-3) / 1e12, 2),
     }
 
+    # HBM-bound companions of the conv kernel, same events: Euler-Maruyama 12 B/element (x in, score in, x out);
+    # GroupNorm apply 4 B/element (bf16 in + out), 6 B with the residual
+    esz = 2 if prec == "bf16" else 4
+    gn_elems, ch, res = 0, NET_CFG["base_channels"], L
+    widths = [NET_CFG["base_channels"] << (i + 1) for i in range(NET_CFG["num_blocks"])]
+    for co in widths:
+        gn_elems += res * res * co; res //= 2
+    gn_elems += res * res * widths[-1]
+    for i in reversed(range(NET_CFG["num_blocks"])):
+        res *= 2; gn_elems += res * res * (NET_CFG["base_channels"] << i)
+    hbm_kernels = {}
+    if prof.get("em_step", (0, 0))[1]:
+        by = 12.0 * B * L * L * NS
+        hbm_kernels["em_step"] = {"bound": "hbm", "achieved": round(by / (prof["em_step"][0] * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"],
+                                  "unit": "GB/s", "frac": round(by / (prof["em_step"][0] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                                  "bytes_per_element": 12}
+    if prof.get("gn_apply", (0, 0))[1]:
+        by = float(gn_elems) * B * NS * (2 * esz + 3 * esz)     # GN1: in + out; GN2: in + residual + out
+        hbm_kernels["gn_apply"] = {"bound": "hbm", "achieved": round(by / (prof["gn_apply"][0] * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"],
+                                   "unit": "GB/s", "frac": round(by / (prof["gn_apply"][0] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                                   "bytes_per_element": "2+2 (GN1), 2+2+2 (GN2 with residual), bf16"}
+
     line = {
         "metric": "diffusion_samples_per_s", "value": round(value, 2), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
@@ -284,6 +306,7 @@ def bench_ours(args, world, rank, local):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "breakdown_ms_per_step": breakdown,
+        "hbm_kernels": hbm_kernels,
         "clocks": clk,
         "observables": {"count": float(last["acc"][0]), "mean_abs_M": float(last["acc"][2] / max(float(last["acc"][0]), 1))},
     }
@@ -355,6 +378,17 @@ def bench_ising(peaks):
     out["metric"] = "ising_spin_flips_per_s"
     out["value"] = out["resident"]["flips_per_s"]
     out["config"] = {"workload": "C3 per-GPU shape: 2D Ising 64x64 checkerboard Metropolis, 8192 chains, 64 temperatures in [1.5,3.5]"}
+    # CPU beside it: the oracle's vectorised numpy checkerboard (same tables, same Philox draws) on a bounded
+    # sample; the reference's own Python per-site loop measured 1.26e4 attempts/s at 64x64
+    from oracle import ising as o_ising
+    nc, ns = 16, 4
+    start = o_ising.unpack(m.random_packed(nc, seed=7).cpu().numpy().view(np.uint32), L)
+    t0 = time.time()
+    o_ising.run_sweeps(start, 1.0, 0.0, temps[:nc], ns, seed=7)
+    dtc = time.time() - t0
+    out["cpu_baseline"] = {"value": float(f"{nc * L * L * ns / dtc:.4e}"), "unit": "flip attempts/s", "cores": 1, "kind": "port",
+                           "sample": f"{nc} chains x {ns} sweeps of 64x64, vectorised numpy checkerboard (oracle/ising.py)",
+                           "reference_python_loop_attempts_per_s": 1.26e4}
     e, mg = m.packed_observables(bits)
     out["mean_abs_M_T1.5"] = round(float(mg[: n // 64].abs().mean()), 4)
     out["mean_abs_M_T3.5"] = round(float(mg[-n // 64:].abs().mean()), 4)
@@ -403,8 +437,80 @@ def bench_lj():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"metric": "lj_configs_per_s", "value": round(B / (ms * 1e-3), 1), "pairs_per_s": float(f"{B * N * N / (ms * 1e-3):.4e}"),
-            "ms_per_launch": round(ms, 4), "config": {"workload": "C5 kernel: N=256, 4096 configurations, energy+forces"}}
+    out = {"metric": "lj_configs_per_s", "value": round(B / (ms * 1e-3), 1), "pairs_per_s": float(f"{B * N * N / (ms * 1e-3):.4e}"),
+           "ms_per_launch": round(ms, 4), "config": {"workload": "C5 kernel: N=256, 4096 configurations, energy+forces"}}
+    # FP32-ALU roofline: 40 flop per ordered pair against SMs x 128 lanes x 2 x SM clock;
+    # HBM figure for completeness: 4100 algorithmic bytes per configuration
+    fp32_peak = 148 * 128 * 2 * 1.965e9
+    ach = B * N * N * 40 / (ms * 1e-3)
+    out["roofline"] = {"bound": "fp32-alu", "achieved": round(ach / 1e12, 2), "peak": round(fp32_peak / 1e12, 2), "unit": "TFLOP/s",
+                       "frac": round(ach / fp32_peak, 4), "flop_per_pair": 40,
+                       "hbm_gbs": round(B * 4100 / (ms * 1e-3) / 1e9, 2)}
+    # CPU beside it: the oracle port (numpy fp32, the reference's dense N x N formulation) on a bounded sample
+    from oracle import lj as o_lj
+    p = o_lj.LJParams(N, box)
+    pc = pos[:16].cpu().numpy()
+    t0 = time.time()
+    o_lj.energy(p, pc); o_lj.forces(p, pc)
+    dtc = time.time() - t0
+    out["cpu_baseline"] = {"value": round(16 / dtc, 2), "unit": "configs/s", "cores": 1, "kind": "port",
+                           "sample": "16 configurations, energy + forces, numpy fp32 (oracle/lj.py)"}
+
+    # ---- C5 "MCMC" leg: batched MALA on the pair kernel (one fused pair pass per step)
+    from backend.ml.samplers.langevin import LangevinDynamics, _State
+    ld = LangevinDynamics(s, temperature=1.0, dt=1e-4, seed=11)
+    st = _State(s, pos)
+    ld._advance(st, 5)
+    torch.cuda.synchronize()
+    e0.record()
+    n_mala = 50
+    ld._advance(st, n_mala)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_m = e0.elapsed_time(e1)
+    from oracle import langevin as o_lang
+    rng = np.random.default_rng(0)
+    x1 = pc[0]
+    t0 = time.time()
+    for _ in range(3):
+        x1, _ = o_lang.mala_step(p, x1, 1.0, 1e-4, rng.standard_normal((N, 2)).astype(np.float32), 0.5)
+    dtm = (time.time() - t0) / 3
+    out["mala"] = {"metric": "lj_mala_config_steps_per_s", "value": round(B * n_mala / (ms_m * 1e-3), 1),
+                   "ms_per_step": round(ms_m / n_mala, 4), "acceptance": round(float(ld.last_accepted.float().mean()), 3),
+                   "sample": f"{B} chains x {n_mala} steps, dt=1e-4, T*=1.0",
+                   "cpu_baseline": {"value": round(1.0 / dtm, 2), "unit": "config-steps/s", "cores": 1, "kind": "port",
+                                    "sample": "1 configuration x 3 MALA steps, numpy fp32 (oracle/langevin.py)"}}
+
+    # ---- C5 diffusion leg: particle score network (random init) + Euler-Maruyama on (B, N, 2)
+    from backend.ml.models.score_network_continuous import ContinuousScoreNetwork
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    from oracle import csn as o_csn
+    torch.manual_seed(0)
+    net = ContinuousScoreNetwork(N).eval()
+    n_em = 5
+    smp = DiffusionSampler(net, num_steps=n_em, device="cuda")
+    smp.sample((B, N, 2), seed=1)
+    torch.cuda.synchronize()
+    e0.record()
+    smp.sample((B, N, 2), seed=2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_d = e0.elapsed_time(e1)
+    H, nb, hd, heads = 128, 4, 32, 4
+    flops_cfg = 2.0 * N * (66 * H + nb * 6 * H * H + H * H // 2 + H) + nb * 4.0 * heads * N * N * hd
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    xc = torch.rand(4, N, 2) * 2 - 1
+    o_csn.csn_forward(sd, xc, torch.full((4,), 0.5))
+    t0 = time.time()
+    o_csn.csn_forward(sd, xc, torch.full((4,), 0.5))
+    dtd = time.time() - t0
+    out["diffusion"] = {"metric": "lj_diffusion_config_steps_per_s", "value": round(B * n_em / (ms_d * 1e-3), 1),
+                        "configs_per_s_at_100_steps": round(B * n_em / (ms_d * 1e-3) / 100, 2),
+                        "ms_per_step": round(ms_d / n_em, 3), "tflops_fp32": round(flops_cfg * B * n_em / (ms_d * 1e-3) / 1e12, 2),
+                        "dtype": "f32", "sample": f"{B} configurations x {n_em} of 100 EM steps, ContinuousScoreNetwork(256) random-init",
+                        "cpu_baseline": {"value": round(4 / dtd, 2), "unit": "config-steps/s", "cores": torch.get_num_threads(),
+                                         "kind": "port", "sample": "4 configurations x 1 forward, torch fp32 (oracle/csn.py)"}}
+    return out
 
 
 # --------------------------------------------------------------------------------------------- reference arm
