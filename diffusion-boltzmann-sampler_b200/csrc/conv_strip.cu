@@ -161,7 +161,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, kEpiWarps);
+      mbar_init(bar_tempty + 8 * s, NCH <= 2 ? kEpiWarps / 2 : kEpiWarps);
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -253,8 +253,19 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
+    // A warp's work per tile is one 16-column chunk of one TMEM lane quadrant, a latency-bound chain
+    // (tcgen05.ld -> shuffles -> convert -> store).  With 64 couts the sixteen warps cover the four chunks
+    // of a tile in lock step (measured: splitting them into two sets that each take two chunks is 15 %
+    // slower).  With <= 32 couts there are only two chunks: the warps then form two sets of eight that
+    // drain alternate tiles (set s owns accumulator stage s), so two epilogues overlap instead of half of
+    // the warps idling.
+    constexpr bool kSplit = NCH <= 2;
     const int q = warp & 3;                 // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;       // which of the quadrant's four warps: takes chunks half, half+4, ...
+    const int half = (warp - 2) >> 2;       // 0..3
+    const int my_set = kSplit ? (half >> 1) : 0;
+    const int hsel = kSplit ? (half & 1) : half;
+    constexpr int MYCH = 1;                 // chunks this warp may own (NCH <= 4)
+    static_assert(NCH <= 4, "one chunk per warp");
     const int row = q * 32 + lane;          // tile-local pixel
     const int hl = row / p.W, wl = row - hl * p.W;
     const float m_right = wl < p.W - 1 ? 1.f : 0.f;   // pixel m+1 is in the same image row
@@ -262,7 +273,6 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     const bool xchg = p.W > 32;             // an image row spans several warps
     constexpr int CG = kWide ? 16 : 2 * NCH;  // channels of a group inside one chunk
     constexpr int GPC = 16 / CG;              // groups per 16-column chunk (1 when kWide)
-    constexpr int MYCH = (NCH + 3) / 4;     // chunks this warp may own
     float st_s[MYCH * GPC], st_ss[MYCH * GPC];
 #pragma unroll
     for (int i = 0; i < MYCH * GPC; ++i) { st_s[i] = 0.f; st_ss[i] = 0.f; }
@@ -270,7 +280,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     auto flush_stats = [&](int n_img, int nt_img) {
 #pragma unroll
       for (int i = 0; i < MYCH * GPC; ++i) {
-        const int chunk = half + 4 * (i / GPC);
+        const int chunk = hsel;
         if (chunk < NCH) {
           const float s_ = warp_sum(st_s[i]), ss_ = warp_sum(st_ss[i]);
           const int gi = kWide ? ((nt_img * p.Nb + chunk * 16) >> p.cg_log2) : chunk * GPC + (i % GPC);
@@ -282,27 +292,34 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         st_s[i] = 0.f; st_ss[i] = 0.f;
       }
     };
-    int it = 0;
+    // tile -> (image, n-tile, row block) kept incrementally: one division per CTA, none per tile
+    const int per_img = p.n_tiles_n * p.tiles_h;
+    int n = tile_lo / per_img;
+    int rem = tile_lo - n * per_img;
+    int nt = rem / p.tiles_h;
+    int hb = rem - nt * p.tiles_h;
     int xb = 0;  // exchange-buffer parity, toggled per chunk (one named barrier per chunk suffices)
+    int it = 0;
     for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+      const int t_n = n, t_nt = nt, t_hb = hb;
+      if (++hb == p.tiles_h) { hb = 0; if (++nt == p.n_tiles_n) { nt = 0; ++n; } }
+      if (kSplit && (it & 1) != my_set) continue;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int per_img = p.n_tiles_n * p.tiles_h;
-      const int n = tile / per_img, rem = tile - n * per_img;
-      const int nt = rem / p.tiles_h, a = (rem - nt * p.tiles_h) * p.Ht + hl, co0 = nt * p.Nb;
-      if (kStats && (n != cur_n || nt != cur_nt)) {
+      const int a = t_hb * p.Ht + hl, co0 = t_nt * p.Nb;
+      if (kStats && (t_n != cur_n || t_nt != cur_nt)) {
         if (cur_n >= 0) flush_stats(cur_n, cur_nt);
-        cur_n = n; cur_nt = nt;
+        cur_n = t_n; cur_nt = t_nt;
       }
       __nv_bfloat16* optr =
-          p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout + co0;
+          p.out + (((int64_t)t_n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout + co0;
 
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
 #pragma unroll
       for (int mc = 0; mc < MYCH; ++mc) {
-        const int chunk = half + 4 * mc;
+        const int chunk = hsel;
         if (chunk >= NCH || (p.dbg & 2)) break;
         const int c = chunk * 16;
         uint32_t v0[16], vp[16], vm[16];
@@ -323,6 +340,24 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         }
+        // neighbour columns: all shuffles of a side are issued back to back, in place (no shared temporary, so
+        // the sixteen of them are in flight together instead of one SHFL -> FFMA round trip per column)
+        if (p.slot_p >= 0 && !(p.dbg & 16)) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vp[j] = __shfl_down_sync(0xffffffffu, vp[j], 1);
+          if (xchg && lane == 31) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vp[j] = __float_as_uint(s_x[xb][half][(q + 1) & 3][0][j]);
+          }
+        }
+        if (p.slot_m >= 0 && !(p.dbg & 16)) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vm[j] = __shfl_up_sync(0xffffffffu, vm[j], 1);
+          if (xchg && lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vm[j] = __float_as_uint(s_x[xb][half][(q + 3) & 3][1][j]);
+          }
+        }
         float f[16];
         const float4* bq = reinterpret_cast<const float4*>(s_bias + co0 + c);
 #pragma unroll
@@ -335,19 +370,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         }
         if (p.slot_p >= 0 && !(p.dbg & 16)) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float nb = __shfl_down_sync(0xffffffffu, __uint_as_float(vp[j]), 1);
-            if (xchg && lane == 31) nb = s_x[xb][half][(q + 1) & 3][0][j];
-            f[j] = fmaf(m_right, nb, f[j]);
-          }
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(m_right, __uint_as_float(vp[j]), f[j]);
         }
         if (p.slot_m >= 0 && !(p.dbg & 16)) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float nb = __shfl_up_sync(0xffffffffu, __uint_as_float(vm[j]), 1);
-            if (xchg && lane == 0) nb = s_x[xb][half][(q + 3) & 3][1][j];
-            f[j] = fmaf(m_left, nb, f[j]);
-          }
+          for (int j = 0; j < 16; ++j) f[j] = fmaf(m_left, __uint_as_float(vm[j]), f[j]);
         }
         if (kStats && !(p.dbg & 32)) {
 #pragma unroll

@@ -16,10 +16,12 @@
 //   space-to-depth view {2C, W/2, 2, H/2, N}; a transposed conv is four stride-1 phase convs whose
 //   epilogue scatters to the odd/even output pixels.
 //
-// CTA = 6 warps, persistent over tiles (static round-robin):
+// CTA = 18 warps, persistent over tiles (static round-robin):
 //   warp 0   TMA producer (one lane)   — kStages-deep full/empty mbarrier ring
 //   warp 1   MMA issuer  (one lane)    — tcgen05.mma cta_group::1, M=128, N=Nb, K=16 per instruction
-//   warps 2-5 epilogue                 — tcgen05.ld 32x32b -> +bias -> GN partial sums -> bf16 -> HBM
+//   warps 2-17 epilogue                — tcgen05.ld 32x32b -> +bias -> GN partial sums -> bf16 -> HBM; warp (q, sub)
+//                                        drains TMEM lane quadrant q, chunk range sub (a warp's chain per chunk is
+//                                        latency-bound, so four warps per quadrant cut the drain time of a tile ~4x)
 // Two TMEM accumulator stages (2*Nb columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 
@@ -33,7 +35,8 @@ namespace dbs {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;             // four warps per TMEM lane quadrant, each a contiguous range of 16-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemBudget = 200 * 1024;
 constexpr int kMaxCout = 512;
@@ -44,6 +47,7 @@ struct TcParams {
   int Nb, KC, chunks0, chunks1, n_taps, stages;
   int B, Hout, Wout, Cout, out_stride, oph, opw;
   int groups, Cg, cg_log2;
+  int epi_subs;       // epilogue warps per TMEM lane quadrant that take part (1 or 4), see conv_tc_launch
   int tap_dw[16], tap_dh[16], tap_p[16], tap_c0[16], tap_c1[16], tap_w[16];
   const float* bias;
   __nv_bfloat16* out;
@@ -84,7 +88,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4);
+      mbar_init(bar_tempty + 8 * s, 4 * p.epi_subs);
     }
     fence_barrier_init();
   }
@@ -170,13 +174,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       }
     }
     __syncwarp();
-  } else {
+  } else if (((warp - 2) >> 2) < p.epi_subs) {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                 // TMEM lane quarter accessible to this warp
+    const int sub = (warp - 2) >> 2;        // which of the quadrant's four warps
+    const int n_chunks = p.Nb >> 4;
+    const int per = (n_chunks + p.epi_subs - 1) / p.epi_subs;    // contiguous chunks per warp
+    const int c_lo = sub * per * 16, c_hi = min(p.Nb, (sub + 1) * per * 16);
     const int row = q * 32 + lane;          // tile-local GEMM row = pixel
     const int ppi = p.Ht * p.Wt;            // pixels per image inside a tile
     const int nl = row / ppi, hl = (row / p.Wt) % p.Ht, wl = row % p.Wt;
-    const int etid = threadIdx.x - 64;      // 0..127
+    const int etid = threadIdx.x - 64;      // 0 .. 32*kEpiWarps-1
     const bool warp_uniform_image = ppi >= 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -194,9 +202,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * p.Nb;
       float run_s = 0.f, run_ss = 0.f;
-      for (int c = 0; c < p.Nb; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
+      uint32_t v[16];
+      if (c_lo < c_hi) tmem_ld16(taddr + c_lo, v);
+      for (int c = c_lo; c < c_hi; c += 16) {
         tmem_ld_wait();
         float f[16];
         const float4* bq = reinterpret_cast<const float4*>(s_bias + co0 + c);
@@ -208,6 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
           f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b4.z;
           f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b4.w;
         }
+        if (c + 16 < c_hi) tmem_ld16(taddr + c + 16, v);   // next chunk in flight behind this one's arithmetic
         if (kRun > 0) {
           if (!valid) {
 #pragma unroll
@@ -227,7 +236,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
             if (R == 16) {
               run_s += s; run_ss += ss;
               s = run_s; ss = run_ss;
-              flush = ((c + 16) & (p.Cg - 1)) == 0;   // warp-uniform: end of a group of >= 16 channels
+              // warp-uniform: end of a group of >= 16 channels, or of this warp's chunk range (partial sum)
+              flush = ((c + 16) & (p.Cg - 1)) == 0 || c + 16 >= c_hi;
               if (flush) { run_s = 0.f; run_ss = 0.f; }
             }
             if (flush) {
@@ -258,9 +268,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
       if (kRun > 0) {
-        epi_bar_sync();
+        asm volatile("bar.sync 1, %0;" ::"r"(128 * p.epi_subs) : "memory");
         float* accb = &s_acc[it & 1][0];
-        for (int i = etid; i < p.Nt * 16; i += 128) {
+        for (int i = etid; i < p.Nt * 16; i += 128 * p.epi_subs) {
           const int img = i >> 4, rest = i & 15, gi = rest >> 1, k = rest & 1;
           const float vsum = accb[i];
           accb[i] = 0.f;
@@ -428,6 +438,9 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
     }
     p.tap_w[t] = g.widx[t];
   }
+  // Four warps per quadrant pay off only when a warp's rows span several images (tiny lattices: per-thread
+  // shared-memory atomics for the GroupNorm sums dominate the drain); measured slower elsewhere.
+  p.epi_subs = (stats && Ht * Wt < 32) ? 4 : 1;
   p.bias = bias; p.out = out; p.stats = stats;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   p.a_bytes = (uint32_t)kTileM * KC * 2;

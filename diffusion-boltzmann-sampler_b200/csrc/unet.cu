@@ -308,6 +308,159 @@ final_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const f
   if (live && c == 0) out[p] = scale * (acc + bias[0]);
 }
 
+// Init conv 1 -> C on the bf16 path: one thread per pixel produces all C channels.  The 9 x C weights and
+// the bias arrive as a __grid_constant__ kernel parameter, so every FFMA reads its weight from the constant
+// bank (warp-uniform index) and the only memory instructions are 9 coalesced x loads and C/8 16-byte stores.
+template <int C> struct InitW { float w[9 * C]; float b[C]; };
+
+template <int C>
+__global__ void __launch_bounds__(256)
+init_conv_fast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n_pix, int H, int W,
+                      const __grid_constant__ InitW<C> iw) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  const int ww = (int)(p % W);
+  const int hh = (int)((p / W) % H);
+  float xv[9];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ih = hh + kh - 1, iw_ = ww + kw - 1;
+      const bool ok = ih >= 0 && ih < H && iw_ >= 0 && iw_ < W;
+      xv[kh * 3 + kw] = ok ? __ldg(x + p + (int64_t)(kh - 1) * W + (kw - 1)) : 0.f;
+    }
+#pragma unroll
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = iw.b[c0 + k];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(xv[t], iw.w[t * C + c0 + k], v[k]);
+    Vec16<__nv_bfloat16>::store(out + p * C + c0, v);
+  }
+}
+
+template <int C>
+int launch_init_fast(const std::vector<float>& w_host, const std::vector<float>& b_host, const float* x,
+                     __nv_bfloat16* out, int64_t n_pix, int H, int W, cudaStream_t st) {
+  InitW<C> iw;
+  for (int i = 0; i < 9 * C; ++i) iw.w[i] = w_host[i];
+  for (int i = 0; i < C; ++i) iw.b[i] = b_host[i];
+  init_conv_fast_kernel<C><<<(unsigned)((n_pix + 255) / 256), 256, 0, st>>>(x, out, n_pix, H, W, iw);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+// Final conv C -> 1 (3x3, pad 1) on the bf16 path, optionally fused with the GroupNorm apply that produces its
+// input (the last decoder block's  SiLU(GN(conv2)) + residual, score_network.py:148-151, 259, 268).
+// A CTA owns TH full-width rows of one image: the rows (+ one halo row each side) are brought into shared
+// memory once with coalesced 16-byte loads — transformed on the way when fused, so the normalised tensor
+// never exists in HBM — then one thread per pixel forms the 9 x C dot product.  The weights arrive as a
+// __grid_constant__ kernel parameter, so every FFMA takes its weight straight from the constant bank.
+// Shared-memory layout: C*2 bytes per pixel, the 16-byte chunk index XOR-swizzled with the pixel index so
+// that the per-pixel LDS.128 of a quarter-warp touch all 32 banks.
+template <int C> struct FinalW { float w[9 * C]; float bias, scale; };
+
+template <int C, bool kFuseGn>
+__global__ void __launch_bounds__(256)
+final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
+                   const float* __restrict__ stats, float inv_cnt, float eps, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ out, int H, int W, int TH,
+                   const __grid_constant__ FinalW<C> fw) {
+  constexpr int NCK = C / 8;                 // 16-byte chunks per pixel
+  constexpr int PPL = NCK >= 8 ? 1 : 8 / NCK;  // pixels per 128 bytes
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __shared__ float s_sc[C], s_sh[C];
+  const int n = blockIdx.y, h0 = blockIdx.x * TH;
+  const int tid = threadIdx.x;
+  if (kFuseGn) {
+    if (tid < C) {
+      const int gi = tid / (C / 8);
+      const float s0 = stats[((int64_t)n * 8 + gi) * 2 + 0], s1 = stats[((int64_t)n * 8 + gi) * 2 + 1];
+      const float mean = s0 * inv_cnt;
+      const float rstd = rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps);
+      const float a = rstd * gamma[tid];
+      s_sc[tid] = a;
+      s_sh[tid] = beta[tid] - mean * a;
+    }
+    __syncthreads();
+  }
+  const int n_vec = (TH + 2) * W * NCK;
+  for (int idx = tid; idx < n_vec; idx += blockDim.x) {
+    const int ck = idx % NCK, pi = idx / NCK;
+    const int r = pi / W, wl = pi - r * W, ih = h0 + r - 1;
+    if (ih < 0 || ih >= H) continue;         // never read: the taps below apply the same bounds
+    const int64_t g = (((int64_t)n * H + ih) * W + wl) * C + ck * 8;
+    uint4 raw = *reinterpret_cast<const uint4*>(y + g);
+    if (kFuseGn) {
+      float v[8], rr[8];
+      Vec16<__nv_bfloat16>::load(y + g, v);
+      Vec16<__nv_bfloat16>::load(res + g, rr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(1.0f, rr[k], silu_fast(fmaf(v[k], s_sc[ck * 8 + k], s_sh[ck * 8 + k])));
+      uint32_t w4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w4[i] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      raw = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+    const int swz = (pi / PPL) & (NCK - 1);
+    *reinterpret_cast<uint4*>(sm_raw + (size_t)pi * (C * 2) + ((ck ^ swz) << 4)) = raw;
+  }
+  __syncthreads();
+  const int hl = tid / W, wl = tid - hl * W;
+  if (hl >= TH || h0 + hl >= H) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = h0 + hl + kh - 1;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = wl + kw - 1;
+      if (iw < 0 || iw >= W) continue;
+      const int pi = (hl + kh) * W + iw;
+      const uint8_t* base = sm_raw + (size_t)pi * (C * 2);
+      const int swz = (pi / PPL) & (NCK - 1);
+#pragma unroll
+      for (int ck = 0; ck < NCK; ++ck) {
+        const uint4 q = *reinterpret_cast<const uint4*>(base + ((ck ^ swz) << 4));
+        const uint32_t wq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&wq[i]);
+          acc = fmaf(__low2float(h2), fw.w[(kh * 3 + kw) * C + ck * 8 + 2 * i], acc);
+          acc = fmaf(__high2float(h2), fw.w[(kh * 3 + kw) * C + ck * 8 + 2 * i + 1], acc);
+        }
+      }
+    }
+  }
+  out[((int64_t)n * H + h0 + hl) * W + wl] = fw.scale * (acc + fw.bias);
+}
+
+template <int C>
+int launch_final_fused(const std::vector<float>& w_host, float bias, float scale, const __nv_bfloat16* y,
+                       const __nv_bfloat16* res, const float* stats, const float* gamma, const float* beta, float* out,
+                       int64_t B, int H, int W, cudaStream_t st) {
+  FinalW<C> fw;
+  for (int i = 0; i < 9 * C; ++i) fw.w[i] = w_host[i];
+  fw.bias = bias; fw.scale = scale;
+  int TH = 256 / W;
+  if (TH > H) TH = H;
+  const size_t smem = (size_t)(TH + 2) * W * C * 2;
+  const dim3 grid((unsigned)((H + TH - 1) / TH), (unsigned)B);
+  const float inv_cnt = 1.0f / (float)((int64_t)H * W * (C / 8));
+  if (res) final_fused_kernel<C, true><<<grid, TH * W, smem, st>>>(y, res, stats, inv_cnt, 1e-5f, gamma, beta, out, H, W, TH, fw);
+  else final_fused_kernel<C, false><<<grid, TH * W, smem, st>>>(y, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, out, H, W, TH, fw);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
 // optional per-sample std normalisation (score_network.py:262-265): score / (std + 1e-8),
 // unbiased std over H*W, applied before output_scale (so undo/redo the scale here).
 __global__ void normalize_output_kernel(float* __restrict__ score, int HW, float scale) {
@@ -551,6 +704,9 @@ struct dbs_unet_plan {
   float *twt = nullptr, *tbt = nullptr;  // concatenated per-block time Linear [sumC][T], [sumC]
   int sumC = 0;
   float *init_w = nullptr, *init_b = nullptr, *final_w = nullptr, *final_b = nullptr;
+  std::vector<float> final_w_host;   // [tap][C], kernel-parameter copy for the fused final conv
+  std::vector<float> init_w_host, init_b_host;   // [tap][C], [C]: kernel-parameter copies for the init conv
+  float final_b_host = 0.f;
   std::vector<dbs::BlockW> enc, dec;
   dbs::BlockW mid;
   std::vector<dbs::ConvWeights> down, up;
@@ -633,6 +789,14 @@ template <typename T> struct WSel;
 template <> struct WSel<float> { using type = float; static const float* get(const ConvWeights& w) { return w.w32; } };
 template <> struct WSel<__nv_bfloat16> { using type = __nv_bfloat16; static const __nv_bfloat16* get(const ConvWeights& w) { return w.w16; } };
 
+// The last decoder block can leave its closing GroupNorm apply to the final conv kernel, which then reads
+// the raw conv2 output + residual and normalises on the fly (final_fused_kernel).
+struct DeferredGn {
+  bool want = false, done = false;
+  const void* y = nullptr; const void* res = nullptr;
+  const float *gamma = nullptr, *beta = nullptr;
+};
+
 struct Ctx {
   dbs_unet_plan* plan;
   cudaStream_t st;
@@ -642,6 +806,7 @@ struct Ctx {
   float* stats;       // [B][8][2]
   bool use_tc;
   const char* tap; float* tap_out; int64_t tap_numel; bool tapped = false;
+  DeferredGn* defer = nullptr;
 };
 
 template <typename T>
@@ -753,6 +918,10 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   } else {
     DBS_REQUIRE(C1 == 0, "unet: identity residual with a concatenated input");
   }
+  if (c.defer && c.defer->want && sd && !c.tap) {
+    c.defer->done = true; c.defer->y = ty; c.defer->res = res; c.defer->gamma = bw.g2; c.defer->beta = bw.b2;
+    return DBS_OK;
+  }
   if ((rc = run_gn<T>(c, ty, out, sd, bw.g2, bw.b2, 0, false, res, H, W, bw.cout))) return rc;
   return maybe_tap<T>(c, name, out, c.B, H, W, bw.cout);
 }
@@ -807,6 +976,12 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
 
   Ctx c{plan, st, B, (int)n_t, tbias, stats, use_tc, tap, tap_out, tap_numel};
   int rc;
+  // fused final conv (bf16 path): C in {16, 32, 64}, power-of-two width <= 128, tile within 48 KB of shared memory
+  const bool final_fused_ok = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && W <= 128 && (W & (W - 1)) == 0 &&
+                              (size_t)(std::min(256 / W, H) + 2) * W * C * 2 <= 48 * 1024;
+  static const bool defer_off = [] { const char* e = getenv("DBS_FINAL_FUSE"); return e && e[0] == '0'; }();
+  DeferredGn defer;
+  defer.want = final_fused_ok && use_tc && !tap && !defer_off;
 
   // ---- time path
   {
@@ -823,8 +998,15 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
     prof_set_label("init_conv");
     ProfScope prof(kProfUnetMisc, st);
     const int64_t nthr = n_pix * (C / (16 / (int)sizeof(T)));
-    init_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(x, plan->init_w, plan->init_b, a0, n_pix, H, W, C);
-    DBS_LAUNCHED();
+    if (sizeof(T) == 2 && (C == 16 || C == 32 || C == 64)) {
+      if (C == 16) rc = launch_init_fast<16>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st);
+      else if (C == 32) rc = launch_init_fast<32>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st);
+      else rc = launch_init_fast<64>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st);
+      if (rc) return rc;
+    } else {
+      init_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(x, plan->init_w, plan->init_b, a0, n_pix, H, W, C);
+      DBS_LAUNCHED();
+    }
     if ((rc = maybe_tap<T>(c, "init", a0, B, H, W, C))) return rc;
   }
 
@@ -917,6 +1099,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
         if ((rc = maybe_tap<T>(cc, name, up, B, h2, w2, ch))) return rc;
         snprintf(name, sizeof(name), "dec%d", i);
       }
+      cc.defer = (i == nb - 1 && cb >= B) ? &defer : nullptr;
       if ((rc = run_block<T>(cc, plan->dec[i], name, up_c, ch, skip[si] + b0 * h2 * w2 * sc[si], sc[si], h2, w2, ty, th, tr,
                              dst + b0 * h2 * w2 * co)))
         return rc;
@@ -937,9 +1120,18 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
                   16 / (int)sizeof(T));
       ProfScope prof(kProfUnetMisc, st);
       const int64_t nthr = n_pix * cvf;
-      final_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(cur, plan->final_w, plan->final_b, score, n_pix,
-                                                                          H, W, C, cfg.output_scale);
-      DBS_LAUNCHED();
+      if (final_fused_ok) {
+        const __nv_bfloat16* yin = defer.done ? (const __nv_bfloat16*)defer.y : (const __nv_bfloat16*)cur;
+        const __nv_bfloat16* rin = defer.done ? (const __nv_bfloat16*)defer.res : nullptr;
+        if (C == 16) rc = launch_final_fused<16>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, stats, defer.gamma, defer.beta, score, B, H, W, st);
+        else if (C == 32) rc = launch_final_fused<32>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, stats, defer.gamma, defer.beta, score, B, H, W, st);
+        else rc = launch_final_fused<64>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, stats, defer.gamma, defer.beta, score, B, H, W, st);
+        if (rc) return rc;
+      } else {
+        final_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(cur, plan->final_w, plan->final_b, score, n_pix,
+                                                                            H, W, C, cfg.output_scale);
+        DBS_LAUNCHED();
+      }
     }
     if (cfg.normalize_output) {
       normalize_output_kernel<<<(unsigned)B, 256, 0, st>>>(score, H * W, cfg.output_scale);
@@ -1014,6 +1206,16 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
     repack_kernel<<<(unsigned)((C * 9 + 255) / 256), 256>>>(raw, plan->init_w, (__nv_bfloat16*)scratch, C, 1, 9, 0);
     repack_kernel<<<(unsigned)((C * 9 + 255) / 256), 256>>>(rawf, plan->final_w, (__nv_bfloat16*)scratch, 1, C, 9, 0);
     if (cudaGetLastError() != cudaSuccess) { set_error("unet_plan_create: repack launch failed"); return fail(DBS_ERR_CUDA); }
+    plan->final_w_host.resize((size_t)C * 9);
+    plan->init_w_host.resize((size_t)C * 9);
+    plan->init_b_host.resize((size_t)C);
+    if (cudaMemcpy(plan->init_w_host.data(), plan->init_w, (size_t)C * 9 * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(plan->init_b_host.data(), plan->init_b, (size_t)C * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(plan->final_w_host.data(), plan->final_w, (size_t)C * 9 * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(&plan->final_b_host, plan->final_b, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("unet_plan_create: reading back the final conv weights failed");
+      return fail(DBS_ERR_CUDA);
+    }
   }
 
   // blocks, with the per-block time Linear layers concatenated into one [sumC][T] matrix
