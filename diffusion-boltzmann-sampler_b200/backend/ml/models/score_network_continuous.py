@@ -13,6 +13,7 @@ used (training is outside the engine's scope).  Without a B200 the engine route 
 """
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -126,6 +127,7 @@ class ContinuousScoreNetwork(nn.Module):
                                  if use_attention else None)
         self.output_proj = nn.Sequential(nn.LayerNorm(hidden_dim), nn.Linear(hidden_dim, hidden_dim // 2), nn.SiLU(),
                                          nn.Linear(hidden_dim // 2, 2))
+        self.precision = os.environ.get("DBS_PRECISION_CSN", "fp32")
         self._plan = None
         self._workspace = None
 
@@ -156,9 +158,9 @@ class ContinuousScoreNetwork(nn.Module):
 
     def engine_forward(self, x: torch.Tensor, t: torch.Tensor, precision=None, out=None):
         """score from the sm_100a kernels.  x (B, N, 2) fp32, t (B,) or (1,); device tensors in -> device
-        tensor out.  Only the fp32 path is built for this network (precision None / "fp32")."""
-        if precision not in (None, "fp32"):
-            raise NotImplementedError("ContinuousScoreNetwork engine: only the fp32 path is built")
+        tensor out.  precision: "fp32" (default; CUDA-core parity path) or "bf16" (tcgen05 path for the MLP and
+        attention layers: hidden_dim 128, head_dim 32, N a multiple of 16 up to 256)."""
+        prec = {"fp32": 0, "bf16": 1}[precision or self.precision]
         if self.training and self.dropout_p > 0:
             raise NotImplementedError("ContinuousScoreNetwork engine: dropout is inference-only (call .eval())")
         plan = self.engine_plan()
@@ -178,7 +180,7 @@ class ContinuousScoreNetwork(nn.Module):
         if ws is None or ws.numel() < need or not ws.is_cuda:
             ws = self._workspace = torch.empty(int(need), dtype=torch.uint8, device=xd.device)
         score = out if out is not None else torch.empty_like(xd)
-        abi.check(abi.lib.dbs_csn_forward(plan, xd.data_ptr(), td.data_ptr(), td.numel(), score.data_ptr(), B, N,
+        abi.check(abi.lib.dbs_csn_forward(plan, xd.data_ptr(), td.data_ptr(), td.numel(), score.data_ptr(), B, N, prec,
                                           ws.data_ptr(), ws.numel(), runtime.current_stream()), "csn_forward")
         return score
 

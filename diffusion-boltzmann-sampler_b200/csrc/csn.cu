@@ -23,7 +23,19 @@
 #include <string>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
+namespace dbs {
+// csn_tc.cu: tcgen05 kernels of the bf16 path
+int csn_tc_convert_weights(const float* src, __nv_bfloat16* dst, int64_t n);
+int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const float* bias, int N_total, const float* pre_g,
+                  const float* pre_b, const float* post_g, const float* post_b, int silu, const float* tbias,
+                  int64_t tb_stride, int tokens_per_cfg, const float* res, void* out, int out_bf16, int64_t M,
+                  cudaStream_t st);
+int csn_tc_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t B, int N, int heads, cudaStream_t st);
+}  // namespace dbs
 
 struct dbs_csn_plan {
   dbs_csn_config cfg;
@@ -35,7 +47,9 @@ struct dbs_csn_plan {
   struct Block {
     float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *n1_g, *n1_b, *n2_g, *n2_b;
     float *an_g, *an_b, *qkv_w, *qkv_b, *proj_w, *proj_b;
+    __nv_bfloat16 *fc1_h, *fc2_h, *qkv_h, *proj_h;   // bf16 copies for the tcgen05 path (null if not eligible)
   };
+  bool tc_ok = false;
   std::vector<Block> blocks;
   float *on_g = nullptr, *on_b = nullptr, *o1_w = nullptr, *o1_b = nullptr, *o2_w = nullptr, *o2_b = nullptr;
 };
@@ -401,7 +415,7 @@ struct Bump {
 };
 
 int forward_impl(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t, float* score, int64_t B, int N,
-                 void* workspace, int64_t ws_bytes, cudaStream_t st, int64_t* need_bytes) {
+                 int precision, void* workspace, int64_t ws_bytes, cudaStream_t st, int64_t* need_bytes) {
   const dbs_csn_config& c = plan->cfg;
   const int H = c.hidden_dim, T = c.time_embed_dim, nb = c.num_blocks;
   const int64_t M = B * N;
@@ -415,6 +429,14 @@ int forward_impl(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t
   DBS_REQUIRE(workspace != nullptr && ws.off <= ws_bytes, "csn_forward: workspace too small (%lld < %lld bytes)",
               (long long)ws_bytes, (long long)ws.off);
   int rc;
+  const bool tc = precision == 1;
+  if (tc) {
+    if (!plan->tc_ok || N % 16 != 0 || N > 256) {
+      set_error("csn_forward: the bf16 tcgen05 path needs hidden_dim 128, head_dim 32, attention on and N in {16, 32, ..., 256} "
+                "(got hidden %d, heads %d, N %d)", c.hidden_dim, c.num_heads, N);
+      return DBS_ERR_UNSUPPORTED;
+    }
+  }
   {
     prof_set_label("csn time");
     ProfScope prof(kProfCsnLinear, st);
@@ -430,6 +452,18 @@ int forward_impl(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t
   if ((rc = run_linear(kProEmbed, a, st))) return rc;
   for (int i = 0; i < nb; ++i) {
     const dbs_csn_plan::Block& b = plan->blocks[i];
+    if (tc) {
+      // bf16 tensor-core route: the same five steps, LayerNorm / SiLU / time bias / residual fused into the GEMM
+      // kernels' prologue and epilogue; h (the residual stream) stays fp32, h1 / qkv / attention output are bf16
+      const float* tb = tbias + (int64_t)i * H;
+      const int64_t tbs = n_t == 1 ? 0 : (int64_t)nb * H;
+      if ((rc = csn_tc_linear(h, 0, b.fc1_h, b.fc1_b, H, nullptr, nullptr, b.n1_g, b.n1_b, 1, tb, tbs, N, nullptr, h1, 1, M, st))) return rc;
+      if ((rc = csn_tc_linear(h1, 1, b.fc2_h, b.fc2_b, H, nullptr, nullptr, b.n2_g, b.n2_b, 1, nullptr, 0, N, h, h, 0, M, st))) return rc;
+      if ((rc = csn_tc_linear(h, 0, b.qkv_h, b.qkv_b, 3 * H, b.an_g, b.an_b, nullptr, nullptr, 0, nullptr, 0, N, nullptr, qkv, 1, M, st))) return rc;
+      if ((rc = csn_tc_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)h1, B, N, c.num_heads, st))) return rc;
+      if ((rc = csn_tc_linear(h1, 1, b.proj_h, b.proj_b, H, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, N, h, h, 0, M, st))) return rc;
+      continue;
+    }
     // MLPBlock (:123-136)
     memset(&a, 0, sizeof(a));
     a.X = h; a.K = H; a.W = b.fc1_w; a.bias = b.fc1_b; a.N = H; a.post_g = b.n1_g; a.post_b = b.n1_b; a.silu = 1;
@@ -526,6 +560,23 @@ extern "C" int dbs_csn_plan_create(const dbs_csn_config* cfg, const dbs_param* p
       up(q + "proj.weight", (int64_t)H * H, &b.proj_w); up(q + "proj.bias", H, &b.proj_b);
     }
   }
+  plan->tc_ok = H == 128 && cfg->use_attention && H / cfg->num_heads == 32;
+  if (plan->tc_ok && !rc) {
+    for (int i = 0; i < nb && !rc; ++i) {
+      dbs_csn_plan::Block& b = plan->blocks[i];
+      struct { const float* src; __nv_bfloat16** dst; int64_t n; } cv[4] = {
+          {b.fc1_w, &b.fc1_h, (int64_t)H * H}, {b.fc2_w, &b.fc2_h, (int64_t)H * H},
+          {b.qkv_w, &b.qkv_h, (int64_t)3 * H * H}, {b.proj_w, &b.proj_h, (int64_t)H * H}};
+      for (auto& e : cv) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, (size_t)e.n * 2) != cudaSuccess) { set_error("csn plan: cudaMalloc failed"); rc = DBS_ERR_CUDA; break; }
+        plan->allocs.push_back(d);
+        *e.dst = (__nv_bfloat16*)d;
+        if ((rc = csn_tc_convert_weights(e.src, *e.dst, e.n))) break;
+      }
+    }
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("csn plan: weight conversion failed"); rc = DBS_ERR_CUDA; }
+  }
   if (!rc) rc = upload_host(plan, wt.data(), (int64_t)nb * H * T, &plan->twt);
   if (!rc) rc = upload_host(plan, bt.data(), (int64_t)nb * H, &plan->tbt);
   up("output_proj.0.weight", H, &plan->on_g); up("output_proj.0.bias", H, &plan->on_b);
@@ -545,14 +596,15 @@ extern "C" void dbs_csn_plan_destroy(dbs_csn_plan* plan) {
 extern "C" int64_t dbs_csn_workspace_bytes(const dbs_csn_plan* plan, int64_t B, int N, int64_t n_t) {
   if (!plan || B <= 0 || N <= 0 || n_t <= 0) { set_error("csn_workspace_bytes: bad argument"); return -1; }
   int64_t need = 0;
-  if (forward_impl(const_cast<dbs_csn_plan*>(plan), nullptr, nullptr, n_t, nullptr, B, N, nullptr, 0, nullptr, &need)) return -1;
+  if (forward_impl(const_cast<dbs_csn_plan*>(plan), nullptr, nullptr, n_t, nullptr, B, N, 0, nullptr, 0, nullptr, &need)) return -1;
   return need;
 }
 
 extern "C" int dbs_csn_forward(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
-                               int64_t B, int N, void* workspace, int64_t workspace_bytes, void* stream) {
+                               int64_t B, int N, int precision, void* workspace, int64_t workspace_bytes, void* stream) {
   DBS_REQUIRE(plan && x && t && score, "csn_forward: null argument");
   DBS_REQUIRE(B > 0 && N > 0, "csn_forward: empty batch (%lld x %d)", (long long)B, N);
   DBS_REQUIRE(n_t == 1 || n_t == B, "csn_forward: t must have 1 or B entries (got %lld)", (long long)n_t);
-  return forward_impl(plan, x, t, n_t, score, B, N, workspace, workspace_bytes, as_stream(stream), nullptr);
+  DBS_REQUIRE(precision == 0 || precision == 1, "csn_forward: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
+  return forward_impl(plan, x, t, n_t, score, B, N, precision, workspace, workspace_bytes, as_stream(stream), nullptr);
 }

@@ -1,0 +1,440 @@
+// csn_tc.cu — tensor-core (tcgen05 / TMEM) kernels of the particle score network, bf16 operands with
+// fp32 accumulation (reference models/score_network_continuous.py:123-180).
+//
+//   csn_tc_linear_kernel     Y[128 tokens x 128] = epi(pro(X)[128 x 128] . W[128 x 128]^T) per tile.
+//       The prologue (LayerNorm of the input rows, ParticleAttention.norm :166) runs while the rows are
+//       converted to bf16 and written straight into the 128-byte-swizzled K-major operand layout the
+//       UMMA descriptor names — no TMA here because the operand is produced, not copied.  Eight
+//       tcgen05.mma (M=128, N=128, K=16) accumulate in TMEM; in the epilogue a thread owns one token row
+//       (TMEM lane = row), so MLPBlock's LayerNorm -> SiLU -> + time bias / + residual (:130-136) is
+//       thread-local arithmetic on tcgen05.ld chunks.  HBM traffic per layer = one read of X, one write
+//       of Y: the normalised / activated intermediates never leave the SM.
+//   csn_tc_attention_kernel  one CTA per (configuration, head), N <= 256 particles, head_dim 32:
+//       S = Q K^T (two 128-row tiles, N columns) into TMEM; softmax per query row is thread-local
+//       (lane = query); P goes to shared memory as the bf16 A operand of O = P V (V transposed into the
+//       K-major B layout on the way in); the N x N matrix never reaches HBM  (:169-178).
+// Both kernels are phase-serial inside a CTA (produce operands -> MMA -> drain TMEM); overlap comes from
+// several CTAs per SM (linear) and from the persistent loop (attention).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dbs {
+namespace {
+
+using namespace tc;
+
+constexpr uint32_t kAtomBytes = 128 * 128;   // one 64-element K slab of 128 rows (128-byte rows)
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// K-major operand descriptor words for 128-byte rows, SWIZZLE_128B (same encoding as conv_tc.cu, KC = 64)
+constexpr uint64_t kDesc128 = (1ull << 16) | ((uint64_t)((8 * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// 64-byte rows, SWIZZLE_64B (conv_tc.cu, KC = 32)
+constexpr uint64_t kDesc64 = (1ull << 16) | ((uint64_t)((8 * 64) >> 4) << 32) | (1ull << 46) | (4ull << 61);
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcLinArgs {
+  const void* X;               // [M][128] fp32 (in_bf16 = 0) or bf16 (in_bf16 = 1)
+  const __nv_bfloat16* W;      // [N_total][128] bf16
+  const float* bias;           // [N_total]
+  int N_total;                 // multiple of 128; blockIdx.y selects the 128-column block
+  const float *pre_g, *pre_b;  // LayerNorm over the 128 inputs (null = none)
+  const float *post_g, *post_b;  // LayerNorm over the 128 outputs (null = none; needs N_total == 128)
+  int silu;
+  const float* tbias; int64_t tb_stride; int tokens_per_cfg;
+  const float* res;            // fp32 [M][N_total] or null
+  void* out;                   // [M][N_total] fp32 (out_bf16 = 0) or bf16
+  int in_bf16, out_bf16;
+  int64_t M;
+};
+
+// a warp converts one 128-wide row to bf16 and stores it into the swizzled K-major operand tile
+template <bool kBf16In>
+__device__ __forceinline__ void stage_row(uint8_t* tile, int r, const void* src_row, bool live, int lane,
+                                          const float* g, const float* b) {
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    if (kBf16In) {
+      const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(src_row) + 4 * lane);
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+      v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(c); v[3] = __high2float(c);
+    } else {
+      const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src_row) + 4 * lane);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+  }
+  if (g) {
+    const float mean = warp_sum((v[0] + v[1]) + (v[2] + v[3])) * (1.0f / 128.0f);
+    const float d0 = v[0] - mean, d1 = v[1] - mean, d2 = v[2] - mean, d3 = v[3] - mean;
+    const float var = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) * (1.0f / 128.0f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    const float4 g4 = *reinterpret_cast<const float4*>(g + 4 * lane);
+    const float4 b4 = *reinterpret_cast<const float4*>(b + 4 * lane);
+    v[0] = d0 * rstd * g4.x + b4.x; v[1] = d1 * rstd * g4.y + b4.y;
+    v[2] = d2 * rstd * g4.z + b4.z; v[3] = d3 * rstd * g4.w + b4.w;
+  }
+  // element k = 4*lane: slab k/64, 16-byte chunk (k%64)/8 XOR (row % 8), 8-byte half (lane & 1)
+  const uint32_t off = (uint32_t)(lane >> 4) * kAtomBytes + (uint32_t)r * 128u +
+                       (uint32_t)((((lane & 15) >> 1) ^ (r & 7)) << 4) + (uint32_t)(lane & 1) * 8u;
+  *reinterpret_cast<uint2*>(tile + off) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+}
+
+__global__ void __launch_bounds__(256, 3)
+csn_tc_linear_kernel(const TcLinArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = smem;                   // 2 slabs x 16 KB
+  uint8_t* Ws = smem + 2 * kAtomBytes;  // 2 slabs x 16 KB
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * 128;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 128);
+  // this CTA's 128 weight rows, once
+  for (int r = warp; r < 128; r += 8) stage_row<true>(Ws, r, a.W + (int64_t)(col0 + r) * 128, true, lane, nullptr, nullptr);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t a_lo = (uint32_t)kDesc128 | ((smem_u32(As) & 0x3FFFFu) >> 4);
+  const uint32_t w_lo = (uint32_t)kDesc128 | ((smem_u32(Ws) & 0x3FFFFu) >> 4);
+  const uint32_t hi32 = (uint32_t)(kDesc128 >> 32);
+  const int64_t n_tiles = (a.M + 127) / 128;
+  uint32_t phase = 0;
+  const int q = warp & 3, ch = warp >> 2;        // epilogue: TMEM lane quadrant, 64-column half
+  const int N = a.N_total;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t m0 = tile * 128;
+    // ---- phase 1: operand rows (prologue fused)
+    for (int r = warp; r < 128; r += 8) {
+      const bool live = m0 + r < a.M;
+      if (a.in_bf16) stage_row<true>(As, r, reinterpret_cast<const __nv_bfloat16*>(a.X) + (m0 + r) * 128, live, lane, a.pre_g, a.pre_b);
+      else stage_row<false>(As, r, reinterpret_cast<const float*>(a.X) + (m0 + r) * 128, live, lane, a.pre_g, a.pre_b);
+    }
+    fence_async_smem();
+    __syncthreads();
+    // ---- phase 2: eight MMAs (K = 128), completion signalled on the mbarrier
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t o = (uint32_t)(k >> 2) * (kAtomBytes >> 4) + (uint32_t)(k & 3) * 2u;
+        umma_bf16_lohi(tmem, a_lo + o, w_lo + o, hi32, idesc_bf16(128, 128), k ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- phase 3: drain TMEM, one token row per thread
+    const int row = q * 32 + lane;
+    const int64_t m = m0 + row;
+    const bool live = m < a.M;
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    float mean = 0.f, rstd = 1.f;
+    if (a.post_g) {
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float f = __uint_as_float(v[j]) + __ldg(a.bias + c + j);
+          s += f; ss = fmaf(f, f, ss);
+        }
+      }
+      mean = s * (1.0f / 128.0f);
+      rstd = rsqrtf(fmaxf(ss * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
+    }
+    const float* tb = a.tbias ? a.tbias + (live ? m / a.tokens_per_cfg : 0) * a.tb_stride : nullptr;
+#pragma unroll 1
+    for (int c = ch * 64; c < ch * 64 + 64; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c, v);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = __uint_as_float(v[j]) + __ldg(a.bias + col0 + c + j);
+        if (a.post_g) x = (x - mean) * rstd * __ldg(a.post_g + c + j) + __ldg(a.post_b + c + j);
+        if (a.silu) x = silu_fast(x);
+        if (tb) x += __ldg(tb + col0 + c + j);
+        f[j] = x;
+      }
+      if (live) {
+        if (a.res) {
+          const float4* rp = reinterpret_cast<const float4*>(a.res + m * N + col0 + c);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 r4 = rp[j4];
+            f[4 * j4] += r4.x; f[4 * j4 + 1] += r4.y; f[4 * j4 + 2] += r4.z; f[4 * j4 + 3] += r4.w;
+          }
+        }
+        if (a.out_bf16) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * N + col0 + c);
+          dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+        } else {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + m * N + col0 + c);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();     // TMEM drained and the operand tile consumed: next tile may overwrite both
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention: qkv bf16 [B][N][3][heads][32]  ->  out bf16 [B][N][heads*32]
+constexpr int kHD = 32;
+constexpr uint32_t kQBytes = 256 * 64;         // Q (two 128-row tiles), K: 64-byte rows, SWIZZLE_64B
+constexpr uint32_t kVtSlab = 32 * 128;         // V^T: 32 rows x 64 keys per slab, SWIZZLE_128B
+constexpr uint32_t kPTile = 4 * kAtomBytes;    // P tile: 128 rows x 256 keys
+
+__global__ void __launch_bounds__(256, 1)
+csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int64_t n_pairs, int N,
+                        int heads, float scale_log2e) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Qs = smem;                       // 16 KB
+  uint8_t* Ks = Qs + kQBytes;               // 16 KB
+  uint8_t* Vt = Ks + kQBytes;               // 4 slabs x 4 KB
+  uint8_t* Ps = Vt + 4 * kVtSlab;           // 2 tiles x 64 KB
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const int H = heads * kHD;
+  const int n_qt = (N + 127) / 128;         // query tiles (1 or 2)
+  const int t_mine = warp >> 2, qd = warp & 3;
+  const int row = qd * 32 + lane;           // my query row inside my tile
+  const int qi = t_mine * 128 + row;        // my query
+  uint32_t phase = 0;
+  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    const int64_t b = pair / heads;
+    const int h = (int)(pair - b * heads);
+    const __nv_bfloat16* base = qkv + b * N * 3 * H + h * kHD;
+    // ---- phase 1: Q, K rows (64 B each) into the SWIZZLE_64B K-major layout; V transposed into V^T slabs
+    for (int idx = threadIdx.x; idx < 256 * 4; idx += 256) {
+      const int r = idx >> 2, c = idx & 3;
+      uint4 qv = make_uint4(0, 0, 0, 0), kv = make_uint4(0, 0, 0, 0);
+      if (r < N) {
+        const __nv_bfloat16* tok = base + (int64_t)r * 3 * H;
+        qv = *reinterpret_cast<const uint4*>(tok + c * 8);
+        kv = *reinterpret_cast<const uint4*>(tok + H + c * 8);
+      }
+      const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(Qs + off) = qv;
+      *reinterpret_cast<uint4*>(Ks + off) = kv;
+    }
+    {
+      const int k = threadIdx.x;            // key
+      uint32_t w[16];
+      if (k < N) {
+        const uint4* vp = reinterpret_cast<const uint4*>(base + (int64_t)k * 3 * H + 2 * H);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const uint4 v4 = vp[i]; w[4 * i] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0u;
+      }
+      uint8_t* slab = Vt + (uint32_t)(k >> 6) * kVtSlab + (uint32_t)(k & 7) * 2u;
+      const int kc = (k & 63) >> 3;
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) {
+        const int n0 = 2 * n2, n1 = 2 * n2 + 1;
+        *reinterpret_cast<uint16_t*>(slab + n0 * 128 + ((kc ^ (n0 & 7)) << 4)) = (uint16_t)(w[n2] & 0xFFFFu);
+        *reinterpret_cast<uint16_t*>(slab + n1 * 128 + ((kc ^ (n1 & 7)) << 4)) = (uint16_t)(w[n2] >> 16);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    // ---- phase 2: S = Q K^T, one N-column accumulator per query tile
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t q_lo = (uint32_t)kDesc64 | ((smem_u32(Qs) & 0x3FFFFu) >> 4);
+      const uint32_t k_lo = (uint32_t)kDesc64 | ((smem_u32(Ks) & 0x3FFFFu) >> 4);
+      const uint32_t hi = (uint32_t)(kDesc64 >> 32);
+      const uint32_t idesc = idesc_bf16(128, N);
+      for (int t = 0; t < n_qt; ++t)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          umma_bf16_lohi(tmem + t * 256, q_lo + (uint32_t)t * ((128u * 64u) >> 4) + ks * 2u, k_lo + ks * 2u, hi, idesc, ks ? 1u : 0u);
+      umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- phase 3: softmax of my query row, P -> shared memory (bf16, A operand of P V)
+    float l = 0.f;
+    if (t_mine < n_qt) {
+      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + t_mine * 256;
+      float mx = -INFINITY;
+      for (int c = 0; c < N; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      const float mxs = mx * scale_log2e;
+      uint8_t* prow = Ps + (uint32_t)t_mine * kPTile + (uint32_t)row * 128u;
+      for (int c = 0; c < N; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        float p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { p[j] = exp2f(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)); }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // the row sum uses the bf16-rounded probabilities that the P V product will see
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+          l += __low2float(h2) + __high2float(h2);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        uint8_t* slab = prow + (uint32_t)(c >> 6) * kAtomBytes;
+        const int kc = (c & 63) >> 3;
+        *reinterpret_cast<uint4*>(slab + (((kc) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(slab + (((kc + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- phase 4: O = P V (N = 32 columns per tile, over the S columns just consumed)
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t p_lo = (uint32_t)kDesc128 | ((smem_u32(Ps) & 0x3FFFFu) >> 4);
+      const uint32_t v_lo = (uint32_t)kDesc128 | ((smem_u32(Vt) & 0x3FFFFu) >> 4);
+      const uint32_t hi = (uint32_t)(kDesc128 >> 32);
+      const uint32_t idesc = idesc_bf16(128, kHD);
+      for (int t = 0; t < n_qt; ++t)
+        for (int ks = 0; ks < N / 16; ++ks) {
+          const uint32_t po = (uint32_t)t * (kPTile >> 4) + (uint32_t)(ks >> 2) * (kAtomBytes >> 4) + (uint32_t)(ks & 3) * 2u;
+          const uint32_t vo = (uint32_t)(ks >> 2) * (kVtSlab >> 4) + (uint32_t)(ks & 3) * 2u;
+          umma_bf16_lohi(tmem + t * 256, p_lo + po, v_lo + vo, hi, idesc, ks ? 1u : 0u);
+        }
+      umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- phase 5: normalise and store my query's head slice
+    if (t_mine < n_qt) {
+      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + t_mine * 256;
+      uint32_t v0[16], v1[16];
+      tmem_ld16(taddr, v0);
+      tmem_ld16(taddr + 16, v1);
+      tmem_ld_wait();
+      if (qi < N) {
+        const float inv = 1.0f / l;
+        uint4* dst = reinterpret_cast<uint4*>(out + (b * N + qi) * H + h * kHD);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pk[j] = pack_bf16(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv);
+          pk[8 + j] = pack_bf16(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace
+
+// ---- host launchers (used by csn.cu) --------------------------------------------------------------
+int csn_tc_convert_weights(const float* src, __nv_bfloat16* dst, int64_t n) {
+  f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, n);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const float* bias, int N_total, const float* pre_g,
+                  const float* pre_b, const float* post_g, const float* post_b, int silu, const float* tbias,
+                  int64_t tb_stride, int tokens_per_cfg, const float* res, void* out, int out_bf16, int64_t M,
+                  cudaStream_t st) {
+  DBS_REQUIRE(N_total % 128 == 0 && (!post_g || N_total == 128), "csn_tc_linear: unsupported width %d", N_total);
+  TcLinArgs a;
+  a.X = X; a.W = W; a.bias = bias; a.N_total = N_total; a.pre_g = pre_g; a.pre_b = pre_b; a.post_g = post_g; a.post_b = post_b;
+  a.silu = silu; a.tbias = tbias; a.tb_stride = tb_stride; a.tokens_per_cfg = tokens_per_cfg; a.res = res; a.out = out;
+  a.in_bf16 = in_bf16; a.out_bf16 = out_bf16; a.M = M;
+  const size_t smem = 4 * kAtomBytes + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBS_CUDA(cudaFuncSetAttribute(csn_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int64_t n_tiles = (M + 127) / 128;
+  const int by = N_total / 128;
+  int64_t bx = (148 * 3 + by - 1) / by;
+  if (bx > n_tiles) bx = n_tiles;
+  prof_set_label("tc linear N%d ln%d/%d", N_total, pre_g ? 1 : 0, post_g ? 1 : 0);
+  ProfScope prof(kProfCsnLinear, st);
+  csn_tc_linear_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, smem, st>>>(a);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+int csn_tc_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t B, int N, int heads, cudaStream_t st) {
+  DBS_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "csn_tc_attention: N = %d not in {16, 32, ..., 256}", N);
+  const size_t smem = 2 * kQBytes + 4 * kVtSlab + 2 * kPTile + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBS_CUDA(cudaFuncSetAttribute(csn_tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int64_t n_pairs = B * heads;
+  const int grid = (int)(n_pairs < 148 ? n_pairs : 148);
+  prof_set_label("tc attention N%d heads%d", N, heads);
+  ProfScope prof(kProfCsnAttention, st);
+  csn_tc_attention_kernel<<<grid, 256, smem, st>>>(qkv, out, n_pairs, N, heads, (1.0f / sqrtf((float)kHD)) * 1.4426950408889634f);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+}  // namespace dbs

@@ -77,7 +77,7 @@ PROTOTYPES = {
     "dbs_csn_plan_create": (i32, [C.POINTER(CsnConfig), C.POINTER(Param), i32, vp, vp, C.POINTER(vp)]),
     "dbs_csn_plan_destroy": (None, [vp]),
     "dbs_csn_workspace_bytes": (i64, [vp, i64, i32, i64]),
-    "dbs_csn_forward": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, i64, vp]),
+    "dbs_csn_forward": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, vp, i64, vp]),
     "dbs_conv_tc": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     "dbs_conv_block_tc": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
 }

@@ -302,9 +302,13 @@ void dbs_csn_plan_destroy(dbs_csn_plan* plan);
 int64_t dbs_csn_workspace_bytes(const dbs_csn_plan* plan, int64_t B, int N, int64_t n_t);
 
 /* score = ContinuousScoreNetwork.forward(x, t)  (score_network_continuous.py:256-282).
- * x, score: fp32 [B][N][2] (positions normalised to [-1,1]); t: fp32 [n_t], n_t = 1 or B. */
+ * x, score: fp32 [B][N][2] (positions normalised to [-1,1]); t: fp32 [n_t], n_t = 1 or B.
+ * precision: 0 = fp32 CUDA-core path (parity mode, <= 1e-4); 1 = bf16 tcgen05 path for the MLP / attention
+ * layers (fc1, fc2, qkv, softmax(QK^T)V, proj; fp32 accumulation, fp32 residual stream), which needs
+ * hidden_dim 128, head_dim 32, attention on and N in {16, 32, ..., 256}: DBS_ERR_UNSUPPORTED otherwise. */
 int dbs_csn_forward(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
-                    int64_t B, int N, void* workspace, int64_t workspace_bytes, void* stream);
+                    int64_t B, int N, int precision, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 
 /* Philox stream tags (ctr.w) and the x0 step tag. */
 #define DBS_STREAM_SWEEP 0x53574550u /* 'SWEP' */

@@ -13,21 +13,22 @@ torch.manual_seed(0)
 net = ContinuousScoreNetwork(N).eval()
 x = (torch.rand(B, N, 2) * 2 - 1).cuda()
 t = torch.full((1,), 0.5).cuda()
+prec = sys.argv[3] if len(sys.argv) > 3 else "fp32"
 for _ in range(2):
-    net.engine_forward(x, t)
+    net.engine_forward(x, t, precision=prec)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(3):
-    net.engine_forward(x, t)
+    net.engine_forward(x, t, precision=prec)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 H, nb, hd = 128, 4, 32
 flops = 2.0 * B * N * (66 * H + nb * (6 * H * H) + H * H // 2 + H) + nb * 4.0 * B * 4 * N * N * hd
-print(f"forward B={B} N={N}: {ms:.3f} ms  ({flops / ms / 1e9:.1f} TFLOP/s fp32 CUDA-core, {B / ms * 1e3:.0f} configs/s)")
+print(f"{prec} forward B={B} N={N}: {ms:.3f} ms  ({flops / ms / 1e9:.1f} TFLOP/s, {B / ms * 1e3:.0f} configs/s)")
 abi.profile_read(reset=True); abi.profile(True)
-net.engine_forward(x, t); torch.cuda.synchronize()
+net.engine_forward(x, t, precision=prec); torch.cuda.synchronize()
 print({k: (round(v[0], 3), v[1]) for k, v in abi.profile_read().items() if v[1]})
 abi.profile(False)
 abi.lib.dbs_profile_dump(b"gpurun_out/csn_layers.tsv")

@@ -77,6 +77,54 @@ def test_forward_matches_oracle_on_shapes(B, N, kw):
     assert _rel(got1, want1) <= 1e-4
 
 
+def _rms_rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()) / (np.sqrt((b ** 2).mean()) + 1e-30))
+
+
+@pytest.mark.parametrize("B,N", [(3, 256), (2, 128), (5, 48), (1, 16), (130, 64)])
+def test_bf16_tensor_core_path_within_stated_bound(B, N):
+    """tcgen05 path (fc1 / fc2 / qkv / attention / proj in bf16, fp32 accumulate and residual stream).
+    Stated bound: rms error <= 2e-2 of the output rms against the fp32 oracle, per forward."""
+    from backend.ml.models.score_network_continuous import ContinuousScoreNetwork
+    torch.manual_seed(11)
+    net = ContinuousScoreNetwork(N).eval()
+    x = torch.rand(B, N, 2) * 2 - 1
+    t = torch.rand(B)
+    want = o_csn.csn_forward(_sd(net), x, t).numpy()
+    with torch.no_grad():
+        got = net.engine_forward(x, t, precision="bf16").cpu().numpy()
+        ref32 = net.engine_forward(x, t, precision="fp32").cpu().numpy()
+    assert np.isfinite(got).all()
+    assert _rms_rel(got, want) <= 2e-2, _rms_rel(got, want)
+    assert _rel(ref32, want) <= 1e-4
+    with torch.no_grad():
+        got1 = net.engine_forward(x, torch.full((1,), 0.3), precision="bf16").cpu().numpy()
+    want1 = o_csn.csn_forward(_sd(net), x, torch.full((B,), 0.3)).numpy()
+    assert _rms_rel(got1, want1) <= 2e-2
+
+
+def test_bf16_path_rejects_ineligible_shapes():
+    from backend.ml.models.score_network_continuous import ContinuousScoreNetwork
+    net = ContinuousScoreNetwork(24).eval()
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        net.engine_forward(torch.zeros(2, 24, 2), torch.zeros(2), precision="bf16")      # N % 16 != 0
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        net.engine_forward(torch.zeros(1, 272, 2), torch.zeros(1), precision="bf16")     # N > 256
+
+
+def test_bf16_sampler_trajectory_close_to_fp32():
+    from backend.ml.models.score_network_continuous import ContinuousScoreNetwork
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    torch.manual_seed(2)
+    N = 64
+    net = ContinuousScoreNetwork(N).eval()
+    x0, nz = torch.randn(4, N, 2), torch.randn(10, 4, N, 2)
+    a = DiffusionSampler(net, num_steps=10, precision="fp32").sample((4, N, 2), x0=x0, noises=nz).numpy()
+    b = DiffusionSampler(net, num_steps=10, precision="bf16").sample((4, N, 2), x0=x0, noises=nz).numpy()
+    assert _rms_rel(b, a) <= 2e-2
+
+
 def test_lj_diffusion_sampling_through_the_sampler_api():
     """Config 5's diffusion leg: DiffusionSampler over (B, N, 2) normalised positions, mapped back to the
     box by LennardJonesSystem.from_continuous; same Philox streams for any sharding of the batch."""
