@@ -62,11 +62,11 @@ struct TcLinArgs {
   int64_t M;
 };
 
-// a warp converts one 128-wide row to bf16 and stores it into the swizzled K-major operand tile
+// a warp converts 128-wide rows to bf16 and stores them into the swizzled K-major operand tile; the loads of
+// kRows rows are issued together so that their latencies overlap
 template <bool kBf16In>
-__device__ __forceinline__ void stage_row(uint8_t* tile, int r, const void* src_row, bool live, int lane,
-                                          const float* g, const float* b) {
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
+__device__ __forceinline__ void load_row(const void* src_row, bool live, int lane, float v[4]) {
+  v[0] = v[1] = v[2] = v[3] = 0.f;
   if (live) {
     if (kBf16In) {
       const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(src_row) + 4 * lane);
@@ -78,6 +78,8 @@ __device__ __forceinline__ void stage_row(uint8_t* tile, int r, const void* src_
       v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
     }
   }
+}
+__device__ __forceinline__ void finish_row(uint8_t* tile, int r, int lane, float v[4], const float* g, const float* b) {
   if (g) {
     const float mean = warp_sum((v[0] + v[1]) + (v[2] + v[3])) * (1.0f / 128.0f);
     const float d0 = v[0] - mean, d1 = v[1] - mean, d2 = v[2] - mean, d3 = v[3] - mean;
@@ -93,6 +95,24 @@ __device__ __forceinline__ void stage_row(uint8_t* tile, int r, const void* src_
                        (uint32_t)((((lane & 15) >> 1) ^ (r & 7)) << 4) + (uint32_t)(lane & 1) * 8u;
   *reinterpret_cast<uint2*>(tile + off) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
 }
+// rows warp, warp + 8, ... of a 128-row tile; src = first row of the tile, rows_live = rows that exist
+template <bool kBf16In>
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int64_t rows_live, int warp, int lane,
+                                           const float* g, const float* b) {
+  constexpr int kRows = 4;
+  const size_t esz = kBf16In ? 2 : 4;
+#pragma unroll 1
+  for (int r0 = warp; r0 < 128; r0 += 8 * kRows) {
+    float v[kRows][4];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      const int r = r0 + 8 * i;
+      load_row<kBf16In>(reinterpret_cast<const uint8_t*>(src) + (size_t)r * 128 * esz, r < rows_live, lane, v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) finish_row(tile, r0 + 8 * i, lane, v[i], g, b);
+  }
+}
 
 __global__ void __launch_bounds__(256, 3)
 csn_tc_linear_kernel(const TcLinArgs a) {
@@ -102,12 +122,23 @@ csn_tc_linear_kernel(const TcLinArgs a) {
   uint8_t* Ws = smem + 2 * kAtomBytes;  // 2 slabs x 16 KB
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_tmem;
+  // per-column epilogue vectors of this CTA's 128 columns: warp-uniform reads, so they are served as
+  // shared-memory broadcasts (float4) instead of ~4 global loads per output element
+  __shared__ __align__(16) float s_bias[128], s_pg[128], s_pb[128], s_tb[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.y * 128;
+  const bool tb_shared = a.tbias != nullptr && a.tb_stride == 0;
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    s_bias[c] = a.bias[col0 + c];
+    s_pg[c] = a.post_g ? a.post_g[c] : 1.f;
+    s_pb[c] = a.post_b ? a.post_b[c] : 0.f;
+    s_tb[c] = tb_shared ? a.tbias[col0 + c] : 0.f;
+  }
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 128);
   // this CTA's 128 weight rows, once
-  for (int r = warp; r < 128; r += 8) stage_row<true>(Ws, r, a.W + (int64_t)(col0 + r) * 128, true, lane, nullptr, nullptr);
+  stage_tile<true>(Ws, a.W + (int64_t)col0 * 128, 128, warp, lane, nullptr, nullptr);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -123,11 +154,8 @@ csn_tc_linear_kernel(const TcLinArgs a) {
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t m0 = tile * 128;
     // ---- phase 1: operand rows (prologue fused)
-    for (int r = warp; r < 128; r += 8) {
-      const bool live = m0 + r < a.M;
-      if (a.in_bf16) stage_row<true>(As, r, reinterpret_cast<const __nv_bfloat16*>(a.X) + (m0 + r) * 128, live, lane, a.pre_g, a.pre_b);
-      else stage_row<false>(As, r, reinterpret_cast<const float*>(a.X) + (m0 + r) * 128, live, lane, a.pre_g, a.pre_b);
-    }
+    if (a.in_bf16) stage_tile<true>(As, reinterpret_cast<const __nv_bfloat16*>(a.X) + m0 * 128, a.M - m0, warp, lane, a.pre_g, a.pre_b);
+    else stage_tile<false>(As, reinterpret_cast<const float*>(a.X) + m0 * 128, a.M - m0, warp, lane, a.pre_g, a.pre_b);
     fence_async_smem();
     __syncthreads();
     // ---- phase 2: eight MMAs (K = 128), completion signalled on the mbarrier
@@ -157,15 +185,18 @@ csn_tc_linear_kernel(const TcLinArgs a) {
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float f = __uint_as_float(v[j]) + __ldg(a.bias + c + j);
-          s += f; ss = fmaf(f, f, ss);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c + 4 * j4]);
+          const float f0 = __uint_as_float(v[4 * j4]) + b4.x, f1 = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+          const float f2 = __uint_as_float(v[4 * j4 + 2]) + b4.z, f3 = __uint_as_float(v[4 * j4 + 3]) + b4.w;
+          s += (f0 + f1) + (f2 + f3);
+          ss = fmaf(f0, f0, ss); ss = fmaf(f1, f1, ss); ss = fmaf(f2, f2, ss); ss = fmaf(f3, f3, ss);
         }
       }
       mean = s * (1.0f / 128.0f);
       rstd = rsqrtf(fmaxf(ss * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
     }
-    const float* tb = a.tbias ? a.tbias + (live ? m / a.tokens_per_cfg : 0) * a.tb_stride : nullptr;
+    const float* tb = (a.tbias && !tb_shared) ? a.tbias + (live ? m / a.tokens_per_cfg : 0) * a.tb_stride : nullptr;
 #pragma unroll 1
     for (int c = ch * 64; c < ch * 64 + 64; c += 16) {
       uint32_t v[16];
@@ -173,12 +204,23 @@ csn_tc_linear_kernel(const TcLinArgs a) {
       tmem_ld_wait();
       float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(v[j]) + __ldg(a.bias + col0 + c + j);
-        if (a.post_g) x = (x - mean) * rstd * __ldg(a.post_g + c + j) + __ldg(a.post_b + c + j);
-        if (a.silu) x = silu_fast(x);
-        if (tb) x += __ldg(tb + col0 + c + j);
-        f[j] = x;
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c + 4 * j4]);
+        const float4 g4 = *reinterpret_cast<const float4*>(&s_pg[c + 4 * j4]);
+        const float4 p4 = *reinterpret_cast<const float4*>(&s_pb[c + 4 * j4]);
+        const float4 t4 = *reinterpret_cast<const float4*>(&s_tb[c + 4 * j4]);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = 4 * j4 + k;
+          float x = __uint_as_float(v[j]) + bb[k];
+          if (a.post_g) x = (x - mean) * rstd * gg[k] + pp[k];
+          if (a.silu) x = silu_fast(x);
+          x += tt[k];
+          if (tb) x += __ldg(tb + col0 + c + j);
+          f[j] = x;
+        }
       }
       if (live) {
         if (a.res) {
