@@ -311,6 +311,8 @@ def bench_ours(args, world, rank, local):
         "observables": {"count": float(last["acc"][0]), "mean_abs_M": float(last["acc"][2] / max(float(last["acc"][0]), 1))},
     }
 
+    c3 = bench_c3(world, rank)      # every rank takes part (sharded chains, NCCL all-reduce of the observable block)
+    line["ising_c3"] = c3
     if rank == 0 and world == 1:
         # ---- CPU baseline: oracle port (torch fp32, all host threads) on a bounded sample of the same workload
         sd = {k: v.detach().clone() for k, v in smp.model.state_dict().items()}
@@ -393,6 +395,37 @@ def bench_ising(peaks):
     out["mean_abs_M_T1.5"] = round(float(mg[: n // 64].abs().mean()), 4)
     out["mean_abs_M_T3.5"] = round(float(mg[-n // 64:].abs().mean()), 4)
     return out
+
+
+def bench_c3(world, rank):
+    """BASELINE config 3 end to end on every world size: 64x64, 65 536 chains = 64 temperatures in [1.5, 3.5] x 1024
+    chains, every temperature striped across all ranks, observables (E/N, |M|, M^2, M^4, C(r)) accumulated on the
+    device every 10 sweeps and all-reduced once over NCCL.  Bounded: 100 burn-in + 100 measured sweeps (config: 1000 +
+    1000).  value = flip attempts of ALL ranks / max-over-ranks time (observable kernels and the all-reduce included)."""
+    from dbs_b200.temperature_sweep import run_temperature_sweep
+    kw = dict(lattice_size=64, chains_per_temperature=1024, burn_in=100, n_measure=100, measure_every=10, seed=1234)
+    run_temperature_sweep(**dict(kw, burn_in=10, n_measure=10))   # warm-up (table upload, allocator)
+    torch.cuda.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = run_temperature_sweep(**kw)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    attempts = 65536.0 * 64 * 64 * out["sweeps"]
+    T = out["temperatures"]
+    onsager_T2 = -1.7455648   # exact E/N of the infinite lattice at T = 2.0 (J = 1)
+    i2 = int(np.argmin(np.abs(T - 2.0)))
+    return {"metric": "ising_spin_flips_per_s", "value": float(f"{attempts / (ms * 1e-3):.4e}"), "n_gpus": world,
+            "ms": round(ms, 2), "sweeps": int(out["sweeps"]), "chains_total": 65536, "chains_per_gpu": 65536 // world,
+            "config": {"workload": "C3: 2D Ising 64x64, 64 temperatures in [1.5,3.5] x 1024 chains striped over the ranks, "
+                                   "100 + 100 sweeps (bounded), observables + C(r) every 10 sweeps, one NCCL all-reduce"},
+            "abs_M_T1.5": round(float(out["abs_magnetization"][0]), 4), "abs_M_T3.5": round(float(out["abs_magnetization"][-1]), 4),
+            "E_per_spin_near_T2": round(float(out["energy_per_spin"][i2]), 4), "T_near_2": round(float(T[i2]), 4),
+            "onsager_E_per_spin_T2.0": onsager_T2, "binder_T1.5": round(float(out["binder"][0]), 4),
+            "count_per_temperature": float(out["count"][0])}
 
 
 def bench_diffusion64(peaks, prec):

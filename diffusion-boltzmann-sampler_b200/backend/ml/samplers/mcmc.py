@@ -53,19 +53,20 @@ class MetropolisHastings:
         return self._tables_dev, self._index_dev
 
     def sweeps_packed(self, bits: torch.Tensor, n_sweeps: int, chain_offset: int = 0, uniforms=None,
-                      sweep_offset: Optional[int] = None) -> torch.Tensor:
+                      sweep_offset: Optional[int] = None, chain_stride: int = 1) -> torch.Tensor:
         """n_sweeps checkerboard sweeps in place on packed GPU state (n_chains, L, W): ONE launch,
         lattices resident in shared memory throughout.  `uniforms` (uint32-as-int32
-        [n_sweeps][n_chains][L][L]) is the test-mode injection port."""
+        [n_sweeps][n_chains][L][L]) is the test-mode injection port.  Chain c draws from the Philox
+        stream of global id chain_offset + c * chain_stride (striped multi-GPU sharding)."""
         tables, index = self._tables()
         n = bits.shape[0]
         if self._per_chain and index.shape[0] != n:
             raise ValueError(f"per-chain temperature has {index.shape[0]} entries for {n} chains")
         off = self._sweeps_done if sweep_offset is None else sweep_offset
-        abi.check(abi.lib.dbs_ising_sweeps(bits.data_ptr(), self.model.size, n, int(n_sweeps), tables.data_ptr(),
-                                           tables.shape[0], runtime.ptr(index), self.seed, chain_offset, off,
-                                           runtime.ptr(uniforms), self.zero_field, runtime.current_stream()),
-                  "ising_sweeps")
+        abi.check(abi.lib.dbs_ising_sweeps_strided(bits.data_ptr(), self.model.size, n, int(n_sweeps), tables.data_ptr(),
+                                                   tables.shape[0], runtime.ptr(index), self.seed, chain_offset,
+                                                   chain_stride, off, runtime.ptr(uniforms), self.zero_field,
+                                                   runtime.current_stream()), "ising_sweeps")
         if sweep_offset is None:
             self._sweeps_done += int(n_sweeps)
         return bits

@@ -63,16 +63,17 @@ class IsingModel:
         out = self.unpack(bits)
         return out if (device is not None and str(device).startswith("cuda")) else out.cpu()
 
-    def random_packed(self, n_chains: int, seed: int, chain_offset: int = 0) -> torch.Tensor:
-        """Bit-packed hot start on the GPU: int32 tensor (n_chains, L, W)."""
+    def random_packed(self, n_chains: int, seed: int, chain_offset: int = 0, chain_stride: int = 1) -> torch.Tensor:
+        """Bit-packed hot start on the GPU: int32 tensor (n_chains, L, W); chain c is the chain of global id
+        chain_offset + c * chain_stride."""
         dev = runtime.require_cuda()
         L = self.size
         wpc = abi.lib.dbs_ising_words_per_chain(L)
         if wpc < 0:
             raise ValueError(f"IsingModel: lattice size {L} is not supported by the packed engine (even, 4..128)")
         bits = torch.empty((n_chains, L, wpc // L), dtype=torch.int32, device=dev)
-        abi.check(abi.lib.dbs_ising_init_packed(bits.data_ptr(), L, n_chains, seed, chain_offset,
-                                                runtime.current_stream()), "ising_init_packed")
+        abi.check(abi.lib.dbs_ising_init_packed_strided(bits.data_ptr(), L, n_chains, seed, chain_offset, chain_stride,
+                                                        runtime.current_stream()), "ising_init_packed")
         return bits
 
     def pack(self, spins: torch.Tensor) -> torch.Tensor:

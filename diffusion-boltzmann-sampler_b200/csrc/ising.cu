@@ -12,6 +12,8 @@
 // lattice lives in shared memory (double-buffered, one __syncthreads per half-sweep) and
 // touches HBM exactly twice per launch.  Per active site the work is one Philox draw
 // (2.5 rounds amortised), a 4-bit class extract, one 8-byte table LDS and two compares.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -29,6 +31,7 @@ struct SweepArgs {
   const uint32_t* uniforms;     // [n_sweeps][n_chains][L][L] or null
   int64_t n_chains;
   int64_t chain_offset;
+  int64_t chain_stride;         // global id of chain c = chain_offset + c * chain_stride (striped sharding)
   int64_t sweep_offset;
   uint32_t seed_lo, seed_hi;
   int L;
@@ -124,7 +127,7 @@ ising_sweep_kernel(SweepArgs a) {
   const bool alw4 = (c4 >> 32) == 0xFFFFFFFFull && (uint32_t)c4 == 0u, alw8 = (c8 >> 32) == 0xFFFFFFFFull && (uint32_t)c8 == 0u;
   const uint32_t t4 = alw4 ? 0u : (uint32_t)(0ull - c4), t8 = alw8 ? 0u : (uint32_t)(0ull - c8);
   (void)t4; (void)t8; (void)one;
-  const uint32_t chain_ctr = (uint32_t)(a.chain_offset + chain);
+  const uint32_t chain_ctr = (uint32_t)(a.chain_offset + chain * a.chain_stride);
 
   uint32_t hs = 0;  // half-sweep counter inside this launch
   for (int s = 0; s < a.n_sweeps; ++s) {
@@ -243,7 +246,7 @@ int launch_sweep(const SweepArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // hot start: one thread per word
 __global__ void ising_init_kernel(uint32_t* bits, int L, int64_t n_words, uint32_t seed_lo,
-                                  uint32_t seed_hi, int64_t chain_offset) {
+                                  uint32_t seed_hi, int64_t chain_offset, int64_t chain_stride) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_words) return;
   const int W = (L + 31) >> 5, tpc = L * W;
@@ -251,7 +254,7 @@ __global__ void ising_init_kernel(uint32_t* bits, int L, int64_t n_words, uint32
   const int r = (int)(g - chain * tpc);
   const int i = r / W, w = r - i * W;
   u32x4 c;
-  c.x = (uint32_t)(chain_offset + chain);
+  c.x = (uint32_t)(chain_offset + chain * chain_stride);
   c.y = (uint32_t)i;
   c.z = (uint32_t)w;
   c.w = DBS_STREAM_INIT;
@@ -429,6 +432,100 @@ ising_corr_kernel(const uint32_t* __restrict__ bits, int L, const uint32_t* __re
                                 (unsigned long long)(long long)sbin[r]);
 }
 
+// C(r) sums with every site a reference site (the ensemble estimator config 3 uses), L <= 64: ONE WARP per
+// chain, the lattice in registers (lane l holds rows l and l + 32 as 64-bit words).  For a row shift di the
+// shifted rows are fetched once with shuffles and serve all column shifts; a column shift is a 64-bit rotate
+// inside L bits (two funnel shifts, warp-uniform amount), a displacement costs 2 x (xor, popcll) per lane and
+// one REDUX when the radial bin changes.  Only the half plane (di > 0, or di = 0 and dj > 0) is visited:
+// sum_x s(x) s(x+d) = sum_x s(x) s(x-d) on the torus and every displacement with 0 < r < L/2 differs from its
+// negative, so each sum counts twice.  Lane r keeps bin r; nothing is staged in shared memory but the bin table.
+constexpr int kCorrWarps = 8;
+
+__device__ __forceinline__ uint64_t rot_right_L(uint64_t v, int s, int L, uint64_t maskL) {
+  // bit j of the result = bit (j + s) mod L of v; v has no bits at or above L; 0 <= s < L
+  if (s == 0) return v;
+  return ((v >> s) | (v << (L - s))) & maskL;
+}
+
+__global__ void __launch_bounds__(32 * kCorrWarps)
+ising_corr_warp_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chains, const int32_t* __restrict__ group,
+                       long long* __restrict__ acc) {
+  const int W = (L + 31) >> 5, R = L / 2;
+  __shared__ unsigned char s_bin[32 * 32];   // radial bin of (di, |dj|), di, |dj| < R; 255 = outside 0 < r < R
+  __shared__ int s_acc[32];
+  __shared__ int s_group;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = threadIdx.x; q < R * R; q += blockDim.x) {
+    const int di = q / R, dj = q - di * R;
+    const int x = di * di + dj * dj;
+    int rr = (int)sqrtf((float)x);
+    while (rr * rr > x) --rr;
+    while ((rr + 1) * (rr + 1) <= x) ++rr;
+    s_bin[q] = (rr <= 0 || rr >= R) ? 255 : (unsigned char)rr;
+  }
+  if (threadIdx.x < 32) s_acc[threadIdx.x] = 0;
+  const int64_t chain0 = (int64_t)blockIdx.x * kCorrWarps;
+  if (threadIdx.x == 0) s_group = group ? group[chain0] : 0;
+  __syncthreads();
+  const int64_t chain = chain0 + warp;
+  int mybin = 0;                     // lane r: sum over the displacements of bin r of (L^2 - 2 * disagreements), x2
+  int g = 0;
+  if (chain < n_chains) {
+    g = group ? group[chain] : 0;
+    const uint32_t* b = bits + chain * (int64_t)(L * W);
+    const uint64_t maskL = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+    uint64_t lo = 0, hi = 0;
+    if (lane < L) lo = W == 2 ? ((uint64_t)b[lane * 2] | ((uint64_t)b[lane * 2 + 1] << 32)) : (uint64_t)b[lane];
+    if (lane + 32 < L) hi = (uint64_t)b[(lane + 32) * 2] | ((uint64_t)b[(lane + 32) * 2 + 1] << 32);
+    const bool has_hi = L > 32;
+    const int LL = L * L;
+    for (int di = 0; di < R; ++di) {
+      // rows (lane + di) mod L and (lane + 32 + di) mod L
+      int r0 = lane + di; if (r0 >= L) r0 -= L;
+      int r1 = lane + 32 + di; while (r1 >= L) r1 -= L;
+      const uint64_t a_lo = __shfl_sync(0xffffffffu, lo, r0 & 31), a_hi = __shfl_sync(0xffffffffu, hi, r0 & 31);
+      const uint64_t b_lo = __shfl_sync(0xffffffffu, lo, r1 & 31), b_hi = __shfl_sync(0xffffffffu, hi, r1 & 31);
+      const uint64_t sa = r0 >= 32 ? a_hi : a_lo;     // partner row of my row `lane`
+      const uint64_t sb = r1 >= 32 ? b_hi : b_lo;     // partner row of my row `lane + 32`
+      const bool v0 = lane < L, v1 = lane + 32 < L;
+      for (int sgn = 0; sgn < (di == 0 ? 1 : 2); ++sgn) {
+        // sgn 0: dj = (di == 0 ? 1 : 0) .. R-1;  sgn 1: dj = -1 .. -(R-1); the bin grows with |dj|
+        int cur_bin = -1, cur = 0, ndisp = 0;
+        for (int k = (sgn == 0 ? (di == 0 ? 1 : 0) : 1); k < R; ++k) {
+          const int bin = s_bin[di * R + k];
+          if (bin == 255) { if (di * di + k * k >= R * R) break; else continue; }   // r = 0 cannot occur here
+          if (bin != cur_bin) {
+            if (cur_bin >= 0) {
+              const int tot = __reduce_add_sync(0xffffffffu, cur);
+              if (lane == cur_bin) mybin += 2 * (ndisp * LL - 2 * tot);
+            }
+            cur_bin = bin; cur = 0; ndisp = 0;
+          }
+          const int s = sgn == 0 ? k : L - k;       // column shift mod L
+          int pc = 0;
+          if (v0) pc += __popcll(lo ^ rot_right_L(sa, s, L, maskL));
+          if (has_hi && v1) pc += __popcll(hi ^ rot_right_L(sb, s, L, maskL));
+          cur += pc;
+          ++ndisp;
+        }
+        if (cur_bin >= 0) {
+          const int tot = __reduce_add_sync(0xffffffffu, cur);
+          if (lane == cur_bin) mybin += 2 * (ndisp * LL - 2 * tot);
+        }
+      }
+    }
+  }
+  // chains of a block usually share their group (temperature): one global atomic per bin per block
+  const bool shared_group = chain < n_chains && g == s_group;
+  if (shared_group && lane < R && mybin != 0) atomicAdd(&s_acc[lane], mybin);
+  if (chain < n_chains && !shared_group && lane < R && mybin != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (int64_t)g * R + lane), (unsigned long long)(long long)mybin);
+  __syncthreads();
+  if (threadIdx.x < R && s_acc[threadIdx.x] != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (int64_t)s_group * R + threadIdx.x),
+              (unsigned long long)(long long)s_acc[threadIdx.x]);
+}
+
 __global__ void obs_accumulate_kernel(const float* __restrict__ energy, const float* __restrict__ mag,
                                       double N, int64_t n, const int32_t* __restrict__ group,
                                       double* __restrict__ acc) {
@@ -471,16 +568,21 @@ extern "C" int dbs_ising_words_per_chain(int L) {
   return L * ((L + 31) / 32);
 }
 
-extern "C" int dbs_ising_init_packed(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
-                                     int64_t chain_offset, void* stream) {
+extern "C" int dbs_ising_init_packed_strided(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
+                                             int64_t chain_offset, int64_t chain_stride, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
-  DBS_REQUIRE(bits && n_chains >= 0, "ising_init: null state or negative chain count");
+  DBS_REQUIRE(bits && n_chains >= 0 && chain_stride >= 1, "ising_init: null state, negative chain count or stride < 1");
   if (n_chains == 0) return DBS_OK;
   const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
   ising_init_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, as_stream(stream)>>>(
-      bits, L, n_words, (uint32_t)seed, (uint32_t)(seed >> 32), chain_offset);
+      bits, L, n_words, (uint32_t)seed, (uint32_t)(seed >> 32), chain_offset, chain_stride);
   DBS_LAUNCHED();
   return DBS_OK;
+}
+
+extern "C" int dbs_ising_init_packed(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
+                                     int64_t chain_offset, void* stream) {
+  return dbs_ising_init_packed_strided(bits, L, n_chains, seed, chain_offset, 1, stream);
 }
 
 extern "C" int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t n_chains, void* stream) {
@@ -506,6 +608,15 @@ extern "C" int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64
 extern "C" int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_sweeps, const uint32_t* thr,
                                 int n_tables, const int32_t* table_index, uint64_t seed, int64_t chain_offset,
                                 int64_t sweep_offset, const uint32_t* uniforms, int zero_field, void* stream) {
+  return dbs_ising_sweeps_strided(bits, L, n_chains, n_sweeps, thr, n_tables, table_index, seed, chain_offset, 1,
+                                  sweep_offset, uniforms, zero_field, stream);
+}
+
+extern "C" int dbs_ising_sweeps_strided(uint32_t* bits, int L, int64_t n_chains, int n_sweeps, const uint32_t* thr,
+                                        int n_tables, const int32_t* table_index, uint64_t seed, int64_t chain_offset,
+                                        int64_t chain_stride, int64_t sweep_offset, const uint32_t* uniforms,
+                                        int zero_field, void* stream) {
+  DBS_REQUIRE(chain_stride >= 1, "ising_sweeps: chain_stride must be >= 1");
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
   DBS_REQUIRE(bits && thr && n_tables >= 1, "ising_sweeps: null state or threshold table");
   DBS_REQUIRE(n_chains >= 0 && n_sweeps >= 0, "ising_sweeps: negative chain or sweep count");
@@ -513,7 +624,7 @@ extern "C" int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_s
   if (n_chains == 0 || n_sweeps == 0) return DBS_OK;
   SweepArgs a;
   a.bits = bits; a.thr = thr; a.table_index = table_index; a.uniforms = uniforms;
-  a.n_chains = n_chains; a.chain_offset = chain_offset; a.sweep_offset = sweep_offset;
+  a.n_chains = n_chains; a.chain_offset = chain_offset; a.chain_stride = chain_stride; a.sweep_offset = sweep_offset;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.L = L; a.n_sweeps = n_sweeps;
   a.one = 1u; a.antiferro = zero_field < 0 ? 1 : 0;
@@ -554,6 +665,13 @@ extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chai
   const int W = (L + 31) / 32, tpc = L * W;
   const size_t smem = (size_t)(2 * tpc + L * (2 * W + 2)) * 4 + (size_t)(L / 2) * 4;
   ProfScope prof(kProfIsingObs, as_stream(stream));
+  static const bool warp_off = [] { const char* e = getenv("DBS_CORR_WARP"); return e && e[0] == '0'; }();
+  if (!ref_mask && L <= 64 && !warp_off) {
+    ising_corr_warp_kernel<<<(unsigned)((n_chains + kCorrWarps - 1) / kCorrWarps), 32 * kCorrWarps, 0, as_stream(stream)>>>(
+        bits, L, n_chains, group, acc);
+    DBS_LAUNCHED();
+    return DBS_OK;
+  }
   ising_corr_kernel<<<(unsigned)n_chains, kCorrThreads, smem, as_stream(stream)>>>(bits, L, ref_mask, group, acc);
   DBS_LAUNCHED();
   return DBS_OK;

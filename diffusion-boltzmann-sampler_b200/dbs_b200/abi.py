@@ -53,6 +53,8 @@ PROTOTYPES = {
     "dbs_profile_dump": (i32, [C.c_char_p]),
     "dbs_ising_words_per_chain": (i32, [i32]),
     "dbs_ising_init_packed": (i32, [vp, i32, i64, u64, i64, vp]),
+    "dbs_ising_init_packed_strided": (i32, [vp, i32, i64, u64, i64, i64, vp]),
+    "dbs_ising_sweeps_strided": (i32, [vp, i32, i64, i32, vp, i32, vp, u64, i64, i64, i64, vp, i32, vp]),
     "dbs_ising_pack": (i32, [vp, vp, i32, i64, vp]),
     "dbs_ising_unpack": (i32, [vp, vp, i32, i64, vp]),
     "dbs_ising_sweeps": (i32, [vp, i32, i64, i32, vp, i32, vp, u64, i64, i64, vp, i32, vp]),

@@ -22,32 +22,33 @@ def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_tempera
     ws = ws_ if world_size is None else world_size
     temps = np.linspace(1.5, 3.5, 64) if temperatures is None else np.asarray(temperatures, dtype=np.float64)
     ids, t_chain, t_idx = striped_temperatures(temps, chains_per_temperature, rank, ws)
-    # chains of one rank are not a contiguous global range: give each its global id through a
-    # contiguous block [rank_lo, rank_lo + n) of the permuted numbering (still world-size invariant
-    # per (temperature, stripe) pair) by sorting ids and launching one block per contiguous run
     model = IsingModel(lattice_size, J=J, h=h)
     L = lattice_size
     n = len(ids)
     dev = runtime.require_cuda()
     group = torch.from_numpy(t_idx).to(dev)
     mh = MetropolisHastings(model, t_chain, seed=seed)
-    # global chain ids are carried by remapping: chain k of this rank uses offset ids[k]; runs of
-    # consecutive ids are launched together
-    runs = np.split(np.arange(n), np.where(np.diff(ids) != 1)[0] + 1) if n else []
+    # A rank's chains carry their GLOBAL ids in the Philox counters.  When the rank count divides the chains
+    # per temperature the striped ids are the arithmetic progression rank, rank + W, rank + 2W, ...: one
+    # strided launch covers them all.  Otherwise fall back to one launch per run of consecutive ids.
+    if n and (ws == 1 or chains_per_temperature % ws == 0):
+        runs = [(0, n, int(ids[0]), ws)]
+    else:
+        idx = np.split(np.arange(n), np.where(np.diff(ids) != 1)[0] + 1) if n else []
+        runs = [(int(r[0]), len(r), int(ids[r[0]]), 1) for r in idx]
     bits = torch.empty((n, L, (L + 31) // 32), dtype=torch.int32, device=dev)
-    for r in runs:
-        sub = model.random_packed(len(r), seed, chain_offset=int(ids[r[0]]))
-        bits[r[0]:r[0] + len(r)] = sub
+    for lo, cnt, gid, stride in runs:
+        bits[lo:lo + cnt] = model.random_packed(cnt, seed, chain_offset=gid, chain_stride=stride)
 
     tables, _ = mh._tables()
     index = torch.from_numpy(mh._table_index_host).to(dev)
 
     def sweeps(k, offset):
-        for r in runs:
-            view = bits[r[0]:r[0] + len(r)]
-            abi.check(abi.lib.dbs_ising_sweeps(view.data_ptr(), L, len(r), k, tables.data_ptr(), tables.shape[0],
-                                               index[r[0]:].data_ptr(), seed, int(ids[r[0]]), offset, 0,
-                                               mh.zero_field, runtime.current_stream()), "ising_sweeps")
+        for lo, cnt, gid, stride in runs:
+            view = bits[lo:lo + cnt]
+            abi.check(abi.lib.dbs_ising_sweeps_strided(view.data_ptr(), L, cnt, k, tables.data_ptr(), tables.shape[0],
+                                                       index[lo:].data_ptr(), seed, gid, stride, offset, 0,
+                                                       mh.zero_field, runtime.current_stream()), "ising_sweeps")
 
     nT = len(temps)
     acc = torch.zeros((nT, 5), dtype=torch.float64, device=dev)

@@ -69,6 +69,11 @@ int dbs_ising_words_per_chain(int L);
 int dbs_ising_init_packed(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
                           int64_t chain_offset, void* stream);
 
+/* Same with global chain id = chain_offset + c * chain_stride: a rank of a striped sharding (rank r of W takes
+ * the ids r, r + W, r + 2W, ...: SURVEY.md 8e, config 3) initialises its chains in ONE launch. */
+int dbs_ising_init_packed_strided(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
+                                  int64_t chain_offset, int64_t chain_stride, void* stream);
+
 /* fp32 (+/-1, sign test x>0) <-> bits.  Replaces the float lattice representation
  * of systems/ising.py:36-45 / samplers/mcmc.py:82-97 at the API boundary. */
 int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t n_chains, void* stream);
@@ -99,6 +104,14 @@ int dbs_ising_sweeps(uint32_t* bits, int L, int64_t n_chains, int n_sweeps,
                      const uint32_t* thr, int n_tables, const int32_t* table_index,
                      uint64_t seed, int64_t chain_offset, int64_t sweep_offset,
                      const uint32_t* uniforms, int zero_field, void* stream);
+
+/* dbs_ising_sweeps with global chain id = chain_offset + c * chain_stride in the Philox counters (striped
+ * sharding: the draws of a chain do not depend on which rank, or how many ranks, run it). */
+int dbs_ising_sweeps_strided(uint32_t* bits, int L, int64_t n_chains, int n_sweeps,
+                             const uint32_t* thr, int n_tables, const int32_t* table_index,
+                             uint64_t seed, int64_t chain_offset, int64_t chain_stride,
+                             int64_t sweep_offset, const uint32_t* uniforms, int zero_field,
+                             void* stream);
 
 /* One random-site Metropolis attempt at (i,j) on fp32 lattices [n][L][L] in place, with draw r:
  * the reference's step() (samplers/mcmc.py:26-50) for API parity (flips at most one spin per
