@@ -441,12 +441,20 @@ ising_corr_kernel(const uint32_t* __restrict__ bits, int L, const uint32_t* __re
 // negative, so each sum counts twice.  Lane r keeps bin r; nothing is staged in shared memory but the bin table.
 constexpr int kCorrWarps = 8;
 
+template <bool k64>
 __device__ __forceinline__ uint64_t rot_right_L(uint64_t v, int s, int L, uint64_t maskL) {
-  // bit j of the result = bit (j + s) mod L of v; v has no bits at or above L; 0 <= s < L
+  // bit j of the result = bit (j + s) mod L of v; v has no bits at or above L; 0 <= s < L (warp-uniform)
+  if (k64) {
+    // L = 64: a 64-bit rotate is two funnel shifts of the 32-bit halves (swapped when s >= 32)
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const uint32_t a = s & 32 ? hi : lo, b = s & 32 ? lo : hi;
+    return (uint64_t)__funnelshift_r(a, b, s) | ((uint64_t)__funnelshift_r(b, a, s) << 32);
+  }
   if (s == 0) return v;
   return ((v >> s) | (v << (L - s))) & maskL;
 }
 
+template <bool k64>
 __global__ void __launch_bounds__(32 * kCorrWarps)
 ising_corr_warp_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chains, const int32_t* __restrict__ group,
                        long long* __restrict__ acc) {
@@ -503,8 +511,12 @@ ising_corr_warp_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chain
           }
           const int s = sgn == 0 ? k : L - k;       // column shift mod L
           int pc = 0;
-          if (v0) pc += __popcll(lo ^ rot_right_L(sa, s, L, maskL));
-          if (has_hi && v1) pc += __popcll(hi ^ rot_right_L(sb, s, L, maskL));
+          if (k64) {
+            pc = __popcll(lo ^ rot_right_L<true>(sa, s, L, maskL)) + __popcll(hi ^ rot_right_L<true>(sb, s, L, maskL));
+          } else {
+            if (v0) pc += __popcll(lo ^ rot_right_L<false>(sa, s, L, maskL));
+            if (has_hi && v1) pc += __popcll(hi ^ rot_right_L<false>(sb, s, L, maskL));
+          }
           cur += pc;
           ++ndisp;
         }
@@ -667,8 +679,9 @@ extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chai
   ProfScope prof(kProfIsingObs, as_stream(stream));
   static const bool warp_off = [] { const char* e = getenv("DBS_CORR_WARP"); return e && e[0] == '0'; }();
   if (!ref_mask && L <= 64 && !warp_off) {
-    ising_corr_warp_kernel<<<(unsigned)((n_chains + kCorrWarps - 1) / kCorrWarps), 32 * kCorrWarps, 0, as_stream(stream)>>>(
-        bits, L, n_chains, group, acc);
+    const unsigned grid = (unsigned)((n_chains + kCorrWarps - 1) / kCorrWarps);
+    if (L == 64) ising_corr_warp_kernel<true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
+    else ising_corr_warp_kernel<false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
     DBS_LAUNCHED();
     return DBS_OK;
   }
