@@ -26,6 +26,7 @@ from backend.ml.systems.lennard_jones import LennardJonesSystem  # noqa: E402
 from backend.ml.models.score_network import ScoreNetwork, SinusoidalTimeEmbedding  # noqa: E402
 from backend.ml.models.diffusion import DiffusionProcess  # noqa: E402
 from backend.ml.models.score_network_continuous import ContinuousScoreNetwork  # noqa: E402
+from backend.ml.models.noise_schedule import get_schedule as ref_get_schedule  # noqa: E402
 from backend.ml.samplers.diffusion import DiffusionSampler  # noqa: E402
 from backend.ml.analysis.correlation import pair_correlation  # noqa: E402
 
@@ -361,6 +362,19 @@ def main():
     g["smp_out"] = out.numpy()
     g["smp_meta"] = np.array([N, 0.9])
     np.savez_compressed(os.path.join(OUT, "csn_tiny.npz"), **g)
+
+    # ---- noise schedules (host-side): sigma tables through DiffusionProcess(schedule=...) ----------
+    g = {}
+    tt = torch.tensor([0.0, 0.01, 0.1, 0.37, 0.5, 0.9, 1.0])
+    g["t"] = tt.numpy()
+    for kind, kw in (("linear", {}), ("cosine", {}), ("cosine_s", {"s": 0.02}), ("sigmoid", {}),
+                     ("sigmoid_k", {"start": -3.0, "end": 4.0, "beta_min": 0.2, "beta_max": 12.0})):
+        sch = ref_get_schedule(kind.split("_")[0], **kw)
+        a, sg = sch.noise_level(tt)
+        g[kind + "_alpha"], g[kind + "_sigma"], g[kind + "_beta"] = a.numpy(), sg.numpy(), sch.beta(tt).numpy()
+        dp = DiffusionProcess(schedule=sch)
+        g[kind + "_table"] = np.array([dp.noise_level(torch.full((1,), i / 20))[1][0].item() for i in range(20, 0, -1)])
+    np.savez_compressed(os.path.join(OUT, "noise_schedules.npz"), **g)
 
 
     for f in sorted(os.listdir(OUT)):
