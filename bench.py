@@ -269,13 +269,18 @@ def bench_ours(args, world, rank, local):
     # HBM-bound companions of the conv kernel, same events: Euler-Maruyama 12 B/element (x in, score in, x out);
     # GroupNorm apply 4 B/element (bf16 in + out), 6 B with the residual
     esz = 2 if prec == "bf16" else 4
-    gn_elems, ch, res = 0, NET_CFG["base_channels"], L
-    widths = [NET_CFG["base_channels"] << (i + 1) for i in range(NET_CFG["num_blocks"])]
-    for co in widths:
-        gn_elems += res * res * co; res //= 2
-    gn_elems += res * res * widths[-1]
-    for i in reversed(range(NET_CFG["num_blocks"])):
-        res *= 2; gn_elems += res * res * (NET_CFG["base_channels"] << i)
+    # GroupNorm-apply launches that remain on the bf16 path: levels whose images exceed one 128-pixel tile
+    # (the others are fused into the conv epilogue), minus the last decoder GN2 (fused into the final conv)
+    nbk, base = NET_CFG["num_blocks"], NET_CFG["base_channels"]
+    levels = [(L >> i, base << (i + 1)) for i in range(nbk)] + [(L >> nbk, base << nbk)] + \
+             [(L >> i, base << i) for i in reversed(range(nbk))]
+    gn_bytes = 0.0
+    for li, (r_, c_) in enumerate(levels):
+        if prec == "bf16" and r_ * r_ <= 128 and 128 <= c_ <= 256:
+            continue
+        gn_bytes += r_ * r_ * c_ * 2 * esz                                     # GN1: in + out
+        if not (prec == "bf16" and li == len(levels) - 1):
+            gn_bytes += r_ * r_ * c_ * 3 * esz                                 # GN2: in + residual + out
     hbm_kernels = {}
     if prof.get("em_step", (0, 0))[1]:
         by = 12.0 * B * L * L * NS
@@ -283,7 +288,7 @@ def bench_ours(args, world, rank, local):
                                   "unit": "GB/s", "frac": round(by / (prof["em_step"][0] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                                   "bytes_per_element": 12}
     if prof.get("gn_apply", (0, 0))[1]:
-        by = float(gn_elems) * B * NS * (2 * esz + 3 * esz)     # GN1: in + out; GN2: in + residual + out
+        by = gn_bytes * B * NS
         hbm_kernels["gn_apply"] = {"bound": "hbm", "achieved": round(by / (prof["gn_apply"][0] * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"],
                                    "unit": "GB/s", "frac": round(by / (prof["gn_apply"][0] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                                    "bytes_per_element": "2+2 (GN1), 2+2+2 (GN2 with residual), bf16"}

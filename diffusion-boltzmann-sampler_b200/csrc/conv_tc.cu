@@ -48,6 +48,12 @@ struct TcParams {
   int B, Hout, Wout, Cout, out_stride, oph, opw;
   int groups, Cg, cg_log2;
   int epi_subs;       // epilogue warps per TMEM lane quadrant that take part (1 or 4), see conv_tc_launch
+  // fused GroupNorm apply (whole images inside one tile): out = SiLU(GN(conv)) [+ time bias] [+ residual]
+  int fuse;
+  const float *gamma, *beta, *tb;
+  int64_t tb_stride;   // floats between the time-bias rows of consecutive samples (0: all samples share one row)
+  const __nv_bfloat16* res;
+  float inv_cnt, eps;
   int tap_dw[16], tap_dh[16], tap_p[16], tap_c0[16], tap_c1[16], tap_w[16];
   const float* bias;
   __nv_bfloat16* out;
@@ -59,6 +65,12 @@ struct TcParams {
 };
 
 using namespace tc;
+
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
 
 // ------------------------------------------------------------------------------------------------
 // kRun: 0 = no GroupNorm statistics, else min(channels per group, 16) in {2, 4, 8, 16}
@@ -73,6 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   __shared__ uint32_t s_tmem_base;
   __shared__ float s_acc[2][kTileM * 8 * 2];  // GroupNorm partial sums, double-buffered by tile parity
   __shared__ __align__(16) float s_bias[kMaxCout];
+  __shared__ __align__(16) float s_gamma[kRun == 16 ? kMaxCout : 4], s_beta[kRun == 16 ? kMaxCout : 4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
@@ -100,6 +113,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   if (warp == 2) tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols);
   for (int i = threadIdx.x; i < 2 * kTileM * 8 * 2; i += kThreads) (&s_acc[0][0])[i] = 0.f;
   for (int i = threadIdx.x; i < p.Cout; i += kThreads) s_bias[i] = p.bias[i];
+  if (kRun == 16 && p.fuse)
+    for (int i = threadIdx.x; i < p.Cout; i += kThreads) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -251,7 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
             }
           }
         }
-        if (valid) {
+        if (valid && !(kRun == 16 && p.fuse)) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -262,6 +277,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+      }
+      if (kRun == 16 && p.fuse) {
+        // ---- fused GroupNorm apply (whole images inside the tile): after the barrier the statistics of the
+        // tile's images are final; a second pass over the TMEM stage normalises the fp32 accumulators, applies
+        // SiLU (+ time bias / + residual) and stores the block's activation — neither the raw conv output nor
+        // a separate GroupNorm kernel exists for these layers.  (Keeping the first pass's outputs in registers
+        // and releasing TMEM early was measured slower: the drain, not the MMA, is the longer side here.)
+        asm volatile("bar.sync 1, %0;" ::"r"(128 * p.epi_subs) : "memory");
+        const float* tbp = p.tb ? p.tb + (int64_t)(valid ? n : 0) * p.tb_stride + co0 : nullptr;
+        const __nv_bfloat16* rptr = p.res ? p.res + (optr - p.out) : nullptr;
+        if (c_lo < c_hi) tmem_ld16(taddr + c_lo, v);
+        for (int c = c_lo; c < c_hi; c += 16) {
+          tmem_ld_wait();
+          float f[16];
+          const int gi = (co0 + c) >> p.cg_log2;
+          const float mean = acc[gi * 2 + 0] * p.inv_cnt;
+          const float rstd = rsqrtf(fmaxf(acc[gi * 2 + 1] * p.inv_cnt - mean * mean, 0.f) + p.eps);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[co0 + c + 4 * j4]);
+            const float4 g4 = *reinterpret_cast<const float4*>(&s_gamma[co0 + c + 4 * j4]);
+            const float4 e4 = *reinterpret_cast<const float4*>(&s_beta[co0 + c + 4 * j4]);
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tbp) t4 = __ldg(reinterpret_cast<const float4*>(tbp + c + 4 * j4));
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float ee[4] = {e4.x, e4.y, e4.z, e4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a = rstd * gg[k];
+              f[4 * j4 + k] = silu_fast(fmaf(__uint_as_float(v[4 * j4 + k]) + bb[k], a, ee[k] - mean * a)) + tt[k];
+            }
+          }
+          if (c + 16 < c_hi) tmem_ld16(taddr + c + 16, v);
+          if (valid) {
+            if (rptr) {
+              const uint4* rq = reinterpret_cast<const uint4*>(rptr + c);
+#pragma unroll
+              for (int hq = 0; hq < 2; ++hq) {
+                const uint4 r4 = rq[hq];
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
+                  f[8 * hq + 2 * i] = fmaf(1.0f, __low2float(h2), f[8 * hq + 2 * i]);
+                  f[8 * hq + 2 * i + 1] = fmaf(1.0f, __high2float(h2), f[8 * hq + 2 * i + 1]);
+                }
+              }
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(optr + c);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        // everyone has read the statistics: clear this buffer for the tile after next
+        asm volatile("bar.sync 1, %0;" ::"r"(128 * p.epi_subs) : "memory");
+        float* accb = &s_acc[it & 1][0];
+        for (int i = etid; i < p.Nt * 16; i += 128 * p.epi_subs) accb[i] = 0.f;
+        continue;
       }
       // TMEM stage drained: hand it back to the MMA warp
       tc_fence_before();
@@ -368,9 +450,9 @@ int encode_w(EncodeTiledFn enc, CUtensorMap* m, const void* ptr, int Cin, int Co
 using namespace tch;
 
 int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1, const __nv_bfloat16* w,
-                   const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st) {
-  // full-resolution small-channel layers go to the strip kernel (conv_strip.cu)
-  {
+                   const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st, const GnFuse* fuse) {
+  // full-resolution small-channel layers go to the strip kernel (conv_strip.cu); it has no fused GroupNorm apply
+  if (!fuse) {
     const int rc_strip = conv_strip_launch(g, in0, in1, w, bias, out, stats, groups, st);
     if (rc_strip != DBS_ERR_UNSUPPORTED) return rc_strip;
   }
@@ -440,7 +522,15 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   }
   // Four warps per quadrant pay off only when a warp's rows span several images (tiny lattices: per-thread
   // shared-memory atomics for the GroupNorm sums dominate the drain); measured slower elsewhere.
-  p.epi_subs = (stats && Ht * Wt < 32) ? 4 : 1;
+  p.epi_subs = (stats && (Ht * Wt < 32 || fuse)) ? 4 : 1;
+  if (fuse) {
+    // whole images inside one tile, all couts in one N tile, groups of >= 16 channels (kRun == 16 variant)
+    if (!stats || Wt != g.Wm || Ht != g.Hm || n_tiles_n != 1 || g.out_stride != 1 || p.Cg < 16 || !fuse->gamma || !fuse->beta)
+      return DBS_ERR_UNSUPPORTED;
+    if (fuse->res && (reinterpret_cast<uintptr_t>(fuse->res) & 15)) return DBS_ERR_UNSUPPORTED;
+    p.fuse = 1; p.gamma = fuse->gamma; p.beta = fuse->beta; p.tb = fuse->tb; p.tb_stride = fuse->tb_stride; p.res = fuse->res;
+    p.inv_cnt = 1.0f / (float)((int64_t)g.Hm * g.Wm * p.Cg); p.eps = 1e-5f;
+  }
   p.bias = bias; p.out = out; p.stats = stats;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   p.a_bytes = (uint32_t)kTileM * KC * 2;
@@ -491,8 +581,8 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   DBS_CUDA(attr_err);
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  prof_set_label("tile H%d W%d C%d+%d->%d taps%d s%d os%d KC%d B%d", g.Hin, g.Win, g.C0, g.C1, g.Cout, g.n_taps, g.in_stride,
-                 g.out_stride, KC, g.B);
+  prof_set_label("tile H%d W%d C%d+%d->%d taps%d s%d os%d KC%d B%d%s", g.Hin, g.Win, g.C0, g.C1, g.Cout, g.n_taps, g.in_stride,
+                 g.out_stride, KC, g.B, fuse ? " +gn" : "");
   ProfScope prof(kProfConvTC, st);
   kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
   DBS_LAUNCHED();

@@ -890,6 +890,37 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   bool sd = false;
   const size_t stat_bytes = (size_t)c.B * G * 2 * sizeof(float);
   ConvGeom g1 = geom_conv((int)c.B, H, W, C0, C1, bw.cout, 3, 1);
+  ConvGeom g2 = geom_conv((int)c.B, H, W, bw.cout, 0, bw.cout, 3, 1);
+  if (!bw.has_res) DBS_REQUIRE(C1 == 0, "unet: identity residual with a concatenated input");
+
+  // Low-resolution levels (an image fits inside one 128-pixel GEMM tile): the GroupNorm statistics of a tile's
+  // images are complete inside the conv epilogue, so normalise + SiLU (+ time bias / + residual) happen there
+  // and neither the raw conv output nor a separate GroupNorm pass exists (conv_tc.cu, second epilogue pass).
+  static const bool fuse_off = [] { const char* e = getenv("DBS_GN_FUSE"); return e && e[0] == '0'; }();
+  if (c.use_tc && sizeof(T) == 2 && !c.tap && !fuse_off && H * W <= 128 && bw.cout >= 128 && bw.cout <= 256) {
+    GnFuse f1{bw.g1, bw.b1, c.tbias + bw.tb_off, c.n_t == 1 ? 0 : (int64_t)c.plan->sumC, nullptr};
+    rc = conv_tc_launch(g1, (const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, bw.conv1.w16, bw.conv1.bias,
+                        (__nv_bfloat16*)th, c.stats, G, c.st, &f1);
+    if (rc == DBS_OK) {
+      const T* res = in0;
+      if (bw.has_res) {
+        ConvGeom gr = geom_conv((int)c.B, H, W, C0, C1, bw.cout, 1, 1);
+        if ((rc = run_conv<T>(c, gr, in0, in1, bw.res, tr, nullptr, G, nullptr))) return rc;
+        res = tr;
+      }
+      GnFuse f2{bw.g2, bw.b2, nullptr, 0, (const __nv_bfloat16*)res};
+      rc = conv_tc_launch(g2, (const __nv_bfloat16*)th, nullptr, bw.conv2.w16, bw.conv2.bias, (__nv_bfloat16*)out, c.stats, G,
+                          c.st, &f2);
+      if (rc == DBS_OK) return DBS_OK;
+      if (rc != DBS_ERR_UNSUPPORTED) return rc;
+      // conv2 not eligible (cannot happen when conv1 was): finish the block on the unfused path below from th
+      DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+      if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
+      return run_gn<T>(c, ty, out, sd, bw.g2, bw.b2, 0, false, res, H, W, bw.cout);
+    }
+    if (rc != DBS_ERR_UNSUPPORTED) return rc;
+  }
+
   if (c.use_tc) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
   bool res_done = false;
   if (c.use_tc && sizeof(T) == 2 && bw.has_res) {
@@ -905,7 +936,6 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     if ((rc = maybe_tap<T>(c, nm.c_str(), ty, c.B, H, W, bw.cout))) return rc;
   }
   if ((rc = run_gn<T>(c, ty, th, sd, bw.g1, bw.b1, bw.tb_off, true, (const T*)nullptr, H, W, bw.cout))) return rc;
-  ConvGeom g2 = geom_conv((int)c.B, H, W, bw.cout, 0, bw.cout, 3, 1);
   if (c.use_tc) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
   if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
   const T* res = in0;
@@ -915,8 +945,6 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
       if ((rc = run_conv<T>(c, gr, in0, in1, bw.res, tr, nullptr, G, nullptr))) return rc;
     }
     res = tr;
-  } else {
-    DBS_REQUIRE(C1 == 0, "unet: identity residual with a concatenated input");
   }
   if (c.defer && c.defer->want && sd && !c.tap) {
     c.defer->done = true; c.defer->y = ty; c.defer->res = res; c.defer->gamma = bw.g2; c.defer->beta = bw.b2;

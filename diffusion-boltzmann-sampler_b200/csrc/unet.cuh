@@ -32,11 +32,20 @@ struct ConvWeights {
   float* bias = nullptr;          // [cout]
 };
 
+// GroupNorm apply fused into the conv epilogue (layers whose images fit inside one 128-pixel tile):
+//   out = SiLU(GN(conv + bias) * gamma + beta) [+ time bias] [+ residual]      (score_network.py:143-151)
+struct GnFuse {
+  const float *gamma, *beta;   // [Cout]
+  const float* tb;             // time bias row of sample 0 (already offset to this block), null = none
+  int64_t tb_stride;           // floats between samples' rows; 0 = one shared row
+  const __nv_bfloat16* res;    // residual, same NHWC shape as out, null = none
+};
+
 // tcgen05 path.  Returns DBS_OK, or DBS_ERR_UNSUPPORTED if this geometry is not eligible
 // (caller then uses the CUDA-core kernel).  stats: fp32 [B][G][2] raw (sum, sumsq) or null.
 int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1,
                    const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, float* stats,
-                   int groups, cudaStream_t st);
+                   int groups, cudaStream_t st, const GnFuse* fuse = nullptr);
 
 // Strip variant of the tcgen05 path for stride-1 convs with Cout <= 64 on full-width row tiles: one
 // halo strip of the input per channel chunk serves every tap, weights stay resident in shared memory
