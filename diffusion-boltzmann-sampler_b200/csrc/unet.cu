@@ -794,7 +794,7 @@ template <> struct WSel<__nv_bfloat16> { using type = __nv_bfloat16; static cons
 struct DeferredGn {
   bool want = false, done = false;
   const void* y = nullptr; const void* res = nullptr;
-  const float *gamma = nullptr, *beta = nullptr;
+  const float *gamma = nullptr, *beta = nullptr, *stats = nullptr;
 };
 
 struct Ctx {
@@ -803,10 +803,18 @@ struct Ctx {
   int64_t B;
   int n_t;            // 1 or B
   float* tbias;       // [n_t][sumC]
-  float* stats;       // [B][8][2]
+  float* stats;       // [B][8][2]: the GroupNorm statistics slice of the conv being run (see next_stats)
   bool use_tc;
   const char* tap; float* tap_out; int64_t tap_numel; bool tapped = false;
   DeferredGn* defer = nullptr;
+  float* stats_base = nullptr; int64_t stats_stride = 0; int* stats_next = nullptr; int stats_slices = 0;
+  // bf16 path: every conv+GroupNorm pair gets its own slice of one region zeroed by ONE memset per forward
+  // (instead of a memset node in front of each conv); returns false when the region is used up
+  bool next_stats() {
+    if (!stats_base || *stats_next >= stats_slices) return false;
+    stats = stats_base + (int64_t)(*stats_next)++ * stats_stride;
+    return true;
+  }
 };
 
 template <typename T>
@@ -914,14 +922,14 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
       if (rc == DBS_OK) return DBS_OK;
       if (rc != DBS_ERR_UNSUPPORTED) return rc;
       // conv2 not eligible (cannot happen when conv1 was): finish the block on the unfused path below from th
-      DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+      if (!c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
       if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
       return run_gn<T>(c, ty, out, sd, bw.g2, bw.b2, 0, false, res, H, W, bw.cout);
     }
     if (rc != DBS_ERR_UNSUPPORTED) return rc;
   }
 
-  if (c.use_tc) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+  if (c.use_tc && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
   bool res_done = false;
   if (c.use_tc && sizeof(T) == 2 && bw.has_res) {
     // conv1 and the 1x1 residual conv read the same input: one pass of the strip kernel does both
@@ -936,7 +944,7 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     if ((rc = maybe_tap<T>(c, nm.c_str(), ty, c.B, H, W, bw.cout))) return rc;
   }
   if ((rc = run_gn<T>(c, ty, th, sd, bw.g1, bw.b1, bw.tb_off, true, (const T*)nullptr, H, W, bw.cout))) return rc;
-  if (c.use_tc) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+  if (c.use_tc && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
   if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
   const T* res = in0;
   if (bw.has_res) {
@@ -948,6 +956,7 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   }
   if (c.defer && c.defer->want && sd && !c.tap) {
     c.defer->done = true; c.defer->y = ty; c.defer->res = res; c.defer->gamma = bw.g2; c.defer->beta = bw.b2;
+    c.defer->stats = c.stats;
     return DBS_OK;
   }
   if ((rc = run_gn<T>(c, ty, out, sd, bw.g2, bw.b2, 0, false, res, H, W, bw.cout))) return rc;
@@ -970,7 +979,8 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
 
   // ---- workspace carve-up (identical in the dry run that sizes it)
   float* tbias = (float*)ws.take((int64_t)n_t * plan->sumC * 4);
-  float* stats = (float*)ws.take(B * 8 * 2 * 4);
+  const int n_stat_slices = 2 * (2 * nb + 1);          // two GroupNorms per ConvBlock, 2 nb + 1 blocks
+  float* stats = (float*)ws.take((int64_t)n_stat_slices * B * 8 * 2 * 4);
   int64_t max_act = (int64_t)B * H * W * C * 2;  // enc0 output has 2C channels at full resolution
   {
     int h = H, w = W, ch = C;
@@ -1004,6 +1014,11 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
 
   Ctx c{plan, st, B, (int)n_t, tbias, stats, use_tc, tap, tap_out, tap_numel};
   int rc;
+  int stats_next = 0;
+  if (use_tc && sizeof(T) == 2) {
+    c.stats_base = stats; c.stats_stride = B * 8 * 2; c.stats_next = &stats_next; c.stats_slices = n_stat_slices;
+    DBS_CUDA(cudaMemsetAsync(stats, 0, (size_t)n_stat_slices * B * 8 * 2 * 4, st));
+  }
   // fused final conv (bf16 path): C in {16, 32, 64}, power-of-two width <= 128, tile within 48 KB of shared memory
   const bool final_fused_ok = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && W <= 128 && (W & (W - 1)) == 0 &&
                               (size_t)(std::min(256 / W, H) + 2) * W * C * 2 <= 48 * 1024;
@@ -1151,9 +1166,9 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
       if (final_fused_ok) {
         const __nv_bfloat16* yin = defer.done ? (const __nv_bfloat16*)defer.y : (const __nv_bfloat16*)cur;
         const __nv_bfloat16* rin = defer.done ? (const __nv_bfloat16*)defer.res : nullptr;
-        if (C == 16) rc = launch_final_fused<16>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, stats, defer.gamma, defer.beta, score, B, H, W, st);
-        else if (C == 32) rc = launch_final_fused<32>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, stats, defer.gamma, defer.beta, score, B, H, W, st);
-        else rc = launch_final_fused<64>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, stats, defer.gamma, defer.beta, score, B, H, W, st);
+        if (C == 16) rc = launch_final_fused<16>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
+        else if (C == 32) rc = launch_final_fused<32>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
+        else rc = launch_final_fused<64>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
         if (rc) return rc;
       } else {
         final_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(cur, plan->final_w, plan->final_b, score, n_pix,
