@@ -24,6 +24,8 @@
 //                                        latency-bound, so four warps per quadrant cut the drain time of a tile ~4x)
 // Two TMEM accumulator stages (2*Nb columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -74,7 +76,12 @@ __device__ __forceinline__ float silu_fast(float x) {
 
 // ------------------------------------------------------------------------------------------------
 // kRun: 0 = no GroupNorm statistics, else min(channels per group, 16) in {2, 4, 8, 16}
-template <int kRun>
+// kPair: two CTAs of a cluster (one TPC) share every MMA (tcgen05 cta_group::2, M = 256): each CTA stages its own
+// 128 pixels of A and HALF of the weight tile, so the weight traffic (L2 -> SM and shared-memory operand reads)
+// per SM halves — the limiter of the 128/256-channel layers.  The leader CTA (cluster rank 0) issues the MMAs;
+// both CTAs' TMA loads signal the leader's full barrier, tcgen05.commit multicasts to both CTAs' empty / tfull
+// barriers, and the peer's epilogue warps hand the TMEM stage back on the leader's tempty barrier.
+template <int kRun, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p) {
@@ -93,6 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
   const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
   const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -101,7 +109,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, 4 * p.epi_subs);
+      mbar_init(bar_tempty + 8 * s, (kPair ? 8 : 4) * p.epi_subs);
     }
     fence_barrier_init();
   }
@@ -110,17 +118,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
     tma_prefetch_desc(&map_in1);
     tma_prefetch_desc(&map_w);
   }
-  if (warp == 2) tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols);
+  if (warp == 2) { if (kPair) tmem_alloc2(smem_u32(&s_tmem_base), p.tmem_cols); else tmem_alloc(smem_u32(&s_tmem_base), p.tmem_cols); }
   for (int i = threadIdx.x; i < 2 * kTileM * 8 * 2; i += kThreads) (&s_acc[0][0])[i] = 0.f;
   for (int i = threadIdx.x; i < p.Cout; i += kThreads) s_bias[i] = p.bias[i];
   if (kRun == 16 && p.fuse)
     for (int i = threadIdx.x; i < p.Cout; i += kThreads) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  // work units: tiles, or pairs of M-adjacent tiles (this CTA takes tile 2k + rank of the pair)
+  const int half_m = p.n_tiles_m >> 1;
+  const int total_tiles = kPair ? half_m * p.n_tiles_n : p.n_tiles_m * p.n_tiles_n;
+  const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_of = [&](int u) { return kPair ? (u / half_m) * p.n_tiles_m + 2 * (u % half_m) + rank : u; };
   const int kblocks_per_tap = p.chunks0 + p.chunks1;
   const int n_kblocks = p.n_taps * kblocks_per_tap;
 
@@ -129,10 +143,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t b_rows_off = kPair ? (uint32_t)rank * (uint32_t)(p.Nb >> 1) : 0u;   // my half of the weight tile
+      for (int u = unit0; u < total_tiles; u += unit_stride) {
+        const int tile = tile_of(u);
         const int nt = tile / p.n_tiles_m, mt = tile - nt * p.n_tiles_m;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Nb;
+        const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Nb + (int)b_rows_off;
         for (int t = 0; t < p.n_taps; ++t) {
           const int cw = w0 + p.tap_dw[t], chh = h0 + p.tap_dh[t], cp = p.tap_p[t];
           for (int ch = 0; ch < kblocks_per_tap; ++ch) {
@@ -140,10 +156,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
             const uint32_t a_dst = smem_base + stage * p.stage_bytes;
             const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
             const uint32_t fb = bar_full + 8 * stage;
-            mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
-            if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, p.tap_c0[t] + ch * p.KC, cw, cp, chh, n0);
-            else tma_load_5d(a_dst, &map_in1, fb, p.tap_c1[t] + (ch - p.chunks0) * p.KC, cw, cp, chh, n0);
-            tma_load_3d(b_dst, &map_w, fb, ch * p.KC, co0, p.tap_w[t]);
+            if (kPair) {
+              // both CTAs' bytes land on the LEADER's barrier (peer bit of the address cleared); the leader posts the
+              // expected total once
+              if (rank == 0) mbar_expect_tx(fb, 2u * (p.a_bytes + p.b_bytes));
+              const uint32_t fbl = fb & 0xFEFFFFFFu;
+              if (ch < p.chunks0) tma_load_5d_2sm(a_dst, &map_in0, fbl, p.tap_c0[t] + ch * p.KC, cw, cp, chh, n0);
+              else tma_load_5d_2sm(a_dst, &map_in1, fbl, p.tap_c1[t] + (ch - p.chunks0) * p.KC, cw, cp, chh, n0);
+              tma_load_3d_2sm(b_dst, &map_w, fbl, ch * p.KC, co0, p.tap_w[t]);
+            } else {
+              mbar_expect_tx(fb, p.a_bytes + p.b_bytes);
+              if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, p.tap_c0[t] + ch * p.KC, cw, cp, chh, n0);
+              else tma_load_5d(a_dst, &map_in1, fb, p.tap_c1[t] + (ch - p.chunks0) * p.KC, cw, cp, chh, n0);
+              tma_load_3d(b_dst, &map_w, fb, ch * p.KC, co0, p.tap_w[t]);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -151,15 +177,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only in pair mode) =====================
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       const int mmas = p.KC / 16;
       const uint32_t lo_bits = (uint32_t)p.desc_hi, hi32 = (uint32_t)(p.desc_hi >> 32), idesc = p.idesc;
       const uint32_t b_off = (p.a_bytes + 1023u) & ~1023u;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int u = unit0; u < total_tiles; u += unit_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
@@ -173,19 +199,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
           const uint32_t a_lo = lo_bits | ((a_addr & 0x3FFFFu) >> 4);
           const uint32_t b_lo = lo_bits | ((b_addr & 0x3FFFFu) >> 4);
           const uint32_t acc0 = kb ? 1u : 0u;
-          if (mmas == 4) {
+          if (kPair) {
+            if (mmas == 4) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
-          } else if (mmas == 2) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
+              for (int k = 0; k < 4; ++k) umma_bf16_lohi_2sm(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
+            } else {
+              for (int k = 0; k < mmas; ++k) umma_bf16_lohi_2sm(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
+            }
+            umma_commit_2sm(bar_empty + 8 * stage);   // both CTAs' slots
           } else {
-            umma_bf16_lohi(d_tmem, a_lo, b_lo, hi32, idesc, acc0);
+            if (mmas == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
+            } else if (mmas == 2) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi32, idesc, k ? 1u : acc0);
+            } else {
+              umma_bf16_lohi(d_tmem, a_lo, b_lo, hi32, idesc, acc0);
+            }
+            umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
           }
-          umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * as);       // accumulator complete -> epilogue
+        if (kPair) umma_commit_2sm(bar_tfull + 8 * as); else umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
       }
     }
     __syncwarp();
@@ -202,7 +238,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
     const int etid = threadIdx.x - 64;      // 0 .. 32*kEpiWarps-1
     const bool warp_uniform_image = ppi >= 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int u = unit0; u < total_tiles; u += unit_stride, ++it) {
+      const int tile = tile_of(u);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int nt = tile / p.n_tiles_m, mt = tile - nt * p.n_tiles_m;
@@ -338,7 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        if (lane == 0) { if (kPair) mbar_arrive_leader(bar_tempty + 8 * as); else mbar_arrive(bar_tempty + 8 * as); }
         // everyone has read the statistics: clear this buffer for the tile after next
         asm volatile("bar.sync 1, %0;" ::"r"(128 * p.epi_subs) : "memory");
         float* accb = &s_acc[it & 1][0];
@@ -348,7 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       // TMEM stage drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+      if (lane == 0) { if (kPair) mbar_arrive_leader(bar_tempty + 8 * as); else mbar_arrive(bar_tempty + 8 * as); }
       if (kRun > 0) {
         asm volatile("bar.sync 1, %0;" ::"r"(128 * p.epi_subs) : "memory");
         float* accb = &s_acc[it & 1][0];
@@ -364,9 +401,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();     // the leader's MMAs read the peer's shared memory; remote arrivals need a live CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (kPair) tmem_dealloc2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -532,9 +570,16 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
     p.inv_cnt = 1.0f / (float)((int64_t)g.Hm * g.Wm * p.Cg); p.eps = 1e-5f;
   }
   p.bias = bias; p.out = out; p.stats = stats;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  // 2-CTA mode (cta_group::2): layers with >= 128 couts, where the weight tile dominates the operand traffic
+  static const int pair_mode = [] { const char* e = getenv("DBS_CONV_PAIR"); return e ? atoi(e) : 1; }();
+  // measured (profiles/pair_sweep.sh, B = 1024): 256-cout 8x8 layers gain 5-14 %; 128-cout layers, 1x1 convs,
+  // transposed phases and 4x4 lattices are neutral or slower, so the pair mode is used where the weight tile is the
+  // larger operand (DBS_CONV_PAIR=2 forces it wherever it is legal, =0 disables it)
+  const bool pair_legal = Nb >= 128 && Nb % 32 == 0 && (p.n_tiles_m % 2 == 0) && p.n_tiles_m >= 2;
+  const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && Nb == 256 && g.n_taps == 9 && g.Hm * g.Wm >= 64));
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)((pair ? 2 * kTileM : kTileM) >> 4) << 24);
   p.a_bytes = (uint32_t)kTileM * KC * 2;
-  p.b_bytes = (uint32_t)Nb * KC * 2;
+  p.b_bytes = (uint32_t)(pair ? Nb / 2 : Nb) * KC * 2;
   p.stage_bytes = ((p.a_bytes + 1023u) & ~1023u) + ((p.b_bytes + 1023u) & ~1023u);
   int stages = (int)(kSmemBudget / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -561,30 +606,48 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   int taps_total = 0;
   for (int t = 0; t < g.n_taps; ++t) taps_total = g.widx[t] + 1 > taps_total ? g.widx[t] + 1 : taps_total;
   if (g.out_stride == 2) taps_total = 16;
-  if ((rc = encode_w(enc, &mw, w, Cin, g.Cout, taps_total, KC, Nb, sw))) return rc;
+  if ((rc = encode_w(enc, &mw, w, Cin, g.Cout, taps_total, KC, pair ? Nb / 2 : Nb, sw))) return rc;
 
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
   const int run = !stats ? 0 : (p.Cg >= 16 ? 16 : p.Cg);
-  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
-      run == 0 ? conv_tc_kernel<0> : run == 2 ? conv_tc_kernel<2> : run == 4 ? conv_tc_kernel<4>
-               : run == 8 ? conv_tc_kernel<8> : conv_tc_kernel<16>;
+  typedef void (*Kern)(CUtensorMap, CUtensorMap, CUtensorMap, TcParams);
+  static const Kern table[2][5] = {
+      {conv_tc_kernel<0, false>, conv_tc_kernel<2, false>, conv_tc_kernel<4, false>, conv_tc_kernel<8, false>, conv_tc_kernel<16, false>},
+      {conv_tc_kernel<0, true>, conv_tc_kernel<2, true>, conv_tc_kernel<4, true>, conv_tc_kernel<8, true>, conv_tc_kernel<16, true>}};
+  const int ri = run == 0 ? 0 : run == 2 ? 1 : run == 4 ? 2 : run == 8 ? 3 : 4;
+  Kern kern = table[pair ? 1 : 0][ri];
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    void (*ks[5])(CUtensorMap, CUtensorMap, CUtensorMap, TcParams) = {conv_tc_kernel<0>, conv_tc_kernel<2>, conv_tc_kernel<4>,
-                                                                      conv_tc_kernel<8>, conv_tc_kernel<16>};
-    for (auto k : ks) {
-      const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
-      if (e != cudaSuccess) attr_err = e;
-    }
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 5; ++b) {
+        const cudaError_t e = cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048));
+        if (e != cudaSuccess) attr_err = e;
+      }
   });
   DBS_CUDA(attr_err);
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  prof_set_label("tile H%d W%d C%d+%d->%d taps%d s%d os%d KC%d B%d%s", g.Hin, g.Win, g.C0, g.C1, g.Cout, g.n_taps, g.in_stride,
-                 g.out_stride, KC, g.B, fuse ? " +gn" : "");
+  const int total_units = pair ? (p.n_tiles_m / 2) * p.n_tiles_n : p.n_tiles_m * p.n_tiles_n;
+  const int sms = num_sms();
+  prof_set_label("tile%s H%d W%d C%d+%d->%d taps%d s%d os%d KC%d B%d%s", pair ? "2" : "", g.Hin, g.Win, g.C0, g.C1, g.Cout,
+                 g.n_taps, g.in_stride, g.out_stride, KC, g.B, fuse ? " +gn" : "");
   ProfScope prof(kProfConvTC, st);
-  kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
+  if (pair) {
+    const int pairs = total_units < sms / 2 ? total_units : sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DBS_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, p));
+  } else {
+    const int grid = total_units < sms ? total_units : sms;
+    kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
+  }
   DBS_LAUNCHED();
   return DBS_OK;
 }
