@@ -12,6 +12,8 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 torch.manual_seed(0)
 net = ScoreNetwork(1, 32, 64, 3).eval()
 smp = DiffusionSampler(net, num_steps=steps, device="cuda", precision="bf16")
+if os.environ.get("DBS_NO_GRAPH"):
+    smp.use_graph = False     # eager launches: a clean per-kernel list under ncu
 x = smp.sample((B, 1, L, L), seed=1)
 torch.cuda.synchronize()
 print("ok", float(x.abs().mean()))
