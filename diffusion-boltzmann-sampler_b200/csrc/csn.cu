@@ -20,6 +20,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -33,7 +34,8 @@ int csn_tc_convert_weights(const float* src, __nv_bfloat16* dst, int64_t n);
 int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const float* bias, int N_total, const float* pre_g,
                   const float* pre_b, const float* post_g, const float* post_b, int silu, const float* tbias,
                   int64_t tb_stride, int tokens_per_cfg, const float* res, void* out, int out_bf16, int64_t M,
-                  cudaStream_t st);
+                  cudaStream_t st, const float* pos_freqs = nullptr, const float* head_w2 = nullptr,
+                  const float* head_b2 = nullptr);
 int csn_tc_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t B, int N, int heads, cudaStream_t st);
 }  // namespace dbs
 
@@ -50,6 +52,9 @@ struct dbs_csn_plan {
     __nv_bfloat16 *fc1_h, *fc2_h, *qkv_h, *proj_h;   // bf16 copies for the tcgen05 path (null if not eligible)
   };
   bool tc_ok = false;
+  __nv_bfloat16 *in_h = nullptr, *o1_h = nullptr;   // input_proj / output_proj.1 zero-padded to [128][128] bf16
+  float* o1_bpad = nullptr;                         // output_proj.1 bias padded to 128
+  bool tc_io_ok = false;                            // pos_embed_dim == 64: embedding + head also run on the tensor cores
   std::vector<Block> blocks;
   float *on_g = nullptr, *on_b = nullptr, *o1_w = nullptr, *o1_b = nullptr, *o2_w = nullptr, *o2_b = nullptr;
 };
@@ -446,10 +451,16 @@ int forward_impl(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t
   }
   LinArgs a;
   // input projection of [Fourier features | raw coordinates]  (:262-266)
-  memset(&a, 0, sizeof(a));
-  a.X = x; a.K = c.pos_embed_dim + 2; a.W = plan->in_w; a.bias = plan->in_b; a.N = H;
-  a.pos_freqs = plan->pos_freqs; a.n_freq = c.pos_embed_dim / 4; a.out = h; a.M = M; a.tokens_per_cfg = N;
-  if ((rc = run_linear(kProEmbed, a, st))) return rc;
+  if (tc && plan->tc_io_ok) {
+    if ((rc = csn_tc_linear(x, 0, plan->in_h, plan->in_b, H, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, N, nullptr, h, 0, M, st,
+                            plan->pos_freqs)))
+      return rc;
+  } else {
+    memset(&a, 0, sizeof(a));
+    a.X = x; a.K = c.pos_embed_dim + 2; a.W = plan->in_w; a.bias = plan->in_b; a.N = H;
+    a.pos_freqs = plan->pos_freqs; a.n_freq = c.pos_embed_dim / 4; a.out = h; a.M = M; a.tokens_per_cfg = N;
+    if ((rc = run_linear(kProEmbed, a, st))) return rc;
+  }
   for (int i = 0; i < nb; ++i) {
     const dbs_csn_plan::Block& b = plan->blocks[i];
     if (tc) {
@@ -494,6 +505,9 @@ int forward_impl(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t
     }
   }
   // output head: LN -> Linear -> SiLU -> Linear (:248-253)
+  if (tc && plan->tc_io_ok)
+    return csn_tc_linear(h, 0, plan->o1_h, plan->o1_bpad, H, plan->on_g, plan->on_b, nullptr, nullptr, 1, nullptr, 0, N, nullptr, score,
+                         0, M, st, nullptr, plan->o2_w, plan->o2_b);
   memset(&a, 0, sizeof(a));
   a.X = h; a.K = H; a.W = plan->o1_w; a.bias = plan->o1_b; a.N = H / 2; a.pre_g = plan->on_g; a.pre_b = plan->on_b;
   a.silu = 1; a.out = o1; a.M = M; a.tokens_per_cfg = N;
@@ -582,6 +596,37 @@ extern "C" int dbs_csn_plan_create(const dbs_csn_config* cfg, const dbs_param* p
   up("output_proj.0.weight", H, &plan->on_g); up("output_proj.0.bias", H, &plan->on_b);
   up("output_proj.1.weight", (int64_t)(H / 2) * H, &plan->o1_w); up("output_proj.1.bias", H / 2, &plan->o1_b);
   up("output_proj.3.weight", (int64_t)2 * (H / 2), &plan->o2_w); up("output_proj.3.bias", 2, &plan->o2_b);
+  plan->tc_io_ok = plan->tc_ok && P == 64;
+  if (!rc && plan->tc_io_ok) {
+    // zero-padded [128][128] copies: input_proj [128][66] -> K 128; output_proj.1 [64][128] -> N 128
+    std::vector<float> hw((size_t)H * (P + 2)), pad((size_t)128 * 128, 0.f), hb(H / 2), bpad(128, 0.f);
+    float* tmp = nullptr;
+    auto to_bf16 = [&](const std::vector<float>& src, __nv_bfloat16** dst) {
+      if (rc) return;
+      void* d = nullptr;
+      if (cudaMalloc(&d, src.size() * 2) != cudaSuccess || cudaMalloc((void**)&tmp, src.size() * 4) != cudaSuccess) { set_error("csn plan: cudaMalloc failed"); rc = DBS_ERR_CUDA; return; }
+      plan->allocs.push_back(d); plan->allocs.push_back(tmp);
+      if (cudaMemcpy(tmp, src.data(), src.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("csn plan: upload failed"); rc = DBS_ERR_CUDA; return; }
+      *dst = (__nv_bfloat16*)d;
+      rc = csn_tc_convert_weights(tmp, *dst, (int64_t)src.size());
+    };
+    if (cudaMemcpy(hw.data(), plan->in_w, hw.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("csn plan: readback failed"); rc = DBS_ERR_CUDA; }
+    if (!rc) {
+      for (int n = 0; n < H; ++n) for (int k = 0; k < P + 2; ++k) pad[(size_t)n * 128 + k] = hw[(size_t)n * (P + 2) + k];
+      to_bf16(pad, &plan->in_h);
+    }
+    std::vector<float> ow((size_t)(H / 2) * H);
+    if (!rc && (cudaMemcpy(ow.data(), plan->o1_w, ow.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(hb.data(), plan->o1_b, hb.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) { set_error("csn plan: readback failed"); rc = DBS_ERR_CUDA; }
+    if (!rc) {
+      std::fill(pad.begin(), pad.end(), 0.f);
+      for (size_t i = 0; i < ow.size(); ++i) pad[i] = ow[i];          // rows 0..63 of [128][128]
+      to_bf16(pad, &plan->o1_h);
+      for (int i = 0; i < H / 2; ++i) bpad[i] = hb[i];
+      if (!rc) rc = upload_host(plan, bpad.data(), 128, &plan->o1_bpad);
+    }
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("csn plan: padded weight conversion failed"); rc = DBS_ERR_CUDA; }
+  }
   if (rc) { dbs_csn_plan_destroy(plan); return rc; }
   *out = plan;
   return DBS_OK;

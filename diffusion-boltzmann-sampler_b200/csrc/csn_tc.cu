@@ -60,6 +60,13 @@ struct TcLinArgs {
   void* out;                   // [M][N_total] fp32 (out_bf16 = 0) or bf16
   int in_bf16, out_bf16;
   int64_t M;
+  // embedding prologue (input_proj, :262-266): X = positions [M][2]; the operand row is
+  // [sin(a_x f) | cos(a_x f) | sin(a_y f) | cos(a_y f) | x | y | 0 ...], 16 frequencies, padded to K = 128
+  const float* pos_freqs;       // null = not the embedding layer
+  // fused output head (:248-253): this layer is Linear(128 -> 64) + SiLU and the final Linear(64 -> 2) is
+  // applied to the thread's row in the epilogue; out = score fp32 [M][2]
+  const float* head_w2;         // [2][64], null = no head
+  const float* head_b2;         // [2]
 };
 
 // a warp converts 128-wide rows to bf16 and stores them into the swizzled K-major operand tile; the loads of
@@ -95,6 +102,35 @@ __device__ __forceinline__ void finish_row(uint8_t* tile, int r, int lane, float
                        (uint32_t)((((lane & 15) >> 1) ^ (r & 7)) << 4) + (uint32_t)(lane & 1) * 8u;
   *reinterpret_cast<uint2*>(tile + off) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
 }
+// Fourier-embedding operand rows: lane l produces features 4l .. 4l+3 of its token
+__device__ __forceinline__ void stage_embed(uint8_t* tile, const float* pos, int64_t rows_live, int warp, int lane,
+                                            const float* freqs) {
+  const int qd = lane >> 2;                 // 0..3: sin x, cos x, sin y, cos y;  4: raw coords (lane 16);  >4: zero padding
+  float fr[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane < 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fr[i] = freqs[4 * (lane & 3) + i];
+  }
+#pragma unroll 1
+  for (int r = warp; r < 128; r += 8) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows_live) {
+      const float2 pq = *reinterpret_cast<const float2*>(pos + (int64_t)r * 2);
+      if (lane < 16) {
+        const float base = __fmul_rn(__fadd_rn(qd < 2 ? pq.x : pq.y, 1.0f), 3.14159265358979323846f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float arg = __fmul_rn(base, fr[i]);
+          v[i] = (qd & 1) ? cosf(arg) : sinf(arg);
+        }
+      } else if (lane == 16) {
+        v[0] = pq.x; v[1] = pq.y;
+      }
+    }
+    finish_row(tile, r, lane, v, nullptr, nullptr);
+  }
+}
+
 // rows warp, warp + 8, ... of a 128-row tile; src = first row of the tile, rows_live = rows that exist
 template <bool kBf16In>
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const void* src, int64_t rows_live, int warp, int lane,
@@ -125,6 +161,7 @@ csn_tc_linear_kernel(const TcLinArgs a) {
   // per-column epilogue vectors of this CTA's 128 columns: warp-uniform reads, so they are served as
   // shared-memory broadcasts (float4) instead of ~4 global loads per output element
   __shared__ __align__(16) float s_bias[128], s_pg[128], s_pb[128], s_tb[128];
+  __shared__ __align__(16) float s_w2[2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = blockIdx.y * 128;
   const bool tb_shared = a.tbias != nullptr && a.tb_stride == 0;
@@ -134,6 +171,7 @@ csn_tc_linear_kernel(const TcLinArgs a) {
     s_pg[c] = a.post_g ? a.post_g[c] : 1.f;
     s_pb[c] = a.post_b ? a.post_b[c] : 0.f;
     s_tb[c] = tb_shared ? a.tbias[col0 + c] : 0.f;
+    if (a.head_w2) s_w2[c >> 6][c & 63] = a.head_w2[c];
   }
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 128);
@@ -154,7 +192,8 @@ csn_tc_linear_kernel(const TcLinArgs a) {
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t m0 = tile * 128;
     // ---- phase 1: operand rows (prologue fused)
-    if (a.in_bf16) stage_tile<true>(As, reinterpret_cast<const __nv_bfloat16*>(a.X) + m0 * 128, a.M - m0, warp, lane, a.pre_g, a.pre_b);
+    if (a.pos_freqs) stage_embed(As, reinterpret_cast<const float*>(a.X) + m0 * 2, a.M - m0, warp, lane, a.pos_freqs);
+    else if (a.in_bf16) stage_tile<true>(As, reinterpret_cast<const __nv_bfloat16*>(a.X) + m0 * 128, a.M - m0, warp, lane, a.pre_g, a.pre_b);
     else stage_tile<false>(As, reinterpret_cast<const float*>(a.X) + m0 * 128, a.M - m0, warp, lane, a.pre_g, a.pre_b);
     fence_async_smem();
     __syncthreads();
@@ -197,6 +236,33 @@ csn_tc_linear_kernel(const TcLinArgs a) {
       rstd = rsqrtf(fmaxf(ss * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
     }
     const float* tb = (a.tbias && !tb_shared) ? a.tbias + (live ? m / a.tokens_per_cfg : 0) * a.tb_stride : nullptr;
+    if (a.head_w2) {
+      // output head: columns 0..63 hold Linear(128 -> 64) of the row (64..127 are zero padding); SiLU, then the
+      // 64 -> 2 projection as two thread-local dot products
+      if (ch == 0) {
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c + 4 * j4]);
+            const float4 u4 = *reinterpret_cast<const float4*>(&s_w2[0][c + 4 * j4]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&s_w2[1][c + 4 * j4]);
+            const float x0 = silu_fast(__uint_as_float(v[4 * j4]) + b4.x), x1 = silu_fast(__uint_as_float(v[4 * j4 + 1]) + b4.y);
+            const float x2 = silu_fast(__uint_as_float(v[4 * j4 + 2]) + b4.z), x3 = silu_fast(__uint_as_float(v[4 * j4 + 3]) + b4.w);
+            y0 = fmaf(x0, u4.x, y0); y0 = fmaf(x1, u4.y, y0); y0 = fmaf(x2, u4.z, y0); y0 = fmaf(x3, u4.w, y0);
+            y1 = fmaf(x0, w4.x, y1); y1 = fmaf(x1, w4.y, y1); y1 = fmaf(x2, w4.z, y1); y1 = fmaf(x3, w4.w, y1);
+          }
+        }
+        if (live) *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.out) + m * 2) = make_float2(y0 + a.head_b2[0], y1 + a.head_b2[1]);
+      }
+      tc_fence_before();
+      __syncthreads();
+      continue;
+    }
 #pragma unroll 1
     for (int c = ch * 64; c < ch * 64 + 64; c += 16) {
       uint32_t v[16];
@@ -439,12 +505,13 @@ int csn_tc_convert_weights(const float* src, __nv_bfloat16* dst, int64_t n) {
 int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const float* bias, int N_total, const float* pre_g,
                   const float* pre_b, const float* post_g, const float* post_b, int silu, const float* tbias,
                   int64_t tb_stride, int tokens_per_cfg, const float* res, void* out, int out_bf16, int64_t M,
-                  cudaStream_t st) {
+                  cudaStream_t st, const float* pos_freqs, const float* head_w2, const float* head_b2) {
   DBS_REQUIRE(N_total % 128 == 0 && (!post_g || N_total == 128), "csn_tc_linear: unsupported width %d", N_total);
   TcLinArgs a;
   a.X = X; a.W = W; a.bias = bias; a.N_total = N_total; a.pre_g = pre_g; a.pre_b = pre_b; a.post_g = post_g; a.post_b = post_b;
   a.silu = silu; a.tbias = tbias; a.tb_stride = tb_stride; a.tokens_per_cfg = tokens_per_cfg; a.res = res; a.out = out;
   a.in_bf16 = in_bf16; a.out_bf16 = out_bf16; a.M = M;
+  a.pos_freqs = pos_freqs; a.head_w2 = head_w2; a.head_b2 = head_b2;
   const size_t smem = 4 * kAtomBytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
