@@ -146,6 +146,19 @@ class DiffusionSampler:
                                       1 if add_noise else 0, seed, sample_offset, step, runtime.current_stream()),
                   "em_step")
 
+    @staticmethod
+    def _lincomb(terms, out: Optional[torch.Tensor] = None, sign_first: bool = False) -> torch.Tensor:
+        """out = sum_i a_i * x_i over up to five (a_i, x_i) terms in ONE engine pass (dbs_lincomb); with
+        sign_first the first term is a_0 * sign(x_0).  `out` may alias a term."""
+        import ctypes
+        xs = [t[1] for t in terms]
+        out = torch.empty_like(xs[0]) if out is None else out
+        ptrs = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+        coef = (ctypes.c_float * len(xs))(*[float(t[0]) for t in terms])
+        abi.check(abi.lib.dbs_lincomb(out.data_ptr(), out.numel(), len(xs), ptrs, coef, 1 if sign_first else 0,
+                                      runtime.current_stream()), "lincomb")
+        return out
+
     def _graph_step(self, shape):
         """Persistent (x, score, t) buffers and, when enabled, a captured graph of one forward for
         this shape.  Returns (x, score, t_dev, graph_or_None)."""
@@ -296,25 +309,25 @@ class DiffusionSampler:
         x = self._gaussian(shape, seed, abi.STEP_X0)
         score = torch.empty_like(x)
 
-        def drift(xin, t_val):
-            return (self._sigma(t_val) ** 2) * self._score(xin, t_val)
-
         for i in range(N, 0, -1):
             t_val = i / N
             if method == "euler":
                 self._score(x, t_val, out=score)
                 self._em(x, score, self._sigma(t_val), 0.0, False, seed, i)
             elif method == "heun":
-                sig, sig_n = self._sigma(t_val), self._sigma((i - 1) / N)
+                # x <- x + dt/2 (sig^2 s(x, t) + sig_n^2 s(x + dt sig^2 s(x, t), t - dt)): two forwards, two fused passes
+                c0, c1 = self._sigma(t_val) ** 2, self._sigma((i - 1) / N) ** 2
                 s0 = self._score(x, t_val)
-                s1 = self._score(x + (sig ** 2) * s0 * dt, (i - 1) / N)
-                x = x + 0.5 * ((sig ** 2) * s0 + (sig_n ** 2) * s1) * dt
+                s1 = self._score(self._lincomb([(1.0, x), (c0 * dt, s0)]), (i - 1) / N)
+                self._lincomb([(1.0, x), (0.5 * c0 * dt, s0), (0.5 * c1 * dt, s1)], out=x)
             else:
-                k1 = drift(x, t_val)
-                k2 = drift(x + 0.5 * dt * k1, t_val - 0.5 * dt)
-                k3 = drift(x + 0.5 * dt * k2, t_val - 0.5 * dt)
-                k4 = drift(x + dt * k3, t_val - dt)
-                x = x + (dt / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+                # classical RK4 on dx/dt = sig(t)^2 s(x, t): four forwards, four fused passes
+                ca, cm, cb = self._sigma(t_val) ** 2, self._sigma(t_val - 0.5 * dt) ** 2, self._sigma(t_val - dt) ** 2
+                s1 = self._score(x, t_val)
+                s2 = self._score(self._lincomb([(1.0, x), (0.5 * dt * ca, s1)]), t_val - 0.5 * dt)
+                s3 = self._score(self._lincomb([(1.0, x), (0.5 * dt * cm, s2)]), t_val - 0.5 * dt)
+                s4 = self._score(self._lincomb([(1.0, x), (dt * cm, s3)]), t_val - dt)
+                self._lincomb([(1.0, x), (dt / 6 * ca, s1), (dt / 3 * cm, s2), (dt / 3 * cm, s3), (dt / 6 * cb, s4)], out=x)
         return self._out(x)
 
     # ------------------------------------------------------------------ post-processing
@@ -409,5 +422,5 @@ class PretrainedDiffusionSampler(DiffusionSampler):
         x = self._gaussian(shape, seed, abi.STEP_X0)
         for i in range(self.num_steps, 0, -1):
             r = (i / self.num_steps) ** 0.5
-            x = (1 - r) * torch.sign(x) + r * self._gaussian(shape, seed, i) * 0.5
+            self._lincomb([(1 - r, x), (0.5 * r, self._gaussian(shape, seed, i))], out=x, sign_first=True)
         return self._out(torch.sign(x))

@@ -143,3 +143,68 @@ extern "C" int dbs_gaussian_fill(float* x, int64_t n_samples, int64_t elems_per_
   a.sample_offset = sample_offset; a.step = (uint32_t)step;
   return launch_em<true>(a, as_stream(stream));
 }
+
+// ------------------------------------------------------------------------------------------------
+// out = sum_i a_i * f_i(x_i), up to five terms, f = identity or sign (torch.sign: sign(0) = 0): the state
+// combinations of the deterministic integrators (Heun, RK4: samplers/diffusion.py:488-519), the Langevin
+// corrector (:441-447) and the heuristic anneal (:762-768) as one fused pass instead of a chain of elementwise ops.
+namespace dbs {
+namespace {
+struct LinCombArgs {
+  float* out;
+  const float* x[5];
+  float a[5];
+  int n_terms;
+  int sign_first;
+  int64_t n;
+};
+__global__ void __launch_bounds__(256) lincomb_kernel(LinCombArgs q) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= q.n) return;
+  if (i4 + 4 <= q.n) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      if (t < q.n_terms) {
+        float4 v = *reinterpret_cast<const float4*>(q.x[t] + i4);
+        if (t == 0 && q.sign_first) {
+          v.x = (v.x > 0.f) - (v.x < 0.f); v.y = (v.y > 0.f) - (v.y < 0.f);
+          v.z = (v.z > 0.f) - (v.z < 0.f); v.w = (v.w > 0.f) - (v.w < 0.f);
+        }
+        acc.x = fmaf(q.a[t], v.x, acc.x); acc.y = fmaf(q.a[t], v.y, acc.y);
+        acc.z = fmaf(q.a[t], v.z, acc.z); acc.w = fmaf(q.a[t], v.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(q.out + i4) = acc;
+  } else {
+    for (int64_t i = i4; i < q.n; ++i) {
+      float acc = 0.f;
+      for (int t = 0; t < q.n_terms; ++t) {
+        float v = q.x[t][i];
+        if (t == 0 && q.sign_first) v = (v > 0.f) - (v < 0.f);
+        acc = fmaf(q.a[t], v, acc);
+      }
+      q.out[i] = acc;
+    }
+  }
+}
+}  // namespace
+}  // namespace dbs
+
+extern "C" int dbs_lincomb(float* out, int64_t n, int n_terms, const float* const* x, const float* a, int sign_first,
+                           void* stream) {
+  DBS_REQUIRE(out && x && a && n >= 0 && n_terms >= 1 && n_terms <= 5, "lincomb: bad arguments (1..5 terms)");
+  if (n == 0) return DBS_OK;
+  dbs::LinCombArgs q;
+  q.out = out; q.n = n; q.n_terms = n_terms; q.sign_first = sign_first ? 1 : 0;
+  for (int t = 0; t < 5; ++t) { q.x[t] = t < n_terms ? x[t] : nullptr; q.a[t] = t < n_terms ? a[t] : 0.f; }
+  for (int t = 0; t < n_terms; ++t) {
+    DBS_REQUIRE(x[t] != nullptr, "lincomb: term %d is null", t);
+    DBS_REQUIRE((reinterpret_cast<uintptr_t>(x[t]) & 15) == 0, "lincomb: term %d is not 16-byte aligned", t);
+  }
+  DBS_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "lincomb: out is not 16-byte aligned");
+  dbs::ProfScope prof(dbs::kProfEm, dbs::as_stream(stream));
+  dbs::lincomb_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, dbs::as_stream(stream)>>>(q);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "dbs_observable_accumulate": (i32, [vp, vp, i32, i64, vp, vp, vp]),
     "dbs_em_step": (i32, [vp, vp, vp, i64, i64, f32, f32, f32, f32, i32, u64, i64, i64, vp]),
     "dbs_gaussian_fill": (i32, [vp, i64, i64, u64, i64, i64, vp]),
+    "dbs_lincomb": (i32, [vp, i64, i32, vp, vp, i32, vp]),
     "dbs_lj_energy_forces": (i32, [vp, i64, i32, f32, f32, f32, f32, f32, vp, vp, vp]),
     "dbs_mala_propose": (i32, [vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, u64, i64, i64, vp]),
     "dbs_mala_accept": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, f32, u64, i64, i64, vp, vp]),

@@ -167,6 +167,13 @@ int dbs_em_step(float* x, const float* score, const float* noise, int64_t n_samp
 int dbs_gaussian_fill(float* x, int64_t n_samples, int64_t elems_per_sample, uint64_t seed,
                       int64_t sample_offset, int64_t step, void* stream);
 
+/* out[i] = sum_t a[t] * f_t(x[t][i]), 1..5 terms, f_0 = torch.sign when sign_first != 0, else identity.
+ * The state combinations of the deterministic integrators and correctors around the score network
+ * (samplers/diffusion.py:441-447 corrector, :488-519 Heun / RK4, :762-768 heuristic anneal) as one pass.
+ * x: HOST array of n_terms DEVICE pointers (16-byte aligned, may alias out); a: HOST array of coefficients. */
+int dbs_lincomb(float* out, int64_t n, int n_terms, const float* const* x, const float* a,
+                int sign_first, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Lennard-Jones pair energy / forces.  Replaces LennardJonesSystem.energy /
  * forces / pairwise_distances / minimum_image (systems/lennard_jones.py:58-155).

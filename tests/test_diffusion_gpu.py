@@ -241,3 +241,55 @@ def test_sample_sharding_invariance():
     full = smp.sample((8, 1, 16, 16), seed=9)
     part = smp.sample((4, 1, 16, 16), seed=9, sample_offset=4)
     assert torch.allclose(part, full[4:], atol=1e-5)
+
+
+@pytest.mark.parametrize("method", ["euler", "heun", "rk4"])
+def test_ode_integrators_match_a_torch_restatement(method):
+    """sample_ode (samplers/diffusion.py:453-521): the engine's loops (forward kernels + fused dbs_lincomb state
+    updates) against the same integrator written with the oracle's fp32 forward on the CPU, same Gaussian start."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    from dbs_b200 import abi
+    net = _net(8, 16, 2, seed=5)
+    sd = _sd(net)
+    N, shape, seed = 6, (3, 1, 16, 16), 91
+    smp = DiffusionSampler(net, num_steps=N, precision="fp32")
+    got = smp.sample_ode(shape, method=method, seed=seed).numpy()
+    x = DiffusionSampler._gaussian(shape, seed, abi.STEP_X0).cpu()
+    dt = 1.0 / N
+
+    def sig2(t):
+        return float(o_em.noise_level(np.full((1,), t, dtype=np.float32))[1][0]) ** 2
+
+    def score(xx, t):
+        return o_unet.unet_forward(sd, xx, torch.full((shape[0],), t))
+
+    for i in range(N, 0, -1):
+        t = i / N
+        if method == "euler":
+            x = x + sig2(t) * score(x, t) * dt
+        elif method == "heun":
+            s0 = score(x, t)
+            s1 = score(x + sig2(t) * s0 * dt, (i - 1) / N)
+            x = x + 0.5 * (sig2(t) * s0 + sig2((i - 1) / N) * s1) * dt
+        else:
+            k1 = sig2(t) * score(x, t)
+            k2 = sig2(t - 0.5 * dt) * score(x + 0.5 * dt * k1, t - 0.5 * dt)
+            k3 = sig2(t - 0.5 * dt) * score(x + 0.5 * dt * k2, t - 0.5 * dt)
+            k4 = sig2(t - dt) * score(x + dt * k3, t - dt)
+            x = x + (dt / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert _rel(got, x.numpy()) <= 1e-4
+
+
+def test_lincomb_kernel_and_heuristic_sampler():
+    from backend.ml.samplers.diffusion import DiffusionSampler, PretrainedDiffusionSampler
+    torch.manual_seed(0)
+    a, b, c = (torch.randn(5, 1, 7, 9).cuda() for _ in range(3))      # 315 elements: exercises the scalar tail
+    a.view(-1)[:4] = torch.tensor([0.0, -0.0, 2.0, -3.0])
+    out = DiffusionSampler._lincomb([(0.25, a), (-1.5, b), (3.0, c)], sign_first=True)
+    want = 0.25 * torch.sign(a) + (-1.5) * b + 3.0 * c
+    assert torch.allclose(out, want, rtol=1e-6, atol=1e-6)
+    DiffusionSampler._lincomb([(1.0, a), (2.0, b)], out=a)             # in place
+    smp = PretrainedDiffusionSampler(lattice_size=16, num_steps=10)
+    x = smp.sample_heuristic(batch_size=3, seed=4)
+    assert x.shape == (3, 1, 16, 16) and set(np.unique(x.numpy())) <= {-1.0, 1.0}
+    assert torch.equal(x, smp.sample_heuristic(batch_size=3, seed=4))
