@@ -36,13 +36,16 @@ constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;              // four warps per TMEM lane quadrant, one 16-column chunk each
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
-constexpr uint32_t kSmemBudget = 200 * 1024;
+constexpr uint32_t kSmemBudget = 216 * 1024;   // + 1 KB alignment slack + 9 KB static = the 227 KB a CTA may use
 constexpr int kMaxCout = 512;             // Cout > 64 is processed as N tiles of 64 couts
 
 struct StripParams {
   int W, Ht, tiles_h, n_tiles;
   int n_tiles_n;      // N tiles of Nb couts; a CTA's tile order is (image, n-tile, row block)
-  int Nb, KC, chunks0, chunks1, n_taps, stages, resident;
+  int Nb, KC, chunks0, chunks1, n_taps, stages;
+  int resident;       // 0: a chunk's weight slabs travel with its strip; 1: the layer's weights stay in shared memory;
+                      // 2: N-tiled layer run as one pass per n-tile over the CTA's row blocks, that n-tile's weights
+                      //    resident for the pass (tile order (n-tile, image, row block) instead of (image, n-tile, row block))
   int B, Hout, Wout, Cout, out_stride, oph, opw;
   int groups, Cg, cg_log2;
   int dh_min;
@@ -76,7 +79,7 @@ struct StripParams {
 template <int G, int MM>
 __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ring, uint32_t w_region, uint32_t tmem_base,
                                                uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tfull,
-                                               uint32_t bar_tempty, uint32_t bar_w, int tile_lo, int tile_hi) {
+                                               uint32_t bar_tempty, uint32_t bar_w, uint32_t bar_wfree, int n_it, int n_s) {
   const int chunks = p.chunks0 + p.chunks1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2;
   const uint32_t chunk_w_bytes = p.slab_bytes * p.n_slabs;
@@ -94,14 +97,21 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
   // fused residual the widest group (dh = 0, nacc + 1 slabs) is issued FIRST so that the same overwrite also
   // covers the residual slot (the host orders the groups accordingly).
   auto acc_flag = [](int ch, int g, int k) -> uint32_t { return (ch == 0 && g == 0 && k == 0) ? 0u : 1u; };
-  if (p.resident) {
+  if (p.resident == 1) {
     mbar_wait(bar_w, 0);
     tc_fence_after();
   }
   int stage = 0;
   uint32_t phase = 0;
-  int it = 0;
-  for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+  int pass_left = 0;       // resident == 2: tiles left in the current pass
+  uint32_t wphase = 0;
+  for (int it = 0; it < n_it; ++it) {
+    if (p.resident == 2 && pass_left == 0) {   // a new pass: its n-tile's weights must have landed
+      mbar_wait(bar_w, wphase);
+      tc_fence_after();
+      wphase ^= 1;
+      pass_left = n_s;
+    }
     const int as = it & 1;
     const uint32_t aphase = (it >> 1) & 1;
     mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
@@ -126,6 +136,7 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
     umma_commit(bar_tfull + 8 * as);
+    if (p.resident == 2 && --pass_left == 0) umma_commit(bar_wfree);   // the pass's MMAs no longer read the weights
   }
 }
 
@@ -139,7 +150,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
                   const __grid_constant__ StripParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 5];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 6];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_bias[kMaxCout];
   __shared__ __align__(16) float s_bias_r[kMaxCout];
@@ -153,6 +164,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxStages]);
   const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
   const uint32_t bar_w = smem_u32(&bars[2 * kMaxStages + 4]);
+  const uint32_t bar_wfree = smem_u32(&bars[2 * kMaxStages + 5]);
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -164,6 +176,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       mbar_init(bar_tempty + 8 * s, NCH <= 2 ? kEpiWarps / 2 : kEpiWarps);
     }
     mbar_init(bar_w, 1);
+    mbar_init(bar_wfree, 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -183,9 +196,13 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   const uint32_t tmem_base = s_tmem_base;
 
   // contiguous tile range per CTA: consecutive tiles are rows of the same image, which lets the
-  // epilogue keep GroupNorm partial sums in registers until the image changes
-  const int tile_lo = (int)(((int64_t)p.n_tiles * blockIdx.x) / gridDim.x);
-  const int tile_hi = (int)(((int64_t)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  // epilogue keep GroupNorm partial sums in registers until the image changes.  resident == 2: the range is
+  // over row blocks (B * tiles_h) and is walked once per n-tile.
+  const int n_units = p.resident == 2 ? p.B * p.tiles_h : p.n_tiles;
+  const int tile_lo = (int)(((int64_t)n_units * blockIdx.x) / gridDim.x);
+  const int tile_hi = (int)(((int64_t)n_units * (blockIdx.x + 1)) / gridDim.x);
+  const int n_s = tile_hi - tile_lo;
+  const int n_it = p.resident == 2 ? n_s * p.n_tiles_n : n_s;
   const int chunks = p.chunks0 + p.chunks1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2;
   const uint32_t chunk_w_bytes = p.slab_bytes * p.n_slabs;
@@ -194,21 +211,38 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      if (p.resident) {
+      auto load_weights = [&](int co0) {
         mbar_expect_tx(bar_w, chunk_w_bytes * chunks);
         for (int ch = 0; ch < chunks; ++ch)
-          for (int t = 0; t < p.n_slabs; ++t) {  // n_tiles_n == 1 here
+          for (int t = 0; t < p.n_slabs; ++t) {
             const uint32_t dst = w_region + (ch * p.n_slabs + t) * p.slab_bytes;
-            if (p.slab_tap[t] >= 0) tma_load_3d(dst, &map_w, bar_w, ch * p.KC, 0, p.slab_tap[t]);
-            else tma_load_3d(dst, &map_wr, bar_w, ch * p.KC, 0, 0);
+            if (p.slab_tap[t] >= 0) tma_load_3d(dst, &map_w, bar_w, ch * p.KC, co0, p.slab_tap[t]);
+            else tma_load_3d(dst, &map_wr, bar_w, ch * p.KC, co0, 0);
           }
-      }
+      };
+      if (p.resident == 1) load_weights(0);  // n_tiles_n == 1 here
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        const int per_img = p.n_tiles_n * p.tiles_h;
-        const int n = tile / per_img, rem = tile - n * per_img;
-        const int nt = rem / p.tiles_h, h0 = (rem - nt * p.tiles_h) * p.Ht, co0 = nt * p.Nb;
+      const int per_img = p.n_tiles_n * p.tiles_h;
+      int pass = 0, in_pass = 0;
+      for (int it = 0; it < n_it; ++it) {
+        int n, nt, h0;
+        if (p.resident == 2) {
+          if (in_pass == 0) {
+            // the previous pass's MMAs must be done with the weight region before it is overwritten
+            if (pass > 0) mbar_wait(bar_wfree, (uint32_t)(pass - 1) & 1u);
+            load_weights(pass * p.Nb);
+          }
+          const int sblk = tile_lo + in_pass;
+          n = sblk / p.tiles_h; h0 = (sblk - n * p.tiles_h) * p.Ht; nt = pass;
+          if (++in_pass == n_s) { in_pass = 0; ++pass; }
+        } else {
+          const int tile = tile_lo + it;
+          n = tile / per_img;
+          const int rem = tile - n * per_img;
+          nt = rem / p.tiles_h; h0 = (rem - nt * p.tiles_h) * p.Ht;
+        }
+        const int co0 = nt * p.Nb;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t a_dst = ring + stage * p.stage_bytes;
@@ -237,7 +271,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     if (lane == 0) {
       // ===================== MMA issuer =====================
 #define DBS_STRIP_ROLE(G, MM) \
-  strip_mma_role<G, MM>(p, ring, w_region, tmem_base, bar_full, bar_empty, bar_tfull, bar_tempty, bar_w, tile_lo, tile_hi)
+  strip_mma_role<G, MM>(p, ring, w_region, tmem_base, bar_full, bar_empty, bar_tfull, bar_tempty, bar_w, bar_wfree, n_it, n_s)
       const int mm = p.KC / 16;
       if (p.n_groups == 3 && mm == 4) DBS_STRIP_ROLE(3, 4);
       else if (p.n_groups == 3 && mm == 2) DBS_STRIP_ROLE(3, 2);
@@ -294,15 +328,25 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     };
     // tile -> (image, n-tile, row block) kept incrementally: one division per CTA, none per tile
     const int per_img = p.n_tiles_n * p.tiles_h;
-    int n = tile_lo / per_img;
-    int rem = tile_lo - n * per_img;
-    int nt = rem / p.tiles_h;
-    int hb = rem - nt * p.tiles_h;
+    int n, nt, hb;
+    if (p.resident == 2) {
+      n = tile_lo / p.tiles_h; hb = tile_lo - n * p.tiles_h; nt = 0;
+    } else {
+      n = tile_lo / per_img;
+      const int rem = tile_lo - n * per_img;
+      nt = rem / p.tiles_h;
+      hb = rem - nt * p.tiles_h;
+    }
+    int in_pass = 0;
     int xb = 0;  // exchange-buffer parity, toggled per chunk (one named barrier per chunk suffices)
-    int it = 0;
-    for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+    for (int it = 0; it < n_it; ++it) {
       const int t_n = n, t_nt = nt, t_hb = hb;
-      if (++hb == p.tiles_h) { hb = 0; if (++nt == p.n_tiles_n) { nt = 0; ++n; } }
+      if (p.resident == 2) {
+        if (++hb == p.tiles_h) { hb = 0; ++n; }
+        if (++in_pass == n_s) { in_pass = 0; ++nt; n = tile_lo / p.tiles_h; hb = tile_lo - n * p.tiles_h; }
+      } else {
+        if (++hb == p.tiles_h) { hb = 0; if (++nt == p.n_tiles_n) { nt = 0; ++n; } }
+      }
       if (kSplit && (it & 1) != my_set) continue;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -539,9 +583,17 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   const uint32_t all_w = chunk_w * (uint32_t)(p.chunks0 + p.chunks1);
   if (p.slab_bytes % 1024u && KC == 64) return DBS_ERR_UNSUPPORTED;   // slab bases must stay atom-aligned
   if (p.slab_bytes % (8u * KC * 2u)) return DBS_ERR_UNSUPPORTED;
-  // resident weights if they leave room for >= 3 strip stages
+  // resident weights if they leave room for >= 3 strip stages; N-tiled layers keep one n-tile's weights resident
+  // per pass (>= 2 stages: the alternative streams chunk_w bytes of weights with every a_pad-byte strip)
+  static const int pass_env = [] { const char* e = getenv("DBS_STRIP_PASS"); return e ? atoi(e) : 1; }();
+  const int sp_tiles = g.B * p.tiles_h;   // row blocks: the unit CTAs split in pass mode
   if (p.n_tiles_n == 1 && all_w + 3 * a_pad <= kSmemBudget) {
     p.resident = 1;
+    p.w_region_bytes = (all_w + 1023u) & ~1023u;
+    p.stage_bytes = a_pad;
+  } else if (pass_env && p.n_tiles_n > 1 && all_w + (uint32_t)(pass_env >= 2 ? 2 : 3) * a_pad <= kSmemBudget &&
+             sp_tiles >= num_sms()) {
+    p.resident = 2;
     p.w_region_bytes = (all_w + 1023u) & ~1023u;
     p.stage_bytes = a_pad;
   } else {
@@ -596,7 +648,7 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
       }
   });
   DBS_CUDA(attr_err);
-  const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();   // resident == 2 has sp_tiles >= num_sms()
   prof_set_label("strip H%d W%d C%d+%d->%d taps%d os%d KC%d B%d res%d st%d%s", H, W, g.C0, g.C1, g.Cout, g.n_taps,
                  g.out_stride, KC, g.B, p.resident, p.stages, fuse_res ? " +res1x1" : "");
   ProfScope prof(kProfConvTC, st);
