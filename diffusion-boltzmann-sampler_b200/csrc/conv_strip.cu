@@ -484,6 +484,7 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
                       const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st,
                       const __nv_bfloat16* w_res, const float* bias_res, __nv_bfloat16* out_res) {
   const bool fuse_res = w_res != nullptr;
+  if (g.n_phases > 1) return DBS_ERR_UNSUPPORTED;   // merged transposed-conv phases: tile kernel only
   if (fuse_res && (!bias_res || !out_res || g.out_stride != 1 || g.n_taps != 9)) return DBS_ERR_UNSUPPORTED;
   static const bool disabled = [] { const char* e = getenv("DBS_CONV_STRIP"); return e && e[0] == '0'; }();
   if (disabled) return DBS_ERR_UNSUPPORTED;

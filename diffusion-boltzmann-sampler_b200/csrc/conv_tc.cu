@@ -47,6 +47,7 @@ struct TcParams {
   int Wt, Ht, Nt;
   int tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n;
   int Nb, KC, chunks0, chunks1, n_taps, stages;
+  int n_phases;       // 4: merged transposed-conv phases (tile index / tiles-per-phase = phase), else 1
   int B, Hout, Wout, Cout, out_stride, oph, opw;
   int groups, Cg, cg_log2;
   int epi_subs;       // epilogue warps per TMEM lane quadrant that take part (1 or 4), see conv_tc_launch
@@ -131,7 +132,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
 
   // work units: tiles, or pairs of M-adjacent tiles (this CTA takes tile 2k + rank of the pair)
   const int half_m = p.n_tiles_m >> 1;
-  const int total_tiles = kPair ? half_m * p.n_tiles_n : p.n_tiles_m * p.n_tiles_n;
+  const int tiles_per_phase = p.n_tiles_m * p.n_tiles_n;
+  const int total_tiles = kPair ? half_m * p.n_tiles_n : tiles_per_phase * p.n_phases;
   const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int unit_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   auto tile_of = [&](int u) { return kPair ? (u / half_m) * p.n_tiles_m + 2 * (u % half_m) + rank : u; };
@@ -145,11 +147,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       uint32_t phase = 0;
       const uint32_t b_rows_off = kPair ? (uint32_t)rank * (uint32_t)(p.Nb >> 1) : 0u;   // my half of the weight tile
       for (int u = unit0; u < total_tiles; u += unit_stride) {
-        const int tile = tile_of(u);
+        const int tile_ph = tile_of(u);
+        const int ph4 = tile_ph / tiles_per_phase, tile = tile_ph - ph4 * tiles_per_phase;
         const int nt = tile / p.n_tiles_m, mt = tile - nt * p.n_tiles_m;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Nb + (int)b_rows_off;
-        for (int t = 0; t < p.n_taps; ++t) {
+        for (int t = ph4 * p.n_taps; t < (ph4 + 1) * p.n_taps; ++t) {
           const int cw = w0 + p.tap_dw[t], chh = h0 + p.tap_dh[t], cp = p.tap_p[t];
           for (int ch = 0; ch < kblocks_per_tap; ++ch) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -239,7 +242,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
     const bool warp_uniform_image = ppi >= 32;
     int it = 0;
     for (int u = unit0; u < total_tiles; u += unit_stride, ++it) {
-      const int tile = tile_of(u);
+      const int tile_ph = tile_of(u);
+      const int ph4 = tile_ph / tiles_per_phase, tile = tile_ph - ph4 * tiles_per_phase;
+      const int oph = p.n_phases > 1 ? (ph4 >> 1) : p.oph, opw = p.n_phases > 1 ? (ph4 & 1) : p.opw;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int nt = tile / p.n_tiles_m, mt = tile - nt * p.n_tiles_m;
@@ -247,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       const int n = tn * p.Nt + nl, a = th * p.Ht + hl, b = tw * p.Wt + wl, co0 = nt * p.Nb;
       const bool valid = n < p.B;
       __nv_bfloat16* optr =
-          p.out + (((int64_t)n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (b * p.out_stride + p.opw)) * p.Cout + co0;
+          p.out + (((int64_t)n * p.Hout + (a * p.out_stride + oph)) * p.Wout + (b * p.out_stride + opw)) * p.Cout + co0;
       float* acc = &s_acc[it & 1][nl * 16];
 
       mbar_wait(bar_tfull + 8 * as, aphase);
@@ -539,12 +544,15 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   p.n_tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   p.n_tiles_n = n_tiles_n;
   p.Nb = Nb; p.KC = KC; p.chunks0 = g.C0 / KC; p.chunks1 = g.C1 / KC; p.n_taps = g.n_taps;
+  p.n_phases = g.n_phases > 1 ? g.n_phases : 1;
+  if (p.n_phases > 1 && (p.n_phases != 4 || g.n_taps != 4 || g.out_stride != 2 || g.in_stride != 1 || stats || fuse))
+    return DBS_ERR_UNSUPPORTED;
   p.B = g.B; p.Hout = g.Hout; p.Wout = g.Wout; p.Cout = g.Cout;
   p.out_stride = g.out_stride; p.oph = g.oph; p.opw = g.opw;
   p.groups = groups; p.Cg = stats ? g.Cout / groups : g.Cout;
   p.cg_log2 = 0;
   while ((1 << p.cg_log2) < p.Cg) ++p.cg_log2;
-  for (int t = 0; t < g.n_taps; ++t) {
+  for (int t = 0; t < g.n_taps * p.n_phases; ++t) {
     if (g.in_stride == 1) {
       p.tap_dw[t] = g.dw[t]; p.tap_dh[t] = g.dh[t]; p.tap_p[t] = 0; p.tap_c0[t] = 0; p.tap_c1[t] = 0;
     } else {
@@ -575,7 +583,7 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   // measured (profiles/pair_sweep.sh, B = 1024): 256-cout 8x8 layers gain 5-14 %; 128-cout layers, 1x1 convs,
   // transposed phases and 4x4 lattices are neutral or slower, so the pair mode is used where the weight tile is the
   // larger operand (DBS_CONV_PAIR=2 forces it wherever it is legal, =0 disables it)
-  const bool pair_legal = Nb >= 128 && Nb % 32 == 0 && (p.n_tiles_m % 2 == 0) && p.n_tiles_m >= 2;
+  const bool pair_legal = p.n_phases == 1 && Nb >= 128 && Nb % 32 == 0 && (p.n_tiles_m % 2 == 0) && p.n_tiles_m >= 2;
   const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && Nb == 256 && g.n_taps == 9 && g.Hm * g.Wm >= 64));
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nb >> 3) << 17) | ((uint32_t)((pair ? 2 * kTileM : kTileM) >> 4) << 24);
   p.a_bytes = (uint32_t)kTileM * KC * 2;
@@ -626,10 +634,10 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
       }
   });
   DBS_CUDA(attr_err);
-  const int total_units = pair ? (p.n_tiles_m / 2) * p.n_tiles_n : p.n_tiles_m * p.n_tiles_n;
+  const int total_units = pair ? (p.n_tiles_m / 2) * p.n_tiles_n : p.n_tiles_m * p.n_tiles_n * p.n_phases;
   const int sms = num_sms();
-  prof_set_label("tile%s H%d W%d C%d+%d->%d taps%d s%d os%d KC%d B%d%s", pair ? "2" : "", g.Hin, g.Win, g.C0, g.C1, g.Cout,
-                 g.n_taps, g.in_stride, g.out_stride, KC, g.B, fuse ? " +gn" : "");
+  prof_set_label("tile%s H%d W%d C%d+%d->%d taps%d s%d os%d KC%d B%d%s%s", pair ? "2" : "", g.Hin, g.Win, g.C0, g.C1, g.Cout,
+                 g.n_taps, g.in_stride, g.out_stride, KC, g.B, fuse ? " +gn" : "", p.n_phases > 1 ? " x4 phases" : "");
   ProfScope prof(kProfConvTC, st);
   if (pair) {
     const int pairs = total_units < sms / 2 ? total_units : sms / 2;
@@ -674,10 +682,22 @@ extern "C" int dbs_conv_tc(const void* in0, int C0, const void* in1, int C1, con
                         as_stream(stream));
   } else {
     DBS_REQUIRE(C1 == 0, "conv_tc: transposed conv takes a single source");
-    for (int ph = 0; ph < 2 && rc == DBS_OK; ++ph)
-      for (int pw = 0; pw < 2 && rc == DBS_OK; ++pw)
-        rc = conv_tc_launch(geom_convT_phase((int)B, H, W, C0, C_out, ph, pw), (const __nv_bfloat16*)in0, nullptr,
-                            (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups, as_stream(stream));
+    // same policy as the U-Net executor: strip kernel phase by phase where it is eligible, else the tile kernel
+    // with the four phases merged into one launch (statistics are not defined for the merged form)
+    rc = conv_strip_launch(geom_convT_phase((int)B, H, W, C0, C_out, 0, 0), (const __nv_bfloat16*)in0, nullptr,
+                           (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups, as_stream(stream));
+    int first = 1;
+    if (rc == DBS_ERR_UNSUPPORTED) {
+      first = 0;
+      rc = stats ? DBS_ERR_UNSUPPORTED
+                 : conv_tc_launch(geom_convT_all((int)B, H, W, C0, C_out), (const __nv_bfloat16*)in0, nullptr,
+                                  (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, nullptr, groups, as_stream(stream));
+      if (rc == DBS_OK) first = 4;
+      else if (rc == DBS_ERR_UNSUPPORTED) rc = DBS_OK;
+    }
+    for (int ph4 = first; ph4 < 4 && rc == DBS_OK; ++ph4)
+      rc = conv_tc_launch(geom_convT_phase((int)B, H, W, C0, C_out, ph4 >> 1, ph4 & 1), (const __nv_bfloat16*)in0, nullptr,
+                          (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups, as_stream(stream));
   }
   if (rc == DBS_ERR_UNSUPPORTED) set_error("conv_tc: this geometry is not eligible for the tcgen05 kernel");
   return rc;

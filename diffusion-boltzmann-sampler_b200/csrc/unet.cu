@@ -67,6 +67,17 @@ ConvGeom geom_convT_phase(int B, int H, int W, int Cin, int Cout, int ph, int pw
   return g;
 }
 
+// All four phases in one geometry (see ConvGeom::n_phases).
+ConvGeom geom_convT_all(int B, int H, int W, int Cin, int Cout) {
+  ConvGeom g = geom_convT_phase(B, H, W, Cin, Cout, 0, 0);
+  g.n_phases = 4;
+  for (int ph4 = 1; ph4 < 4; ++ph4) {
+    const ConvGeom q = geom_convT_phase(B, H, W, Cin, Cout, ph4 >> 1, ph4 & 1);
+    for (int t = 0; t < 4; ++t) { g.dh[4 * ph4 + t] = q.dh[t]; g.dw[4 * ph4 + t] = q.dw[t]; g.widx[4 * ph4 + t] = q.widx[t]; }
+  }
+  return g;
+}
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1131,12 +1142,37 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
       const int64_t nbc = std::min<int64_t>(cb, B - b0);
       Ctx cc = sub_ctx(b0, nbc);
       T* up_c = up + b0 * h2 * w2 * ch;
-      for (int ph = 0; ph < 2; ++ph)
-        for (int pw = 0; pw < 2; ++pw) {
-          ConvGeom gu = geom_convT_phase((int)nbc, h, w, ch, ch, ph, pw);
-          if ((rc = run_conv<T>(cc, gu, cur + b0 * h * w * ch, (const T*)nullptr, plan->up[i], up_c, nullptr, 8, nullptr)))
-            return rc;
+      // ConvTranspose2d(4, 2, 1) = four stride-1 phase convs.  Strip-kernel levels run them one launch per phase;
+      // elsewhere the tile kernel takes all four phases in ONE persistent launch (low-resolution phases are less
+      // than a wave each: 4 launches of 17-23 us -> one)
+      bool up_done = false;
+      if (cc.use_tc && sizeof(T) == 2) {
+        const ConvGeom g0 = geom_convT_phase((int)nbc, h, w, ch, ch, 0, 0);
+        rc = conv_strip_launch(g0, (const __nv_bfloat16*)(cur + b0 * h * w * ch), nullptr, plan->up[i].w16, plan->up[i].bias,
+                               (__nv_bfloat16*)up_c, nullptr, 8, cc.st);
+        if (rc == DBS_OK) {
+          for (int ph4 = 1; ph4 < 4; ++ph4) {
+            const ConvGeom gu = geom_convT_phase((int)nbc, h, w, ch, ch, ph4 >> 1, ph4 & 1);
+            if ((rc = run_conv<T>(cc, gu, cur + b0 * h * w * ch, (const T*)nullptr, plan->up[i], up_c, nullptr, 8, nullptr)))
+              return rc;
+          }
+          up_done = true;
+        } else if (rc != DBS_ERR_UNSUPPORTED) {
+          return rc;
+        } else {
+          rc = conv_tc_launch(geom_convT_all((int)nbc, h, w, ch, ch), (const __nv_bfloat16*)(cur + b0 * h * w * ch), nullptr,
+                              plan->up[i].w16, plan->up[i].bias, (__nv_bfloat16*)up_c, nullptr, 8, cc.st);
+          if (rc == DBS_OK) up_done = true;
+          else if (rc != DBS_ERR_UNSUPPORTED) return rc;
         }
+      }
+      if (!up_done)
+        for (int ph = 0; ph < 2; ++ph)
+          for (int pw = 0; pw < 2; ++pw) {
+            ConvGeom gu = geom_convT_phase((int)nbc, h, w, ch, ch, ph, pw);
+            if ((rc = run_conv<T>(cc, gu, cur + b0 * h * w * ch, (const T*)nullptr, plan->up[i], up_c, nullptr, 8, nullptr)))
+              return rc;
+          }
       if (cb >= B) {
         snprintf(name, sizeof(name), "up%d", i);
         if ((rc = maybe_tap<T>(cc, name, up, B, h2, w2, ch))) return rc;

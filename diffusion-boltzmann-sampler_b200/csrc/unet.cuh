@@ -23,6 +23,10 @@ struct ConvGeom {
   int n_taps;
   signed char dh[16], dw[16];
   unsigned char widx[16];
+  // n_phases == 4: all four output phases of a ConvTranspose2d(4, 2, 1) in one geometry — phase ph4 = 2*ph + pw
+  // uses taps [ph4*n_taps, (ph4+1)*n_taps) and writes output pixels (2a + ph, 2b + pw); oph / opw are ignored.
+  // 0 or 1: a single phase / an ordinary conv.  Only the tile kernel (conv_tc_launch) takes the merged form.
+  int n_phases;
 };
 
 struct ConvWeights {
@@ -60,5 +64,6 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
 // geometry builders
 ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 ConvGeom geom_convT_phase(int B, int H, int W, int Cin, int Cout, int ph, int pw);
+ConvGeom geom_convT_all(int B, int H, int W, int Cin, int Cout);
 
 }  // namespace dbs

@@ -89,6 +89,14 @@ def test_conv_tc_vs_torch(case):
     _run(*case)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(3, 8, 8, 256), (5, 4, 4, 256), (40, 4, 4, 128), (2, 8, 16, 128), (3, 8, 8, 512)])
+def test_conv_tc_transposed_phases_merged(B, H, W, C):
+    """ConvTranspose2d(4, 2, 1) below the strip kernel's resolutions, no statistics: the tile kernel runs the four
+    output phases in ONE persistent launch (ConvGeom::n_phases = 4); B = 40 at 4x4 gives more (tile, phase) units
+    than a wave's worth per phase and a batch that is not a multiple of the images per tile."""
+    _run(2, 4, B, H, W, C, 0, C, stats=False)
+
+
 def test_conv_tc_wide_cout_two_n_tiles():
     _run(0, 3, 2, 8, 8, 64, 0, 512, stats=True)
 
