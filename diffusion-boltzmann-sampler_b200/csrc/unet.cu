@@ -324,11 +324,61 @@ final_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const f
 // bank (warp-uniform index) and the only memory instructions are 9 coalesced x loads and C/8 16-byte stores.
 template <int C> struct InitW { float w[9 * C]; float b[C]; };
 
+// time path (score_network.py:20-41, 185-189, 126/146) as a device function: the small embedding MLP is recomputed by
+// each of the n_parts CTAs working on time value t_idx, which then split the concatenated per-block Linear layers
+// (sumC outputs) between them.  One thread per output row, float4 weight loads issued back to back: three
+// dependent stages of ~L2 latency each.  sm: 4*T floats.
+struct TimeArgs {
+  const float *t, *freqs, *w0, *b0, *w2, *b2, *wt, *bt;
+  float* tbias;
+  int T, sumC;
+  int n_ctas;   // init_conv_fast_kernel: leading CTAs that run the time path instead of pixels (0 = none)
+};
+__device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const float* __restrict__ v, int n) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int k = 0; k < n; k += 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(wrow + k));
+    a0 = fmaf(q.x, v[k], a0); a1 = fmaf(q.y, v[k + 1], a1);
+    a2 = fmaf(q.z, v[k + 2], a2); a3 = fmaf(q.w, v[k + 3], a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ void time_path(const TimeArgs& a, int t_idx, int part, int n_parts, float* sm) {
+  const int T = a.T;
+  float* emb = sm;           // [T]
+  float* hid = sm + T;       // [2T]
+  float* temb = sm + 3 * T;  // [T]
+  const int half = T / 2;
+  const float tv = a.t[t_idx];
+  for (int k = threadIdx.x; k < T; k += blockDim.x) {
+    const int f = k < half ? k : k - half;
+    const float arg = __fmul_rn(__fmul_rn(tv, a.freqs[f]), 1000.0f);
+    emb[k] = k < half ? sinf(arg) : cosf(arg);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * T; j += blockDim.x) hid[j] = silu(dot_row(a.w0 + (int64_t)j * T, emb, T) + a.b0[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x) temb[i] = dot_row(a.w2 + (int64_t)i * 2 * T, hid, 2 * T) + a.b2[i];
+  __syncthreads();
+  const int per = (a.sumC + n_parts - 1) / n_parts;
+  const int c_lo = part * per, c_hi = min(a.sumC, c_lo + per);
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x)
+    a.tbias[(int64_t)t_idx * a.sumC + c] = dot_row(a.wt + (int64_t)c * T, temb, T) + a.bt[c];
+}
+
 template <int C>
 __global__ void __launch_bounds__(256)
 init_conv_fast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n_pix, int H, int W,
-                      const __grid_constant__ InitW<C> iw) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                      const __grid_constant__ InitW<C> iw, const __grid_constant__ TimeArgs ta) {
+  // horizontal fusion: when all samples share t (the sampler's case) the first ta.n_ctas CTAs compute the time
+  // biases of every ConvBlock while the others run the init conv — the time MLP's ~20 us of dependent L2 round
+  // trips disappear behind the conv instead of preceding it as a launch of their own
+  if ((int)blockIdx.x < ta.n_ctas) {
+    extern __shared__ float sm_time[];
+    time_path(ta, 0, blockIdx.x, ta.n_ctas, sm_time);
+    return;
+  }
+  const int64_t p = (int64_t)(blockIdx.x - ta.n_ctas) * blockDim.x + threadIdx.x;
   if (p >= n_pix) return;
   const int ww = (int)(p % W);
   const int hh = (int)((p / W) % H);
@@ -356,11 +406,12 @@ init_conv_fast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ o
 
 template <int C>
 int launch_init_fast(const std::vector<float>& w_host, const std::vector<float>& b_host, const float* x,
-                     __nv_bfloat16* out, int64_t n_pix, int H, int W, cudaStream_t st) {
+                     __nv_bfloat16* out, int64_t n_pix, int H, int W, cudaStream_t st, const TimeArgs& ta) {
   InitW<C> iw;
   for (int i = 0; i < 9 * C; ++i) iw.w[i] = w_host[i];
   for (int i = 0; i < C; ++i) iw.b[i] = b_host[i];
-  init_conv_fast_kernel<C><<<(unsigned)((n_pix + 255) / 256), 256, 0, st>>>(x, out, n_pix, H, W, iw);
+  init_conv_fast_kernel<C><<<(unsigned)((n_pix + 255) / 256) + (unsigned)ta.n_ctas, 256,
+                             ta.n_ctas ? (size_t)4 * ta.T * 4 : 0, st>>>(x, out, n_pix, H, W, iw, ta);
   DBS_LAUNCHED();
   return DBS_OK;
 }
@@ -628,45 +679,11 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
   }
 }
 
-// time path (score_network.py:20-41, 185-189, 126/146): gridDim.x = distinct t values; the small
-// embedding MLP is recomputed by each of the gridDim.y CTAs, which then split the concatenated
-// per-block Linear layers (sumC outputs) between them.  One thread per output row, float4 weight
-// loads issued back to back: three dependent stages of ~L2 latency each.
-__device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const float* __restrict__ v, int n) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int k = 0; k < n; k += 4) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(wrow + k));
-    a0 = fmaf(q.x, v[k], a0); a1 = fmaf(q.y, v[k + 1], a1);
-    a2 = fmaf(q.z, v[k + 2], a2); a3 = fmaf(q.w, v[k + 3], a3);
-  }
-  return (a0 + a1) + (a2 + a3);
-}
-
+// stand-alone time path: gridDim.x = distinct t values, gridDim.y CTAs per value (see time_path above)
 __global__ void __launch_bounds__(256)
-time_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int T,
-            const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
-            const float* __restrict__ b2, const float* __restrict__ wt, const float* __restrict__ bt, int sumC,
-            float* __restrict__ tbias) {
+time_kernel(const __grid_constant__ TimeArgs ta) {
   extern __shared__ float sm[];
-  float* emb = sm;           // [T]
-  float* hid = sm + T;       // [2T]
-  float* temb = sm + 3 * T;  // [T]
-  const int half = T / 2;
-  const float tv = t[blockIdx.x];
-  for (int k = threadIdx.x; k < T; k += blockDim.x) {
-    const int f = k < half ? k : k - half;
-    const float arg = __fmul_rn(__fmul_rn(tv, freqs[f]), 1000.0f);
-    emb[k] = k < half ? sinf(arg) : cosf(arg);
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < 2 * T; j += blockDim.x) hid[j] = silu(dot_row(w0 + (int64_t)j * T, emb, T) + b0[j]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < T; i += blockDim.x) temb[i] = dot_row(w2 + (int64_t)i * 2 * T, hid, 2 * T) + b2[i];
-  __syncthreads();
-  const int per = (sumC + gridDim.y - 1) / gridDim.y;
-  const int c_lo = blockIdx.y * per, c_hi = min(sumC, c_lo + per);
-  for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x)
-    tbias[(int64_t)blockIdx.x * sumC + c] = dot_row(wt + (int64_t)c * T, temb, T) + bt[c];
+  time_path(ta, blockIdx.x, blockIdx.y, gridDim.y, sm);
 }
 
 // weight repack: Conv2d [co][ci][kh][kw] (transposed = 0) or ConvTranspose2d [ci][co][kh][kw]
@@ -1037,25 +1054,29 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   DeferredGn defer;
   defer.want = final_fused_ok && use_tc && !tap && !defer_off;
 
-  // ---- time path
-  {
+  // ---- time path: its own launch, unless the bf16 init conv below can carry it (all samples share t)
+  TimeArgs ta{t, plan->freqs, plan->tw0, plan->tb0, plan->tw2, plan->tb2, plan->twt, plan->tbt, tbias, Td, plan->sumC, 0};
+  static const bool tfuse_off = [] { const char* e = getenv("DBS_TIME_FUSE"); return e && e[0] == '0'; }();
+  const bool time_fused = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && n_t == 1 && !tfuse_off;
+  if (!time_fused) {
     prof_set_label("time");
     ProfScope prof(kProfUnetMisc, st);
-    time_kernel<<<dim3((unsigned)n_t, n_t == 1 ? 16u : 2u), 256, (size_t)4 * Td * 4, st>>>(t, plan->freqs, Td, plan->tw0, plan->tb0, plan->tw2,
-                                                               plan->tb2, plan->twt, plan->tbt, plan->sumC, tbias);
+    time_kernel<<<dim3((unsigned)n_t, n_t == 1 ? 16u : 2u), 256, (size_t)4 * Td * 4, st>>>(ta);
     DBS_LAUNCHED();
+  } else {
+    ta.n_ctas = 16;
   }
 
   // ---- init conv
   {
     const int64_t n_pix = B * H * W;
-    prof_set_label("init_conv");
+    prof_set_label(time_fused ? "time+init_conv" : "init_conv");
     ProfScope prof(kProfUnetMisc, st);
     const int64_t nthr = n_pix * (C / (16 / (int)sizeof(T)));
     if (sizeof(T) == 2 && (C == 16 || C == 32 || C == 64)) {
-      if (C == 16) rc = launch_init_fast<16>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st);
-      else if (C == 32) rc = launch_init_fast<32>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st);
-      else rc = launch_init_fast<64>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st);
+      if (C == 16) rc = launch_init_fast<16>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st, ta);
+      else if (C == 32) rc = launch_init_fast<32>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st, ta);
+      else rc = launch_init_fast<64>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st, ta);
       if (rc) return rc;
     } else {
       init_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(x, plan->init_w, plan->init_b, a0, n_pix, H, W, C);
