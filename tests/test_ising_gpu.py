@@ -198,6 +198,48 @@ def test_mcmc_physics_envelopes():
     assert abs(e2 - (-1.7456)) < 0.02
 
 
+def test_ensemble_observables_vs_reference_chain():
+    """north_star: "ensemble observables agree within statistical error".  tests/golden/ising_ensemble.npz holds per-chain
+    time averages of E/N, |M|, M^2, M^4 from the UNMODIFIED reference's random-site Metropolis chain
+    (oracle/make_golden_ensemble.py: BASELINE config 1 as-is — 16x16, T = 2.269, 64 chains, 1000 sweeps — plus
+    T = 1.5 and T = 3.5).  The engine's checkerboard chains follow the same protocol (start, burn-in, one
+    measurement per sweep) with 4096 chains; different dynamics, same Boltzmann distribution: the ensemble means agree
+    within 3.5 sigma of the combined standard error (chains are independent, so the chain-to-chain spread is the
+    error whatever the autocorrelation time), and so does the Binder cumulant."""
+    IsingModel, MetropolisHastings = _mods()
+    g = load_golden("ising_ensemble.npz")
+    L = int(g["L"])
+    m = IsingModel(L)
+    n_eng = 4096
+    for i, (T, n_ref, hot, burn, meas) in enumerate(g["runs"]):
+        ref = g[f"chains_{i}"]
+        burn, meas = int(burn), int(meas)
+        if hot:
+            bits = m.random_packed(n_eng, seed=100 + i)
+        else:
+            bits = m.pack(torch.ones(n_eng, L, L))
+        mh = MetropolisHastings(m, float(T), seed=200 + i)
+        mh.sweeps_packed(bits, burn, sweep_offset=0)
+        acc = torch.zeros(4, n_eng, dtype=torch.float64, device=bits.device)
+        for s in range(meas):
+            mh.sweeps_packed(bits, 1, sweep_offset=burn + s)
+            e, mag = m.packed_observables(bits)
+            mag = mag.double()
+            acc[0] += e.double() / (L * L); acc[1] += mag.abs(); acc[2] += mag ** 2; acc[3] += mag ** 4
+        eng = (acc / meas).T.cpu().numpy()                       # [chain][4]
+        mean_r, sem_r = ref.mean(0), ref.std(0, ddof=1) / np.sqrt(len(ref))
+        mean_e, sem_e = eng.mean(0), eng.std(0, ddof=1) / np.sqrt(n_eng)
+        z = np.abs(mean_e - mean_r) / np.sqrt(sem_r ** 2 + sem_e ** 2 + 1e-24)
+        assert (z <= 3.5).all(), (float(T), mean_e.tolist(), mean_r.tolist(), z.tolist())
+
+        def binder(ch):
+            return 1.0 - ch[:, 3].mean() / (3.0 * ch[:, 2].mean() ** 2)
+        # jackknife error of the reference's Binder cumulant over its chains
+        jk = np.array([binder(np.delete(ref, k, axis=0)) for k in range(len(ref))])
+        err = np.sqrt((len(ref) - 1) * ((jk - jk.mean()) ** 2).mean())
+        assert abs(binder(eng) - binder(ref)) <= 3.5 * err + 2e-3, (float(T), binder(eng), binder(ref), err)
+
+
 def test_full_size_sharding_invariance():
     """BASELINE config-3 shape (64x64, per-chain temperatures): chains carry global indices, so a
     rank's shard equals the same rows of the single-GPU run for any world size."""
