@@ -57,6 +57,11 @@ struct StripParams {
   int grp_nslab[4];   // slabs stacked along N in each group
   int slab_tap[16];   // weight tap index of each slab in smem order; -1 = the residual 1x1 weights
   int slot_c, slot_p, slot_m, nacc;  // accumulator slots of dw = 0, +1, -1 (-1 = unused)
+  // transposed-conv phase PAIR (ConvGeom::n_phases == 2): the two horizontal output phases pw = 0, 1 of one vertical
+  // phase share their A rows, so their four (pw, dw) slabs are stacked along N per dh group (N = 4 * Nb: A is read once
+  // for four taps) and the epilogue emits two outputs: output 1 from slots slot2_*, out2_off elements after output 0
+  int n_out, slot2_c, slot2_p, slot2_m;
+  int64_t out2_off;
   const float* bias;
   __nv_bfloat16* out;
   float* stats;
@@ -361,24 +366,28 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
-#pragma unroll
-      for (int mc = 0; mc < MYCH; ++mc) {
+      // outputs of this tile: 1, or 2 for a transposed-conv phase pair (never with statistics); idle warps: 0
+      const int n_out = (hsel >= NCH || (p.dbg & 2)) ? 0 : (kStats ? 1 : p.n_out);
+#pragma unroll 1
+      for (int o = 0; o < n_out; ++o) {
+        constexpr int mc = 0;
         const int chunk = hsel;
-        if (chunk >= NCH || (p.dbg & 2)) break;
         const int c = chunk * 16;
+        const int slot_c = o ? p.slot2_c : p.slot_c, slot_p = o ? p.slot2_p : p.slot_p, slot_m = o ? p.slot2_m : p.slot_m;
+        __nv_bfloat16* const optr_o = optr + o * p.out2_off;
         uint32_t v0[16], vp[16], vm[16];
-        tmem_ld16(tbase + p.slot_c * p.Nb + c, v0);
-        if (p.slot_p >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + p.slot_p * p.Nb + c, vp);
-        if (p.slot_m >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + p.slot_m * p.Nb + c, vm);
+        tmem_ld16(tbase + slot_c * p.Nb + c, v0);
+        if (slot_p >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + slot_p * p.Nb + c, vp);
+        if (slot_m >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + slot_m * p.Nb + c, vm);
         tmem_ld_wait();
         if (xchg) {
           // publish the edge lanes: my lane 0's P_{+1} is pixel m+1 of the previous warp's lane 31,
           // my lane 31's P_{-1} is pixel m-1 of the next warp's lane 0
-          if (lane == 0 && p.slot_p >= 0) {
+          if (lane == 0 && slot_p >= 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) s_x[xb][half][q][0][j] = __uint_as_float(vp[j]);
           }
-          if (lane == 31 && p.slot_m >= 0) {
+          if (lane == 31 && slot_m >= 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) s_x[xb][half][q][1][j] = __uint_as_float(vm[j]);
           }
@@ -386,7 +395,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         }
         // neighbour columns: all shuffles of a side are issued back to back, in place (no shared temporary, so
         // the sixteen of them are in flight together instead of one SHFL -> FFMA round trip per column)
-        if (p.slot_p >= 0 && !(p.dbg & 16)) {
+        if (slot_p >= 0 && !(p.dbg & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) vp[j] = __shfl_down_sync(0xffffffffu, vp[j], 1);
           if (xchg && lane == 31) {
@@ -394,7 +403,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             for (int j = 0; j < 16; ++j) vp[j] = __float_as_uint(s_x[xb][half][(q + 1) & 3][0][j]);
           }
         }
-        if (p.slot_m >= 0 && !(p.dbg & 16)) {
+        if (slot_m >= 0 && !(p.dbg & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) vm[j] = __shfl_up_sync(0xffffffffu, vm[j], 1);
           if (xchg && lane == 0) {
@@ -412,11 +421,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           f[4 * j4 + 2] = __uint_as_float(v0[4 * j4 + 2]) + b4.z;
           f[4 * j4 + 3] = __uint_as_float(v0[4 * j4 + 3]) + b4.w;
         }
-        if (p.slot_p >= 0 && !(p.dbg & 16)) {
+        if (slot_p >= 0 && !(p.dbg & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaf(m_right, __uint_as_float(vp[j]), f[j]);
         }
-        if (p.slot_m >= 0 && !(p.dbg & 16)) {
+        if (slot_m >= 0 && !(p.dbg & 16)) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaf(m_left, __uint_as_float(vm[j]), f[j]);
         }
@@ -436,7 +445,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        uint4* dst = reinterpret_cast<uint4*>(optr + c);
+        uint4* dst = reinterpret_cast<uint4*>(optr_o + c);
         if (!(p.dbg & 4)) {
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -484,7 +493,10 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
                       const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st,
                       const __nv_bfloat16* w_res, const float* bias_res, __nv_bfloat16* out_res) {
   const bool fuse_res = w_res != nullptr;
-  if (g.n_phases > 1) return DBS_ERR_UNSUPPORTED;   // merged transposed-conv phases: tile kernel only
+  const bool pairw = g.n_phases == 2;   // transposed-conv phase pair: taps [0, n_taps) = (ph, pw = 0), [n_taps, 2 n_taps) = (ph, 1)
+  if (g.n_phases > 2) return DBS_ERR_UNSUPPORTED;   // all four phases merged: tile kernel only
+  if (pairw && (fuse_res || stats || g.out_stride != 2 || g.n_taps != 4)) return DBS_ERR_UNSUPPORTED;
+  const int n_taps_all = pairw ? 2 * g.n_taps : g.n_taps;
   if (fuse_res && (!bias_res || !out_res || g.out_stride != 1 || g.n_taps != 9)) return DBS_ERR_UNSUPPORTED;
   static const bool disabled = [] { const char* e = getenv("DBS_CONV_STRIP"); return e && e[0] == '0'; }();
   if (disabled) return DBS_ERR_UNSUPPORTED;
@@ -506,7 +518,7 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
        reinterpret_cast<uintptr_t>(out)) & 15)
     return DBS_ERR_UNSUPPORTED;
   int dh_min = 0, dh_max = 0;
-  for (int t = 0; t < g.n_taps; ++t) {
+  for (int t = 0; t < n_taps_all; ++t) {
     if (g.dw[t] < -1 || g.dw[t] > 1) return DBS_ERR_UNSUPPORTED;
     dh_min = g.dh[t] < dh_min ? g.dh[t] : dh_min;
     dh_max = g.dh[t] > dh_max ? g.dh[t] : dh_max;
@@ -531,16 +543,21 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   int dhs[4], dws[3], G = 0, nacc = 0;
   for (int v = dh_min; v <= dh_max; ++v) {
     bool present = false;
-    for (int t = 0; t < g.n_taps; ++t) present |= g.dh[t] == v;
+    for (int t = 0; t < n_taps_all; ++t) present |= g.dh[t] == v;
     if (present) { if (G == 4) return DBS_ERR_UNSUPPORTED; dhs[G++] = v; }
   }
   int slot_of[3] = {-1, -1, -1};  // index dw + 1
-  for (int v = -1; v <= 1; ++v) {
-    bool present = false;
-    for (int t = 0; t < g.n_taps; ++t) present |= g.dw[t] == v;
-    if (present) { slot_of[v + 1] = nacc; dws[nacc++] = v; }
+  if (!pairw) {
+    for (int v = -1; v <= 1; ++v) {
+      bool present = false;
+      for (int t = 0; t < g.n_taps; ++t) present |= g.dw[t] == v;
+      if (present) { slot_of[v + 1] = nacc; dws[nacc++] = v; }
+    }
+    if (slot_of[1] < 0 || G > 3 || G * nacc != g.n_taps) return DBS_ERR_UNSUPPORTED;
+  } else {
+    nacc = 4;   // slots [pw0: dw = -1 | pw0: dw = 0 | pw1: dw = 0 | pw1: dw = +1]
+    if (G != 2) return DBS_ERR_UNSUPPORTED;
   }
-  if (slot_of[1] < 0 || G > 3 || G * nacc != g.n_taps) return DBS_ERR_UNSUPPORTED;
   if ((nacc + (fuse_res ? 1 : 0)) * Nb > 256) return DBS_ERR_UNSUPPORTED;
   // issue order of the groups: with a fused residual the dh = 0 group (one slab wider) goes first, so the
   // tile's zero-initialising MMA covers the residual slot too
@@ -554,12 +571,24 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   for (int gi = 0; gi < G; ++gi) {
     p.grp_row[gi] = dhs[gi] - dh_min;
     p.grp_off[gi] = slab;
-    for (int si = 0; si < nacc; ++si) {
-      int found = -1;
-      for (int t = 0; t < g.n_taps; ++t)
-        if (g.dh[t] == dhs[gi] && g.dw[t] == dws[si]) { if (found >= 0) return DBS_ERR_UNSUPPORTED; found = t; }
-      if (found < 0) return DBS_ERR_UNSUPPORTED;
-      p.slab_tap[slab++] = g.widx[found];
+    if (!pairw) {
+      for (int si = 0; si < nacc; ++si) {
+        int found = -1;
+        for (int t = 0; t < g.n_taps; ++t)
+          if (g.dh[t] == dhs[gi] && g.dw[t] == dws[si]) { if (found >= 0) return DBS_ERR_UNSUPPORTED; found = t; }
+        if (found < 0) return DBS_ERR_UNSUPPORTED;
+        p.slab_tap[slab++] = g.widx[found];
+      }
+    } else {
+      const int want_dw[4] = {-1, 0, 0, 1};
+      for (int si = 0; si < 4; ++si) {
+        const int t0 = (si >> 1) * g.n_taps;   // taps of pw = si / 2
+        int found = -1;
+        for (int t = t0; t < t0 + g.n_taps; ++t)
+          if (g.dh[t] == dhs[gi] && g.dw[t] == want_dw[si]) { if (found >= 0) return DBS_ERR_UNSUPPORTED; found = t; }
+        if (found < 0) return DBS_ERR_UNSUPPORTED;
+        p.slab_tap[slab++] = g.widx[found];
+      }
     }
     if (fuse_res && dhs[gi] == 0) p.slab_tap[slab++] = -1;
     p.grp_nslab[gi] = slab - p.grp_off[gi];
@@ -570,7 +599,16 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   p.has_res = fuse_res ? 1 : 0;
   p.bias_res = bias_res; p.out_res = out_res;
   p.n_groups = G;
-  p.slot_c = slot_of[1]; p.slot_p = slot_of[2]; p.slot_m = slot_of[0]; p.nacc = nacc;
+  p.nacc = nacc;
+  if (!pairw) {
+    p.slot_c = slot_of[1]; p.slot_p = slot_of[2]; p.slot_m = slot_of[0];
+    p.n_out = 1; p.slot2_c = p.slot2_p = p.slot2_m = -1; p.out2_off = 0;
+  } else {
+    p.slot_m = 0; p.slot_c = 1; p.slot_p = -1;
+    p.slot2_c = 2; p.slot2_p = 3; p.slot2_m = -1;
+    p.n_out = 2; p.out2_off = g.Cout;     // output pixel (2a + ph, 2b + 1) follows (2a + ph, 2b)
+    p.opw = 0;
+  }
   p.bias = bias; p.out = out; p.stats = stats;
   { const char* e = getenv("DBS_STRIP_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.a_bytes = (uint32_t)rows * W * KC * 2;
@@ -650,8 +688,8 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   });
   DBS_CUDA(attr_err);
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();   // resident == 2 has sp_tiles >= num_sms()
-  prof_set_label("strip H%d W%d C%d+%d->%d taps%d os%d KC%d B%d res%d st%d%s", H, W, g.C0, g.C1, g.Cout, g.n_taps,
-                 g.out_stride, KC, g.B, p.resident, p.stages, fuse_res ? " +res1x1" : "");
+  prof_set_label("strip H%d W%d C%d+%d->%d taps%d os%d KC%d B%d res%d st%d%s%s", H, W, g.C0, g.C1, g.Cout, g.n_taps,
+                 g.out_stride, KC, g.B, p.resident, p.stages, fuse_res ? " +res1x1" : "", pairw ? " x2 phases" : "");
   ProfScope prof(kProfConvTC, st);
   kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, mwr, p);
   DBS_LAUNCHED();

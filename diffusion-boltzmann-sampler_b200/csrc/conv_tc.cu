@@ -682,22 +682,33 @@ extern "C" int dbs_conv_tc(const void* in0, int C0, const void* in1, int C1, con
                         as_stream(stream));
   } else {
     DBS_REQUIRE(C1 == 0, "conv_tc: transposed conv takes a single source");
-    // same policy as the U-Net executor: strip kernel phase by phase where it is eligible, else the tile kernel
-    // with the four phases merged into one launch (statistics are not defined for the merged form)
-    rc = conv_strip_launch(geom_convT_phase((int)B, H, W, C0, C_out, 0, 0), (const __nv_bfloat16*)in0, nullptr,
-                           (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups, as_stream(stream));
-    int first = 1;
-    if (rc == DBS_ERR_UNSUPPORTED) {
-      first = 0;
-      rc = stats ? DBS_ERR_UNSUPPORTED
-                 : conv_tc_launch(geom_convT_all((int)B, H, W, C0, C_out), (const __nv_bfloat16*)in0, nullptr,
-                                  (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, nullptr, groups, as_stream(stream));
-      if (rc == DBS_OK) first = 4;
-      else if (rc == DBS_ERR_UNSUPPORTED) rc = DBS_OK;
+    // same policy as the U-Net executor: strip kernel (horizontal phase pairs, else phase by phase) where it is
+    // eligible, else the tile kernel with the four phases merged into one launch (statistics: per-phase launches only)
+    const __nv_bfloat16 *xin = (const __nv_bfloat16*)in0, *wq = (const __nv_bfloat16*)weight;
+    int first = 0;   // phases [first, 4) still to run one by one
+    rc = stats ? DBS_ERR_UNSUPPORTED
+               : conv_strip_launch(geom_convT_pair((int)B, H, W, C0, C_out, 0), xin, nullptr, wq, bias, (__nv_bfloat16*)out,
+                                   nullptr, groups, as_stream(stream));
+    if (rc == DBS_OK) {
+      rc = conv_strip_launch(geom_convT_pair((int)B, H, W, C0, C_out, 1), xin, nullptr, wq, bias, (__nv_bfloat16*)out, nullptr,
+                             groups, as_stream(stream));
+      first = 4;
+    } else if (rc == DBS_ERR_UNSUPPORTED) {
+      rc = conv_strip_launch(geom_convT_phase((int)B, H, W, C0, C_out, 0, 0), xin, nullptr, wq, bias, (__nv_bfloat16*)out, stats,
+                             groups, as_stream(stream));
+      if (rc == DBS_OK) {
+        first = 1;
+      } else if (rc == DBS_ERR_UNSUPPORTED) {
+        rc = stats ? DBS_ERR_UNSUPPORTED
+                   : conv_tc_launch(geom_convT_all((int)B, H, W, C0, C_out), xin, nullptr, wq, bias, (__nv_bfloat16*)out, nullptr,
+                                    groups, as_stream(stream));
+        if (rc == DBS_OK) first = 4;
+        else if (rc == DBS_ERR_UNSUPPORTED) rc = DBS_OK;
+      }
     }
     for (int ph4 = first; ph4 < 4 && rc == DBS_OK; ++ph4)
-      rc = conv_tc_launch(geom_convT_phase((int)B, H, W, C0, C_out, ph4 >> 1, ph4 & 1), (const __nv_bfloat16*)in0, nullptr,
-                          (const __nv_bfloat16*)weight, bias, (__nv_bfloat16*)out, stats, groups, as_stream(stream));
+      rc = conv_tc_launch(geom_convT_phase((int)B, H, W, C0, C_out, ph4 >> 1, ph4 & 1), xin, nullptr, wq, bias,
+                          (__nv_bfloat16*)out, stats, groups, as_stream(stream));
   }
   if (rc == DBS_ERR_UNSUPPORTED) set_error("conv_tc: this geometry is not eligible for the tcgen05 kernel");
   return rc;

@@ -78,6 +78,15 @@ ConvGeom geom_convT_all(int B, int H, int W, int Cin, int Cout) {
   return g;
 }
 
+// The two horizontal phases of vertical phase ph in one geometry (see ConvGeom::n_phases).
+ConvGeom geom_convT_pair(int B, int H, int W, int Cin, int Cout, int ph) {
+  ConvGeom g = geom_convT_phase(B, H, W, Cin, Cout, ph, 0);
+  const ConvGeom q = geom_convT_phase(B, H, W, Cin, Cout, ph, 1);
+  g.n_phases = 2;
+  for (int t = 0; t < 4; ++t) { g.dh[4 + t] = q.dh[t]; g.dw[4 + t] = q.dw[t]; g.widx[4 + t] = q.widx[t]; }
+  return g;
+}
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1163,28 +1172,42 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
       const int64_t nbc = std::min<int64_t>(cb, B - b0);
       Ctx cc = sub_ctx(b0, nbc);
       T* up_c = up + b0 * h2 * w2 * ch;
-      // ConvTranspose2d(4, 2, 1) = four stride-1 phase convs.  Strip-kernel levels run them one launch per phase;
+      // ConvTranspose2d(4, 2, 1) = four stride-1 phase convs.  Strip-kernel levels run them as two launches, each the
+      // pair of horizontal phases of one vertical phase (shared A rows, four tap slabs per MMA, two outputs per tile);
       // elsewhere the tile kernel takes all four phases in ONE persistent launch (low-resolution phases are less
       // than a wave each: 4 launches of 17-23 us -> one)
       bool up_done = false;
       if (cc.use_tc && sizeof(T) == 2) {
-        const ConvGeom g0 = geom_convT_phase((int)nbc, h, w, ch, ch, 0, 0);
-        rc = conv_strip_launch(g0, (const __nv_bfloat16*)(cur + b0 * h * w * ch), nullptr, plan->up[i].w16, plan->up[i].bias,
-                               (__nv_bfloat16*)up_c, nullptr, 8, cc.st);
+        const __nv_bfloat16* uin = (const __nv_bfloat16*)(cur + b0 * h * w * ch);
+        static const bool pair_off = [] { const char* e = getenv("DBS_STRIP_PHASE_PAIR"); return e && e[0] == '0'; }();
+        rc = pair_off ? DBS_ERR_UNSUPPORTED
+                      : conv_strip_launch(geom_convT_pair((int)nbc, h, w, ch, ch, 0), uin, nullptr, plan->up[i].w16,
+                                          plan->up[i].bias, (__nv_bfloat16*)up_c, nullptr, 8, cc.st);
         if (rc == DBS_OK) {
-          for (int ph4 = 1; ph4 < 4; ++ph4) {
-            const ConvGeom gu = geom_convT_phase((int)nbc, h, w, ch, ch, ph4 >> 1, ph4 & 1);
-            if ((rc = run_conv<T>(cc, gu, cur + b0 * h * w * ch, (const T*)nullptr, plan->up[i], up_c, nullptr, 8, nullptr)))
-              return rc;
-          }
+          if ((rc = conv_strip_launch(geom_convT_pair((int)nbc, h, w, ch, ch, 1), uin, nullptr, plan->up[i].w16,
+                                      plan->up[i].bias, (__nv_bfloat16*)up_c, nullptr, 8, cc.st)))
+            return rc;
           up_done = true;
         } else if (rc != DBS_ERR_UNSUPPORTED) {
           return rc;
         } else {
-          rc = conv_tc_launch(geom_convT_all((int)nbc, h, w, ch, ch), (const __nv_bfloat16*)(cur + b0 * h * w * ch), nullptr,
-                              plan->up[i].w16, plan->up[i].bias, (__nv_bfloat16*)up_c, nullptr, 8, cc.st);
-          if (rc == DBS_OK) up_done = true;
-          else if (rc != DBS_ERR_UNSUPPORTED) return rc;
+          rc = conv_strip_launch(geom_convT_phase((int)nbc, h, w, ch, ch, 0, 0), uin, nullptr, plan->up[i].w16,
+                                 plan->up[i].bias, (__nv_bfloat16*)up_c, nullptr, 8, cc.st);
+          if (rc == DBS_OK) {
+            for (int ph4 = 1; ph4 < 4; ++ph4) {
+              const ConvGeom gu = geom_convT_phase((int)nbc, h, w, ch, ch, ph4 >> 1, ph4 & 1);
+              if ((rc = run_conv<T>(cc, gu, cur + b0 * h * w * ch, (const T*)nullptr, plan->up[i], up_c, nullptr, 8, nullptr)))
+                return rc;
+            }
+            up_done = true;
+          } else if (rc != DBS_ERR_UNSUPPORTED) {
+            return rc;
+          } else {
+            rc = conv_tc_launch(geom_convT_all((int)nbc, h, w, ch, ch), uin, nullptr, plan->up[i].w16, plan->up[i].bias,
+                                (__nv_bfloat16*)up_c, nullptr, 8, cc.st);
+            if (rc == DBS_OK) up_done = true;
+            else if (rc != DBS_ERR_UNSUPPORTED) return rc;
+          }
         }
       }
       if (!up_done)

@@ -25,7 +25,9 @@ struct ConvGeom {
   unsigned char widx[16];
   // n_phases == 4: all four output phases of a ConvTranspose2d(4, 2, 1) in one geometry — phase ph4 = 2*ph + pw
   // uses taps [ph4*n_taps, (ph4+1)*n_taps) and writes output pixels (2a + ph, 2b + pw); oph / opw are ignored.
-  // 0 or 1: a single phase / an ordinary conv.  Only the tile kernel (conv_tc_launch) takes the merged form.
+  // n_phases == 2: the two horizontal phases pw = 0, 1 of vertical phase oph — taps [0, n_taps) belong to pw = 0,
+  // [n_taps, 2 n_taps) to pw = 1 (strip kernel only: the pair shares its A rows, conv_strip.cu).
+  // 0 or 1: a single phase / an ordinary conv.  The tile kernel (conv_tc_launch) takes only the 4-phase form.
   int n_phases;
 };
 
@@ -65,5 +67,6 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
 ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int stride);
 ConvGeom geom_convT_phase(int B, int H, int W, int Cin, int Cout, int ph, int pw);
 ConvGeom geom_convT_all(int B, int H, int W, int Cin, int Cout);
+ConvGeom geom_convT_pair(int B, int H, int W, int Cin, int Cout, int ph);
 
 }  // namespace dbs

@@ -97,6 +97,15 @@ def test_conv_tc_transposed_phases_merged(B, H, W, C):
     _run(2, 4, B, H, W, C, 0, C, stats=False)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (3, 16, 16, 64), (2, 16, 16, 128), (2, 64, 64, 32), (1, 128, 128, 32),
+                                     (150, 16, 16, 128), (3, 16, 8, 32)])
+def test_conv_tc_transposed_phase_pairs_strip(B, H, W, C):
+    """ConvTranspose2d(4, 2, 1) at the strip kernel's resolutions, no statistics: two launches, each the pair of
+    horizontal phases of one vertical phase (ConvGeom::n_phases = 2: four tap slabs per MMA, two outputs per tile).
+    Covers the cross-warp neighbour exchange (W >= 64), N-tiled layers in pass mode (128 couts, B = 150) and Nb = 32."""
+    _run(2, 4, B, H, W, C, 0, C, stats=False)
+
+
 def test_conv_tc_wide_cout_two_n_tiles():
     _run(0, 3, 2, 8, 8, 64, 0, 512, stats=True)
 
