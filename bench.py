@@ -332,6 +332,7 @@ def bench_ours(args, world, rank, local):
 
     c3 = bench_c3(world, rank)      # every rank takes part (sharded chains, NCCL all-reduce of the observable block)
     line["ising_c3"] = c3
+    line["diffusion_c4"] = bench_c4(peaks, prec, world, rank)     # every rank: batch 16384 sharded, 64x64, bf16
     if rank == 0 and world == 1:
         # ---- CPU baseline: oracle port (torch fp32, all host threads) on a bounded sample of the same workload
         sd = {k: v.detach().clone() for k, v in smp.model.state_dict().items()}
@@ -445,6 +446,36 @@ def bench_c3(world, rank):
             "E_per_spin_near_T2": round(float(out["energy_per_spin"][i2]), 4), "T_near_2": round(float(T[i2]), 4),
             "onsager_E_per_spin_T2.0": onsager_T2, "binder_T1.5": round(float(out["binder"][0]), 4),
             "count_per_temperature": float(out["count"][0])}
+
+
+def bench_c4(peaks, prec, world, rank):
+    """BASELINE config 4: 64x64 lattices, batch 16384 sharded over the ranks (strong scaling: 16384 / world samples per
+    GPU, processed in on-GPU chunks of <= 2048), bf16, Euler-Maruyama — bounded to 8 of the 1000 steps per timed pass
+    (every step costs the same: one forward + one EM update), device-resident, max over ranks."""
+    B_total, L, NS, chunk = 16384, 64, 8, 2048
+    Bp = B_total // world
+    smp = make_sampler(L, NS, prec, "cuda")
+    sizes = [min(chunk, Bp - b0) for b0 in range(0, Bp, chunk)]
+
+    def one_pass(k):
+        off = rank * Bp
+        for cb in sizes:
+            smp.sample((cb, 1, L, L), seed=500 + k, sample_offset=off)      # device="cuda": the result stays on the GPU
+            off += cb
+
+    one_pass(-1)
+    one_pass(-2)
+    reps = 2
+    ms = timed(one_pass, reps, world)
+    sss = B_total * NS * reps / (ms * 1e-3)
+    tf = sss * unet_flops_per_sample(L) / 1e12
+    return {"metric": "diffusion_samples_per_s_64x64_1000_steps", "value": round(sss / 1000, 3), "unit": "samples/s",
+            "sample_steps_per_s": round(sss, 1), "n_gpus": world, "scaling": "strong",
+            "global_batch": B_total, "batch_per_gpu": Bp, "chunk": chunk, "ms_per_pass": round(ms / reps, 2),
+            "whole_step_tflops_per_gpu": round(tf / world, 2),
+            "frac_of_sustained_bf16": round(tf / world / peaks["bf16_sustained"], 4),
+            "sample": f"{NS} of the 1000 EM steps per pass over all {B_total} samples (64x64, bf16), x{reps} passes; "
+                      "value = samples/s at the full 1000 steps"}
 
 
 def bench_diffusion64(peaks, prec):
