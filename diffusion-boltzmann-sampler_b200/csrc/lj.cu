@@ -7,6 +7,7 @@
 // reference operation by operation (IEEE div/sqrt, round-half-even minimum image, the
 // 1e-10 epsilons, the 0.1 < d < rc mask); only the summation order differs.
 // FP32-ALU bound: N^2 ordered pairs * ~40 flop; 16 N + 4 bytes of HBM traffic per configuration.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -22,6 +23,7 @@ struct LjArgs {
   float box, inv_box, four_eps, twentyfour_eps, sigma, cutoff, shift;
   float d2_lo, d2_hi;   // dist > 0.1f && dist < cutoff  <=>  d2_lo <= (dx^2+dy^2+1e-10) <= d2_hi  (exact, see host)
   int fast_image;       // 1: rint(dx * (1/box)) instead of rint(dx / box) (identical unless |dx| ~ box/2 >= cutoff)
+  float pre_thr;        // half-precision prefilter: squared acceptance radius (cutoff + error margin)^2, see lj_pre_kernel
 };
 
 // Two phases per 32-wide block of partners j: (1) cheap minimum-image distance test for all 32,
@@ -97,6 +99,120 @@ __global__ void __launch_bounds__(256) lj_kernel(LjArgs a) {
   }
 }
 
+// Same result, bit for bit, as lj_kernel — the expensive fp32 minimum-image distance test (~16 instructions per
+// ordered pair, 94 % of them rejected at rho* = 0.8) is preceded by a CONSERVATIVE half-precision prefilter that
+// handles two partners per instruction (HFMA2 pipe) on box-wrapped coordinates:
+//   phase 1  for every partner pair: wrapped minimum-image d^2 in fp16 <= (cutoff + margin)^2 ?  -> one bit per
+//            partner in a 256-bit candidate mask per thread block of partners (shared memory, N/32 words per thread);
+//            the margin (host side) covers the fp16 rounding of the wrapped coordinates, so no in-range pair is lost;
+//   phase 2  ONE flattened loop over the set bits of the whole mask, in ascending partner order: the exact fp32
+//            test of the reference on the ORIGINAL coordinates, then the Lennard-Jones arithmetic of lj_kernel.
+//            Flattening matters: a per-block loop costs the maximum over the 32 lanes for every block of partners.
+// Partner order stays ascending, so energies and forces are bit-identical to lj_kernel (and thus deterministic).
+__global__ void __launch_bounds__(256) lj_pre_kernel(LjArgs a) {
+  extern __shared__ float sp[];                 // [N][2] original coordinates
+  const int N = a.N, NP = (N + 31) & ~31;       // partners padded to whole 32-blocks
+  __half2* xh = reinterpret_cast<__half2*>(sp + 2 * N);        // [NP/2] wrapped x of partners (2m, 2m+1)
+  __half2* yh = xh + NP / 2;                                   // [NP/2]
+  uint32_t* cand = reinterpret_cast<uint32_t*>(yh + NP / 2);   // [NP/32][blockDim.x] candidate masks, word-major
+  const float* p = a.pos + (int64_t)blockIdx.x * N * 2;
+  int far = 0;
+  for (int k = threadIdx.x; k < 2 * N; k += blockDim.x) {
+    const float v = p[k];
+    sp[k] = v;
+    far |= fabsf(v) > 16.0f * a.box;      // (NaN / inf compare false or wrap to NaN: rejected by both tests alike)
+  }
+  // coordinates many boxes away lose the wrap's fp32 precision: such a configuration takes every partner as a
+  // candidate (exact test only), which is lj_kernel's arithmetic at lj_kernel's cost
+  const bool all_cand = __syncthreads_or(far) != 0;
+  for (int m = threadIdx.x; m < NP / 2; m += blockDim.x) {
+    float w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 2 * m + (e >> 1);
+      // out-of-range partners: NaN, every comparison fails
+      const float v = j < N ? sp[2 * j + (e & 1)] : __int_as_float(0x7fc00000);
+      w[e] = v - a.box * floorf(v * a.inv_box);
+    }
+    xh[m] = __floats2half2_rn(w[0], w[2]);
+    yh[m] = __floats2half2_rn(w[1], w[3]);
+  }
+  __syncthreads();
+  const __half2 invb2 = __float2half2_rn(a.inv_box), nbox2 = __float2half2_rn(-a.box), thr2 = __float2half2_rn(a.pre_thr);
+  const __half2 magic2 = __float2half2_rn(1536.0f);   // 1.5 * 2^10: x + magic - magic = rint(x) in fp16 for |x| <= 512
+  const int n_words = NP / 32;
+  float e_acc = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float xi = sp[2 * i], yi = sp[2 * i + 1];
+    const __half2 xi2 = __float2half2_rn(xi - a.box * floorf(xi * a.inv_box));
+    const __half2 yi2 = __float2half2_rn(yi - a.box * floorf(yi * a.inv_box));
+    // ---- phase 1: candidate mask
+    for (int wd = 0; wd < n_words; ++wd) {
+      uint32_t mask = 0;
+#pragma unroll
+      for (int h = 0; h < 16; ++h) {
+        __half2 dx = __hsub2(xi2, xh[wd * 16 + h]), dy = __hsub2(yi2, yh[wd * 16 + h]);
+        // rint by the magic-number add (|dx / box| < 1 << 512): two full-rate HADD2 instead of a conversion-pipe op
+        dx = __hfma2(__hsub2(__hfma2(dx, invb2, magic2), magic2), nbox2, dx);
+        dy = __hfma2(__hsub2(__hfma2(dy, invb2, magic2), magic2), nbox2, dy);
+        const __half2 d2 = __hfma2(dy, dy, __hmul2(dx, dx));
+        const uint32_t t = __hle2_mask(d2, thr2) & 0x00010001u;     // bit 0: partner 2h, bit 16: partner 2h + 1
+        mask |= ((t | (t >> 15)) & 3u) << (2 * h);
+      }
+      if (all_cand) mask = N - 32 * wd >= 32 ? 0xFFFFFFFFu : ((1u << (N - 32 * wd)) - 1u);
+      cand[wd * blockDim.x + threadIdx.x] = mask;
+    }
+    // ---- phase 2: exact test + Lennard-Jones arithmetic over the candidates, ascending partner order
+    float fx = 0.f, fy = 0.f, ei = 0.f;
+    int wd = 0;
+    uint32_t mask = cand[threadIdx.x];
+    while (true) {
+      while (mask == 0 && wd + 1 < n_words) mask = cand[++wd * blockDim.x + threadIdx.x];
+      if (mask == 0) break;
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float2 pj = *reinterpret_cast<const float2*>(&sp[2 * (32 * wd + b)]);
+      float dx = __fsub_rn(xi, pj.x), dy = __fsub_rn(yi, pj.y);
+      const float kx = a.fast_image ? rintf(__fmul_rn(dx, a.inv_box)) : rintf(__fdiv_rn(dx, a.box));
+      const float ky = a.fast_image ? rintf(__fmul_rn(dy, a.inv_box)) : rintf(__fdiv_rn(dy, a.box));
+      dx = __fsub_rn(dx, __fmul_rn(a.box, kx));
+      dy = __fsub_rn(dy, __fmul_rn(a.box, ky));
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), 1e-10f);
+      if (d2 >= a.d2_lo && d2 <= a.d2_hi) {
+        const float ds = __fsqrt_rn(d2);
+        const float q = __fdiv_rn(a.sigma, ds);
+        const float q2 = __fmul_rn(q, q);
+        const float r6 = __fmul_rn(__fmul_rn(q2, q2), q2);
+        const float r12 = __fmul_rn(r6, r6);
+        ei = __fadd_rn(ei, __fsub_rn(__fmul_rn(a.four_eps, __fsub_rn(r12, r6)), a.shift));
+        const float fm = __fmul_rn(__fdiv_rn(a.twentyfour_eps, ds), __fsub_rn(__fmul_rn(2.0f, r12), r6));
+        const float den = __fadd_rn(ds, 1e-10f);
+        fx = __fadd_rn(fx, __fmul_rn(fm, __fdiv_rn(dx, den)));
+        fy = __fadd_rn(fy, __fmul_rn(fm, __fdiv_rn(dy, den)));
+      }
+    }
+    e_acc += ei;
+    if (a.forces) {
+      float* f = a.forces + ((int64_t)blockIdx.x * N + i) * 2;
+      f[0] = fx;
+      f[1] = fy;
+    }
+  }
+  if (a.energy) {
+    __shared__ double red[32];
+    double e = warp_sum((double)e_acc);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) red[wid] = e;
+    __syncthreads();
+    if (wid == 0) {
+      const int nw = (blockDim.x + 31) >> 5;
+      e = lane < nw ? red[lane] : 0.0;
+      e = warp_sum(e);
+      if (lane == 0) a.energy[blockIdx.x] = (float)(0.5 * e);
+    }
+  }
+}
+
 // smallest / largest fp32 x with sqrtf(x) > lo resp. sqrtf(x) < hi: maps the reference's mask on
 // dist = sqrt(d2 + 1e-10) (systems/lennard_jones.py:104) onto the squared distance exactly.
 float d2_threshold_above(float lo) {
@@ -135,10 +251,31 @@ extern "C" int dbs_lj_energy_forces(const float* pos, int64_t B, int N, float bo
   a.fast_image = cutoff <= 0.5f * box ? 1 : 0;
   int threads = N >= 256 ? 256 : ((N + 31) / 32) * 32;
   const size_t smem = (size_t)N * 2 * sizeof(float);
-  if (smem > 48 * 1024)
-    DBS_CUDA(cudaFuncSetAttribute(lj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // Half-precision prefilter (lj_pre_kernel): wrapped coordinates in [0, box) carry an fp16 rounding error of at most
+  // box * 2^-11 each; through the difference, the image shift and the squares the distance is off by < 6 * box * 2^-11
+  // + d * 2^-9.  The acceptance radius adds 0.05 + 8 * box * 2^-11 + cutoff * 2^-8 on top of the cutoff, and the two
+  // candidate images of a pair near |dx| = box/2 must both lie outside it, hence the box/2 condition.  Everything a
+  // prefilter bit admits is re-tested in fp32 exactly like lj_kernel, so the results are bit-identical.
+  const char* pre_env = getenv("DBS_LJ_PREFILTER");   // read per call: the parity test toggles it in-process
+  const bool pre_off = pre_env && pre_env[0] == '0';
+  const float margin = 0.05f + 8.0f * box * (1.0f / 2048.0f) + cutoff * (1.0f / 256.0f);
+  const float r_acc = cutoff + margin;
+  const int NP = (N + 31) & ~31;
+  const size_t smem_pre = smem + (size_t)NP * 2 * sizeof(__half) + (size_t)(NP / 32) * threads * sizeof(uint32_t);
+  const bool use_pre = !pre_off && N >= 64 && a.fast_image && box <= 256.f && 0.5f * box > r_acc + 2.0f * margin &&
+                       r_acc * r_acc < 60000.f && smem_pre <= 200 * 1024;
   ProfScope prof(kProfLj, as_stream(stream));
-  lj_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(a);
+  if (use_pre) {
+    a.pre_thr = r_acc * r_acc;
+    if (smem_pre > 48 * 1024)
+      DBS_CUDA(cudaFuncSetAttribute(lj_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pre));
+    lj_pre_kernel<<<(unsigned)B, threads, smem_pre, as_stream(stream)>>>(a);
+  } else {
+    a.pre_thr = 0.f;
+    if (smem > 48 * 1024)
+      DBS_CUDA(cudaFuncSetAttribute(lj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lj_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(a);
+  }
   DBS_LAUNCHED();
   return DBS_OK;
 }

@@ -84,3 +84,26 @@ def test_overlap_mask_edge_cases():
     np.testing.assert_allclose(s.energy(pos).numpy(), o_lj.energy(p, pos.numpy()), rtol=1e-5)
     np.testing.assert_allclose(s.forces(pos).numpy(), o_lj.forces(p, pos.numpy()), rtol=1e-4, atol=1e-2)
     assert s.energy(pos)[1].item() == 0.0
+
+
+@pytest.mark.parametrize("N,B,rho", [(256, 64, 0.8), (64, 16, 0.5), (200, 8, 0.8), (1024, 3, 0.6)])
+def test_half_precision_prefilter_is_bit_identical(N, B, rho, monkeypatch):
+    """lj_pre_kernel puts a conservative fp16 distance prefilter (two partners per instruction, box-wrapped
+    coordinates) in front of the exact fp32 test; everything it admits is re-tested exactly and summed in the same
+    ascending partner order, so energies and forces equal the plain kernel's bit for bit — for the config-5 lattice
+    + jitter set, for uniform-random positions (near-overlaps), for unwrapped positions several boxes away, for a
+    configuration beyond the wrap's precision guard (> 16 boxes: every partner becomes a candidate) and with NaNs."""
+    s = _sys(N, float(np.sqrt(N / rho)))
+    torch.manual_seed(N)
+    lat = s.lattice_configuration(B) + 0.05 * torch.randn(B, N, 2)
+    uni = torch.rand(B, N, 2) * s.box_size
+    shifted = lat + s.box_size * torch.randint(-6, 7, (B, N, 2)).float()
+    far = lat.clone(); far[0] += 40.0 * s.box_size; far[1, 3, 0] = 1e9
+    nan = lat.clone(); nan[0, 5, 1] = float("nan"); nan[1, 0, 0] = float("inf")
+    for pos in (lat, uni, shifted, far, nan):
+        monkeypatch.setenv("DBS_LJ_PREFILTER", "0")
+        e0, f0 = s.energy_and_forces(pos.cuda())
+        monkeypatch.setenv("DBS_LJ_PREFILTER", "1")
+        e1, f1 = s.energy_and_forces(pos.cuda())
+        assert torch.equal(e0.cpu().view(torch.int32), e1.cpu().view(torch.int32))
+        assert torch.equal(f0.cpu().view(torch.int32), f1.cpu().view(torch.int32))
