@@ -232,11 +232,25 @@ template <> struct Vec16<float> {
   static constexpr int N = 4;
   static __device__ __forceinline__ void load(const float* p, float v[4]) { Quad<float>::load(p, v); }
   static __device__ __forceinline__ void store(float* p, const float v[4]) { Quad<float>::store(p, v); }
+  // the 16 bytes as loaded (kept packed while a load is in flight) and their conversion
+  static __device__ __forceinline__ uint4 load_raw(const float* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const uint4& q, float v[4]) {
+    v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+  }
 };
 template <> struct Vec16<__nv_bfloat16> {
   static constexpr int N = 8;
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float v[8]) {
     const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
+    }
+  }
+  static __device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const uint4& q, float v[8]) {
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -618,7 +632,7 @@ gn_stats_kernel(const T* __restrict__ y, float* __restrict__ stats, int HW, int 
 // scale/shift once (shared memory), then streams 16-byte vectors: HBM-bound, 2 B read + 2 B
 // written per element in bf16 (+2 B for the residual).
 template <typename T, int UN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __restrict__ stats, int raw,
                 float inv_cnt, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ tbias, int t_stride, const T* __restrict__ res, float res_scale,
@@ -631,6 +645,24 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
   const int c = (threadIdx.x % cv) * V;
   const int prow = threadIdx.x / cv;          // pixel offset of this thread inside a block-row
   const int ppb = blockDim.x / cv;            // pixels per block iteration
+  const T* yb = y + (int64_t)n * HW * C + c;
+  const T* rb = res ? res + (int64_t)n * HW * C + c : nullptr;
+  T* ob = out + (int64_t)n * HW * C + c;
+  const int stride = gridDim.x * ppb;
+  int p0 = blockIdx.x * ppb + prow;
+  // The first batch of data loads is issued BEFORE the statistics -> scale/shift prologue: the prologue is a chain of
+  // dependent L2 round trips (stats, then gamma / beta), and an in-order warp would otherwise sit through it with no
+  // data load in flight (a CTA lives for only a few microseconds, so that latency was ~15 % of its life).
+  uint4 qv[UN], qr[UN];                       // kept packed while in flight (registers: 4 per vector, not V)
+  const bool first_full = p0 + (UN - 1) * stride < HW;
+  if (first_full) {
+#pragma unroll
+    for (int u = 0; u < UN; ++u) qv[u] = Vec16<T>::load_raw(yb + (int64_t)(p0 + u * stride) * C);
+    if (rb) {
+#pragma unroll
+      for (int u = 0; u < UN; ++u) qr[u] = Vec16<T>::load_raw(rb + (int64_t)(p0 + u * stride) * C);
+    }
+  }
   float sc[V], sh[V], tb[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
@@ -649,29 +681,30 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
     sh[k] = beta[c + k] - mean * a;
     tb[k] = tbias ? tbias[(int64_t)n * t_stride + c + k] : 0.f;
   }
-  const T* yb = y + (int64_t)n * HW * C + c;
-  const T* rb = res ? res + (int64_t)n * HW * C + c : nullptr;
-  T* ob = out + (int64_t)n * HW * C + c;
-  const int stride = gridDim.x * ppb;
-  int p0 = blockIdx.x * ppb + prow;
   // UN pixels per iteration: UN (2*UN with a residual) independent 16-byte loads in flight per thread
-  for (; p0 + (UN - 1) * stride < HW; p0 += UN * stride) {
-    float v[UN][V], r[UN][V];
+  if (first_full) {
+    while (true) {
 #pragma unroll
-    for (int u = 0; u < UN; ++u) Vec16<T>::load(yb + (int64_t)(p0 + u * stride) * C, v[u]);
-    if (rb) {
+      for (int u = 0; u < UN; ++u) {
+        float v[V], r[V];
+        Vec16<T>::unpack(qv[u], v);
+        if (rb) Vec16<T>::unpack(qr[u], r);
 #pragma unroll
-      for (int u = 0; u < UN; ++u) Vec16<T>::load(rb + (int64_t)(p0 + u * stride) * C, r[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        float h = silu_t<T>(fmaf(v[u][k], sc[k], sh[k])) + tb[k];
-        if (rb) h = fmaf(res_scale, r[u][k], h);
-        v[u][k] = h;
+        for (int k = 0; k < V; ++k) {
+          float h = silu_t<T>(fmaf(v[k], sc[k], sh[k])) + tb[k];
+          if (rb) h = fmaf(res_scale, r[k], h);
+          v[k] = h;
+        }
+        Vec16<T>::store(ob + (int64_t)(p0 + u * stride) * C, v);
       }
-      Vec16<T>::store(ob + (int64_t)(p0 + u * stride) * C, v[u]);
+      p0 += UN * stride;
+      if (!(p0 + (UN - 1) * stride < HW)) break;
+#pragma unroll
+      for (int u = 0; u < UN; ++u) qv[u] = Vec16<T>::load_raw(yb + (int64_t)(p0 + u * stride) * C);
+      if (rb) {
+#pragma unroll
+        for (int u = 0; u < UN; ++u) qr[u] = Vec16<T>::load_raw(rb + (int64_t)(p0 + u * stride) * C);
+      }
     }
   }
   for (; p0 < HW; p0 += stride) {
