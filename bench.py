@@ -268,9 +268,9 @@ def bench_ours(args, world, rank, local):
         "frac": round(achieved / peaks["bf16_sustained"], 4), "frac_of_burst": round(achieved / peaks["bf16_burst"], 4),
         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
         # dram__bytes_read+write summed over the conv launches of one forward (ncu --set full,
-        # profiles/r1_conv_ncu_final.csv: 1.55 GB read + 0.62 GB written at B=1024, 32x32) x EM steps,
+        # profiles/r1_conv_ncu_final.csv: 1.48 GB read + 0.65 GB written at B=1024, 32x32) x EM steps,
         # scaled by the batch; per step like `achieved`
-        "traffic": round(2.17e9 * (B / 1024.0) * (L * L / 1024.0) * NS, 0),
+        "traffic": round(2.13e9 * (B / 1024.0) * (L * L / 1024.0) * NS, 0),
         "traffic_note": "ncu capture of the same build (profiles/r1_conv_ncu_final.csv), cold L2 per launch (ncu cache "
                         "control): equals the layers' activation in+out bytes, i.e. no wasted DRAM re-reads; in a real "
                         "step part of the next layer's input is still in the 126 MB L2",
