@@ -152,3 +152,18 @@ def test_fused_conv3x3_plus_residual_1x1(B, H, W, C0, C1, Cout):
     r = ref3.reshape(B, 8, -1)
     want = torch.stack([r.sum(-1), (r * r).sum(-1)], dim=-1)
     np.testing.assert_allclose(st.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-2)
+
+
+def test_conv_tc_repeated_runs_are_identical_and_correct():
+    """Hazard check for the persistent pipelines (pass-resident weights reloaded behind the `weights free` barrier,
+    merged / paired transposed-conv phases, TMEM double buffering): DBS_CONV_STRESS (default 3) fresh random problems
+    per regime, each launched twice (without and, where defined, with GroupNorm statistics) and checked against torch;
+    run with DBS_CONV_STRESS=12 after touching the barriers."""
+    import os
+    reps = int(os.environ.get("DBS_CONV_STRESS", "3"))
+    regimes = [(0, 3, 300, 16, 16, 128, 0, 128), (0, 3, 300, 16, 16, 64, 0, 128), (2, 4, 150, 16, 16, 128, 0, 128),
+               (2, 4, 300, 8, 8, 128, 0, 128), (2, 4, 160, 32, 32, 64, 0, 64), (0, 3, 160, 32, 32, 64, 64, 32)]
+    for r in range(reps):
+        for case in regimes:
+            _run(*case, seed=1000 + r, stats=False)
+            _run(*case, seed=1000 + r, stats=case[0] != 2)
