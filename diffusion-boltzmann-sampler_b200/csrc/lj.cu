@@ -173,16 +173,8 @@ __global__ void __launch_bounds__(256) lj_pre_kernel(LjArgs a) {
       mask &= mask - 1;
       const float2 pj = *reinterpret_cast<const float2*>(&sp[2 * (32 * wd + b)]);
       float dx = __fsub_rn(xi, pj.x), dy = __fsub_rn(yi, pj.y);
-      // fast_image holds for this kernel (host); with every coordinate within 16 boxes |dx / box| <= 32, where
-      // rint(t) == (t + 1.5 * 2^23) - 1.5 * 2^23 exactly (round-to-nearest-even add): two FADDs instead of FRND (XU pipe)
-      float kx, ky;
-      if (all_cand) {
-        kx = rintf(__fmul_rn(dx, a.inv_box));
-        ky = rintf(__fmul_rn(dy, a.inv_box));
-      } else {
-        kx = __fsub_rn(__fadd_rn(__fmul_rn(dx, a.inv_box), 12582912.0f), 12582912.0f);
-        ky = __fsub_rn(__fadd_rn(__fmul_rn(dy, a.inv_box), 12582912.0f), 12582912.0f);
-      }
+      const float kx = a.fast_image ? rintf(__fmul_rn(dx, a.inv_box)) : rintf(__fdiv_rn(dx, a.box));
+      const float ky = a.fast_image ? rintf(__fmul_rn(dy, a.inv_box)) : rintf(__fdiv_rn(dy, a.box));
       dx = __fsub_rn(dx, __fmul_rn(a.box, kx));
       dy = __fsub_rn(dy, __fmul_rn(a.box, ky));
       const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), 1e-10f);
