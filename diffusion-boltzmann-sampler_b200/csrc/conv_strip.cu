@@ -33,7 +33,14 @@ using namespace tc;
 using namespace tch;
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 16;              // four warps per TMEM lane quadrant, one 16-column chunk each
+// Epilogue warps: 16 (default) = four per TMEM lane quadrant, one 16-column chunk each, 96 registers per thread;
+// 8 (-DDBS_STRIP_EPI_WARPS=8) = two per quadrant with up to two chunks each and a 168-register cap.  Measured equal
+// within 1-2 % (conv 1.382 vs 1.373 ms per forward at C2): the drain is a latency chain per tile, not issue-bound, so
+// half the warps do the same work in the same time — the knob that buys register headroom for epilogue fusion.
+#ifndef DBS_STRIP_EPI_WARPS
+#define DBS_STRIP_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = DBS_STRIP_EPI_WARPS;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kSmemBudget = 216 * 1024;   // + 1 KB alignment slack + 9 KB static = the 227 KB a CTA may use
@@ -300,10 +307,12 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     // the warps idling.
     constexpr bool kSplit = NCH <= 2;
     const int q = warp & 3;                 // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;       // 0..3
-    const int my_set = kSplit ? (half >> 1) : 0;
-    const int hsel = kSplit ? (half & 1) : half;
-    constexpr int MYCH = 1;                 // chunks this warp may own (NCH <= 4)
+    constexpr int kSubs = kEpiWarps / 4;    // warps per TMEM lane quadrant
+    const int half = (warp - 2) >> 2;       // 0..kSubs-1
+    constexpr int kSetSubs = kSplit ? kSubs / 2 : kSubs;   // warps of a quadrant that work on the same tile
+    const int my_set = kSplit ? half / kSetSubs : 0;
+    const int hsel = half % kSetSubs;
+    constexpr int MYCH = (NCH + kSetSubs - 1) / kSetSubs;   // chunks this warp owns: hsel * MYCH .. + MYCH - 1
     static_assert(NCH <= 4, "one chunk per warp");
     const int row = q * 32 + lane;          // tile-local pixel
     const int hl = row / p.W, wl = row - hl * p.W;
@@ -319,7 +328,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     auto flush_stats = [&](int n_img, int nt_img) {
 #pragma unroll
       for (int i = 0; i < MYCH * GPC; ++i) {
-        const int chunk = hsel;
+        const int chunk = hsel * MYCH + i / GPC;
         if (chunk < NCH) {
           const float s_ = warp_sum(st_s[i]), ss_ = warp_sum(st_ss[i]);
           const int gi = kWide ? ((nt_img * p.Nb + chunk * 16) >> p.cg_log2) : chunk * GPC + (i % GPC);
@@ -367,11 +376,14 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       // outputs of this tile: 1, or 2 for a transposed-conv phase pair (never with statistics); idle warps: 0
-      const int n_out = (hsel >= NCH || (p.dbg & 2)) ? 0 : (kStats ? 1 : p.n_out);
+      const int n_out = (p.dbg & 2) ? 0 : (kStats ? 1 : p.n_out);
+#pragma unroll
+      for (int mc = 0; mc < MYCH; ++mc) {
+      const int chunk = hsel * MYCH + mc;
+      if (chunk >= NCH) break;                 // idle warps / chunks beyond the tile's columns
 #pragma unroll 1
       for (int o = 0; o < n_out; ++o) {
-        constexpr int mc = 0;
-        const int chunk = hsel;
+        // (with MYCH = 2, requesting both chunks from TMEM before using the first was measured: no gain)
         const int c = chunk * 16;
         const int slot_c = o ? p.slot2_c : p.slot_c, slot_p = o ? p.slot2_p : p.slot_p, slot_m = o ? p.slot2_m : p.slot_m;
         __nv_bfloat16* const optr_o = optr + o * p.out2_off;
@@ -472,6 +484,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           dr[1] = make_uint4(pr[4], pr[5], pr[6], pr[7]);
         }
         xb ^= 1;
+      }
       }
       tc_fence_before();
       __syncwarp();
