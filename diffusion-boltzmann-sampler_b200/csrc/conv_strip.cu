@@ -78,6 +78,7 @@ struct StripParams {
   uint32_t a_bytes, slab_bytes, stage_bytes, w_region_bytes;
   uint32_t tmem_cols;
   uint64_t desc_hi;
+  int s2d_cpp;  // > 0: input read through the space-to-depth view, chunks per row parity (= 2C / KC), see ConvGeom::s2d
   int dbg;  // diagnostics (env DBS_STRIP_DBG): 1 no MMA, 2 no epilogue body, 4 no stores, 8 no strip loads
 };
 
@@ -265,7 +266,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             continue;
           }
           mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : chunk_w_bytes));
-          if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, ch * p.KC, 0, 0, h0 + p.dh_min, n);
+          if (p.s2d_cpp) {
+            // chunk -> (row parity py, channel offset inside the 2C-wide pixel pair)
+            const int py = ch / p.s2d_cpp;
+            tma_load_5d(a_dst, &map_in0, fb, (ch - py * p.s2d_cpp) * p.KC, 0, py, h0 + p.dh_min, n);
+          } else if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, ch * p.KC, 0, 0, h0 + p.dh_min, n);
           else tma_load_5d(a_dst, &map_in1, fb, (ch - p.chunks0) * p.KC, 0, 0, h0 + p.dh_min, n);
           if (!p.resident) {
             const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
@@ -653,6 +658,9 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
     p.w_region_bytes = 0;
     p.stage_bytes = a_pad + ((chunk_w + 1023u) & ~1023u);
   }
+  // space-to-depth stride-2 convs pay 78 % more MMA work for their zero taps: only worth it with resident weights
+  // (64 channels: 45 vs 58 us; with streamed weights at 128 channels the tile kernel is faster, 37 vs 60 us)
+  if (g.s2d && p.resident != 1) return DBS_ERR_UNSUPPORTED;
   int stages = (int)((kSmemBudget - p.w_region_bytes) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return DBS_ERR_UNSUPPORTED;
@@ -664,7 +672,12 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
                                          : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap m0, m1, mw;
   int rc;
-  if ((rc = encode_act(enc, &m0, in0, g.C0, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
+  if (g.s2d) {
+    // {2C, W, 2, H, N} view of the [N][2H][2W][C] tensor (encode_act's stride-2 form takes the FULL sizes)
+    if (g.C1 != 0 || (g.C0 / 2) % KC) return DBS_ERR_UNSUPPORTED;
+    p.s2d_cpp = (g.C0 / 2) / KC;
+    if ((rc = encode_act(enc, &m0, in0, g.C0 / 4, 2 * H, 2 * W, g.B, 2, KC, W, rows, 1, sw))) return rc;
+  } else if ((rc = encode_act(enc, &m0, in0, g.C0, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
   if (g.C1 > 0) {
     if ((rc = encode_act(enc, &m1, in1, g.C1, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
   } else {

@@ -78,6 +78,20 @@ ConvGeom geom_convT_all(int B, int H, int W, int Cin, int Cout) {
   return g;
 }
 
+// 3x3 stride-2 pad-1 conv as a 2x2 stride-1 conv on the space-to-depth view (see ConvGeom::s2d).
+ConvGeom geom_conv_s2d(int B, int H, int W, int C, int Cout) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.Hin = H / 2; g.Win = W / 2; g.Hm = H / 2; g.Wm = W / 2; g.Hout = H / 2; g.Wout = W / 2;
+  g.C0 = 4 * C; g.C1 = 0; g.Cout = Cout;
+  g.in_stride = 1; g.out_stride = 1; g.s2d = 1;
+  g.n_taps = 4;
+  int t = 0;
+  for (int dh = -1; dh <= 0; ++dh)
+    for (int dw = -1; dw <= 0; ++dw, ++t) { g.dh[t] = (signed char)dh; g.dw[t] = (signed char)dw; g.widx[t] = (unsigned char)t; }
+  return g;
+}
+
 // The two horizontal phases of vertical phase ph in one geometry (see ConvGeom::n_phases).
 ConvGeom geom_convT_pair(int B, int H, int W, int Cin, int Cout, int ph) {
   ConvGeom g = geom_convT_phase(B, H, W, Cin, Cout, ph, 0);
@@ -744,6 +758,20 @@ __global__ void repack_kernel(const float* __restrict__ src, float* __restrict__
   w16[i] = __float2bfloat16_rn(v);
 }
 
+// [9][Cout][C] (tap = kh * 3 + kw) -> [4][Cout][4C]: tap t = (dh' + 1) * 2 + (dw' + 1), channel k = py * 2C + px * C + c,
+// source tap kh = 2 dh' + py + 1, kw = 2 dw' + px + 1 (zero where that falls outside the 3x3 kernel)
+__global__ void repack_s2d_kernel(const __nv_bfloat16* __restrict__ w9, __nv_bfloat16* __restrict__ w4, int Cout, int C) {
+  const int64_t total = (int64_t)4 * Cout * 4 * C;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % (4 * C));
+  const int co = (int)((i / (4 * C)) % Cout);
+  const int t = (int)(i / ((int64_t)4 * C * Cout));
+  const int py = k / (2 * C), px = (k / C) & 1, c = k % C;
+  const int kh = 2 * (t / 2 - 1) + py + 1, kw = 2 * (t % 2 - 1) + px + 1;
+  w4[i] = (kh >= 0 && kh < 3 && kw >= 0 && kw < 3) ? w9[((int64_t)(kh * 3 + kw) * Cout + co) * C + c] : __float2bfloat16_rn(0.f);
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t total, int HW, int C) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into NCHW output
@@ -1172,7 +1200,14 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
       T* skip_c = skip[i] + b0 * h * w * co;
       if ((rc = run_block<T>(cc, plan->enc[i], name, in_c, ch, (const T*)nullptr, 0, h, w, ty, th, tr, skip_c))) return rc;
       ConvGeom gd = geom_conv((int)nbc, h, w, co, 0, co, 3, 2);
-      if ((rc = run_conv<T>(cc, gd, skip_c, (const T*)nullptr, plan->down[i], dst + b0 * ho * wo * co, nullptr, 8, nullptr)))
+      static const bool s2d_off = [] { const char* e = getenv("DBS_STRIP_S2D"); return e && e[0] == '0'; }();
+      rc = DBS_ERR_UNSUPPORTED;
+      if (cc.use_tc && sizeof(T) == 2 && !s2d_off && plan->down[i].w16_s2d && !(h & 1) && !(w & 1))
+        rc = conv_strip_launch(geom_conv_s2d((int)nbc, h, w, co, co), (const __nv_bfloat16*)skip_c, nullptr, plan->down[i].w16_s2d,
+                               plan->down[i].bias, (__nv_bfloat16*)(dst + b0 * ho * wo * co), nullptr, 8, cc.st);
+      if (rc != DBS_OK && rc != DBS_ERR_UNSUPPORTED) return rc;
+      if (rc == DBS_ERR_UNSUPPORTED &&
+          (rc = run_conv<T>(cc, gd, skip_c, (const T*)nullptr, plan->down[i], dst + b0 * ho * wo * co, nullptr, 8, nullptr)))
         return rc;
       c.tapped |= cc.tapped;
     }
@@ -1386,6 +1421,13 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
     if ((rc = make_block(plan, pt, p, ch, co, &plan->enc[i]))) return fail(rc);
     plan->enc[i].tb_off = off; off += co; tls.push_back({p, co});
     if ((rc = make_conv(plan, pt, "downsample." + std::to_string(i), co, co, 3, false, &plan->down[i]))) return fail(rc);
+    {
+      void* w4 = nullptr;
+      const int64_t n4 = (int64_t)4 * co * 4 * co;
+      if ((rc = dev_alloc(plan, (size_t)n4 * 2, &w4))) return fail(rc);
+      plan->down[i].w16_s2d = (__nv_bfloat16*)w4;
+      repack_s2d_kernel<<<(unsigned)((n4 + 255) / 256), 256>>>(plan->down[i].w16, plan->down[i].w16_s2d, co, co);
+    }
     ch = co; enc_ch.push_back(co);
   }
   if ((rc = make_block(plan, pt, "middle.", ch, ch, &plan->mid))) return fail(rc);

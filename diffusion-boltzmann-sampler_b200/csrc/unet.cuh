@@ -29,6 +29,11 @@ struct ConvGeom {
   // [n_taps, 2 n_taps) to pw = 1 (strip kernel only: the pair shares its A rows, conv_strip.cu).
   // 0 or 1: a single phase / an ordinary conv.  The tile kernel (conv_tc_launch) takes only the 4-phase form.
   int n_phases;
+  // s2d == 1 (strip kernel only): a 3x3 stride-2 pad-1 conv run as a 2x2 stride-1 conv on the space-to-depth view of its
+  // input: Hin x Win are the HALVED sizes, C0 = 4 * C with channel k = py * 2C + px * C + c standing for input pixel
+  // (2a + py, 2b + px), taps (dh', dw') in {-1, 0}^2, weights repacked (with zeros) by repack_s2d_kernel.  The strips then
+  // cost 9 * Win rows of TMA per 4C-chunk and tile instead of one box per tap (the stride-2 convs are TMA-row-bound).
+  int s2d;
 };
 
 struct ConvWeights {
@@ -36,6 +41,7 @@ struct ConvWeights {
   float* w32 = nullptr;           // [taps][cout][cin]
   __nv_bfloat16* w16 = nullptr;   // same layout
   float* bias = nullptr;          // [cout]
+  __nv_bfloat16* w16_s2d = nullptr;   // stride-2 3x3 convs: [4 taps (dh', dw')][cout][4 * cin], see ConvGeom::s2d
 };
 
 // GroupNorm apply fused into the conv epilogue (layers whose images fit inside one 128-pixel tile):
@@ -68,5 +74,6 @@ ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int
 ConvGeom geom_convT_phase(int B, int H, int W, int Cin, int Cout, int ph, int pw);
 ConvGeom geom_convT_all(int B, int H, int W, int Cin, int Cout);
 ConvGeom geom_convT_pair(int B, int H, int W, int Cin, int Cout, int ph);
+ConvGeom geom_conv_s2d(int B, int H, int W, int C, int Cout);   // H, W: the conv's (even) input size
 
 }  // namespace dbs
