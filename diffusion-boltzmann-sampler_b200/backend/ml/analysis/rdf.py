@@ -1,7 +1,7 @@
 """Radial distribution function — engine-backed replacement for compute_rdf / compute_rdf_from_system
-(analysis/rdf.py:9-109 of the reference).  rdf_statistics / compare_rdfs of that file are O(n_bins)
-host post-processing and stay with the reference."""
-from typing import Optional, Tuple
+(analysis/rdf.py:9-109 of the reference) plus that file's O(n_bins) curve statistics (rdf_statistics,
+compare_rdfs: host arithmetic on the finished g(r), no lattice or particle data involved)."""
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -35,3 +35,41 @@ def compute_rdf(positions: torch.Tensor, box_size: float, n_bins: int = 100, r_m
 
 def compute_rdf_from_system(positions: torch.Tensor, system, n_bins: int = 100, r_max: Optional[float] = None):
     return compute_rdf(positions=positions, box_size=system.box_size, n_bins=n_bins, r_max=r_max)
+
+
+def _trapezoid(y: np.ndarray, x: np.ndarray) -> float:
+    return float(np.sum(0.5 * (y[1:] + y[:-1]) * np.diff(x))) if len(x) > 1 else 0.0
+
+
+def rdf_statistics(r: np.ndarray, g_r: np.ndarray, sigma: float = 1.0) -> Dict[str, float]:
+    """Position and height of the highest g(r) value beyond 0.9 sigma, and the 2-D coordination integral
+    2 pi * int r g(r) dr from 0.9 sigma up to the first local minimum after that peak
+    (analysis/rdf.py:111-177; the reference's integral carries no density factor and neither does this)."""
+    r, g_r = np.asarray(r), np.asarray(g_r)
+    keep = r > 0.9 * sigma
+    if not keep.any():
+        return {"first_peak_r": 0.0, "first_peak_height": 0.0, "coordination_number": 0.0}
+    rv, gv = r[keep], g_r[keep]
+    peak = int(np.argmax(gv))
+    coordination = 0.0
+    if peak + 1 < len(gv) - 1:
+        inner = np.arange(peak + 1, len(gv) - 1)
+        is_min = (gv[inner] < gv[inner - 1]) & (gv[inner] < gv[inner + 1])
+        stop = int(inner[is_min][0]) if is_min.any() else len(gv) - 1
+        coordination = 2 * np.pi * _trapezoid(rv[:stop + 1] * gv[:stop + 1], rv[:stop + 1])
+    return {"first_peak_r": float(rv[peak]), "first_peak_height": float(gv[peak]),
+            "coordination_number": float(coordination)}
+
+
+def compare_rdfs(r1: np.ndarray, g_r1: np.ndarray, r2: np.ndarray, g_r2: np.ndarray) -> Dict[str, float]:
+    """Mean squared and maximum difference of two g(r) curves (linearly interpolated onto the overlap of
+    their grids when the grids differ) and the distance between their first peaks (analysis/rdf.py:180-226)."""
+    r1, g_r1, r2, g_r2 = (np.asarray(v) for v in (r1, g_r1, r2, g_r2))
+    if len(r1) == len(r2) and np.allclose(r1, r2):
+        a, b = g_r1, g_r2
+    else:
+        grid = np.linspace(max(r1.min(), r2.min()), min(r1.max(), r2.max()), min(len(r1), len(r2)))
+        a, b = np.interp(grid, r1, g_r1), np.interp(grid, r2, g_r2)
+    peak1, peak2 = rdf_statistics(r1, g_r1)["first_peak_r"], rdf_statistics(r2, g_r2)["first_peak_r"]
+    return {"mse": float(np.mean((a - b) ** 2)), "max_diff": float(np.max(np.abs(a - b))),
+            "peak_diff": float(abs(peak1 - peak2))}
