@@ -2,7 +2,7 @@
 
 Replacement for the parts of models/diffusion.py the sampling path uses (`noise_level` :68-97,
 `beta` :52-66, `get_config` :40-46), with the training helpers (`forward`, `score_target`,
-`reverse_step`) kept so the module still satisfies its callers.  This is O(num_steps) scalar
+`reverse_step`, `compute_loss`) kept so the module still satisfies its callers.  This is O(num_steps) scalar
 work per sampling call; the engine consumes the resulting fp32 coefficients.
 """
 from typing import Optional, Tuple
@@ -76,3 +76,22 @@ class DiffusionProcess:
         if stochastic:
             x = x + torch.sqrt(b * abs(dt)) * torch.randn_like(x_t)
         return x
+
+    def compute_loss(self, score_pred: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, loss_type: str = "l2",
+                     weighting: str = "uniform") -> torch.Tensor:
+        """Denoising score-matching loss against the target -eps / (sigma_t + EPS): squared ("l2") or absolute
+        ("l1") error, weighted by 1 ("uniform") or sigma_t^2 ("snr"), mean over every element
+        (models/diffusion.py:181-227).  Differentiable torch code for the trainer; not on the sampling path."""
+        sigma = self.noise_level(t)[1].view((-1,) + (1,) * (score_pred.dim() - 1))
+        err = score_pred - self.score_target(noise, sigma)
+        if loss_type == "l2":
+            err = err.pow(2)
+        elif loss_type == "l1":
+            err = err.abs()
+        else:
+            raise ValueError(f"Unknown loss type: {loss_type}")
+        if weighting == "snr":
+            err = err * sigma.pow(2)
+        elif weighting != "uniform":
+            raise ValueError(f"Unknown weighting: {weighting}")
+        return err.mean()

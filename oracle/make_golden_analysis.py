@@ -6,7 +6,7 @@ Run in the build container only (the reference does not exist on the GPU box):
     python oracle/make_golden_analysis.py
 Only inputs and outputs are stored.  Sample sets: two 16x16 Ising ensembles produced by the
 reference's own MetropolisHastings at T = 2.0 and T = 3.0 (time-ordered, so the autocorrelation
-estimate sees a real chain), one continuous (B, 1, L, L) set, and two synthetic g(r) curves.
+estimate sees a real chain), one continuous (B, 1, L, L) set, and two synthetic g(r) curves; plus DiffusionProcess.compute_loss values.
 """
 import os
 import sys
@@ -95,6 +95,15 @@ def main():
     flat("rdfstat_mono.", rr.rdf_statistics(r1, mono), out)
     flat("rdfcmp_same.", rr.compare_rdfs(r1, g1, r1, g1 * 0.9 + 0.05), out)
     flat("rdfcmp_diff.", rr.compare_rdfs(r1, g1, r2, g2), out)
+
+    # DiffusionProcess.compute_loss (models/diffusion.py:181-227): a trainer-side helper the replacement module keeps
+    from backend.ml.models.diffusion import DiffusionProcess
+    torch.manual_seed(5)
+    sp, nz, t = torch.randn(6, 1, 8, 8), torch.randn(6, 1, 8, 8), torch.rand(6)
+    out["closs_pred"], out["closs_noise"], out["closs_t"] = sp.numpy(), nz.numpy(), t.numpy()
+    for lt in ("l2", "l1"):
+        for w in ("uniform", "snr"):
+            out[f"closs_{lt}_{w}"] = np.float64(DiffusionProcess().compute_loss(sp, nz, t, lt, w).item())
 
     path = os.path.join(ROOT, "tests", "golden", "analysis.npz")
     np.savez_compressed(path, **out)

@@ -170,3 +170,27 @@ def test_two_sample_comparisons_equal_reference():
     _check_dict(an.correlation_function_comparison(a, b), "corrcmp.", rtol=1e-12, atol=1e-15)
     np.random.seed(43)
     _check_dict(an.comprehensive_comparison(a, b, model, 20), "comp.", rtol=1e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------ module surface kept for callers
+def test_compute_loss_and_physical_system_kept_for_the_trainer():
+    """training/trainer.py:11-14 imports DiffusionProcess and calls compute_loss; systems/__init__.py:1 exports
+    PhysicalSystem.  Both are host-side torch code outside the sampling path; values pinned to the reference."""
+    from backend.ml.models.diffusion import DiffusionProcess
+    from backend.ml.systems import PhysicalSystem
+    sp, nz, t = (torch.tensor(G[k]) for k in ("closs_pred", "closs_noise", "closs_t"))
+    sp.requires_grad_(True)
+    for lt in ("l2", "l1"):
+        for w in ("uniform", "snr"):
+            loss = DiffusionProcess().compute_loss(sp, nz, t, lt, w)
+            np.testing.assert_allclose(loss.item(), G[f"closs_{lt}_{w}"], rtol=1e-6)
+    loss.backward()
+    assert torch.isfinite(sp.grad).all()
+    with pytest.raises(ValueError, match="Unknown loss type"):
+        DiffusionProcess().compute_loss(sp, nz, t, "huber")
+    with pytest.raises(ValueError, match="Unknown weighting"):
+        DiffusionProcess().compute_loss(sp, nz, t, "l2", "min-snr")
+    with pytest.raises(TypeError):
+        PhysicalSystem()
+    assert {"energy", "random_configuration", "energy_per_particle", "to_continuous", "from_continuous",
+            "num_particles", "configuration_shape"} == set(PhysicalSystem.__abstractmethods__)
