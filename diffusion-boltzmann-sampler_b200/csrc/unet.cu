@@ -772,6 +772,40 @@ __global__ void repack_s2d_kernel(const __nv_bfloat16* __restrict__ w9, __nv_bfl
   w4[i] = (kh >= 0 && kh < 3 && kw >= 0 && kw < 3) ? w9[((int64_t)(kh * 3 + kw) * Cout + co) * C + c] : __float2bfloat16_rn(0.f);
 }
 
+// Bilinear resize (align_corners = false) of an NHWC tensor: the size fix-up ScoreNetwork.forward applies to an
+// upsampled map whose side is not the skip connection's (score_network.py:253-255, torch's upsample_bilinear2d rule:
+// src = (dst + 0.5) * in/out - 0.5 clamped at 0, neighbour i1 = min(i0 + 1, in - 1)).  One thread per 4 channels of
+// one output pixel; only lattices whose side is not divisible by 2^num_blocks ever reach it.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bilinear_resize_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t total_quads, int Hi, int Wi, int Ho, int Wo,
+                       int C, float scale_h, float scale_w) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total_quads) return;
+  const int cq = C >> 2;
+  const int c4 = (int)(q % cq) * 4;
+  int64_t pix = q / cq;
+  const int ow = (int)(pix % Wo); pix /= Wo;
+  const int oh = (int)(pix % Ho);
+  const int64_t n = pix / Ho;
+  const float sh = fmaxf(__fmaf_rn(scale_h, (float)oh + 0.5f, -0.5f), 0.0f);
+  const float sw = fmaxf(__fmaf_rn(scale_w, (float)ow + 0.5f, -0.5f), 0.0f);
+  const int h0 = min((int)sh, Hi - 1), w0 = min((int)sw, Wi - 1);
+  const int h1 = min(h0 + 1, Hi - 1), w1 = min(w0 + 1, Wi - 1);
+  const float lh1 = fminf(fmaxf(sh - (float)h0, 0.0f), 1.0f), lw1 = fminf(fmaxf(sw - (float)w0, 0.0f), 1.0f);
+  const float lh0 = 1.0f - lh1, lw0 = 1.0f - lw1;
+  const T* base = in + n * Hi * Wi * C + c4;
+  float v00[4], v01[4], v10[4], v11[4], r[4];
+  Quad<T>::load(base + ((int64_t)h0 * Wi + w0) * C, v00);
+  Quad<T>::load(base + ((int64_t)h0 * Wi + w1) * C, v01);
+  Quad<T>::load(base + ((int64_t)h1 * Wi + w0) * C, v10);
+  Quad<T>::load(base + ((int64_t)h1 * Wi + w1) * C, v11);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    r[k] = lh0 * (lw0 * v00[k] + lw1 * v01[k]) + lh1 * (lw0 * v10[k] + lw1 * v11[k]);
+  Quad<T>::store(out + ((n * Ho + oh) * Wo + ow) * C + c4, r);
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t total, int HW, int C) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into NCHW output
@@ -1079,16 +1113,23 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   float* tbias = (float*)ws.take((int64_t)n_t * plan->sumC * 4);
   const int n_stat_slices = 2 * (2 * nb + 1);          // two GroupNorms per ConvBlock, 2 nb + 1 blocks
   float* stats = (float*)ws.take((int64_t)n_stat_slices * B * 8 * 2 * 4);
-  int64_t max_act = (int64_t)B * H * W * C * 2;  // enc0 output has 2C channels at full resolution
+  // a lattice side that is not divisible by 2^num_blocks makes some transposed conv overshoot its skip connection by one
+  // row / column: that level's output is resized (bilinear fix-up below); buffers are sized for the overshoot
+  const bool fixup = (H % (1 << nb)) != 0 || (W % (1 << nb)) != 0;
+  auto even_up = [](int v) { return (v + 1) & ~1; };
+  int64_t max_act = (int64_t)B * even_up(H) * even_up(W) * C * 2;  // enc0 output has 2C channels at full resolution
   {
     int h = H, w = W, ch = C;
     for (int i = 0; i < nb; ++i) {
       const int co = C << (i + 1);
-      max_act = std::max(max_act, (int64_t)B * h * w * co);
+      max_act = std::max(max_act, (int64_t)B * even_up(h) * even_up(w) * co);
       h = (h - 1) / 2 + 1; w = (w - 1) / 2 + 1; ch = co;
     }
     (void)ch;
   }
+  // the tcgen05 / TMA kernels and the fused init / final kernels are built for the divisible lattices every BASELINE
+  // config uses; the fix-up shapes run the generic CUDA-core kernels of the same precision
+  if (fixup) use_tc = false;
   T* a0 = (T*)ws.take(B * H * W * C * (int64_t)sizeof(T));
   T* ty = (T*)ws.take(max_act * (int64_t)sizeof(T));
   T* th = (T*)ws.take(max_act * (int64_t)sizeof(T));
@@ -1119,7 +1160,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   }
   // fused final conv (bf16 path): C in {16, 32, 64}, power-of-two width <= 128, tile within 48 KB of shared memory
   const bool final_fused_ok = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && W <= 128 && (W & (W - 1)) == 0 &&
-                              (size_t)(std::min(256 / W, H) + 2) * W * C * 2 <= 48 * 1024;
+                              (size_t)(std::min(256 / W, H) + 2) * W * C * 2 <= 48 * 1024 && !fixup;
   static const bool defer_off = [] { const char* e = getenv("DBS_FINAL_FUSE"); return e && e[0] == '0'; }();
   DeferredGn defer;
   defer.want = final_fused_ok && use_tc && !tap && !defer_off;
@@ -1127,7 +1168,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- time path: its own launch, unless the bf16 init conv below can carry it (all samples share t)
   TimeArgs ta{t, plan->freqs, plan->tw0, plan->tb0, plan->tw2, plan->tb2, plan->twt, plan->tbt, tbias, Td, plan->sumC, 0};
   static const bool tfuse_off = [] { const char* e = getenv("DBS_TIME_FUSE"); return e && e[0] == '0'; }();
-  const bool time_fused = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && n_t == 1 && !tfuse_off;
+  const bool time_fused = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && n_t == 1 && !tfuse_off && !fixup;
   if (!time_fused) {
     prof_set_label("time");
     ProfScope prof(kProfUnetMisc, st);
@@ -1143,7 +1184,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
     prof_set_label(time_fused ? "time+init_conv" : "init_conv");
     ProfScope prof(kProfUnetMisc, st);
     const int64_t nthr = n_pix * (C / (16 / (int)sizeof(T)));
-    if (sizeof(T) == 2 && (C == 16 || C == 32 || C == 64)) {
+    if (sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && !fixup) {
       if (C == 16) rc = launch_init_fast<16>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st, ta);
       else if (C == 32) rc = launch_init_fast<32>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st, ta);
       else rc = launch_init_fast<64>(plan->init_w_host, plan->init_b_host, x, (__nv_bfloat16*)a0, n_pix, H, W, st, ta);
@@ -1164,7 +1205,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // L2 hits, so this is OFF by default (DBS_L2_CHUNK_MB=<MB> enables it for experiments).
   static const double chunk_mb = [] { const char* e = getenv("DBS_L2_CHUNK_MB"); return e ? atof(e) : 0.0; }();
   auto chunk_of = [&](int hh, int ww, int cmax) -> int64_t {
-    if (chunk_mb <= 0 || tap) return B;
+    if (chunk_mb <= 0 || tap || fixup) return B;
     const double per_sample = (double)hh * ww * cmax * sizeof(T);
     int64_t cb = (int64_t)(chunk_mb * 1048576.0 / per_sample);
     const int64_t min_cb = (2 * 148 * 128 + (int64_t)hh * ww - 1) / ((int64_t)hh * ww);   // >= 2 waves of tiles
@@ -1226,15 +1267,16 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- decoder
   for (int i = 0; i < nb; ++i) {
     const int si = nb - 1 - i;
-    DBS_REQUIRE(2 * h == sh[si] && 2 * w == sw_[si],
-                "unet: lattice %dx%d is not divisible by 2^%d; the bilinear fix-up of score_network.py:254-255 is not built",
-                H, W, nb);
+    const int hs = sh[si], wsk = sw_[si];      // the skip connection's size: what the level runs at
+    const bool resize = 2 * h != hs || 2 * w != wsk;
+    DBS_REQUIRE(!resize || (fixup && ci >= 0), "unet: internal size mismatch at decoder level %d", i);
     const int ui = pick(ci, -1), di = pick(ci, ui);
     T* up = pp[ui];
     T* dst = pp[di];
     const int co = plan->dec[i].cout;
     const int h2 = 2 * h, w2 = 2 * w;
     const int64_t cb = chunk_of(h2, w2, ch + sc[si]);
+    T* fixed = resize ? pp[ci] : nullptr;     // the level's input buffer is dead once the transposed conv has read it
     snprintf(name, sizeof(name), "dec%d", i);
     for (int64_t b0 = 0; b0 < B; b0 += cb) {
       const int64_t nbc = std::min<int64_t>(cb, B - b0);
@@ -1290,13 +1332,22 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
         if ((rc = maybe_tap<T>(cc, name, up, B, h2, w2, ch))) return rc;
         snprintf(name, sizeof(name), "dec%d", i);
       }
+      if (resize) {   // cb == B here (fix-up lattices are never chunked)
+        const int64_t quads = nbc * hs * wsk * (ch / 4);
+        prof_set_label("resize");
+        ProfScope prof(kProfUnetMisc, st);
+        bilinear_resize_kernel<T><<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(
+            up_c, fixed, quads, h2, w2, hs, wsk, ch, (float)h2 / (float)hs, (float)w2 / (float)wsk);
+        DBS_LAUNCHED();
+        up_c = fixed;
+      }
       cc.defer = (i == nb - 1 && cb >= B) ? &defer : nullptr;
-      if ((rc = run_block<T>(cc, plan->dec[i], name, up_c, ch, skip[si] + b0 * h2 * w2 * sc[si], sc[si], h2, w2, ty, th, tr,
-                             dst + b0 * h2 * w2 * co)))
+      if ((rc = run_block<T>(cc, plan->dec[i], name, up_c, ch, skip[si] + b0 * hs * wsk * sc[si], sc[si], hs, wsk, ty, th, tr,
+                             dst + b0 * hs * wsk * co)))
         return rc;
       c.tapped |= cc.tapped;
     }
-    h = h2; w = w2;
+    h = hs; w = wsk;
     ch = co;
     cur = dst; ci = di;
   }
@@ -1342,10 +1393,6 @@ int check_forward_args(const dbs_unet_plan* plan, int64_t B, int H, int W, int p
   DBS_REQUIRE(precision == 0 || precision == 1, "unet: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
   DBS_REQUIRE(precision == 0 || plan->cfg.base_channels % 8 == 0,
               "unet: the bf16 path needs base_channels to be a multiple of 8 (got %d)", plan->cfg.base_channels);
-  const int div = 1 << plan->cfg.num_blocks;
-  DBS_REQUIRE(H % div == 0 && W % div == 0,
-              "unet: lattice %dx%d is not divisible by 2^num_blocks=%d; the bilinear fix-up of score_network.py:254-255 is not built",
-              H, W, div);
   return DBS_OK;
 }
 

@@ -169,11 +169,51 @@ def test_unet_bf16_vs_fp32_across_batch_sizes(H, B):
     assert np.sqrt(((a - b) ** 2).mean()) <= 2e-2 * np.sqrt((a ** 2).mean())
 
 
-def test_unet_rejects_unsupported_shapes_loudly():
-    net = _net(16, 32, 2, seed=1)
-    with pytest.raises(ValueError, match="not divisible"):
+@pytest.mark.parametrize("H,W", [(12, 12), (10, 10), (9, 9), (20, 20), (12, 16), (9, 14), (33, 33)])
+def test_unet_lattices_not_divisible_by_the_downsampling_factor(H, W):
+    """score_network.py:253-255: a transposed conv that overshoots its skip connection is resized bilinearly
+    (align_corners=False).  The API admits every lattice_size in 8..128 (routes/sampling.py:26), so odd sides and
+    sides not divisible by 2^num_blocks must run: fp32 <= 1e-4 of the oracle per tap and end to end, and the
+    bf16 request (CUDA-core kernels with bf16 storage on these shapes) within the stated bf16 bound."""
+    net = _net(16, 32, 3, seed=H * 7 + W)
+    torch.manual_seed(H + W)
+    B = 3
+    x, t = torch.randn(B, 1, H, W), torch.rand(B)
+    taps = {}
+    want = o_unet.unet_forward(_sd(net), x, t, taps=taps).numpy()
+    got = net.engine_forward(x, t, precision="fp32").cpu().numpy()
+    assert got.shape == want.shape and _rel(got, want) <= 1e-4
+    for name in ("up0", "dec0", "up1", "dec1", "up2", "dec2"):
+        ref = taps[name].numpy()
+        _, tap = net.engine_forward(x, t, precision="fp32", tap=(name, tuple(ref.shape)))
+        assert _rel(tap.cpu().numpy(), ref) <= 1e-4, name
+    with torch.no_grad():                                   # the module call a route makes: host in, host out
+        out = net(x, t)
+    assert not out.is_cuda and _rel(out.numpy(), want) <= 1e-4
+    lo = net.engine_forward(x, t, precision="bf16").cpu().numpy()
+    assert np.isfinite(lo).all()
+    assert np.sqrt(((lo - want) ** 2).mean()) <= 2e-2 * np.sqrt((want ** 2).mean())
+
+
+def test_sampler_on_a_non_divisible_lattice_matches_oracle():
+    """DiffusionSampler.sample on a 10x10 lattice (lattice_size = 10 is a legal /sample/diffusion request) with injected
+    noise against the oracle's sampler: <= 1e-4 relative after 8 steps."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net(8, 16, 2, seed=5)
+    torch.manual_seed(9)
+    shape, N = (4, 1, 10, 10), 8
+    x0, noises = torch.randn(shape), torch.randn((N,) + shape)
+    want = o_unet.sample(_sd(net), shape, N, x0, noises).numpy()
+    got = DiffusionSampler(net, num_steps=N).sample(shape, x0=x0, noises=noises)
+    assert _rel(got.cpu().numpy(), want) <= 1e-4
+
+
+def test_unet_rejects_unsupported_configurations_loudly():
+    from backend.ml.models.score_network import ScoreNetwork
+    net = ScoreNetwork(2, 16, 32, 2).eval()
+    with pytest.raises((NotImplementedError, RuntimeError, ValueError), match="in_channels"):
         with torch.no_grad():
-            net(torch.randn(1, 1, 10, 10), torch.rand(1))
+            net(torch.randn(1, 2, 8, 8), torch.rand(1))
 
 
 # ----------------------------------------------------------------------------- samplers
