@@ -70,7 +70,7 @@ class IsingModel:
         L = self.size
         wpc = abi.lib.dbs_ising_words_per_chain(L)
         if wpc < 0:
-            raise ValueError(f"IsingModel: lattice size {L} is not supported by the packed engine (even, 4..128)")
+            raise ValueError(f"IsingModel: lattice size {L} is not supported by the packed engine (4..128, not 3)")
         bits = torch.empty((n_chains, L, wpc // L), dtype=torch.int32, device=dev)
         abi.check(abi.lib.dbs_ising_init_packed_strided(bits.data_ptr(), L, n_chains, seed, chain_offset, chain_stride,
                                                         runtime.current_stream()), "ising_init_packed")
@@ -82,7 +82,7 @@ class IsingModel:
         x = runtime.to_device(spins).reshape(-1, L, L)
         wpc = abi.lib.dbs_ising_words_per_chain(L)
         if wpc < 0:
-            raise ValueError(f"IsingModel: lattice size {L} is not supported by the packed engine (even, 4..128)")
+            raise ValueError(f"IsingModel: lattice size {L} is not supported by the packed engine (4..128, not 3)")
         bits = torch.empty((x.shape[0], L, wpc // L), dtype=torch.int32, device=x.device)
         abi.check(abi.lib.dbs_ising_pack(x.data_ptr(), bits.data_ptr(), L, x.shape[0], runtime.current_stream()),
                   "ising_pack")

@@ -22,7 +22,8 @@ namespace {
 
 constexpr int kMaxL = 128;
 
-__host__ __device__ inline bool supported_L(int L) { return L >= 4 && L <= kMaxL && (L & 1) == 0; }
+// even L: the bit-packed checkerboard kernel; odd L (>= 5): the three-colour kernel below (an odd torus is not bipartite)
+__host__ __device__ inline bool supported_L(int L) { return L >= 4 && L <= kMaxL && ((L & 1) == 0 || L >= 5); }
 
 struct SweepArgs {
   uint32_t* bits;
@@ -241,6 +242,89 @@ int launch_sweep(const SweepArgs& a, cudaStream_t st) {
     case 128: return launch_sweep_t<128, kInject, kMode>(a, st);
     default: return launch_sweep_t<0, kInject, kMode>(a, st);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Odd L.  A torus with an odd side is not two-colourable: sites (i, L-1) and (i, 0) are neighbours with the same
+// (i + j) parity.  The cycle of L sites is three-coloured c(k) = k & 1 for k < L-1, c(L-1) = 2, and
+// colour(i, j) = (c(i) + c(j)) mod 3 is a proper colouring of the torus; one sweep = colours 0, 1, 2 in turn, every
+// site attempted once with the reference's acceptance rule.  Odd lattices are an API corner (lattice_size is any
+// integer in 8..128, routes/sampling.py:26), not a BASELINE configuration: one CTA per chain, one spin per byte in
+// shared memory, a Philox call per group of four consecutive sites, the same {lo, hi} class table.
+__device__ __forceinline__ int cycle_colour(int k, int L) { return k == L - 1 ? 2 : (k & 1); }
+
+template <bool kInject>
+__global__ void __launch_bounds__(256)
+ising_sweep3_kernel(SweepArgs a) {
+  const int L = a.L, N = L * L;
+  const int W = (L + 31) >> 5, tpc = L * W;
+  extern __shared__ uint32_t smem[];
+  uint64_t* tbl = reinterpret_cast<uint64_t*>(smem);             // 16 class constants
+  unsigned char* sp = reinterpret_cast<unsigned char*>(smem + 32);   // [L][L] spin bits
+  const int64_t chain = blockIdx.x;
+  uint32_t* b = a.bits + chain * tpc;
+  if (threadIdx.x < 16) {
+    const int ti = a.table_index ? a.table_index[chain] : 0;
+    tbl[threadIdx.x] = threshold_constant(a.thr[(ti * 16 + threadIdx.x) * 2 + 0], a.thr[(ti * 16 + threadIdx.x) * 2 + 1]);
+  }
+  for (int q = threadIdx.x; q < N; q += blockDim.x) {
+    const int i = q / L, j = q - i * L;
+    sp[q] = (unsigned char)((b[i * W + (j >> 5)] >> (j & 31)) & 1u);
+  }
+  __syncthreads();
+  const uint32_t chain_ctr = (uint32_t)(a.chain_offset + chain * a.chain_stride);
+  const int n_groups = (N + 3) >> 2;
+  for (int s = 0; s < a.n_sweeps; ++s) {
+    for (int colour = 0; colour < 3; ++colour) {
+      for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
+        uint32_t rr[4] = {0u, 0u, 0u, 0u};
+        bool have = false;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int q = 4 * g + d;
+          if (q >= N) break;
+          const int i = q / L, j = q - i * L;
+          int cs = cycle_colour(i, L) + cycle_colour(j, L);
+          cs = cs >= 3 ? cs - 3 : cs;
+          if (cs != colour) continue;
+          if (kInject) {
+            rr[d] = a.uniforms[((int64_t)s * a.n_chains + chain) * N + q];
+          } else if (!have) {
+            u32x4 c;
+            c.x = chain_ctr;
+            c.y = (uint32_t)(a.sweep_offset + s);
+            c.z = (uint32_t)g;
+            c.w = DBS_STREAM_SWEEP3;
+            const u32x4 o = philox4x32_10(c, a.seed_lo, a.seed_hi);
+            rr[0] = o.x; rr[1] = o.y; rr[2] = o.z; rr[3] = o.w;
+            have = true;
+          }
+          const int iu = i == 0 ? L - 1 : i - 1, id = i == L - 1 ? 0 : i + 1;
+          const int jl = j == 0 ? L - 1 : j - 1, jr = j == L - 1 ? 0 : j + 1;
+          const int self = sp[q];
+          const int k = 8 * self + sp[iu * L + j] + sp[id * L + j] + sp[i * L + jl] + sp[i * L + jr];
+          if (accept_mask(rr[d], a.one, tbl[k])) sp[q] = (unsigned char)(self ^ 1);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = threadIdx.x; r < tpc; r += blockDim.x) {
+    const int i = r / W, w = r - i * W;
+    const int vb = valid_bits(L, w);
+    uint32_t word = 0;
+    for (int bb = 0; bb < vb; ++bb) word |= (uint32_t)sp[i * L + 32 * w + bb] << bb;
+    b[r] = word;
+  }
+}
+
+int launch_sweep3(const SweepArgs& a, cudaStream_t st) {
+  const size_t smem = 32 * 4 + (size_t)a.L * a.L;
+  ProfScope prof(kProfIsingSweep, st);
+  if (a.uniforms) ising_sweep3_kernel<true><<<(unsigned)a.n_chains, 256, smem, st>>>(a);
+  else ising_sweep3_kernel<false><<<(unsigned)a.n_chains, 256, smem, st>>>(a);
+  DBS_LAUNCHED();
+  return DBS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -582,7 +666,7 @@ extern "C" int dbs_ising_words_per_chain(int L) {
 
 extern "C" int dbs_ising_init_packed_strided(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
                                              int64_t chain_offset, int64_t chain_stride, void* stream) {
-  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
   DBS_REQUIRE(bits && n_chains >= 0 && chain_stride >= 1, "ising_init: null state, negative chain count or stride < 1");
   if (n_chains == 0) return DBS_OK;
   const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
@@ -598,7 +682,7 @@ extern "C" int dbs_ising_init_packed(uint32_t* bits, int L, int64_t n_chains, ui
 }
 
 extern "C" int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t n_chains, void* stream) {
-  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
   DBS_REQUIRE(spins && bits && n_chains >= 0, "ising_pack: null pointer");
   if (n_chains == 0) return DBS_OK;
   const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
@@ -608,7 +692,7 @@ extern "C" int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t
 }
 
 extern "C" int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64_t n_chains, void* stream) {
-  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
   DBS_REQUIRE(spins && bits && n_chains >= 0, "ising_unpack: null pointer");
   if (n_chains == 0) return DBS_OK;
   const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
@@ -629,7 +713,7 @@ extern "C" int dbs_ising_sweeps_strided(uint32_t* bits, int L, int64_t n_chains,
                                         int64_t chain_stride, int64_t sweep_offset, const uint32_t* uniforms,
                                         int zero_field, void* stream) {
   DBS_REQUIRE(chain_stride >= 1, "ising_sweeps: chain_stride must be >= 1");
-  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
   DBS_REQUIRE(bits && thr && n_tables >= 1, "ising_sweeps: null state or threshold table");
   DBS_REQUIRE(n_chains >= 0 && n_sweeps >= 0, "ising_sweeps: negative chain or sweep count");
   DBS_REQUIRE(zero_field >= -1 && zero_field <= 1, "ising_sweeps: zero_field must be -1, 0 or +1");
@@ -643,13 +727,14 @@ extern "C" int dbs_ising_sweeps_strided(uint32_t* bits, int L, int64_t n_chains,
   const int tpc = dbs_ising_words_per_chain(L);
   a.cpb = tpc >= 128 ? 1 : 128 / tpc;
   cudaStream_t st = as_stream(stream);
+  if (L & 1) return launch_sweep3(a, st);
   if (zero_field != 0) return uniforms ? launch_sweep<true, 1>(a, st) : launch_sweep<false, 1>(a, st);
   return uniforms ? launch_sweep<true, 0>(a, st) : launch_sweep<false, 0>(a, st);
 }
 
 extern "C" int dbs_ising_observables(const uint32_t* bits, int L, int64_t n_chains, float J, float h,
                                      float* energy, float* magnetization, void* stream) {
-  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
   DBS_REQUIRE(bits && n_chains >= 0, "ising_observables: null state");
   if (n_chains == 0) return DBS_OK;
   ProfScope prof(kProfIsingObs, as_stream(stream));
@@ -671,7 +756,7 @@ extern "C" int dbs_ising_observables_f32(const float* spins, int L, int64_t n, f
 
 extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chains, const uint32_t* ref_mask,
                                      const int32_t* group, long long* acc, void* stream) {
-  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (even, 4..%d)", L, kMaxL);
+  DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
   DBS_REQUIRE(bits && acc && n_chains >= 0, "ising_correlation: null pointer");
   if (n_chains == 0) return DBS_OK;
   const int W = (L + 31) / 32, tpc = L * W;

@@ -57,7 +57,7 @@ int dbs_profile_dump(const char* path);
 /* ------------------------------------------------------------------------- *
  * Ising lattice state: bit-packed, 1 bit per spin (1 = +1, 0 = -1).
  * Layout: uint32 words[n_chains][L][W], W = ceil(L/32); bit (j%32) of word
- * (j/32) of row i is spin (i,j); unused high bits are zero.  L even, 4<=L<=128.
+ * (j/32) of row i is spin (i,j); unused high bits are zero.  4<=L<=128 (odd L from 5).
  * ------------------------------------------------------------------------- */
 
 /* words per chain for lattice size L (L*ceil(L/32)); <0 if L unsupported. */
@@ -95,6 +95,10 @@ int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64_t n_chains
  *                q = rank of the site among its colour in row i, GPR = ceil(L/8);
  *                uniforms != NULL (test-mode injection port): uint32
  *                [n_sweeps][n_chains][L][L], r of site (i,j) in sweep s.
+ *   odd L        a torus with an odd side is not bipartite: one sweep = THREE colour classes in turn, colour(i,j) =
+ *                (c(i)+c(j)) mod 3 with c(k) = k&1 for k < L-1 and c(L-1) = 2; same classes, table and acceptance;
+ *                draw of site q = i*L+j: Philox4x32-10(key=seed, ctr={chain_offset+c, sweep_offset+s, q/4,
+ *                DBS_STREAM_SWEEP3}).v[q%4]; the injection port keeps its [n_sweeps][n_chains][L][L] layout.
  *   zero_field   0: general (J, h) table path.  +1 / -1: the caller guarantees h == 0 with J > 0 / J < 0;
  *                the kernel then counts agreeing (disagreeing) neighbours for 32 sites at once and
  *                compares draws only against the two uphill thresholds of the table — the same
@@ -334,6 +338,7 @@ int dbs_csn_forward(dbs_csn_plan* plan, const float* x, const float* t, int64_t 
 #define DBS_STREAM_SWEEP 0x53574550u /* 'SWEP' */
 #define DBS_STREAM_INIT  0x494e4954u /* 'INIT' */
 #define DBS_STREAM_NOISE 0x4e4f4953u /* 'NOIS' */
+#define DBS_STREAM_SWEEP3 0x53575033u /* 'SWP3': three-colour sweeps of odd lattices */
 #define DBS_STEP_X0 (-1)
 
 #ifdef __cplusplus

@@ -15,7 +15,7 @@ import math
 
 import numpy as np
 
-from .philox import philox4x32_10, STREAM_INIT, STREAM_SWEEP
+from .philox import philox4x32_10, STREAM_INIT, STREAM_SWEEP, STREAM_SWEEP3
 
 
 # --------------------------------------------------------------------------- acceptance table
@@ -92,6 +92,17 @@ def pack(spins):
     return out
 
 
+def site_colours(L):
+    """(n_colours, colour_of [L][L]).  Even L: the checkerboard (i + j) & 1.  Odd L: the torus is not bipartite
+    ((i, L-1) and (i, 0) are neighbours of equal parity), so the cycle is three-coloured c(k) = k & 1 for k < L-1,
+    c(L-1) = 2 and colour(i, j) = (c(i) + c(j)) mod 3 — adjacent sites differ in exactly one coordinate's colour."""
+    k = np.arange(L)
+    if L % 2 == 0:
+        return 2, (k[:, None] + k[None, :]) & 1
+    c = np.where(k == L - 1, 2, k & 1)
+    return 3, (c[:, None] + c[None, :]) % 3
+
+
 def sweep_draws(seed, chain_ids, sweep_index, L):
     """uint32 [n][L][L]: the draw of every site in sweep `sweep_index` (each site is visited once
     per sweep, in its colour's half-sweep).  Counter layout of dbs_ising_sweeps:
@@ -99,6 +110,13 @@ def sweep_draws(seed, chain_ids, sweep_index, L):
     among the sites of its colour in row i."""
     chain_ids = np.asarray(chain_ids, dtype=np.uint64)
     n = chain_ids.shape[0]
+    if L % 2:
+        # odd L (three colour classes): ctr = {chain, sweep, q//4, STREAM_SWEEP3}, word q%4, q = i*L + j
+        q = np.arange(L * L).reshape(L, L)
+        y = np.uint64(sweep_index & 0xFFFFFFFF)
+        o = philox4x32_10(chain_ids[:, None, None], y, (q // 4).astype(np.uint64)[None], STREAM_SWEEP3, seed)
+        r = np.choose(np.broadcast_to((q % 4)[None], (n, L, L)), [np.broadcast_to(x, (n, L, L)) for x in o])
+        return r.astype(np.uint32)
     gpr = (L + 7) // 8
     i = np.arange(L)[:, None]
     j = np.arange(L)[None, :]
@@ -114,21 +132,19 @@ def sweep_draws(seed, chain_ids, sweep_index, L):
 
 # --------------------------------------------------------------------------- the sweep
 def checkerboard_sweeps(spins, tables, table_index, draws):
-    """In-place checkerboard Metropolis.
+    """In-place colour-class Metropolis (checkerboard for even L, three classes for odd L: site_colours).
     spins int8 [n][L][L]; tables uint32 [T][16][2]; table_index int [n] or None;
     draws: callable(sweep)->uint32 [n][L][L], one sweep per call."""
     n, L, _ = spins.shape
     tables = np.asarray(tables, dtype=np.uint32).reshape(-1, 16, 2)
     ti = np.zeros(n, dtype=np.int64) if table_index is None else np.asarray(table_index, dtype=np.int64)
-    i = np.arange(L)[:, None]
-    j = np.arange(L)[None, :]
-    colour_of = (i + j) & 1
+    n_colours, colour_of = site_colours(L)
     s_idx = 0
     while True:
         r = draws(s_idx)
         if r is None:
             break
-        for colour in (0, 1):
+        for colour in range(n_colours):
             up = (spins > 0).astype(np.int64)
             u = np.roll(up, 1, axis=1) + np.roll(up, -1, axis=1) + np.roll(up, 1, axis=2) + np.roll(up, -1, axis=2)
             k = 8 * up + u

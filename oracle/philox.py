@@ -11,6 +11,7 @@ MASK32 = np.uint64(0xFFFFFFFF)
 
 STREAM_SWEEP = 0x53574550
 STREAM_INIT = 0x494E4954
+STREAM_SWEEP3 = 0x53575033
 STREAM_NOISE = 0x4E4F4953
 
 

@@ -30,8 +30,10 @@ def test_argument_validation_needs_no_gpu():
     from dbs_b200 import abi
     assert abi.lib.dbs_ising_words_per_chain(64) == 128
     assert abi.lib.dbs_ising_words_per_chain(16) == 16
-    assert abi.lib.dbs_ising_words_per_chain(7) < 0      # odd L is not checkerboard-decomposable
-    rc = abi.lib.dbs_ising_sweeps(0, 15, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0)
+    assert abi.lib.dbs_ising_words_per_chain(7) == 7     # odd L: three-colour sweep kernel
+    assert abi.lib.dbs_ising_words_per_chain(33) == 66
+    assert abi.lib.dbs_ising_words_per_chain(3) < 0 and abi.lib.dbs_ising_words_per_chain(129) < 0
+    rc = abi.lib.dbs_ising_sweeps(0, 130, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0)
     assert rc == abi.ERR_INVALID and "unsupported" in abi.last_error()
     with pytest.raises(ValueError):
         abi.check(rc, "ising_sweeps")

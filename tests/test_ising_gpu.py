@@ -21,12 +21,15 @@ def _words(t):
 
 
 def _sweep_cases():
-    g = load_golden("ising_sweeps.npz")
     keys = ["L", "J", "h", "T", "n_sweeps", "seed", "start", "r", "final"]
-    return [{k: g[f"c{i}_{k}"] for k in keys} for i in range(int(g["n_cases"]))]
+    out = []
+    for name in ("ising_sweeps.npz", "ising_odd.npz"):   # even: checkerboard kernel; odd: three-colour kernel
+        g = load_golden(name)
+        out += [{k: g[f"c{i}_{k}"] for k in keys} for i in range(int(g["n_cases"]))]
+    return out
 
 
-@pytest.mark.parametrize("L", [4, 8, 12, 16, 32, 48, 64, 96, 128])
+@pytest.mark.parametrize("L", [4, 8, 12, 16, 32, 48, 64, 96, 128, 5, 9, 33, 65, 127])
 def test_hot_start_pack_unpack_bit_exact(L):
     IsingModel, _ = _mods()
     m = IsingModel(L)
@@ -66,7 +69,8 @@ def test_sweeps_bit_exact_vs_reference_golden(case):
     assert n == 2
 
 
-@pytest.mark.parametrize("L,n_chains,n_sweeps", [(16, 64, 20), (64, 33, 6), (128, 3, 3), (24, 7, 5), (40, 5, 4), (8, 130, 9)])
+@pytest.mark.parametrize("L,n_chains,n_sweeps", [(16, 64, 20), (64, 33, 6), (128, 3, 3), (24, 7, 5), (40, 5, 4), (8, 130, 9),
+                                                   (9, 40, 6), (33, 9, 4), (65, 3, 3), (127, 2, 2)])
 def test_sweeps_vs_oracle_many_chains_per_chain_temperature(L, n_chains, n_sweeps):
     IsingModel, MetropolisHastings = _mods()
     m = IsingModel(L, J=1.0, h=0.05)
@@ -127,6 +131,35 @@ def test_pair_correlation_equals_reference(L):
     # same numpy seed -> same reference sites as the reference draws (analysis/correlation.py:25-26)
     np.random.seed(100 + L)
     assert np.array_equal(np.array(pair_correlation(s)["C_r"]), g[f"corr_L{L}_C"])
+
+
+@pytest.mark.parametrize("L", [9, 33, 127])
+def test_odd_lattice_observables_and_correlation_equal_reference(L):
+    """Odd lattices (lattice_size is any integer in 8..128 at the API, routes/sampling.py:26): E, M from fp32 and from
+    packed state, and C(r) with the reference's own sites, against tests/golden/ising_odd.npz."""
+    from backend.ml.analysis.correlation import pair_correlation
+    IsingModel, MetropolisHastings = _mods()
+    g = load_golden("ising_odd.npz")
+    m = IsingModel(L, J=0.7, h=-0.45)
+    s = torch.tensor(g[f"obs_L{L}_spins"].astype(np.float32))
+    assert np.array_equal(m.energy(s).numpy(), g[f"obs_L{L}_E"])
+    assert np.array_equal(m.magnetization(s).numpy(), g[f"obs_L{L}_M"])
+    e, mag = m.packed_observables(m.pack(s))
+    assert np.array_equal(e.cpu().numpy(), g[f"obs_L{L}_E"]) and np.array_equal(mag.cpu().numpy(), g[f"obs_L{L}_M"])
+    if L == 127:
+        L = 15
+    c = torch.tensor(g[f"corr_L{L}_samples"].astype(np.float32))
+    assert np.array_equal(np.array(pair_correlation(c, ref_indices=g[f"corr_L{L}_ref_indices"])["C_r"]), g[f"corr_L{L}_C"])
+    np.random.seed(200 + L)
+    assert np.array_equal(np.array(pair_correlation(c)["C_r"]), g[f"corr_L{L}_C"])
+    assert np.array_equal(np.array(pair_correlation(c, ref_indices="all")["C_r"]),
+                          np.array(o.pair_correlation(c.numpy(), None)["C_r"]))
+    # the reference API on an odd lattice: shapes, +/-1 values, ordering at low temperature
+    mh = MetropolisHastings(IsingModel(L), 1.0, seed=3)
+    out = mh.sample(n_samples=3, n_sweeps=2, burn_in=60, initial=torch.ones(L, L))
+    assert out.shape == (3, L, L) and set(out.unique().tolist()) <= {-1.0, 1.0} and out.mean() > 0.9
+    x = torch.ones(L, L)
+    assert mh.sweep(x) is x
 
 
 @pytest.mark.parametrize("L", [12, 32, 64, 128])
