@@ -12,6 +12,7 @@ Additive keyword extensions: `precision` ("fp32" parity path | "bf16" tcgen05 pa
 `x0`/`noises` injection ports on `sample` (parity tests), `sample_offset` (multi-GPU sharding with
 global sample indices so results do not depend on the world size).
 """
+import threading
 from typing import Any, Dict, Generator, Optional, Tuple
 
 import numpy as np
@@ -19,6 +20,8 @@ import torch
 
 from dbs_b200 import abi, runtime
 from ..models.diffusion import DiffusionProcess
+
+_CAPTURE_LOCK = threading.Lock()   # CUDA-graph captures of different samplers never overlap (see _graph_step)
 
 
 def _f32(v: float) -> float:
@@ -184,10 +187,17 @@ class DiffusionSampler:
                     self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
-                before = abi.launch_count()
-                with torch.cuda.graph(graph):
-                    self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
-                graph.n_kernels = abi.launch_count() - before    # kernels recorded in this graph
+                # thread_local: the capture records kernel launches only (workspace and buffers exist already), so
+                # CUDA calls of OTHER threads — an MCMC job on the server's thread pool allocating its lattices
+                # (routes/training.py:191) — must neither fail nor invalidate it, as they would in "global" mode.
+                # torch.cuda.graph captures on ONE process-wide side stream by default: two samplers capturing from
+                # two threads would begin a capture on a stream that is already capturing, so captures are serialised
+                # and each gets a stream of its own.
+                with _CAPTURE_LOCK:
+                    before = abi.launch_count()
+                    with torch.cuda.graph(graph, stream=torch.cuda.Stream(), capture_error_mode="thread_local"):
+                        self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
+                    graph.n_kernels = abi.launch_count() - before    # kernels recorded in this graph
             ent = (x, score, t_dev, graph)
             self._graphs[key] = ent
         return ent
