@@ -181,7 +181,7 @@ class DiffusionSampler:
             score = torch.empty_like(x)
             t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
             graph = None
-            if want and hasattr(self.model, "engine_forward"):
+            if want and hasattr(self.model, "engine_forward") and shape[0] > 0:   # nothing to capture for an empty batch
                 x.zero_()
                 for _ in range(2):          # warm-up: workspace allocation, one-time function attributes
                     self.model.engine_forward(x, t_dev, precision=self.precision, out=score)

@@ -639,6 +639,7 @@ extern "C" void dbs_csn_plan_destroy(dbs_csn_plan* plan) {
 }
 
 extern "C" int64_t dbs_csn_workspace_bytes(const dbs_csn_plan* plan, int64_t B, int N, int64_t n_t) {
+  if (plan && B == 0) return 0;   // empty batch
   if (!plan || B <= 0 || N <= 0 || n_t <= 0) { set_error("csn_workspace_bytes: bad argument"); return -1; }
   int64_t need = 0;
   if (forward_impl(const_cast<dbs_csn_plan*>(plan), nullptr, nullptr, n_t, nullptr, B, N, 0, nullptr, 0, nullptr, &need)) return -1;
@@ -647,6 +648,7 @@ extern "C" int64_t dbs_csn_workspace_bytes(const dbs_csn_plan* plan, int64_t B, 
 
 extern "C" int dbs_csn_forward(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
                                int64_t B, int N, int precision, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (plan && B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(plan && x && t && score, "csn_forward: null argument");
   DBS_REQUIRE(B > 0 && N > 0, "csn_forward: empty batch (%lld x %d)", (long long)B, N);
   DBS_REQUIRE(n_t == 1 || n_t == B, "csn_forward: t must have 1 or B entries (got %lld)", (long long)n_t);

@@ -118,6 +118,7 @@ using namespace dbs;
 extern "C" int dbs_em_step(float* x, const float* score, const float* noise, int64_t n_samples,
                            int64_t elems_per_sample, float c1, float dt, float c2, float temperature,
                            int add_noise, uint64_t seed, int64_t sample_offset, int64_t step, void* stream) {
+  if (n_samples == 0 || elems_per_sample == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(x && score, "em_step: null x or score");
   DBS_REQUIRE(n_samples >= 0 && elems_per_sample >= 0, "em_step: negative size");
   if (n_samples == 0 || elems_per_sample == 0) return DBS_OK;
@@ -132,6 +133,7 @@ extern "C" int dbs_em_step(float* x, const float* score, const float* noise, int
 
 extern "C" int dbs_gaussian_fill(float* x, int64_t n_samples, int64_t elems_per_sample, uint64_t seed,
                                  int64_t sample_offset, int64_t step, void* stream) {
+  if (n_samples == 0 || elems_per_sample == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(x, "gaussian_fill: null x");
   DBS_REQUIRE(n_samples >= 0 && elems_per_sample >= 0, "gaussian_fill: negative size");
   if (n_samples == 0 || elems_per_sample == 0) return DBS_OK;
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(256) lincomb_kernel(LinCombArgs q) {
 
 extern "C" int dbs_lincomb(float* out, int64_t n, int n_terms, const float* const* x, const float* a, int sign_first,
                            void* stream) {
+  if (n == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(out && x && a && n >= 0 && n_terms >= 1 && n_terms <= 5, "lincomb: bad arguments (1..5 terms)");
   if (n == 0) return DBS_OK;
   dbs::LinCombArgs q;

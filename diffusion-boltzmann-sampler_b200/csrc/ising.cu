@@ -667,6 +667,7 @@ extern "C" int dbs_ising_words_per_chain(int L) {
 extern "C" int dbs_ising_init_packed_strided(uint32_t* bits, int L, int64_t n_chains, uint64_t seed,
                                              int64_t chain_offset, int64_t chain_stride, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
+  if (n_chains == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(bits && n_chains >= 0 && chain_stride >= 1, "ising_init: null state, negative chain count or stride < 1");
   if (n_chains == 0) return DBS_OK;
   const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
@@ -683,6 +684,7 @@ extern "C" int dbs_ising_init_packed(uint32_t* bits, int L, int64_t n_chains, ui
 
 extern "C" int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t n_chains, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
+  if (n_chains == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(spins && bits && n_chains >= 0, "ising_pack: null pointer");
   if (n_chains == 0) return DBS_OK;
   const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
@@ -693,6 +695,7 @@ extern "C" int dbs_ising_pack(const float* spins, uint32_t* bits, int L, int64_t
 
 extern "C" int dbs_ising_unpack(const uint32_t* bits, float* spins, int L, int64_t n_chains, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
+  if (n_chains == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(spins && bits && n_chains >= 0, "ising_unpack: null pointer");
   if (n_chains == 0) return DBS_OK;
   const int64_t n_words = n_chains * dbs_ising_words_per_chain(L);
@@ -714,6 +717,7 @@ extern "C" int dbs_ising_sweeps_strided(uint32_t* bits, int L, int64_t n_chains,
                                         int zero_field, void* stream) {
   DBS_REQUIRE(chain_stride >= 1, "ising_sweeps: chain_stride must be >= 1");
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
+  if (n_chains == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(bits && thr && n_tables >= 1, "ising_sweeps: null state or threshold table");
   DBS_REQUIRE(n_chains >= 0 && n_sweeps >= 0, "ising_sweeps: negative chain or sweep count");
   DBS_REQUIRE(zero_field >= -1 && zero_field <= 1, "ising_sweeps: zero_field must be -1, 0 or +1");
@@ -735,6 +739,7 @@ extern "C" int dbs_ising_sweeps_strided(uint32_t* bits, int L, int64_t n_chains,
 extern "C" int dbs_ising_observables(const uint32_t* bits, int L, int64_t n_chains, float J, float h,
                                      float* energy, float* magnetization, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
+  if (n_chains == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(bits && n_chains >= 0, "ising_observables: null state");
   if (n_chains == 0) return DBS_OK;
   ProfScope prof(kProfIsingObs, as_stream(stream));
@@ -746,6 +751,7 @@ extern "C" int dbs_ising_observables(const uint32_t* bits, int L, int64_t n_chai
 
 extern "C" int dbs_ising_observables_f32(const float* spins, int L, int64_t n, float J, float h, float* energy,
                                          float* magnetization, void* stream) {
+  if (n == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(L >= 1 && spins && n >= 0, "ising_observables_f32: bad arguments");
   if (n == 0) return DBS_OK;
   const int threads = L * L >= 1024 ? 256 : (L * L >= 128 ? 128 : 32);
@@ -757,6 +763,7 @@ extern "C" int dbs_ising_observables_f32(const float* spins, int L, int64_t n, f
 extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chains, const uint32_t* ref_mask,
                                      const int32_t* group, long long* acc, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
+  if (n_chains == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(bits && acc && n_chains >= 0, "ising_correlation: null pointer");
   if (n_chains == 0) return DBS_OK;
   const int W = (L + 31) / 32, tpc = L * W;
@@ -777,6 +784,7 @@ extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chai
 
 extern "C" int dbs_observable_accumulate(const float* energy, const float* magnetization, int L, int64_t n_chains,
                                          const int32_t* group, double* acc, void* stream) {
+  if (n_chains == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(energy && magnetization && acc && L >= 1 && n_chains >= 0, "observable_accumulate: bad arguments");
   if (n_chains == 0) return DBS_OK;
   obs_accumulate_kernel<<<(unsigned)((n_chains + 255) / 256), 256, 0, as_stream(stream)>>>(
@@ -787,6 +795,7 @@ extern "C" int dbs_observable_accumulate(const float* energy, const float* magne
 
 extern "C" int dbs_ising_site_update(float* spins, int L, int64_t n, int i, int j, const uint32_t* thr, uint32_t r,
                                      void* stream) {
+  if (n == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(spins && thr && L >= 1 && n >= 0, "ising_site_update: bad arguments");
   DBS_REQUIRE(i >= 0 && i < L && j >= 0 && j < L, "ising_site_update: site (%d,%d) outside a %dx%d lattice", i, j, L, L);
   if (n == 0) return DBS_OK;

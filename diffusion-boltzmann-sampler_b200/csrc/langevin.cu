@@ -195,6 +195,7 @@ using namespace dbs;
 extern "C" int dbs_mala_propose(const float* pos, const float* force, const float* noise, float* pos_new, int64_t B,
                                 int N, float dt, float temperature, float noise_scale, float box, uint64_t seed,
                                 int64_t cfg_offset, int64_t step, void* stream) {
+  if (B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(pos && force && pos_new && B >= 0 && N >= 1, "mala_propose: bad arguments");
   DBS_REQUIRE(temperature > 0.f && box > 0.f, "mala_propose: temperature and box must be positive");
   if (B == 0) return DBS_OK;
@@ -210,6 +211,7 @@ extern "C" int dbs_mala_accept(float* pos, float* force, float* energy, const fl
                                const float* energy_new, const float* uniforms, int64_t B, int N, float dt,
                                float temperature, uint64_t seed, int64_t cfg_offset, int64_t step, int* accepted,
                                void* stream) {
+  if (B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(pos && force && energy && pos_new && force_new && energy_new && B >= 0 && N >= 1, "mala_accept: bad arguments");
   if (B == 0) return DBS_OK;
   mala_accept_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(pos, force, energy, pos_new, force_new, energy_new,
@@ -223,6 +225,7 @@ extern "C" int dbs_mala_accept(float* pos, float* force, float* energy, const fl
 extern "C" int dbs_baoab_first(float* pos, float* vel, const float* force, const float* noise, int64_t B, int N,
                                float dt, float mass, float c1, float c2, float box, uint64_t seed, int64_t cfg_offset,
                                int64_t step, void* stream) {
+  if (B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(pos && vel && force && B >= 0 && N >= 1 && mass > 0.f && box > 0.f, "baoab_first: bad arguments");
   if (B == 0) return DBS_OK;
   const int64_t elems = 2 * (int64_t)N, total = B * ((elems + 3) / 4);
@@ -234,6 +237,7 @@ extern "C" int dbs_baoab_first(float* pos, float* vel, const float* force, const
 }
 
 extern "C" int dbs_baoab_second(float* vel, const float* force, int64_t B, int N, float dt, float mass, void* stream) {
+  if (B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(vel && force && B >= 0 && N >= 1 && mass > 0.f, "baoab_second: bad arguments");
   if (B == 0) return DBS_OK;
   const int64_t total = B * 2 * (int64_t)N;
@@ -244,6 +248,7 @@ extern "C" int dbs_baoab_second(float* vel, const float* force, int64_t B, int N
 
 extern "C" int dbs_rdf_histogram(const float* pos, int64_t B, int N, float box, const double* edges, int n_bins,
                                  unsigned long long* hist, void* stream) {
+  if (B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(pos && edges && hist && B >= 0 && N >= 2 && n_bins >= 1, "rdf_histogram: bad arguments");
   DBS_REQUIRE(N <= 8192 && n_bins <= 8192, "rdf_histogram: N and n_bins must be <= 8192");
   if (B == 0) return DBS_OK;

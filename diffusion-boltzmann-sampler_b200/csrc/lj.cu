@@ -236,6 +236,7 @@ using namespace dbs;
 extern "C" int dbs_lj_energy_forces(const float* pos, int64_t B, int N, float box, float epsilon, float sigma,
                                     float cutoff, float energy_shift, float* energy, float* forces,
                                     void* stream) {
+  if (B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   DBS_REQUIRE(pos && B >= 0, "lj: null positions");
   DBS_REQUIRE(N >= 1 && N <= 8192, "lj: n_particles %d unsupported (1..8192)", N);
   DBS_REQUIRE(box > 0.f, "lj: box_size must be positive");

@@ -1524,6 +1524,7 @@ extern "C" void dbs_unet_plan_destroy(dbs_unet_plan* plan) {
 }
 
 extern "C" int64_t dbs_unet_workspace_bytes(const dbs_unet_plan* plan, int64_t B, int H, int W, int precision) {
+  if (plan && B == 0) return 0;   // empty batch
   if (check_forward_args(plan, B, H, W, precision)) return -1;
   int64_t need = 0;
   // n_t = B sizes the time-bias block for the general per-sample-t call
@@ -1538,6 +1539,7 @@ extern "C" int64_t dbs_unet_workspace_bytes(const dbs_unet_plan* plan, int64_t B
 static int unet_forward_common(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_t, float* score,
                                int64_t B, int H, int W, int precision, void* workspace, int64_t workspace_bytes,
                                const char* tap, float* tap_out, int64_t tap_numel, void* stream) {
+  if (plan && B == 0) return DBS_OK;   // empty batch: nothing to do, pointers may be NULL
   int rc = check_forward_args(plan, B, H, W, precision);
   if (rc) return rc;
   DBS_REQUIRE(x && t && score, "unet_forward: null tensor");

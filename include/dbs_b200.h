@@ -55,6 +55,11 @@ int dbs_profile_read(double* ms, uint64_t* launches, int n, int reset);
 int dbs_profile_dump(const char* path);
 
 /* ------------------------------------------------------------------------- *
+ * Empty batches: every batched entry point returns DBS_OK for n_chains / n / B == 0 without touching its
+ * pointers (they may be NULL), as the reference's tensor code does for empty tensors.
+ * ------------------------------------------------------------------------- */
+
+/* ------------------------------------------------------------------------- *
  * Ising lattice state: bit-packed, 1 bit per spin (1 = +1, 0 = -1).
  * Layout: uint32 words[n_chains][L][W], W = ceil(L/32); bit (j%32) of word
  * (j/32) of row i is spin (i,j); unused high bits are zero.  4<=L<=128 (odd L from 5).
