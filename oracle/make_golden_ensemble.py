@@ -10,7 +10,7 @@ sample the same Boltzmann distribution with different dynamics: tests/test_ising
 ensembles within 3 sigma (north_star: "ensemble observables agree within statistical error").
 
 Run in the build container only (the reference does not exist on the GPU box), ~3 min on 8 cores:
-    python oracle/make_golden_ensemble.py
+    python oracle/make_golden_ensemble.py            (and with --odd: a 9x9 lattice -> ising_ensemble_odd.npz)
 Nothing from the reference is copied: only its outputs are stored.
 """
 import os
@@ -24,9 +24,14 @@ REF = os.environ.get("DBS_REFERENCE", "/root/reference")
 sys.path.insert(0, REF)
 sys.dont_write_bytecode = True
 
-L = 16
 # (T, n_chains, start, burn_in sweeps, measured sweeps)
-RUNS = [(2.269, 64, "hot", 200, 800), (1.5, 16, "cold", 100, 300), (3.5, 16, "hot", 100, 300)]
+if "--odd" in sys.argv:
+    # an odd lattice (the engine sweeps three colour classes there): python oracle/make_golden_ensemble.py --odd
+    L, OUT = 9, "ising_ensemble_odd.npz"
+    RUNS = [(2.269, 48, "hot", 150, 450), (1.5, 16, "cold", 100, 300), (3.5, 16, "hot", 100, 300)]
+else:
+    L, OUT = 16, "ising_ensemble.npz"
+    RUNS = [(2.269, 64, "hot", 200, 800), (1.5, 16, "cold", 100, 300), (3.5, 16, "hot", 100, 300)]
 
 
 def one_chain(job):
@@ -64,7 +69,7 @@ def main():
         sem = out[f"chains_{i}"].std(0, ddof=1) / np.sqrt(n)
         print(f"T={T}: E/N={mean[0]:.4f}+-{sem[0]:.4f} |M|={mean[1]:.4f}+-{sem[1]:.4f} "
               f"M2={mean[2]:.4f}+-{sem[2]:.4f} M4={mean[3]:.4f}+-{sem[3]:.4f}")
-    path = os.path.join(ROOT, "tests", "golden", "ising_ensemble.npz")
+    path = os.path.join(ROOT, "tests", "golden", OUT)
     np.savez_compressed(path, **out)
     print("wrote", path)
 

@@ -231,7 +231,8 @@ def test_mcmc_physics_envelopes():
     assert abs(e2 - (-1.7456)) < 0.02
 
 
-def test_ensemble_observables_vs_reference_chain():
+@pytest.mark.parametrize("fixture", ["ising_ensemble.npz", "ising_ensemble_odd.npz"])
+def test_ensemble_observables_vs_reference_chain(fixture):
     """north_star: "ensemble observables agree within statistical error".  tests/golden/ising_ensemble.npz holds per-chain
     time averages of E/N, |M|, M^2, M^4 from the UNMODIFIED reference's random-site Metropolis chain
     (oracle/make_golden_ensemble.py: BASELINE config 1 as-is — 16x16, T = 2.269, 64 chains, 1000 sweeps — plus
@@ -240,7 +241,7 @@ def test_ensemble_observables_vs_reference_chain():
     within 3.5 sigma of the combined standard error (chains are independent, so the chain-to-chain spread is the
     error whatever the autocorrelation time), and so does the Binder cumulant."""
     IsingModel, MetropolisHastings = _mods()
-    g = load_golden("ising_ensemble.npz")
+    g = load_golden(fixture)       # ..._odd: a 9x9 lattice, swept in three colour classes
     L = int(g["L"])
     m = IsingModel(L)
     n_eng = 4096
