@@ -622,6 +622,108 @@ ising_corr_warp_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chain
               (unsigned long long)(long long)s_acc[threadIdx.x]);
 }
 
+// Second cut of the warp-per-chain C(r) kernel: same half-plane visit order and the same integer sums, fewer
+// instructions per displacement.  (1) The partner rows are rotated by ONE column per step (two funnel shifts for a
+// 64-bit row) instead of by a fresh amount; (2) a lane adds its disagreement count straight into its own column of a
+// per-warp [bin][lane] table in shared memory (one conflict-free RED.shared) instead of carrying a running sum with a
+// warp reduction at every change of the radial bin — at small di the bin changes with every column; the 32 bins are
+// reduced once per chain; (3) the number of displacements per bin is a per-block table, not counted in the loop.
+template <bool k64>
+__device__ __forceinline__ uint64_t rot1_right_L(uint64_t v, int L) {
+  return k64 ? ((v >> 1) | (v << 63)) : ((v >> 1) | ((v & 1ull) << (L - 1)));
+}
+template <bool k64>
+__device__ __forceinline__ uint64_t rot1_left_L(uint64_t v, int L, uint64_t maskL) {
+  return k64 ? ((v << 1) | (v >> 63)) : (((v << 1) & maskL) | (v >> (L - 1)));
+}
+
+template <bool k64>
+__global__ void __launch_bounds__(32 * kCorrWarps)
+ising_corr_warp2_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chains, const int32_t* __restrict__ group,
+                        long long* __restrict__ acc) {
+  const int W = (L + 31) >> 5, R = L / 2;
+  __shared__ unsigned char s_bin[32 * 32];   // radial bin of (di, |dj|), di, |dj| < R; 255 = outside 0 < r < R
+  __shared__ int s_nd[32];                   // half-plane displacements per bin
+  __shared__ int s_part[kCorrWarps][32][32]; // [warp][bin][lane] disagreement counts
+  __shared__ int s_acc[32];
+  __shared__ int s_group;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 32) { s_acc[threadIdx.x] = 0; s_nd[threadIdx.x] = 0; }
+  for (int b = 0; b < 32; ++b) s_part[warp][b][lane] = 0;
+  __syncthreads();
+  for (int q = threadIdx.x; q < R * R; q += blockDim.x) {
+    const int di = q / R, dj = q - di * R;
+    const int x = di * di + dj * dj;
+    int rr = (int)sqrtf((float)x);
+    while (rr * rr > x) --rr;
+    while ((rr + 1) * (rr + 1) <= x) ++rr;
+    const bool in = rr > 0 && rr < R;
+    s_bin[q] = in ? (unsigned char)rr : 255;
+    // visits: di = 0: dj = 1..R-1 once; di > 0: dj = 0 once, +-dj twice
+    if (in) atomicAdd(&s_nd[rr], (di == 0 || dj == 0) ? 1 : 2);
+  }
+  const int64_t chain0 = (int64_t)blockIdx.x * kCorrWarps;
+  if (threadIdx.x == 0) s_group = group ? group[chain0] : 0;
+  __syncthreads();
+  const int64_t chain = chain0 + warp;
+  int mybin = 0;
+  int g = 0;
+  if (chain < n_chains) {
+    g = group ? group[chain] : 0;
+    const uint32_t* b = bits + chain * (int64_t)(L * W);
+    const uint64_t maskL = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+    uint64_t lo = 0, hi = 0;
+    if (lane < L) lo = W == 2 ? ((uint64_t)b[lane * 2] | ((uint64_t)b[lane * 2 + 1] << 32)) : (uint64_t)b[lane];
+    if (lane + 32 < L) hi = (uint64_t)b[(lane + 32) * 2] | ((uint64_t)b[(lane + 32) * 2 + 1] << 32);
+    const bool v0 = lane < L, v1 = lane + 32 < L;
+    int* part = &s_part[warp][0][lane];
+    for (int di = 0; di < R; ++di) {
+      int r0 = lane + di; if (r0 >= L) r0 -= L;
+      int r1 = lane + 32 + di; while (r1 >= L) r1 -= L;
+      const uint64_t a_lo = __shfl_sync(0xffffffffu, lo, r0 & 31), a_hi = __shfl_sync(0xffffffffu, hi, r0 & 31);
+      const uint64_t b_lo = __shfl_sync(0xffffffffu, lo, r1 & 31), b_hi = __shfl_sync(0xffffffffu, hi, r1 & 31);
+      // partner rows; zero where this lane holds no row, so such lanes count no disagreements (their own row is zero too)
+      const uint64_t sa = v0 ? (r0 >= 32 ? a_hi : a_lo) : 0ull;
+      const uint64_t sb = v1 ? (r1 >= 32 ? b_hi : b_lo) : 0ull;
+      const unsigned char* brow = s_bin + di * R;
+      {   // dj = k >= 0: bit j of the shifted row = bit (j + k) mod L
+        const int k0 = di == 0 ? 1 : 0;
+        uint64_t ra = sa, rb = sb;
+        if (k0) { ra = rot1_right_L<k64>(ra, L); rb = rot1_right_L<k64>(rb, L); }
+        for (int k = k0; k < R; ++k) {
+          const int bin = brow[k];
+          if (bin == 255) break;       // r >= R from here on (r = 0 only at di = dj = 0, which is never visited)
+          atomicAdd(part + bin * 32, __popcll(lo ^ ra) + __popcll(hi ^ rb));
+          ra = rot1_right_L<k64>(ra, L); rb = rot1_right_L<k64>(rb, L);
+        }
+      }
+      if (di > 0) {   // dj = -k: a right rotation by L - k = a left rotation by k
+        uint64_t ra = rot1_left_L<k64>(sa, L, maskL), rb = rot1_left_L<k64>(sb, L, maskL);
+        for (int k = 1; k < R; ++k) {
+          const int bin = brow[k];
+          if (bin == 255) break;
+          atomicAdd(part + bin * 32, __popcll(lo ^ ra) + __popcll(hi ^ rb));
+          ra = rot1_left_L<k64>(ra, L, maskL); rb = rot1_left_L<k64>(rb, L, maskL);
+        }
+      }
+    }
+    __syncwarp();
+    const int LL = L * L;
+    for (int bn = 1; bn < R; ++bn) {
+      const int tot = __reduce_add_sync(0xffffffffu, s_part[warp][bn][lane]);
+      if (lane == bn) mybin = 2 * (s_nd[bn] * LL - 2 * tot);
+    }
+  }
+  const bool shared_group = chain < n_chains && g == s_group;
+  if (shared_group && lane < R && mybin != 0) atomicAdd(&s_acc[lane], mybin);
+  if (chain < n_chains && !shared_group && lane < R && mybin != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (int64_t)g * R + lane), (unsigned long long)(long long)mybin);
+  __syncthreads();
+  if (threadIdx.x < R && s_acc[threadIdx.x] != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc + (int64_t)s_group * R + threadIdx.x),
+              (unsigned long long)(long long)s_acc[threadIdx.x]);
+}
+
 __global__ void obs_accumulate_kernel(const float* __restrict__ energy, const float* __restrict__ mag,
                                       double N, int64_t n, const int32_t* __restrict__ group,
                                       double* __restrict__ acc) {
@@ -772,8 +874,14 @@ extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chai
   static const bool warp_off = [] { const char* e = getenv("DBS_CORR_WARP"); return e && e[0] == '0'; }();
   if (!ref_mask && L <= 64 && !warp_off) {
     const unsigned grid = (unsigned)((n_chains + kCorrWarps - 1) / kCorrWarps);
-    if (L == 64) ising_corr_warp_kernel<true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
-    else ising_corr_warp_kernel<false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
+    static const bool v1 = [] { const char* e = getenv("DBS_CORR_V2"); return e && e[0] == '0'; }();
+    if (v1) {
+      if (L == 64) ising_corr_warp_kernel<true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
+      else ising_corr_warp_kernel<false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
+    } else {
+      if (L == 64) ising_corr_warp2_kernel<true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
+      else ising_corr_warp2_kernel<false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
+    }
     DBS_LAUNCHED();
     return DBS_OK;
   }
