@@ -38,6 +38,8 @@ struct SweepArgs {
   int L;
   int n_sweeps;
   int cpb;                      // chains per block
+  uint32_t rk[20];              // Philox round keys {seed_lo + r*W0, seed_hi + r*W1}, r = 0..9: read straight from the
+                                // kernel-parameter constant bank by the LOP3 of each round (no key-schedule adds in the loop)
   uint32_t one;                 // = 1, a run-time multiplier that keeps the compares on IMAD.WIDE (FMA pipe)
   int antiferro;                // zero-field mode: count disagreeing neighbours (J < 0)
 };
@@ -59,6 +61,28 @@ __device__ __forceinline__ uint32_t accept_mask(uint32_t r, uint32_t one, uint64
 }
 __device__ __forceinline__ uint64_t threshold_constant(uint32_t lo, uint32_t hi) {
   return hi ? 0xFFFFFFFF00000000ull : (0ull - (uint64_t)lo);
+}
+
+// b |= bit where r < t, as ISETP + one predicated LOP3 (the compiler's own choice is ISETP + SEL + a shared LOP3)
+__device__ __forceinline__ void or_if_less(uint32_t& b, uint32_t r, uint32_t t, uint32_t bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(b) : "r"(r), "r"(t), "r"(bit));
+}
+
+// Philox4x32-10 with the ten round-key pairs given (same function as philox4x32_10: key schedule precomputed on the host)
+__device__ __forceinline__ u32x4 philox4x32_10_rk(u32x4 c, const uint32_t (&rk)[20]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    mulhilo(kPhiloxM0, c.x, hi0, lo0);
+    mulhilo(kPhiloxM1, c.z, hi1, lo1);
+    u32x4 n;
+    n.x = hi1 ^ c.y ^ rk[2 * r];
+    n.y = lo1;
+    n.z = hi0 ^ c.w ^ rk[2 * r + 1];
+    n.w = lo0;
+    c = n;
+  }
+  return c;
 }
 
 // kMode 0: any (J, h): per-site class k = 8*s + #up-neighbours, 16-entry table lookup.
@@ -179,7 +203,7 @@ ising_sweep_kernel(SweepArgs a) {
               c.y = ctr_y;
               c.z = (uint32_t)(i * gpr + w * 4 + call);
               c.w = DBS_STREAM_SWEEP;
-              const u32x4 o = philox4x32_10(c, a.seed_lo, a.seed_hi);
+              const u32x4 o = philox4x32_10_rk(c, a.rk);
               rr[0] = o.x; rr[1] = o.y; rr[2] = o.z; rr[3] = o.w;
             }
 #pragma unroll
@@ -192,8 +216,8 @@ ising_sweep_kernel(SweepArgs a) {
               } else {
                 // plain compares here: with Philox already filling the FMA pipe with IMAD.WIDE, two more per
                 // site measured slower (946 vs 1054 Gflips/s at 64x64) than ISETP + predicated LOP on the ALU pipe
-                if (rr[d] < t4) b4 |= (1u << (2 * m));
-                if (rr[d] < t8) b8 |= (1u << (2 * m));
+                or_if_less(b4, rr[d], t4, 1u << (2 * m));
+                or_if_less(b8, rr[d], t8, 1u << (2 * m));
               }
             }
           }
@@ -828,6 +852,10 @@ extern "C" int dbs_ising_sweeps_strided(uint32_t* bits, int L, int64_t n_chains,
   a.bits = bits; a.thr = thr; a.table_index = table_index; a.uniforms = uniforms;
   a.n_chains = n_chains; a.chain_offset = chain_offset; a.chain_stride = chain_stride; a.sweep_offset = sweep_offset;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    a.rk[2 * r] = a.seed_lo + (uint32_t)r * kPhiloxW0;
+    a.rk[2 * r + 1] = a.seed_hi + (uint32_t)r * kPhiloxW1;
+  }
   a.L = L; a.n_sweeps = n_sweeps;
   a.one = 1u; a.antiferro = zero_field < 0 ? 1 : 0;
   const int tpc = dbs_ising_words_per_chain(L);
