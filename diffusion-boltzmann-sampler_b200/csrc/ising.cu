@@ -90,10 +90,16 @@ __device__ __forceinline__ u32x4 philox4x32_10_rk(u32x4 c, const uint32_t (&rk)[
 //          counted for all 32 sites of a word at once with a bit-sliced adder; only the two uphill
 //          classes (3 and 4 agreeing: dE = 4|J|, 8|J|) need a draw comparison, done against two per-chain
 //          constants: no table lookup, no per-site class extraction.
+#ifndef DBS_ISING_MINB
+#define DBS_ISING_MINB 8    // resident CTAs per SM the register cap is set for (build knob; sweep below)
+#endif
 template <int LT, bool kInject, int kMode>
-// 16/32/64-wide lattices run 128-thread CTAs: cap registers at 40 so 12 CTAs (48 warps) fit on an SM
-// (A/B/C-tested on a B200: 930 vs 907 Gflips/s uncapped; a 256-thread cap was slower, 816)
-__global__ void __launch_bounds__((LT == 16 || LT == 32 || LT == 64) ? 128 : 512, (LT == 16 || LT == 32 || LT == 64) ? 12 : 1)
+// 16/32/64-wide lattices run 128-thread CTAs.  Register cap, A/B-tested on a B200 with the final loop (64x64, 8192
+// chains): 12 CTAs/SM (40 registers: the compiler recomputes ~25 loop-invariant address / mask words per half-sweep)
+// 1225 Gflips/s, 10 CTAs (48) 1272, 8 CTAs (64 registers, everything hoisted) 1337, 7 / 6 CTAs 1332; 16x16 and 32x32
+// lattices gain the same way (1007 -> 1075, 1232 -> 1311).  The earlier loop (key-schedule adds inside) preferred 12
+// (930 vs 907 Gflips/s uncapped; a 256-thread CTA was slower, 816).
+__global__ void __launch_bounds__((LT == 16 || LT == 32 || LT == 64) ? 128 : 512, (LT == 16 || LT == 32 || LT == 64) ? DBS_ISING_MINB : 1)
 ising_sweep_kernel(SweepArgs a) {
   const int L = LT ? LT : a.L;
   const int W = (L + 31) >> 5;
@@ -142,16 +148,18 @@ ising_sweep_kernel(SweepArgs a) {
   const uint64_t* mytbl = tbl + lc * 16;
   // zero-field constants: classes (s=1, 3 or 4 up-neighbours) for J > 0, (s=1, 1 or 0) for J < 0 — same
   // dE as their s=0 mirror images
-  uint64_t c4 = 0, c8 = 0;
+  // the two thresholds as plain 32-bit compare operands plus an all-ones mask where the threshold rounds to "always"
+  // (c = 2^64 - thr, or the always / never codes); only these four words stay live in the sweep loop
+  uint32_t t4 = 0, t8 = 0, am4 = 0, am8 = 0;
   if (kMode == 1 && lc < cpb) {
-    c4 = mytbl[a.antiferro ? 8 + 1 : 8 + 3];
-    c8 = mytbl[a.antiferro ? 8 + 0 : 8 + 4];
+    const uint64_t c4 = mytbl[a.antiferro ? 8 + 1 : 8 + 3];
+    const uint64_t c8 = mytbl[a.antiferro ? 8 + 0 : 8 + 4];
+    const bool alw4 = (c4 >> 32) == 0xFFFFFFFFull && (uint32_t)c4 == 0u, alw8 = (c8 >> 32) == 0xFFFFFFFFull && (uint32_t)c8 == 0u;
+    t4 = alw4 ? 0u : (uint32_t)(0ull - c4); t8 = alw8 ? 0u : (uint32_t)(0ull - c8);
+    am4 = alw4 ? 0xffffffffu : 0u; am8 = alw8 ? 0xffffffffu : 0u;
   }
   const uint32_t one = a.one;
-  // the same two thresholds as plain 32-bit compare operands (c = 2^64 - thr, or the always / never codes)
-  const bool alw4 = (c4 >> 32) == 0xFFFFFFFFull && (uint32_t)c4 == 0u, alw8 = (c8 >> 32) == 0xFFFFFFFFull && (uint32_t)c8 == 0u;
-  const uint32_t t4 = alw4 ? 0u : (uint32_t)(0ull - c4), t8 = alw8 ? 0u : (uint32_t)(0ull - c8);
-  (void)t4; (void)t8; (void)one;
+  (void)t4; (void)t8; (void)am4; (void)am8; (void)one;
   const uint32_t chain_ctr = (uint32_t)(a.chain_offset + chain * a.chain_stride);
 
   uint32_t hs = 0;  // half-sweep counter inside this launch
@@ -222,14 +230,11 @@ ising_sweep_kernel(SweepArgs a) {
             }
           }
         }
-        if (kMode == 1) {   // thresholds that round to "always" (p == 1.0 in float64)
-          if (alw4) b4 = 0xffffffffu;
-          if (alw8) b8 = 0xffffffffu;
-        }
         if (kMode == 1) {
           // downhill / flat moves (count <= 2) always flip; counts 3 and 4 flip where the draw allowed it
+          // (am4 / am8: thresholds that round to "always", p == 1.0 in float64)
           const uint32_t up3 = is3 >> par, up4 = is4 >> par;
-          flips = ~(up3 | up4) | (up3 & b4) | (up4 & b8);
+          flips = ~(up3 | up4) | (up3 & (b4 | am4)) | (up4 & (b8 | am8));
         }
         const uint32_t amask = (par ? 0xAAAAAAAAu : 0x55555555u) & vmask;
         self ^= (flips << par) & amask;
