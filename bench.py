@@ -389,13 +389,13 @@ def bench_ising(peaks):
     out["roofline_streaming"] = {"bound": "hbm", "achieved": round(ach, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": round(ach / peaks["hbm_gbs"], 5), "bytes_per_attempt": 0.25,
                                  "note": "512 B lattices: launch/ALU bound by design, see DESIGN.md"}
-    # resident mode is INT-pipe bound: 18.6 thread-instructions per attempt (zero-field path; ncu smsp__inst_executed,
+    # resident mode is INT-pipe bound: 17.0 thread-instructions per attempt (zero-field path; ncu smsp__inst_executed,
     # profiles/README.md) against the issue peak of 148 SMs x 128 lanes x SM clock
-    ipa, sm_hz = 18.6, 1.965e9
+    ipa, sm_hz = 17.0, 1.965e9
     ach = out["resident"]["flips_per_s"] * ipa
     out["roofline_int"] = {"bound": "int-issue", "achieved": float(f"{ach:.4e}"), "peak": float(f"{148 * 128 * sm_hz:.4e}"),
                            "unit": "thread-instr/s", "frac": round(ach / (148 * 128 * sm_hz), 4),
-                           "instr_per_attempt": ipa, "alu_pipe_busy_pct_ncu": 63.9,
+                           "instr_per_attempt": ipa, "alu_pipe_busy_pct_ncu": 67.0,
                            "note": "HBM traffic ~0 by design (4 MB of state read once, written once per launch)"}
     out["metric"] = "ising_spin_flips_per_s"
     out["value"] = out["resident"]["flips_per_s"]
