@@ -1,14 +1,10 @@
 """Hot-path ML package: same import paths and class/method signatures as the reference's
-backend/ml (ml/__init__.py:16-36 re-exports), backed by libdbs_b200.so."""
-from .samplers.mcmc import MetropolisHastings
-from .samplers.diffusion import DiffusionSampler, PretrainedDiffusionSampler
-from .analysis import (pair_correlation, magnetization_distribution, autocorrelation_time, energy_histogram,
-                       compare_distributions, kl_divergence, symmetric_kl_divergence, magnetization_kl_divergence,
-                       energy_kl_divergence, wasserstein_distance_1d, magnetization_wasserstein, energy_wasserstein,
-                       correlation_function_comparison, comprehensive_comparison)
+backend/ml (ml/__init__.py:16-36 re-exports samplers and the Ising analysis), backed by libdbs_b200.so."""
+from . import analysis as _analysis, samplers as _samplers
+from .analysis.correlation import *  # noqa: F401,F403  (the fourteen Ising analysis functions)
 
-__all__ = ["MetropolisHastings", "DiffusionSampler", "PretrainedDiffusionSampler", "pair_correlation",
-           "magnetization_distribution", "autocorrelation_time", "energy_histogram", "compare_distributions",
-           "kl_divergence", "symmetric_kl_divergence", "magnetization_kl_divergence", "energy_kl_divergence",
-           "wasserstein_distance_1d", "magnetization_wasserstein", "energy_wasserstein",
-           "correlation_function_comparison", "comprehensive_comparison"]
+MetropolisHastings = _samplers.MetropolisHastings
+DiffusionSampler = _samplers.DiffusionSampler
+PretrainedDiffusionSampler = _samplers.PretrainedDiffusionSampler
+
+__all__ = ("MetropolisHastings", "DiffusionSampler", "PretrainedDiffusionSampler") + tuple(_analysis.correlation.__all__)

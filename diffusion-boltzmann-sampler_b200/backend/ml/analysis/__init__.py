@@ -1,15 +1,6 @@
-"""Same export list as the reference's analysis/__init__.py."""
-from .correlation import (pair_correlation, magnetization_distribution, autocorrelation_time, energy_histogram,
-                          compare_distributions, kl_divergence, symmetric_kl_divergence,
-                          magnetization_kl_divergence, energy_kl_divergence, wasserstein_distance_1d,
-                          magnetization_wasserstein, energy_wasserstein, correlation_function_comparison,
-                          comprehensive_comparison)
-from .rdf import compute_rdf, compute_rdf_from_system, rdf_statistics, compare_rdfs
+"""Ensemble analysis; exports exactly the names of the reference's analysis package (each submodule lists its own)."""
+from . import correlation as _correlation, rdf as _rdf
+from .correlation import *  # noqa: F401,F403
+from .rdf import *  # noqa: F401,F403
 
-__all__ = [
-    "pair_correlation", "magnetization_distribution", "autocorrelation_time", "energy_histogram",
-    "compare_distributions", "kl_divergence", "symmetric_kl_divergence", "magnetization_kl_divergence",
-    "energy_kl_divergence", "wasserstein_distance_1d", "magnetization_wasserstein", "energy_wasserstein",
-    "correlation_function_comparison", "comprehensive_comparison", "compute_rdf", "compute_rdf_from_system",
-    "rdf_statistics", "compare_rdfs",
-]
+__all__ = tuple(_correlation.__all__) + tuple(_rdf.__all__)

@@ -15,6 +15,11 @@ import torch
 from dbs_b200 import abi, runtime
 from ..systems.ising import IsingModel
 
+__all__ = ("pair_correlation", "magnetization_distribution", "autocorrelation_time", "energy_histogram",
+           "compare_distributions", "kl_divergence", "symmetric_kl_divergence", "magnetization_kl_divergence",
+           "energy_kl_divergence", "wasserstein_distance_1d", "magnetization_wasserstein", "energy_wasserstein",
+           "correlation_function_comparison", "comprehensive_comparison")
+
 
 
 def _displacement_counts(L: int) -> np.ndarray:

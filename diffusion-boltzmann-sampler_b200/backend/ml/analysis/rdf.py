@@ -8,6 +8,8 @@ import torch
 
 from dbs_b200 import abi, runtime
 
+__all__ = ("compute_rdf", "compute_rdf_from_system", "rdf_statistics", "compare_rdfs")
+
 
 def compute_rdf(positions: torch.Tensor, box_size: float, n_bins: int = 100, r_max: Optional[float] = None
                 ) -> Tuple[np.ndarray, np.ndarray]:

@@ -1,5 +1,8 @@
-from .base import PhysicalSystem
-from .ising import IsingModel
-from .lennard_jones import LennardJonesSystem
+"""Physical systems on the hot path; the names the reference's systems package exports."""
+from . import base as _base, ising as _ising, lennard_jones as _lj
 
-__all__ = ["PhysicalSystem", "IsingModel", "LennardJonesSystem"]
+PhysicalSystem = _base.PhysicalSystem
+IsingModel = _ising.IsingModel
+LennardJonesSystem = _lj.LennardJonesSystem
+
+__all__ = ("PhysicalSystem", "IsingModel", "LennardJonesSystem")
