@@ -103,7 +103,7 @@ class _Plan:
     def __del__(self):
         try:
             if self.handle:
-                abi.lib.dbs_csn_plan_destroy(self.handle)
+                runtime.release_plan(abi.lib.dbs_csn_plan_destroy, self.handle)   # deferred if this thread is capturing a graph
         except Exception:
             pass
 
@@ -140,6 +140,7 @@ class ContinuousScoreNetwork(nn.Module):
         ver = self._param_version()
         if self._plan is not None and self._plan.version == ver:
             return self._plan.handle
+        runtime.flush_released()    # plans whose finaliser ran during a graph capture
         sd = {k: v.detach().to(torch.float32).contiguous() for k, v in self.state_dict().items()}
         keep, arr = [], (abi.Param * len(sd))()
         for n, (k, v) in enumerate(sd.items()):

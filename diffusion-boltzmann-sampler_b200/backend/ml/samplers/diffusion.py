@@ -12,6 +12,7 @@ Additive keyword extensions: `precision` ("fp32" parity path | "bf16" tcgen05 pa
 `x0`/`noises` injection ports on `sample` (parity tests), `sample_offset` (multi-GPU sharding with
 global sample indices so results do not depend on the world size).
 """
+import gc
 import threading
 from typing import Any, Dict, Generator, Optional, Tuple
 
@@ -193,11 +194,20 @@ class DiffusionSampler:
                 # torch.cuda.graph captures on ONE process-wide side stream by default: two samplers capturing from
                 # two threads would begin a capture on a stream that is already capturing, so captures are serialised
                 # and each gets a stream of its own.
+                # The cyclic garbage collector may run finalisers (cudaFree of a dropped plan, ...) on whichever thread
+                # happens to allocate — also on this one in mid-capture, where they are not permitted: it is paused for
+                # the capture (plan finalisers additionally defer themselves, runtime.release_plan).
                 with _CAPTURE_LOCK:
-                    before = abi.launch_count()
-                    with torch.cuda.graph(graph, stream=torch.cuda.Stream(), capture_error_mode="thread_local"):
-                        self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
-                    graph.n_kernels = abi.launch_count() - before    # kernels recorded in this graph
+                    gc_was_on = gc.isenabled()
+                    gc.disable()
+                    try:
+                        before = abi.launch_count()
+                        with torch.cuda.graph(graph, stream=torch.cuda.Stream(), capture_error_mode="thread_local"):
+                            self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
+                        graph.n_kernels = abi.launch_count() - before    # kernels recorded in this graph
+                    finally:
+                        if gc_was_on:
+                            gc.enable()
             ent = (x, score, t_dev, graph)
             self._graphs[key] = ent
         return ent

@@ -1,9 +1,14 @@
 """Device plumbing shared by the reference-facing modules: torch is used for device memory and
 streams only.  Every compute entry point calls require_cuda() first, so a box without a B200
 fails loudly instead of computing anything on the host."""
+import threading
+
 import torch
 
 from . import abi
+
+_parked = []                       # (destroy_fn, handle) of plans whose release had to wait for a stream capture to end
+_parked_lock = threading.Lock()
 
 
 def require_cuda():
@@ -39,4 +44,34 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-__all__ = ["abi", "require_cuda", "current_stream", "to_device", "like_input", "ptr"]
+def _capturing():
+    try:
+        return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:              # interpreter shutdown
+        return False
+
+
+def flush_released():
+    """Free the plans parked by release_plan (no-op while this thread is capturing)."""
+    if _capturing():
+        return
+    with _parked_lock:
+        todo, _parked[:] = list(_parked), []
+    for destroy_fn, handle in todo:
+        destroy_fn(handle)
+
+
+def release_plan(destroy_fn, handle):
+    """Free an engine plan (cudaFree inside).  Python may run a plan's finaliser on ANY thread at ANY time — also on a
+    thread that is in the middle of a CUDA-graph capture, where cudaFree fails with "operation not permitted when
+    stream is capturing" and invalidates the capture.  Such handles are parked and freed by the next release or
+    plan build outside a capture."""
+    if _capturing():
+        with _parked_lock:
+            _parked.append((destroy_fn, handle))
+        return
+    flush_released()
+    destroy_fn(handle)
+
+
+__all__ = ["abi", "require_cuda", "current_stream", "to_device", "like_input", "ptr", "release_plan", "flush_released"]

@@ -1,7 +1,8 @@
 """Re-entrancy of the engine (SURVEY §8b "who calls it"): the FastAPI handlers run on the event-loop thread while
 training's generate_training_data calls MetropolisHastings.sample from a thread-pool thread (routes/training.py:191),
 so kernels of different jobs are in flight from several Python threads on several streams, and one thread may be
-capturing a CUDA graph while another allocates.  Every job must return exactly what it returns when run alone."""
+capturing a CUDA graph while another allocates or while the garbage collector finalises a dropped plan.  Every job must
+return exactly what it returns when run alone.  (Named zz so that it runs after the parity tests.)"""
 import threading
 
 import numpy as np
