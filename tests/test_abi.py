@@ -94,3 +94,20 @@ def test_module_surface_and_checkpoint_names():
     gs = load_golden("diffusion_scalar.npz")
     assert DiffusionProcess().sigma_table(100) == list(gs["sigma_N100"])
     assert DiffusionProcess(0.05, 12.0).sigma_table(50) == list(gs["sigma_alt_N50"])
+
+
+def test_plan_release_is_deferred_while_the_thread_captures(monkeypatch):
+    """runtime.release_plan: a plan finaliser that runs on a thread in mid-capture must not call cudaFree there; the
+    handle is parked and freed by the next release / plan build outside a capture (capture state simulated here)."""
+    from dbs_b200 import runtime
+    freed = []
+    monkeypatch.setattr(runtime, "_capturing", lambda: True)
+    runtime.release_plan(freed.append, 11)
+    runtime.release_plan(freed.append, 12)
+    runtime.flush_released()                       # still capturing: nothing may be freed
+    assert freed == [] and len(runtime._parked) == 2
+    monkeypatch.setattr(runtime, "_capturing", lambda: False)
+    runtime.release_plan(freed.append, 13)         # parked handles go first, then this one
+    assert freed == [11, 12, 13] and runtime._parked == []
+    runtime.flush_released()
+    assert freed == [11, 12, 13]
