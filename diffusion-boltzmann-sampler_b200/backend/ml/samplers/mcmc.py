@@ -91,7 +91,6 @@ class MetropolisHastings:
     def sweep(self, spins: torch.Tensor) -> torch.Tensor:
         """One sweep = L*L attempts (samplers/mcmc.py:52-60), done as one checkerboard sweep.
         Mutates and returns `spins` ((L, L) or (n, L, L))."""
-        L = self.model.size
         bits = self.model.pack(spins)
         self.sweeps_packed(bits, 1)
         out = self.model.unpack(bits)
@@ -136,7 +135,6 @@ class MetropolisHastings:
                                ) -> Generator[torch.Tensor, None, None]:
         """Yield the lattice after every sweep, first frame = the initial state
         (samplers/mcmc.py:99-124)."""
-        L = self.model.size
         bits = self._initial_bits(initial if initial is None or initial.dim() == 2 else initial[0], 1)
         yield self.model.unpack(bits)[0].cpu()
         for _ in range(n_steps):

@@ -56,7 +56,6 @@ class IsingModel:
         """(batch, L, L) of +/-1 (systems/ising.py:36-45).  The bits come from the engine's Philox
         INIT stream; `seed` defaults to a draw from torch's global generator so that
         torch.manual_seed() keeps the call reproducible.  Host tensor unless device='cuda'."""
-        L = self.size
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         bits = self.random_packed(batch_size, seed)
