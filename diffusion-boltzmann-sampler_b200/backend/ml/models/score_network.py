@@ -14,6 +14,7 @@ Two execution routes, chosen by autograd mode and never by hardware availability
     same network in PyTorch ops, so `loss.backward()` keeps working (backend/tests/test_models.py:225-260).
 """
 import ctypes
+import itertools
 import math
 import os
 
@@ -83,11 +84,16 @@ class ConvBlock(nn.Module):
         return h + self.residual_scale * self.residual(x)
 
 
+_PLAN_GENERATION = itertools.count(1)
+
+
 class _Plan:
-    """Owns a dbs_unet_plan* and frees it with the module."""
+    """Owns a dbs_unet_plan* and frees it with its last holder (the module, and every captured sampler step that
+    was recorded against it).  `generation` is unique per process and never re-used, unlike id()."""
 
     def __init__(self, handle, version):
         self.handle, self.version = handle, version
+        self.generation = next(_PLAN_GENERATION)
 
     def __del__(self):
         try:
@@ -163,17 +169,29 @@ class ScoreNetwork(nn.Module):
         self._plan = _Plan(handle, ver)
         return handle
 
-    def _get_workspace(self, plan, B, H, W, prec):
+    def _workspace_bytes(self, plan, B, H, W, prec):
         need = abi.lib.dbs_unet_workspace_bytes(plan, B, H, W, prec)
         if need < 0:
             abi.check(abi.ERR_INVALID, "unet_workspace_bytes")
+        return int(need)
+
+    def _get_workspace(self, plan, B, H, W, prec):
+        """The module's own scratch for EAGER forwards, regrown on demand.  Captured graphs never use it: a graph has
+        its workspace address baked into every kernel node, so each captured step owns one (engine_workspace)."""
+        need = self._workspace_bytes(plan, B, H, W, prec)
         ws = self._workspace
         if ws is None or ws.numel() < need or not ws.is_cuda:
-            ws = torch.empty(int(need), dtype=torch.uint8, device=runtime.require_cuda())
+            ws = torch.empty(need, dtype=torch.uint8, device=runtime.require_cuda())
             self._workspace = ws
         return ws
 
-    def engine_forward(self, x: torch.Tensor, t: torch.Tensor, precision=None, out=None, tap=None):
+    def engine_workspace(self, shape, precision=None) -> torch.Tensor:
+        """A fresh workspace for forwards of `shape`, owned by the caller (pass it as engine_forward(workspace=...))."""
+        B, _, H, W = shape
+        need = self._workspace_bytes(self.engine_plan(), B, H, W, PRECISIONS[precision or self.precision])
+        return torch.empty(max(need, 16), dtype=torch.uint8, device=runtime.require_cuda())
+
+    def engine_forward(self, x: torch.Tensor, t: torch.Tensor, precision=None, out=None, tap=None, workspace=None):
         """score (and optionally one named intermediate, fp32 NCHW) from the sm_100a kernels.
         x (B,1,H,W) fp32, t (B,) or (1,) fp32; device tensors in -> device tensor out."""
         prec = PRECISIONS[precision or self.precision]
@@ -187,7 +205,7 @@ class ScoreNetwork(nn.Module):
             raise ValueError(f"t must have 1 or {B} entries, got {td.numel()}")
         if td.numel() == B and B > 1 and bool((td == td[0]).all()):
             td = td[:1].contiguous()  # the sampler's case: one shared time (samplers/diffusion.py:223)
-        ws = self._get_workspace(plan, B, H, W, prec)
+        ws = workspace if workspace is not None else self._get_workspace(plan, B, H, W, prec)
         score = out if out is not None else torch.empty_like(xd)
         if tap is None:
             abi.check(abi.lib.dbs_unet_forward(plan, xd.data_ptr(), td.data_ptr(), td.numel(), score.data_ptr(), B, H,

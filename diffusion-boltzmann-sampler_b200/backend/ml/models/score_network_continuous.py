@@ -12,6 +12,7 @@ shared-memory attention kernel); with autograd enabled the differentiable PyTorc
 used (training is outside the engine's scope).  Without a B200 the engine route raises.
 """
 import ctypes
+import itertools
 import math
 import os
 
@@ -96,9 +97,13 @@ class ParticleAttention(nn.Module):
         return self.proj((w @ v).transpose(1, 2).reshape(b, n, self.hidden_dim)) + x
 
 
+_PLAN_GENERATION = itertools.count(1)
+
+
 class _Plan:
     def __init__(self, handle, version):
         self.handle, self.version = handle, version
+        self.generation = next(_PLAN_GENERATION)   # unique per process, never re-used (unlike id())
 
     def __del__(self):
         try:
@@ -157,7 +162,16 @@ class ContinuousScoreNetwork(nn.Module):
         self._plan = _Plan(handle, ver)
         return handle
 
-    def engine_forward(self, x: torch.Tensor, t: torch.Tensor, precision=None, out=None):
+    def engine_workspace(self, shape, precision=None) -> torch.Tensor:
+        """A fresh workspace for forwards of `shape` = (B, N, 2), owned by the caller (captured graphs bake the
+        address into their kernel nodes, so each captured sampler step owns one; sized for per-sample t)."""
+        B, N, _ = shape
+        need = abi.lib.dbs_csn_workspace_bytes(self.engine_plan(), B, N, B)
+        if need < 0:
+            abi.check(abi.ERR_INVALID, "csn_workspace_bytes")
+        return torch.empty(max(int(need), 16), dtype=torch.uint8, device=runtime.require_cuda())
+
+    def engine_forward(self, x: torch.Tensor, t: torch.Tensor, precision=None, out=None, workspace=None):
         """score from the sm_100a kernels.  x (B, N, 2) fp32, t (B,) or (1,); device tensors in -> device
         tensor out.  precision: "fp32" (default; CUDA-core parity path) or "bf16" (tcgen05 path for the MLP and
         attention layers: hidden_dim 128, head_dim 32, N a multiple of 16 up to 256)."""
@@ -177,9 +191,13 @@ class ContinuousScoreNetwork(nn.Module):
         need = abi.lib.dbs_csn_workspace_bytes(plan, B, N, td.numel())
         if need < 0:
             abi.check(abi.ERR_INVALID, "csn_workspace_bytes")
-        ws = self._workspace
-        if ws is None or ws.numel() < need or not ws.is_cuda:
-            ws = self._workspace = torch.empty(int(need), dtype=torch.uint8, device=xd.device)
+        ws = workspace
+        if ws is None:
+            ws = self._workspace     # eager forwards only; captured graphs pass the workspace they own
+            if ws is None or ws.numel() < need or not ws.is_cuda:
+                ws = self._workspace = torch.empty(int(need), dtype=torch.uint8, device=xd.device)
+        elif ws.numel() < need:
+            raise ValueError(f"engine_forward: workspace of {ws.numel()} bytes, {need} needed")
         score = out if out is not None else torch.empty_like(xd)
         abi.check(abi.lib.dbs_csn_forward(plan, xd.data_ptr(), td.data_ptr(), td.numel(), score.data_ptr(), B, N, prec,
                                           ws.data_ptr(), ws.numel(), runtime.current_stream()), "csn_forward")

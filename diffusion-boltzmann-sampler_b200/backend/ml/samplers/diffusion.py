@@ -22,12 +22,145 @@ import torch
 from dbs_b200 import abi, runtime
 from ..models.diffusion import DiffusionProcess
 
-_CAPTURE_LOCK = threading.Lock()   # CUDA-graph captures of different samplers never overlap (see _graph_step)
+_CAPTURE_LOCK = threading.Lock()   # CUDA-graph captures of different samplers never overlap (see _StepProgram)
 
 
 def _f32(v: float) -> float:
     """A Python float after rounding to fp32 — what `python_float * fp32_tensor` multiplies by."""
     return float(np.float32(v))
+
+
+class _StepProgram:
+    """One sampler step as a captured CUDA graph, with everything the graph's kernel nodes point at.
+
+    The step's scalars (times, sigma^2 dt, noise scales, Philox step ids) are row k of a device table; the graph begins
+    with dbs_step_table_next, which copies the row selected by a device counter into `cur` — where the U-Net reads
+    its time and the update kernels their coefficients — and advances the counter.  A trajectory is then N replays of
+    ONE graph: no per-step host-side parameter updates, no eager launches, no host synchronisation
+    (the loops of samplers/diffusion.py:222-243, 425-449, 476-519).
+
+    Row layouts (fp32, STRIDE columns; ids are int32 bit patterns):
+      em    [t, c1, dt, c2, temperature, add_noise, step id]
+      pc    em columns, then per corrector step c: [temperature, active, step id] at 7 + 3 c
+      heun  [t0, t1, 1, a, 1, b0, b1]
+      rk4   [t0, t_half, t1, 1, a1, 1, a2, 1, a3, 1, b1, b2, b3, b4]
+    """
+    STRIDE = 20
+    MAX_CORRECTORS = 4
+
+    def __init__(self, sampler: "DiffusionSampler", method: str, shape, n_corr: int, snr: float, plan):
+        dev = runtime.require_cuda()
+        self.method, self.shape, self.plan = method, shape, plan
+        self.model, self.precision = sampler.model, sampler.precision
+        n = shape[0]
+        self.n, self.elems = n, int(np.prod(shape[1:]))
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x = torch.empty(shape, **f32)
+        n_aux = {"em": 1, "pc": 1, "heun": 3, "rk4": 5}[method]        # scores (+ the intermediate state)
+        self.aux = [torch.empty(shape, **f32) for _ in range(n_aux)]
+        self.table = torch.zeros((DiffusionSampler._TABLE_ROWS, self.STRIDE), **f32)
+        self.cur = torch.zeros(self.STRIDE, **f32)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seed_off = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.norms = torch.empty(max(n, 1), **f32)
+        self.cc = torch.empty(2, **f32)
+        self.n_corr, self.snr = n_corr, float(snr)
+        self.ws = self.model.engine_workspace(shape, self.precision)
+        self._stage = torch.empty((DiffusionSampler._TABLE_ROWS, self.STRIDE), dtype=torch.float32).pin_memory()
+        self._issue()                      # warm-up: one-time function attributes, tensor-map encoder lookup
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        # thread_local: the capture records kernel launches only (workspace and buffers exist already), so CUDA calls of
+        # OTHER threads — an MCMC job on the server's thread pool allocating its lattices (routes/training.py:191) — must
+        # neither fail nor invalidate it, as they would in "global" mode.  torch.cuda.graph captures on ONE process-wide
+        # side stream by default: two samplers capturing from two threads would begin a capture on a stream that is
+        # already capturing, so captures are serialised and each gets a stream of its own.  The cyclic garbage collector
+        # may run finalisers (cudaFree of a dropped plan, ...) on whichever thread happens to allocate — also on this
+        # one in mid-capture, where they are not permitted: it is paused for the capture (plan finalisers additionally
+        # defer themselves, runtime.release_plan).
+        with _CAPTURE_LOCK:
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                before = abi.launch_count()
+                with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(), capture_error_mode="thread_local"):
+                    self._issue()
+                self.n_kernels = abi.launch_count() - before
+            finally:
+                if gc_was_on:
+                    gc.enable()
+
+    # ---- the step, as a sequence of engine launches on the current stream (captured once)
+    def _coef(self, off: int) -> int:
+        return self.cur.data_ptr() + 4 * off
+
+    def _forward(self, x, t_off: int, out):
+        self.model.engine_forward(x, self.cur[t_off:t_off + 1], precision=self.precision, out=out, workspace=self.ws)
+
+    def _lincomb(self, out, terms, coef_off: int):
+        import ctypes
+        ptrs = (ctypes.c_void_p * len(terms))(*[t.data_ptr() for t in terms])
+        abi.check(abi.lib.dbs_lincomb_dev(out.data_ptr(), out.numel(), len(terms), ptrs, self._coef(coef_off), 0,
+                                          runtime.current_stream()), "lincomb_dev")
+
+    def _issue(self):
+        st = runtime.current_stream()
+        x, a = self.x, self.aux
+        abi.check(abi.lib.dbs_step_table_next(self.cur.data_ptr(), self.table.data_ptr(), self.counter.data_ptr(),
+                                              self.STRIDE, st), "step_table_next")
+        if self.method in ("em", "pc"):
+            self._forward(x, 0, a[0])
+            abi.check(abi.lib.dbs_em_step_dev(x.data_ptr(), a[0].data_ptr(), self.n, self.elems, self._coef(1),
+                                              self.seed_off.data_ptr(), st), "em_step_dev")
+            for c in range(self.n_corr if self.method == "pc" else 0):
+                self._forward(x, 0, a[0])
+                abi.check(abi.lib.dbs_corrector_coef(a[0].data_ptr(), self.n, self.elems, self.snr, self.norms.data_ptr(),
+                                                     self.cc.data_ptr(), st), "corrector_coef")
+                abi.check(abi.lib.dbs_corrector_update(x.data_ptr(), a[0].data_ptr(), 0, self.n, self.elems,
+                                                       self.cc.data_ptr(), self._coef(7 + 3 * c), self.seed_off.data_ptr(),
+                                                       st), "corrector_update")
+        elif self.method == "heun":
+            s0, s1, x1 = a
+            self._forward(x, 0, s0)
+            self._lincomb(x1, [x, s0], 2)
+            self._forward(x1, 1, s1)
+            self._lincomb(x, [x, s0, s1], 4)
+        else:   # rk4
+            s1, s2, s3, s4, xt = a
+            self._forward(x, 0, s1)
+            self._lincomb(xt, [x, s1], 3)
+            self._forward(xt, 1, s2)
+            self._lincomb(xt, [x, s2], 5)
+            self._forward(xt, 1, s3)
+            self._lincomb(xt, [x, s3], 7)
+            self._forward(xt, 2, s4)
+            self._lincomb(x, [x, s1, s2, s3, s4], 9)
+
+    # ---- a trajectory: upload the table, reset the counter, replay once per row
+    def run(self, rows: np.ndarray, seed: int, sample_offset: int, x0, first_index: int, index_of):
+        x, n_rows = self.x, rows.shape[0]
+        if x0 is not None:
+            x.copy_(runtime.to_device(x0).reshape(self.shape))
+        else:
+            abi.check(abi.lib.dbs_gaussian_fill(x.data_ptr(), self.n, self.elems, seed, sample_offset, abi.STEP_X0,
+                                                runtime.current_stream()), "gaussian_fill")
+        s64 = seed & 0xFFFFFFFFFFFFFFFF        # the ABI's uint64 seed as the int64 bit pattern the device table holds
+        self.seed_off.copy_(torch.tensor([s64 - (1 << 64) if s64 >= (1 << 63) else s64, sample_offset], dtype=torch.int64))
+        yield first_index, x
+        cap = self.table.shape[0]
+        for seg in range(0, n_rows, cap):
+            m = min(cap, n_rows - seg)
+            if seg:
+                torch.cuda.current_stream().synchronize()     # the staging rows of the previous segment have been read
+            self._stage[:m, :rows.shape[1]].copy_(torch.from_numpy(rows[seg:seg + m]))
+            self.table[:m].copy_(self._stage[:m], non_blocking=True)
+            self.counter.zero_()
+            for k in range(seg, seg + m):
+                self.graph.replay()
+                self.sampler_launches += self.n_kernels
+                yield index_of(k), x
+
+    sampler_launches = 0     # kernels executed through replays of this program (launch accounting)
 
 
 class DiffusionSampler:
@@ -40,12 +173,17 @@ class DiffusionSampler:
         self.device = device
         self.precision = precision  # None -> the network's default (env DBS_PRECISION or fp32)
         self._training_temperature: Optional[float] = None
-        # One U-Net forward is ~70 kernel launches: the forward is captured once per shape into a CUDA
-        # graph and replayed every step (measured +7 % at batch 1024, +10 % at batch 1-8).
-        # True / False / "auto" (= True; kept as a switch for debugging).
+        # One U-Net forward is ~35 kernel launches: the whole step (forward + fused update, step scalars from a
+        # device table) is captured once per shape into a CUDA graph and replayed N times (_StepProgram).
+        # True / False / "auto" (= True; False = eager launches, kept for debugging and per-kernel profiling).
         self.use_graph = "auto"
         self._graphs: Dict[Any, Any] = {}
-        self.graph_kernel_launches = 0   # kernels executed through graph replays (for launch accounting)
+        self._launches_dropped = 0       # replayed kernels of programs that have left the cache
+
+    @property
+    def graph_kernel_launches(self) -> int:
+        """Kernels executed through graph replays (for launch accounting: abi.launch_count() sees eager launches only)."""
+        return self._launches_dropped + sum(p.sampler_launches for p in self._graphs.values())
 
     # ------------------------------------------------------------------ temperature scaling
     @property
@@ -163,62 +301,45 @@ class DiffusionSampler:
                                       runtime.current_stream()), "lincomb")
         return out
 
-    def _graph_step(self, shape):
-        """Persistent (x, score, t) buffers and, when enabled, a captured graph of one forward for
-        this shape.  Returns (x, score, t_dev, graph_or_None)."""
-        dev = runtime.require_cuda()
+    # ------------------------------------------------------------------ captured step programs
+    _TABLE_ROWS = 4096      # rows of a program's device step table (longer trajectories run in segments)
+    _MAX_PROGRAMS = 3       # programs (each owns a U-Net workspace) kept per sampler, least recently used dropped
+
+    def _graph_wanted(self) -> bool:
         want = self.use_graph
-        if want == "auto":
-            want = True
-        plan_version = None
+        return True if want == "auto" else bool(want)
+
+    def _program(self, method: str, shape, n_corr: int = 0, snr: float = 0.0) -> "_StepProgram":
+        """The captured step of `method` for this shape / precision / set of weights (built on first use).
+
+        A program owns everything its graph's kernel nodes point at — state and score buffers, the step table, the
+        U-Net workspace — and holds the model's plan object, so nothing a cached graph references can be freed or
+        re-used while the program is alive (a workspace shared with the model was regrown under cached graphs)."""
+        runtime.require_cuda()
+        plan = None
         if hasattr(self.model, "engine_plan"):
             self.model.engine_plan()
-            plan_version = id(self.model._plan)
-        key = (tuple(shape), self.precision, bool(want), plan_version, torch.cuda.current_device())
-        ent = self._graphs.get(key)
-        if ent is None:
-            self._graphs = {k: v for k, v in self._graphs.items() if k[3] == plan_version}  # drop stale plans
-            x = torch.empty(shape, dtype=torch.float32, device=dev)
-            score = torch.empty_like(x)
-            t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-            graph = None
-            if want and hasattr(self.model, "engine_forward") and shape[0] > 0:   # nothing to capture for an empty batch
-                x.zero_()
-                for _ in range(2):          # warm-up: workspace allocation, one-time function attributes
-                    self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                # thread_local: the capture records kernel launches only (workspace and buffers exist already), so
-                # CUDA calls of OTHER threads — an MCMC job on the server's thread pool allocating its lattices
-                # (routes/training.py:191) — must neither fail nor invalidate it, as they would in "global" mode.
-                # torch.cuda.graph captures on ONE process-wide side stream by default: two samplers capturing from
-                # two threads would begin a capture on a stream that is already capturing, so captures are serialised
-                # and each gets a stream of its own.
-                # The cyclic garbage collector may run finalisers (cudaFree of a dropped plan, ...) on whichever thread
-                # happens to allocate — also on this one in mid-capture, where they are not permitted: it is paused for
-                # the capture (plan finalisers additionally defer themselves, runtime.release_plan).
-                with _CAPTURE_LOCK:
-                    gc_was_on = gc.isenabled()
-                    gc.disable()
-                    try:
-                        before = abi.launch_count()
-                        with torch.cuda.graph(graph, stream=torch.cuda.Stream(), capture_error_mode="thread_local"):
-                            self.model.engine_forward(x, t_dev, precision=self.precision, out=score)
-                        graph.n_kernels = abi.launch_count() - before    # kernels recorded in this graph
-                    finally:
-                        if gc_was_on:
-                            gc.enable()
-            ent = (x, score, t_dev, graph)
-            self._graphs[key] = ent
-        return ent
+            plan = self.model._plan
+        key = (method, tuple(shape), self.precision, n_corr, float(snr), plan.generation if plan is not None else None,
+               torch.cuda.current_device())
+        prog = self._graphs.pop(key, None)
+        if prog is None:
+            # programs of superseded plans first (their weights are gone), then the least recently used
+            gen = key[5]
+            for k in [k for k in self._graphs if k[5] != gen]:
+                self._launches_dropped += self._graphs.pop(k).sampler_launches
+            while len(self._graphs) >= self._MAX_PROGRAMS:
+                self._launches_dropped += self._graphs.pop(next(iter(self._graphs))).sampler_launches
+            prog = _StepProgram(self, method, tuple(shape), n_corr, snr, plan)
+        self._graphs[key] = prog       # (re-)inserted last = most recently used
+        return prog
 
-    def _reverse_sde(self, shape, temperature, seed, x0=None, noises=None, sample_offset=0):
-        """Generator over the Euler–Maruyama trajectory: first (num_steps + 1, x_1) — the Gaussian
-        start — then (i, x) after step i = num_steps .. 1.  x is a persistent buffer updated in place
-        (callers copy what they keep)."""
-        runtime.require_cuda()
-        shape = tuple(shape)
-        x, score, t_dev, graph = self._graph_step(shape)
+    def _reverse_sde_eager(self, shape, temperature, seed, x0=None, noises=None, sample_offset=0):
+        """Euler–Maruyama trajectory with one eager launch sequence per step: the parity port (injected noise tensors)
+        and the un-captured reference for the step programs.  Yields like _reverse_sde."""
+        dev = runtime.require_cuda()
+        x = torch.empty(shape, dtype=torch.float32, device=dev)
+        score = torch.empty_like(x)
         if x0 is not None:
             x.copy_(runtime.to_device(x0).reshape(shape))
         else:
@@ -226,21 +347,43 @@ class DiffusionSampler:
             abi.check(abi.lib.dbs_gaussian_fill(x.data_ptr(), n, x.numel() // max(n, 1), seed, sample_offset, abi.STEP_X0,
                                                 runtime.current_stream()), "gaussian_fill")
         sig = self.diffusion.sigma_table(self.num_steps)
-        t_table = torch.tensor([i / self.num_steps for i in range(self.num_steps, 0, -1)], dtype=torch.float32,
-                               device=x.device)
         yield self.num_steps + 1, x
         for k, i in enumerate(range(self.num_steps, 0, -1)):
-            if graph is not None:
-                t_dev.copy_(t_table[k:k + 1])
-                graph.replay()
-                self.graph_kernel_launches += graph.n_kernels
-            else:
-                self._score(x, i / self.num_steps, out=score)
+            self._score(x, i / self.num_steps, out=score)
             nz = None
             if noises is not None and i > 1:
                 nz = runtime.to_device(noises[k])
             self._em(x, score, sig[k], temperature, i > 1, seed, i, noise=nz, sample_offset=sample_offset)
             yield i, x
+
+    def _em_rows(self, temperature: float, stochastic: bool = True) -> np.ndarray:
+        """Step table of the Euler–Maruyama loop: row k = step i = N - k."""
+        N = self.num_steps
+        dt = 1.0 / N
+        sig = self.diffusion.sigma_table(N)
+        rows = np.zeros((N, _StepProgram.STRIDE), dtype=np.float32)
+        steps = np.zeros(N, dtype=np.int32)
+        for k, i in enumerate(range(N, 0, -1)):
+            rows[k, 0] = i / N
+            rows[k, 1:5] = (_f32(sig[k] ** 2), _f32(dt), _f32(sig[k] * dt ** 0.5), _f32(temperature))
+            rows[k, 5] = 1.0 if (stochastic and i > 1) else 0.0
+            steps[k] = i
+        rows[:, 6] = steps.view(np.float32)
+        return rows
+
+    def _reverse_sde(self, shape, temperature, seed, x0=None, noises=None, sample_offset=0):
+        """Generator over the Euler–Maruyama trajectory: first (num_steps + 1, x_1) — the Gaussian
+        start — then (i, x) after step i = num_steps .. 1.  x is a persistent buffer updated in place
+        (callers copy what they keep).  One CUDA-graph replay per step: the forward, the fused update and the step's
+        scalars (device step table) are all inside the captured step."""
+        runtime.require_cuda()
+        shape = tuple(shape)
+        if noises is not None or not self._graph_wanted() or shape[0] == 0 or not hasattr(self.model, "engine_forward"):
+            yield from self._reverse_sde_eager(shape, temperature, seed, x0, noises, sample_offset)
+            return
+        prog = self._program("em", shape)
+        yield from prog.run(self._em_rows(temperature), seed, sample_offset, x0, first_index=self.num_steps + 1,
+                            index_of=lambda k: self.num_steps - k)
 
     # ------------------------------------------------------------------ samplers
     @torch.no_grad()
@@ -264,6 +407,78 @@ class DiffusionSampler:
                 yield self._result(x), 1.0
             elif i % yield_every == 0 or i == 1:
                 yield self._result(x), (i - 1) / self.num_steps
+
+    @torch.no_grad()
+    def stream_spin_frames(self, shape: Tuple[int, ...], temperature: float = 1.0, yield_every: int = 1,
+                           seed: Optional[int] = None, ring_slots: int = 8, ising_model=None
+                           ) -> Generator[Dict[str, Any], None, None]:
+        """Frame adaptor for streaming consumers (api/websocket.py:163-211 discretises every yielded state with
+        torch.sign and asks for its energy and magnetisation).  Same frame schedule as sample_with_trajectory, but a frame
+        is produced ON THE DEVICE — sign bits packed 1 bit per spin, E/N and M from the packed words — and copied
+        asynchronously into a pinned host ring; the sampling loop never waits for a frame.  A frame is handed out once
+        its copy has completed (or when the ring is full), so frames arrive in order, up to `ring_slots` emits late.
+
+        Yields {"bits": uint32 host array (B, L, W) [a ring slot: consume before `ring_slots` more frames],
+                "energy_per_spin": (B,), "magnetization": (B,), "t": float, "step": int, "frame": int}."""
+        from ..systems.ising import IsingModel
+        shape = tuple(shape)
+        B, L = shape[0], shape[-1]
+        if len(shape) != 4 or shape[1] != 1 or shape[2] != shape[3]:
+            raise ValueError("stream_spin_frames: shape must be (batch, 1, L, L)")
+        model = ising_model if ising_model is not None else IsingModel(L)
+        dev = runtime.require_cuda()
+        wpc = abi.lib.dbs_ising_words_per_chain(L)
+        if wpc < 0:
+            abi.check(abi.ERR_INVALID, "ising_words_per_chain")
+        slots = max(2, int(ring_slots))
+        bits_d = torch.empty((slots, B, wpc), dtype=torch.int32, device=dev)
+        obs_d = torch.empty((slots, 2, B), dtype=torch.float32, device=dev)
+        bits_h = torch.empty((slots, B, wpc), dtype=torch.int32).pin_memory()
+        obs_h = torch.empty((slots, 2, B), dtype=torch.float32).pin_memory()
+        events = [torch.cuda.Event() for _ in range(slots)]
+        pending = []                  # (slot, t, step, frame index) in emission order
+        seed = self._fresh_seed() if seed is None else seed
+        st = runtime.current_stream
+        n_frames = 0
+
+        def emit(x, t, step):
+            nonlocal n_frames
+            slot = n_frames % slots
+            abi.check(abi.lib.dbs_ising_pack(x.data_ptr(), bits_d[slot].data_ptr(), L, B, st()), "ising_pack")
+            abi.check(abi.lib.dbs_ising_observables(bits_d[slot].data_ptr(), L, B, float(model.J), float(model.h),
+                                                    obs_d[slot, 0].data_ptr(), obs_d[slot, 1].data_ptr(), st()),
+                      "ising_observables")
+            bits_h[slot].copy_(bits_d[slot], non_blocking=True)
+            obs_h[slot].copy_(obs_d[slot], non_blocking=True)
+            events[slot].record()
+            pending.append((slot, t, step, n_frames))
+            n_frames += 1
+
+        def take(block):
+            slot, t, step, idx = pending[0]
+            if not events[slot].query():
+                if not block:
+                    return None
+                events[slot].synchronize()
+            pending.pop(0)
+            return {"bits": bits_h[slot].numpy().view(np.uint32).reshape(B, L, -1),
+                    "energy_per_spin": (obs_h[slot, 0] / float(L * L)).numpy(), "magnetization": obs_h[slot, 1].numpy(),
+                    "t": t, "step": step, "frame": idx}
+
+        for i, x in self._reverse_sde(shape, temperature, seed):
+            due = i > self.num_steps or i % yield_every == 0 or i == 1
+            if due:
+                # the slot about to be overwritten must have been handed out
+                while len(pending) >= slots:
+                    yield take(True)
+                emit(x, 1.0 if i > self.num_steps else (i - 1) / self.num_steps, min(i, self.num_steps + 1) - 1)
+            while pending:
+                fr = take(False)
+                if fr is None:
+                    break
+                yield fr
+        while pending:
+            yield take(True)
 
     @torch.no_grad()
     def sample_trajectory_with_metadata(self, shape: Tuple[int, ...], temperature: float = 1.0, n_frames: int = 50,
@@ -297,36 +512,101 @@ class DiffusionSampler:
             elif (i - 1) in wanted or i == 1:
                 yield frame(x, i - 1)
 
-    @torch.no_grad()
-    def sample_predictor_corrector(self, shape: Tuple[int, ...], temperature: float = 1.0, n_corrector_steps: int = 1,
-                                   corrector_snr: float = 0.16, seed: Optional[int] = None) -> torch.Tensor:
-        """EM predictor + Langevin corrector (samplers/diffusion.py:399-451).  The corrector's
-        step size needs a batch-wide norm, so it is a device reduction followed by an axpy."""
-        seed = self._fresh_seed() if seed is None else seed
-        shape = tuple(shape)
+    def _pc_rows(self, temperature: float, n_corr: int) -> np.ndarray:
+        """Step table of the predictor-corrector loop: the Euler–Maruyama columns, then per corrector step
+        {temperature, active, Philox step id}; correctors are inactive at the final predictor step (i = 1)."""
         N = self.num_steps
-        noise_norm = (int(np.prod(shape[1:]))) ** 0.5
-        for i, x in self._reverse_sde(shape, temperature, seed):
-            if 1 < i <= N:
-                for c in range(n_corrector_steps):
-                    score = self._score(x, i / N)
-                    grad_norm = score.flatten(1).norm(dim=1).mean()
-                    step_size = (corrector_snr * noise_norm / grad_norm) ** 2 * 2
-                    z = self._gaussian(shape, seed, N + 1 + (N - i) * n_corrector_steps + c)
-                    x.add_(step_size * score + (2 * step_size) ** 0.5 * z * temperature)
-        return self._result(x)
+        rows = self._em_rows(temperature)
+        ids = np.zeros(N, dtype=np.int32)
+        for c in range(n_corr):
+            for k, i in enumerate(range(N, 0, -1)):
+                ids[k] = N + 1 + (N - i) * n_corr + c
+            rows[:, 7 + 3 * c] = _f32(temperature)
+            rows[:, 8 + 3 * c] = [1.0 if i > 1 else 0.0 for i in range(N, 0, -1)]
+            rows[:, 9 + 3 * c] = ids.view(np.float32)
+        return rows
 
     @torch.no_grad()
-    def sample_ode(self, shape: Tuple[int, ...], method: str = "euler", seed: Optional[int] = None) -> torch.Tensor:
+    def sample_predictor_corrector(self, shape: Tuple[int, ...], temperature: float = 1.0, n_corrector_steps: int = 1,
+                                   corrector_snr: float = 0.16, seed: Optional[int] = None, x0=None, noises=None,
+                                   corrector_noises=None) -> torch.Tensor:
+        """EM predictor + Langevin corrector (samplers/diffusion.py:399-451).  The corrector's step size needs a
+        batch-wide norm: a device reduction (dbs_corrector_coef) feeding the fused update, no host round trip, and the
+        whole predictor + corrector step is one captured graph.  `x0` / `noises` [N] / `corrector_noises`
+        [N][n_corrector_steps] are the parity ports (the reference's torch.randn draws in call order)."""
+        seed = self._fresh_seed() if seed is None else seed
+        shape = tuple(shape)
+        N, nc = self.num_steps, int(n_corrector_steps)
+        B = shape[0]
+        if B == 0:
+            return self._result(torch.empty(shape, dtype=torch.float32, device=runtime.require_cuda()))
+        if nc > _StepProgram.MAX_CORRECTORS:
+            raise NotImplementedError(f"predictor-corrector: at most {_StepProgram.MAX_CORRECTORS} corrector steps are built")
+        if noises is None and corrector_noises is None and self._graph_wanted() and hasattr(self.model, "engine_forward"):
+            prog = self._program("pc", shape, nc, corrector_snr)
+            x = None
+            for _, x in prog.run(self._pc_rows(temperature, nc), seed, 0, x0, first_index=N + 1, index_of=lambda k: N - k):
+                pass
+            return self._result(x)
+        # eager path (parity port / use_graph = False): the same kernels, launched step by step
+        elems = int(np.prod(shape[1:]))
+        dev = runtime.require_cuda()
+        norms = torch.empty(B, dtype=torch.float32, device=dev)
+        cc = torch.empty(2, dtype=torch.float32, device=dev)
+        seed_off = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+        rows = torch.from_numpy(self._pc_rows(temperature, nc)).to(dev)
+        score = None
+        for i, x in self._reverse_sde_eager(shape, temperature, seed, x0, noises):
+            if 1 < i <= N:
+                k = N - i
+                for c in range(nc):
+                    score = self._score(x, i / N, out=score)
+                    abi.check(abi.lib.dbs_corrector_coef(score.data_ptr(), B, elems, float(corrector_snr), norms.data_ptr(),
+                                                         cc.data_ptr(), runtime.current_stream()), "corrector_coef")
+                    nz = None if corrector_noises is None else runtime.to_device(corrector_noises[k][c])
+                    abi.check(abi.lib.dbs_corrector_update(x.data_ptr(), score.data_ptr(), runtime.ptr(nz), B, elems,
+                                                           cc.data_ptr(), rows[k, 7 + 3 * c:].data_ptr(),
+                                                           seed_off.data_ptr(), runtime.current_stream()), "corrector_update")
+        return self._result(x)
+
+    def _ode_rows(self, method: str) -> np.ndarray:
+        """Step tables of the deterministic integrators; sigma^2 products in fp32 as `python_float * fp32_tensor` does."""
+        N = self.num_steps
+        dt = 1.0 / N
+        rows = np.zeros((N, _StepProgram.STRIDE), dtype=np.float32)
+        for k, i in enumerate(range(N, 0, -1)):
+            t_val = i / N
+            if method == "heun":
+                c0, c1 = self._sigma(t_val) ** 2, self._sigma((i - 1) / N) ** 2
+                rows[k, :7] = (t_val, (i - 1) / N, 1.0, c0 * dt, 1.0, 0.5 * c0 * dt, 0.5 * c1 * dt)
+            else:
+                ca, cm, cb = self._sigma(t_val) ** 2, self._sigma(t_val - 0.5 * dt) ** 2, self._sigma(t_val - dt) ** 2
+                rows[k, :14] = (t_val, t_val - 0.5 * dt, t_val - dt, 1.0, 0.5 * dt * ca, 1.0, 0.5 * dt * cm, 1.0, dt * cm,
+                                1.0, dt / 6 * ca, dt / 3 * cm, dt / 3 * cm, dt / 6 * cb)
+        return rows
+
+    @torch.no_grad()
+    def sample_ode(self, shape: Tuple[int, ...], method: str = "euler", seed: Optional[int] = None, x0=None
+                   ) -> torch.Tensor:
         """Probability-flow style deterministic integrators: euler / heun / rk4
-        (samplers/diffusion.py:453-521)."""
+        (samplers/diffusion.py:453-521).  Each step — two (Heun) or four (RK4) forwards and the fused state
+        combinations between them — is one captured graph replayed N times."""
         if method not in ("euler", "heun", "rk4"):
             raise ValueError(f"Unknown ODE method: {method}")
         seed = self._fresh_seed() if seed is None else seed
         shape = tuple(shape)
         N = self.num_steps
         dt = 1.0 / N
-        x = self._gaussian(shape, seed, abi.STEP_X0)
+        if shape[0] > 0 and self._graph_wanted() and hasattr(self.model, "engine_forward"):
+            if method == "euler":
+                prog, rows = self._program("em", shape), self._em_rows(0.0, stochastic=False)
+            else:
+                prog, rows = self._program(method, shape), self._ode_rows(method)
+            x = None
+            for _, x in prog.run(rows, seed, 0, x0, first_index=N + 1, index_of=lambda k: N - k):
+                pass
+            return self._result(x)
+        x = self._gaussian(shape, seed, abi.STEP_X0) if x0 is None else runtime.to_device(x0).reshape(shape).clone()
         score = torch.empty_like(x)
 
         for i in range(N, 0, -1):

@@ -66,6 +66,11 @@ PROTOTYPES = {
     "dbs_em_step": (i32, [vp, vp, vp, i64, i64, f32, f32, f32, f32, i32, u64, i64, i64, vp]),
     "dbs_gaussian_fill": (i32, [vp, i64, i64, u64, i64, i64, vp]),
     "dbs_lincomb": (i32, [vp, i64, i32, vp, vp, i32, vp]),
+    "dbs_lincomb_dev": (i32, [vp, i64, i32, vp, vp, i32, vp]),
+    "dbs_step_table_next": (i32, [vp, vp, vp, i32, vp]),
+    "dbs_em_step_dev": (i32, [vp, vp, i64, i64, vp, vp, vp]),
+    "dbs_corrector_coef": (i32, [vp, i64, i64, C.c_double, vp, vp, vp]),
+    "dbs_corrector_update": (i32, [vp, vp, vp, i64, i64, vp, vp, vp, vp]),
     "dbs_lj_energy_forces": (i32, [vp, i64, i32, f32, f32, f32, f32, f32, vp, vp, vp]),
     "dbs_mala_propose": (i32, [vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, u64, i64, i64, vp]),
     "dbs_mala_accept": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, f32, u64, i64, i64, vp, vp]),

@@ -183,6 +183,35 @@ int dbs_gaussian_fill(float* x, int64_t n_samples, int64_t elems_per_sample, uin
 int dbs_lincomb(float* out, int64_t n, int n_terms, const float* const* x, const float* a,
                 int sign_first, void* stream);
 
+/* Same with device-resident coefficients (lincomb_dev) — see the step tables below. */
+int dbs_lincomb_dev(float* out, int64_t n, int n_terms, const float* const* x, const float* coef_dev,
+                    int sign_first, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Step tables for graph-captured sampler loops (the loops of samplers/diffusion.py:222-243,
+ * :425-449, :476-519).  The scalars of step k — times, sigma^2, noise scale, Philox step id ... — are row k of a
+ * DEVICE table; one captured CUDA graph of a step then serves the whole trajectory with no host-side parameter
+ * update and no host synchronisation.
+ *   dbs_step_table_next: cur[0..stride) = table[*counter * stride ...], then ++*counter (one tiny launch at the head
+ *                        of the captured step; the step's kernels read `cur`, the U-Net its time from cur + offset).
+ *   dbs_em_step_dev:     dbs_em_step with coef = {c1, dt, c2, temperature, add_noise (0/1), step id (int32 bits)} and
+ *                        seed_offset = {seed, sample_offset} (int64) read on the device.
+ *   dbs_corrector_coef:  Langevin corrector step size of samplers/diffusion.py:441-445 as a device reduction:
+ *                        g = mean_b ||score_b||_2, step = 2 * ((snr * sqrt(elems)) / g)^2; coef_out = {step, sqrt(2 step)};
+ *                        norms: scratch fp32 [B].
+ *   dbs_corrector_update: x <- (x + step*score) + ((sqrt(2 step)*z)*temperature), :447; step_size2 = coef_out above,
+ *                        coef = {temperature, active (0 = leave x untouched), step id (int32 bits)}; z from `noise`
+ *                        (injection port) or Philox(seed_offset).
+ * ------------------------------------------------------------------------- */
+int dbs_step_table_next(float* cur, const float* table, int* counter, int stride, void* stream);
+int dbs_em_step_dev(float* x, const float* score, int64_t n_samples, int64_t elems_per_sample,
+                    const float* coef, const int64_t* seed_offset, void* stream);
+int dbs_corrector_coef(const float* score, int64_t B, int64_t elems_per_sample, double snr, float* norms,
+                       float* coef_out, void* stream);
+int dbs_corrector_update(float* x, const float* score, const float* noise, int64_t n_samples,
+                         int64_t elems_per_sample, const float* step_size2, const float* coef,
+                         const int64_t* seed_offset, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Lennard-Jones pair energy / forces.  Replaces LennardJonesSystem.energy /
  * forces / pairwise_distances / minimum_image (systems/lennard_jones.py:58-155).

@@ -235,3 +235,28 @@ def pair_correlation(samples, ref_indices=None):
     c = np.divide(sums.astype(np.float64), counts.astype(np.float64), where=counts > 0,
                   out=np.zeros(len(sums), dtype=np.float64))
     return {"r": list(range(len(sums))), "C_r": c.tolist()}
+
+
+# --------------------------------------------------------------------------- the reference's own chain, as is
+def random_site_sweeps(spins, J, h, temperature, n_sweeps):
+    """MetropolisHastings.step / sweep exactly as the reference runs them (samplers/mcmc.py:26-60 with
+    IsingModel.local_energy_diff, systems/ising.py:68-91): one random site per attempt from the GLOBAL NumPy generator
+    (two randint calls), dE from five torch tensor reads, `dE <= 0` or `np.random.random() < np.exp(-beta * dE.item())`
+    (the uniform is drawn only when dE > 0), flip in place; a sweep is L*L such attempts.  `spins` is a torch fp32
+    (L, L) tensor of +/-1, updated in place and returned.  This is the CPU baseline timed for BASELINE configs 1 and 3
+    ("reference CPU path as-is"): same operations, same draw order, so under np.random.seed it reproduces the
+    reference's chain bit for bit (tests/golden/ising_random_site.npz)."""
+    L = spins.shape[-1]
+    beta = 1.0 / temperature if temperature > 0 else float("inf")
+    for _ in range(n_sweeps * L * L):
+        i = np.random.randint(L)
+        j = np.random.randint(L)
+        s = spins[..., i, j]
+        neighbors = (spins[..., (i + 1) % L, j] + spins[..., (i - 1) % L, j]
+                     + spins[..., i, (j + 1) % L] + spins[..., i, (j - 1) % L])
+        dE = 2 * s * (J * neighbors + h)
+        if dE <= 0:
+            spins[..., i, j] *= -1
+        elif np.random.random() < np.exp(-beta * dE.item()):
+            spins[..., i, j] *= -1
+    return spins

@@ -344,6 +344,117 @@ def test_ode_integrators_match_a_torch_restatement(method):
     assert _rel(got, x.numpy()) <= 1e-4
 
 
+@pytest.mark.parametrize("tag", ["pc", "pc1"])
+def test_predictor_corrector_vs_reference_golden_recorded_draws(tag):
+    """sample_predictor_corrector (samplers/diffusion.py:399-451) against the reference's own output with its recorded
+    torch.randn draws (predictor and corrector noises in call order, tests/golden/samplers_f4.npz): <= 1e-4 relative."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net, _ = _tiny_from_golden()
+    f4 = load_golden("samplers_f4.npz")
+    N, nc, snr, temp = f4[tag + "_meta"]
+    x0 = torch.tensor(f4[tag + "_x0"])
+    smp = DiffusionSampler(net, num_steps=int(N), precision="fp32")
+    out = smp.sample_predictor_corrector(tuple(x0.shape), temperature=float(temp), n_corrector_steps=int(nc),
+                                         corrector_snr=float(snr), x0=x0, noises=torch.tensor(f4[tag + "_noises"]),
+                                         corrector_noises=torch.tensor(f4[tag + "_corrector_noises"]))
+    assert _rel(out.numpy(), f4[tag + "_out"]) <= 1e-4
+
+
+@pytest.mark.parametrize("method", ["euler", "heun", "rk4"])
+@pytest.mark.parametrize("graph", [True, False])
+def test_ode_integrators_vs_reference_golden(method, graph):
+    """sample_ode against the reference's output from its recorded Gaussian start, through the captured step program
+    and through eager launches: <= 1e-4 relative."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net, _ = _tiny_from_golden()
+    f4 = load_golden("samplers_f4.npz")
+    x0 = torch.tensor(f4[f"ode_{method}_x0"])
+    smp = DiffusionSampler(net, num_steps=int(f4["ode_meta"][0]), precision="fp32")
+    smp.use_graph = graph
+    out = smp.sample_ode(tuple(x0.shape), method=method, x0=x0)
+    assert _rel(out.numpy(), f4[f"ode_{method}_out"]) <= 1e-4
+
+
+def test_captured_step_programs_equal_eager_launches():
+    """Every captured step program (EM, predictor-corrector with the device-side step-size reduction, Heun, RK4)
+    replays exactly the kernels of the eager loop with the same scalars and the same in-kernel Philox noise: bit-identical
+    states on the fp32 path; on the bf16 path the GroupNorm sums are accumulated with atomics (run-to-run summation order),
+    so two runs agree to rounding, not to the bit."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net(16, 32, 2, seed=3)
+    shape = (5, 1, 16, 16)
+
+    def same(a, b, prec):
+        if prec == "fp32":
+            return torch.equal(a, b)
+        return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()) <= 5e-3
+
+    for prec in ("fp32", "bf16"):
+        g = DiffusionSampler(net, num_steps=7, device="cuda", precision=prec)
+        e = DiffusionSampler(net, num_steps=7, device="cuda", precision=prec)
+        e.use_graph = False
+        assert same(g.sample(shape, seed=5, temperature=0.8, sample_offset=3),
+                    e.sample(shape, seed=5, temperature=0.8, sample_offset=3), prec)
+        assert same(g.sample_predictor_corrector(shape, seed=6, n_corrector_steps=2, corrector_snr=0.2),
+                    e.sample_predictor_corrector(shape, seed=6, n_corrector_steps=2, corrector_snr=0.2), prec)
+        for m in ("euler", "heun", "rk4"):
+            assert same(g.sample_ode(shape, method=m, seed=7), e.sample_ode(shape, method=m, seed=7), prec), m
+        assert g.graph_kernel_launches > 0 and e.graph_kernel_launches == 0
+
+
+def test_graph_cache_survives_shape_changes_and_weight_updates():
+    """Each captured step owns its buffers and U-Net workspace and pins the plan it was recorded against: sampling shape
+    A, a larger B, then A again replays A's graph into memory it still owns (a workspace shared with the model was
+    regrown under cached graphs), and a weight update between calls builds a new program instead of replaying the old
+    plan's graph."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net(16, 32, 2, seed=8)
+    smp = DiffusionSampler(net, num_steps=5, device="cuda", precision="fp32")     # fp32: deterministic to the bit
+    ref = DiffusionSampler(net, num_steps=5, device="cuda", precision="fp32")
+    ref.use_graph = False
+    small, large = (4, 1, 16, 16), (64, 1, 32, 32)
+    a0 = smp.sample(small, seed=1)
+    junk = [torch.full((1 << 20,), float("nan"), device="cuda") for _ in range(8)]   # lands in any freed block
+    b0 = smp.sample(large, seed=2)
+    a1 = smp.sample(small, seed=1)
+    assert torch.equal(a0, a1) and torch.equal(a0, ref.sample(small, seed=1)) and torch.equal(b0, ref.sample(large, seed=2))
+    del junk
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.01)
+    with torch.no_grad():
+        net(torch.randn(2, 1, 16, 16), torch.rand(2))            # plan rebuilt outside the sampler
+        for p in net.parameters():
+            p.mul_(0.99)
+    a2 = smp.sample(small, seed=1)                                 # and again at the next sample
+    assert torch.equal(a2, ref.sample(small, seed=1)) and not torch.equal(a2, a0)
+    assert len(smp._graphs) <= smp._MAX_PROGRAMS
+
+
+def test_spin_frame_stream_matches_the_trajectory():
+    """stream_spin_frames (the consumer is api/websocket.py:163-211: sign, energy_per_spin, magnetization per frame):
+    packed frames from the pinned ring equal sign(x) of sample_with_trajectory's states, observables those of the
+    Ising model on them, in order, for a ring smaller than the number of frames."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    from backend.ml.systems.ising import IsingModel
+    net = _net(16, 32, 2, seed=4)
+    shape, N = (3, 1, 16, 16), 12
+    smp = DiffusionSampler(net, num_steps=N, precision="fp32")
+    model = IsingModel(16)
+    states = list(smp.sample_with_trajectory(shape, yield_every=2, seed=21))
+    frames = []
+    for fr in smp.stream_spin_frames(shape, yield_every=2, seed=21, ring_slots=3):
+        frames.append({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in fr.items()})
+    assert len(frames) == len(states) and [f["frame"] for f in frames] == list(range(len(states)))
+    for fr, (x, t) in zip(frames, states):
+        assert fr["t"] == t
+        spins = torch.where(x[:, 0] > 0, 1.0, -1.0)
+        bits = ((fr["bits"][:, :, 0][:, :, None] >> np.arange(16)[None, None, :]) & 1).astype(np.float32) * 2 - 1
+        assert np.array_equal(bits, spins.numpy())
+        np.testing.assert_allclose(fr["energy_per_spin"], model.energy_per_spin(spins).cpu().numpy(), rtol=1e-6)
+        np.testing.assert_allclose(fr["magnetization"], model.magnetization(spins).cpu().numpy(), rtol=1e-6)
+
+
 def test_lincomb_kernel_and_heuristic_sampler():
     from backend.ml.samplers.diffusion import DiffusionSampler, PretrainedDiffusionSampler
     torch.manual_seed(0)
