@@ -67,6 +67,7 @@ class _StepProgram:
         self.n_corr, self.snr = n_corr, float(snr)
         self.ws = self.model.engine_workspace(shape, self.precision)
         self._stage = torch.empty((DiffusionSampler._TABLE_ROWS, self.STRIDE), dtype=torch.float32).pin_memory()
+        self._seed_stage = torch.zeros(2, dtype=torch.int64).pin_memory()
         self._issue()                      # warm-up: one-time function attributes, tensor-map encoder lookup
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -137,28 +138,40 @@ class _StepProgram:
             self._lincomb(x, [x, s1, s2, s3, s4], 9)
 
     # ---- a trajectory: upload the table, reset the counter, replay once per row
-    def run(self, rows: np.ndarray, seed: int, sample_offset: int, x0, first_index: int, index_of):
-        x, n_rows = self.x, rows.shape[0]
+    def begin(self, rows: np.ndarray, seed: int, sample_offset: int, x0):
+        """Initial state (Gaussian start or the caller's x0), the Philox key, and the first table segment, on the current
+        stream."""
+        x = self.x
         if x0 is not None:
-            x.copy_(runtime.to_device(x0).reshape(self.shape))
+            x.copy_(runtime.to_device(x0).reshape(self.shape), non_blocking=True)
         else:
             abi.check(abi.lib.dbs_gaussian_fill(x.data_ptr(), self.n, self.elems, seed, sample_offset, abi.STEP_X0,
                                                 runtime.current_stream()), "gaussian_fill")
         s64 = seed & 0xFFFFFFFFFFFFFFFF        # the ABI's uint64 seed as the int64 bit pattern the device table holds
-        self.seed_off.copy_(torch.tensor([s64 - (1 << 64) if s64 >= (1 << 63) else s64, sample_offset], dtype=torch.int64))
-        yield first_index, x
-        cap = self.table.shape[0]
-        for seg in range(0, n_rows, cap):
-            m = min(cap, n_rows - seg)
-            if seg:
-                torch.cuda.current_stream().synchronize()     # the staging rows of the previous segment have been read
-            self._stage[:m, :rows.shape[1]].copy_(torch.from_numpy(rows[seg:seg + m]))
+        self._seed_stage[0] = s64 - (1 << 64) if s64 >= (1 << 63) else s64
+        self._seed_stage[1] = sample_offset
+        self.seed_off.copy_(self._seed_stage, non_blocking=True)
+        self._rows, self._next = rows, 0
+
+    def step(self):
+        """Replay the captured step for the next row (uploading the next table segment when the previous one is used up)."""
+        k, cap = self._next, self.table.shape[0]
+        if k % cap == 0:
+            m = min(cap, self._rows.shape[0] - k)
+            torch.cuda.current_stream().synchronize()     # the staging rows of the previous trajectory / segment have been read
+            self._stage[:m].copy_(torch.from_numpy(self._rows[k:k + m]))
             self.table[:m].copy_(self._stage[:m], non_blocking=True)
             self.counter.zero_()
-            for k in range(seg, seg + m):
-                self.graph.replay()
-                self.sampler_launches += self.n_kernels
-                yield index_of(k), x
+        self.graph.replay()
+        self.sampler_launches += self.n_kernels
+        self._next = k + 1
+
+    def run(self, rows: np.ndarray, seed: int, sample_offset: int, x0, first_index: int, index_of):
+        self.begin(rows, seed, sample_offset, x0)
+        yield first_index, self.x
+        for k in range(rows.shape[0]):
+            self.step()
+            yield index_of(k), self.x
 
     sampler_launches = 0     # kernels executed through replays of this program (launch accounting)
 
@@ -179,6 +192,11 @@ class DiffusionSampler:
         self.use_graph = "auto"
         self._graphs: Dict[Any, Any] = {}
         self._launches_dropped = 0       # replayed kernels of programs that have left the cache
+        # True: large bf16 batches run as two half-batch programs on two streams (see _sample_split).  Off by default:
+        # measured at the config-4 shape (profiles/README.md, round 2) the halves' kernels co-reside but a strip conv slows
+        # down under a co-running bandwidth-bound kernel by about what the overlap saves (12.8 vs 13.1 ms per step).
+        self.split_streams = False
+        self._streams = None
 
     @property
     def graph_kernel_launches(self) -> int:
@@ -303,13 +321,13 @@ class DiffusionSampler:
 
     # ------------------------------------------------------------------ captured step programs
     _TABLE_ROWS = 4096      # rows of a program's device step table (longer trajectories run in segments)
-    _MAX_PROGRAMS = 3       # programs (each owns a U-Net workspace) kept per sampler, least recently used dropped
+    _MAX_PROGRAMS = 4       # programs (each owns a U-Net workspace) kept per sampler, least recently used dropped
 
     def _graph_wanted(self) -> bool:
         want = self.use_graph
         return True if want == "auto" else bool(want)
 
-    def _program(self, method: str, shape, n_corr: int = 0, snr: float = 0.0) -> "_StepProgram":
+    def _program(self, method: str, shape, n_corr: int = 0, snr: float = 0.0, slot: int = 0) -> "_StepProgram":
         """The captured step of `method` for this shape / precision / set of weights (built on first use).
 
         A program owns everything its graph's kernel nodes point at — state and score buffers, the step table, the
@@ -321,7 +339,7 @@ class DiffusionSampler:
             self.model.engine_plan()
             plan = self.model._plan
         key = (method, tuple(shape), self.precision, n_corr, float(snr), plan.generation if plan is not None else None,
-               torch.cuda.current_device())
+               torch.cuda.current_device(), slot)
         prog = self._graphs.pop(key, None)
         if prog is None:
             # programs of superseded plans first (their weights are gone), then the least recently used
@@ -386,13 +404,62 @@ class DiffusionSampler:
                             index_of=lambda k: self.num_steps - k)
 
     # ------------------------------------------------------------------ samplers
+    # Two half-batch programs on two streams.  A conv CTA of the tcgen05 kernels owns its SM's shared memory but only
+    # half of its registers and a fraction of its issue slots, while GroupNorm apply / Euler-Maruyama / the init conv are
+    # HBM-bound kernels that need no shared memory: with the batch split in two independent trajectories, the memory-bound
+    # kernels of one half run UNDER the convs of the other half instead of between them (samples are independent, so
+    # the halves never synchronise until the end).  Threshold: each half must still fill the GPU with conv tiles.
+    SPLIT_MIN_PIXELS = 2 * 148 * 128 * 4      # per half: >= 4 tiles of 128 pixels per SM at full resolution
+
+    def _split_sizes(self, shape):
+        if not self.split_streams or not self._graph_wanted() or len(shape) != 4:
+            return None
+        b = shape[0]
+        pix = shape[2] * shape[3]
+        if self.precision != "bf16" or b < 2 or (b // 2) * pix < self.SPLIT_MIN_PIXELS:
+            return None
+        return (b + 1) // 2, b // 2
+
+    def _sample_split(self, shape, sizes, temperature, seed, x0, sample_offset):
+        main = torch.cuda.current_stream()
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        rows = self._em_rows(temperature)
+        progs, off = [], 0
+        for slot, (b, st) in enumerate(zip(sizes, self._streams)):
+            prog = self._program("em", (b,) + tuple(shape[1:]), slot=slot)
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                prog.begin(rows, seed, sample_offset + off, None if x0 is None else x0[off:off + b])
+            progs.append(prog)
+            off += b
+        for _ in range(self.num_steps):
+            for prog, st in zip(progs, self._streams):
+                with torch.cuda.stream(st):
+                    prog.step()
+        out = torch.empty(shape, dtype=torch.float32, device=progs[0].x.device)
+        off = 0
+        for prog, st in zip(progs, self._streams):
+            with torch.cuda.stream(st):
+                out[off:off + prog.n].copy_(prog.x, non_blocking=True)
+            off += prog.n
+            main.wait_stream(st)
+        out.record_stream(self._streams[0])
+        out.record_stream(self._streams[1])
+        return out
+
     @torch.no_grad()
     def sample(self, shape: Tuple[int, ...], temperature: float = 1.0, seed: Optional[int] = None, x0=None,
                noises=None, sample_offset: int = 0) -> torch.Tensor:
         """Euler–Maruyama reverse SDE (samplers/diffusion.py:197-245)."""
         seed = self._fresh_seed() if seed is None else seed
+        shape = tuple(shape)
+        sizes = self._split_sizes(shape) if (noises is None and hasattr(self.model, "engine_forward")) else None
+        if sizes is not None:
+            out = self._sample_split(shape, sizes, temperature, seed, x0, sample_offset)
+            return out if str(self.device).startswith("cuda") else out.cpu()
         x = None
-        for _, x in self._reverse_sde(tuple(shape), temperature, seed, x0, noises, sample_offset):
+        for _, x in self._reverse_sde(shape, temperature, seed, x0, noises, sample_offset):
             pass
         return self._result(x)
 

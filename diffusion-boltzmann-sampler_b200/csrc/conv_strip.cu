@@ -33,15 +33,23 @@ using namespace tc;
 using namespace tch;
 
 constexpr int kTileM = 128;
-// Epilogue warps: 16 (default) = four per TMEM lane quadrant, one 16-column chunk each, 96 registers per thread;
-// 8 (-DDBS_STRIP_EPI_WARPS=8) = two per quadrant with up to two chunks each and a 168-register cap.  Measured equal
-// within 1-2 % (conv 1.382 vs 1.373 ms per forward at C2): the drain is a latency chain per tile, not issue-bound, so
-// half the warps do the same work in the same time — the knob that buys register headroom for epilogue fusion.
+// Epilogue warps: 8 (default) = two per TMEM lane quadrant with up to two 16-column chunks each; 16
+// (-DDBS_STRIP_EPI_WARPS=16) = four per quadrant, one chunk each.  Measured equal within 1-2 % in round 1 (conv 1.382 vs
+// 1.373 ms per forward at C2): the drain is a latency chain per tile, not issue-bound, so half the warps do the same
+// work in the same time.  Eight warps at a 96-register cap leave half of the SM's register file free: the HBM-bound
+// kernels of the OTHER half-batch's stream (GroupNorm apply, Euler-Maruyama, init conv) become co-resident with a conv CTA
+// and run under it (samplers/diffusion.py: two half-batch programs on two streams).
 #ifndef DBS_STRIP_EPI_WARPS
 #define DBS_STRIP_EPI_WARPS 16
 #endif
-constexpr int kEpiWarps = DBS_STRIP_EPI_WARPS;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiWarpsDefault = DBS_STRIP_EPI_WARPS;
+// GroupNorm-prologue variants (kPre): 8 epilogue warps + kXW transform warps, 576 threads -> a 112-register cap.  The
+// epilogue of this kernel sits at its register cap with sixteen warps (96), so the prologue cannot live in the epilogue
+// warps (round-1 experiments, profiles/experiments/); dedicated warps with their own loop keep the per-channel
+// scale / shift / time-bias vector of a thread in registers and touch the epilogue only through issue slots.
+constexpr int kXW = 8;
+constexpr int kEpiWarpsPre = 8;
+__host__ __device__ constexpr int strip_threads(int ew, bool pre) { return 64 + 32 * ew + (pre ? 32 * kXW : 0); }
 constexpr int kMaxStages = 6;
 constexpr uint32_t kSmemBudget = 216 * 1024;   // + 1 KB alignment slack + 9 KB static = the 227 KB a CTA may use
 constexpr int kMaxCout = 512;             // Cout > 64 is processed as N tiles of 64 couts
@@ -78,8 +86,18 @@ struct StripParams {
   uint32_t a_bytes, slab_bytes, stage_bytes, w_region_bytes;
   uint32_t tmem_cols;
   uint64_t desc_hi;
+  // GroupNorm prologue (kPre kernels): the input strips are the RAW output of the block's first conv (plus, in the
+  // residual form, the block's residual in a second strip behind it); the transform warps rewrite each landed strip in
+  // shared memory as  SiLU(GN(y)) + time bias [+ residual]  (score_network.py:143-151) before the MMAs read it, so
+  // that activation never exists in HBM and its gn_apply launch disappears.  pre_stats: raw (sum, sumsq) per
+  // (sample, group) of the producing conv's output, [B][8][2].
+  const float *pre_stats, *pre_gamma, *pre_beta, *pre_tb;
+  int64_t pre_tb_stride;
+  float pre_inv_cnt;
+  int pre_H, pre_cg_log2, pre_rows, pre_res;
   int s2d_cpp;  // > 0: input read through the space-to-depth view, chunks per row parity (= 2C / KC), see ConvGeom::s2d
-  int dbg;  // diagnostics (env DBS_STRIP_DBG): 1 no MMA, 2 no epilogue body, 4 no stores, 8 no strip loads
+  int dbg;  // diagnostics (env DBS_STRIP_DBG): 1 no MMA, 2 no epilogue body, 4 no stores, 8 no strip loads, 128 MMA issuer ignores
+            // the TMEM-empty barrier, 512 epilogue ignores the TMEM-full barrier, 256 producer ignores the stage-empty barrier (timing experiments only: results are garbage)
 };
 
 
@@ -92,7 +110,8 @@ struct StripParams {
 template <int G, int MM>
 __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ring, uint32_t w_region, uint32_t tmem_base,
                                                uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tfull,
-                                               uint32_t bar_tempty, uint32_t bar_w, uint32_t bar_wfree, int n_it, int n_s) {
+                                               uint32_t bar_tempty, uint32_t bar_w, uint32_t bar_wfree, int n_it, int n_s,
+                                               uint32_t bar_xfull) {
   const int chunks = p.chunks0 + p.chunks1;
   const uint32_t row_bytes = (uint32_t)p.KC * 2;
   const uint32_t chunk_w_bytes = p.slab_bytes * p.n_slabs;
@@ -127,11 +146,14 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
     }
     const int as = it & 1;
     const uint32_t aphase = (it >> 1) & 1;
-    mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+    if (!(p.dbg & 128)) mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + as * acc_cols;
     for (int ch = 0; ch < chunks; ++ch) {
       mbar_wait(bar_full + 8 * stage, phase);
+      // GroupNorm prologue: the strip is ready once the transform warps have rewritten it (their generic-proxy stores
+      // are made visible to the tensor core's async-proxy reads by the fence.proxy.async they execute before arriving)
+      if (bar_xfull) mbar_wait(bar_xfull + 8 * stage, phase);
       tc_fence_after();
       const uint32_t a_base = ring + stage * p.stage_bytes;
       const uint32_t b_base = p.resident ? w_region + ch * chunk_w_bytes : a_base + ((p.a_bytes + 1023u) & ~1023u);
@@ -145,10 +167,10 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
             umma_bf16_lohi(d_tmem, a_lo + aoff[g] + 2 * k, b_lo + boff[g] + 2 * k, hi32, idesc[g], acc_flag(ch, g, k));
         }
       }
-      umma_commit(bar_empty + 8 * stage);
+      if (p.dbg & 1024) mbar_arrive(bar_empty + 8 * stage); else umma_commit(bar_empty + 8 * stage);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    umma_commit(bar_tfull + 8 * as);
+    if (p.dbg & 2048) mbar_arrive(bar_tfull + 8 * as); else umma_commit(bar_tfull + 8 * as);
     if (p.resident == 2 && --pass_left == 0) umma_commit(bar_wfree);   // the pass's MMAs no longer read the weights
   }
 }
@@ -156,14 +178,22 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
 // kStats: accumulate GroupNorm(8) sums; NCH = Nb / 16 column chunks.  kWide = false: Cout <= 64, group
 // width Cg = 2 * NCH <= 8 (several groups per chunk); kWide = true: Cout >= 128, Cg >= 16 (a chunk lies
 // inside one group).
-template <bool kStats, int NCH, bool kWide>
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ float strip_silu(float x) {   // same form as gn_apply's bf16 path (unet.cu)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);       // sigmoid(x); the caller multiplies by x (and adds the time bias in the same FMA)
+}
+
+template <bool kStats, int NCH, bool kWide, int kEpiWarps = kEpiWarpsDefault, bool kPre = false>
+__global__ void __launch_bounds__(strip_threads(kEpiWarps, kPre), (kEpiWarps <= 8 && !kPre) ? 2 : 1)   // <= 8 warps: cap at 96 registers
 conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wr,
                   const __grid_constant__ StripParams p) {
+  constexpr int kThreads = strip_threads(kEpiWarps, kPre);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 6];
+  __shared__ __align__(8) uint64_t bars[3 * kMaxStages + 6];
+  __shared__ __align__(16) float s_tab[kPre ? 3 : 1][kPre ? 256 : 4];   // kPre: scale / shift / time bias per input channel
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_bias[kMaxCout];
   __shared__ __align__(16) float s_bias_r[kMaxCout];
@@ -178,11 +208,13 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   const uint32_t bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
   const uint32_t bar_w = smem_u32(&bars[2 * kMaxStages + 4]);
   const uint32_t bar_wfree = smem_u32(&bars[2 * kMaxStages + 5]);
+  const uint32_t bar_xfull = smem_u32(&bars[2 * kMaxStages + 6]);   // kPre: strip rewritten, the MMAs may read it
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
+      if (kPre) mbar_init(bar_xfull + 8 * s, kXW);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_tfull + 8 * s, 1);
@@ -257,7 +289,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         }
         const int co0 = nt * p.Nb;
         for (int ch = 0; ch < chunks; ++ch) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (!(p.dbg & 256)) mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t a_dst = ring + stage * p.stage_bytes;
           const uint32_t fb = bar_full + 8 * stage;
           if (p.dbg & 8) {
@@ -265,7 +297,9 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             continue;
           }
-          mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : chunk_w_bytes));
+          mbar_expect_tx(fb, p.a_bytes * (kPre && p.pre_res ? 2u : 1u) + (p.resident ? 0u : chunk_w_bytes));
+          if (kPre && p.pre_res)   // the block's residual for the same rows, [strip | residual strip] in one stage
+            tma_load_5d(a_dst + ((p.a_bytes + 1023u) & ~1023u), &map_in1, fb, ch * p.KC, 0, 0, h0 + p.dh_min, n);
           if (p.s2d_cpp) {
             // chunk -> (row parity py, channel offset inside the 2C-wide pixel pair)
             const int py = ch / p.s2d_cpp;
@@ -288,7 +322,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     if (lane == 0) {
       // ===================== MMA issuer =====================
 #define DBS_STRIP_ROLE(G, MM) \
-  strip_mma_role<G, MM>(p, ring, w_region, tmem_base, bar_full, bar_empty, bar_tfull, bar_tempty, bar_w, bar_wfree, n_it, n_s)
+  strip_mma_role<G, MM>(p, ring, w_region, tmem_base, bar_full, bar_empty, bar_tfull, bar_tempty, bar_w, bar_wfree, n_it, n_s, \
+                        kPre ? bar_xfull : 0u)
       const int mm = p.KC / 16;
       if (p.n_groups == 3 && mm == 4) DBS_STRIP_ROLE(3, 4);
       else if (p.n_groups == 3 && mm == 2) DBS_STRIP_ROLE(3, 2);
@@ -302,6 +337,90 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
 #undef DBS_STRIP_ROLE
     }
     __syncwarp();
+  } else if (kPre && warp >= 2 + kEpiWarps) {
+    // ===================== transform warps (GroupNorm prologue) =====================
+    // A thread owns ONE logical 16-byte channel vector (8 channels) of every pixel row it visits, so the vector's
+    // scale / shift / time bias stay in registers for a whole chunk; the strip is rewritten in place (the residual form
+    // reads the second strip of the stage).  Rows outside the image keep the TMA's zero fill: the conv pads the
+    // NORMALISED activation with zeros.
+    constexpr int nx = 32 * kXW;
+    const int xt = (int)threadIdx.x - 32 * (2 + kEpiWarps);
+    const int vpr = p.KC >> 3;                           // 16-byte vectors per pixel row of a chunk: 8 / 4 / 2
+    const int vlog = 31 - __clz(vpr), wlog = 31 - __clz(p.W);
+    const int v = xt & (vpr - 1);
+    const int pix0 = xt >> vlog, pstep = nx >> vlog;
+    const int xs = 3 - vlog;                             // swizzle XOR term = (row byte offset >> 7) = pix >> xs
+    const int n_pix = p.pre_rows * p.W;
+    const int Cin = p.chunks0 * p.KC;
+    const uint32_t res_off = (p.a_bytes + 1023u) & ~1023u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int cur_n = -1;
+    for (int it = 0; it < n_it; ++it) {
+      const int tile = tile_lo + it;                      // resident == 1: tile = image * tiles_h + row block
+      const int n_img = tile / p.tiles_h, h0 = (tile - n_img * p.tiles_h) * p.Ht;
+      if (n_img != cur_n) {
+        // every transform thread is done with the previous image's table before it is overwritten
+        asm volatile("bar.sync 8, %0;" ::"n"(nx) : "memory");
+        for (int c = xt; c < Cin; c += nx) {
+          const int gi = c >> p.pre_cg_log2;
+          const float s0 = __ldg(p.pre_stats + ((int64_t)n_img * 8 + gi) * 2), s1 = __ldg(p.pre_stats + ((int64_t)n_img * 8 + gi) * 2 + 1);
+          const float mean = s0 * p.pre_inv_cnt;
+          const float rstd = rsqrtf(fmaxf(s1 * p.pre_inv_cnt - mean * mean, 0.f) + 1e-5f);
+          const float a_ = rstd * __ldg(p.pre_gamma + c);
+          s_tab[0][c] = a_;
+          s_tab[1][c] = __ldg(p.pre_beta + c) - mean * a_;
+          s_tab[2][c] = p.pre_tb ? __ldg(p.pre_tb + (int64_t)n_img * p.pre_tb_stride + c) : 0.f;
+        }
+        asm volatile("bar.sync 8, %0;" ::"n"(nx) : "memory");
+        cur_n = n_img;
+      }
+      for (int ch = 0; ch < chunks; ++ch) {
+        float sc[8], sh[8], tb[8];
+        {
+          const int c0 = ch * p.KC + v * 8;
+          const float4 a0 = *reinterpret_cast<const float4*>(&s_tab[0][c0]), a1 = *reinterpret_cast<const float4*>(&s_tab[0][c0 + 4]);
+          const float4 b0 = *reinterpret_cast<const float4*>(&s_tab[1][c0]), b1 = *reinterpret_cast<const float4*>(&s_tab[1][c0 + 4]);
+          const float4 t0 = *reinterpret_cast<const float4*>(&s_tab[2][c0]), t1 = *reinterpret_cast<const float4*>(&s_tab[2][c0 + 4]);
+          sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+          sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+          tb[0] = t0.x; tb[1] = t0.y; tb[2] = t0.z; tb[3] = t0.w; tb[4] = t1.x; tb[5] = t1.y; tb[6] = t1.z; tb[7] = t1.w;
+        }
+        mbar_wait(bar_full + 8 * stage, phase);
+        uint8_t* base = smem + p.w_region_bytes + (size_t)stage * p.stage_bytes;
+#pragma unroll 2
+        for (int pix = pix0; pix < n_pix; pix += pstep) {
+          const int ih = h0 + p.dh_min + (pix >> wlog);
+          if (ih < 0 || ih >= p.pre_H) continue;
+          const int pc = v ^ ((pix >> xs) & (vpr - 1));    // physical position of my logical vector (hardware swizzle)
+          uint4* ptr = reinterpret_cast<uint4*>(base + ((((size_t)pix << vlog) + pc) << 4));
+          const uint4 q = *ptr;
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+          uint32_t r4[4] = {0u, 0u, 0u, 0u};
+          if (p.pre_res) {
+            const uint4 rq = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(ptr) + res_off);
+            r4[0] = rq.x; r4[1] = rq.y; r4[2] = rq.z; r4[3] = rq.w;
+          }
+          uint32_t o4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x0 = fmaf(__uint_as_float(w4[i] << 16), sc[2 * i], sh[2 * i]);
+            const float x1 = fmaf(__uint_as_float(w4[i] & 0xffff0000u), sc[2 * i + 1], sh[2 * i + 1]);
+            float y0 = fmaf(x0, strip_silu(x0), tb[2 * i]);
+            float y1 = fmaf(x1, strip_silu(x1), tb[2 * i + 1]);
+            if (p.pre_res) { y0 += __uint_as_float(r4[i] << 16); y1 += __uint_as_float(r4[i] & 0xffff0000u); }
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+            o4[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          *ptr = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+        // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_xfull + 8 * stage);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
   } else {
     // ===================== epilogue warps =====================
     // A warp's work per tile is one 16-column chunk of one TMEM lane quadrant, a latency-bound chain
@@ -377,7 +496,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       __nv_bfloat16* optr =
           p.out + (((int64_t)t_n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout + co0;
 
-      mbar_wait(bar_tfull + 8 * as, aphase);
+      if (!(p.dbg & 512)) mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       // outputs of this tile: 1, or 2 for a transposed-conv phase pair (never with statistics); idle warps: 0
@@ -509,8 +628,17 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
 
 int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1, const __nv_bfloat16* w,
                       const float* bias, __nv_bfloat16* out, float* stats, int groups, cudaStream_t st,
-                      const __nv_bfloat16* w_res, const float* bias_res, __nv_bfloat16* out_res) {
+                      const __nv_bfloat16* w_res, const float* bias_res, __nv_bfloat16* out_res, const GnFuse* pre,
+                      const float* pre_stats) {
   const bool fuse_res = w_res != nullptr;
+  // Measured (round 2, profiles/README.md): parity-green but break-even at best — the strip kernel is bound by shared-memory
+  // traffic (MMA operand reads + epilogue shuffles), and an in-place rewrite of every strip adds 2 x strip bytes to it —
+  // so the prologue is opt-in (DBS_GN_PROLOGUE=1); GroupNorm apply is instead overlapped with the other half-batch's convs.
+  static const bool pre_disabled = [] { const char* e = getenv("DBS_GN_PROLOGUE"); return !(e && e[0] == '1'); }();
+  if (pre && (pre_disabled || !pre_stats || !pre->gamma || !pre->beta || fuse_res || g.C1 != 0 || in1 != nullptr ||
+              g.out_stride != 1 || g.n_phases > 1 || g.s2d || g.n_taps != 9 || g.C0 > 256 || g.C0 % 16 ||
+              !is_pow2(g.C0 / 8)))
+    return DBS_ERR_UNSUPPORTED;
   const bool pairw = g.n_phases == 2;   // transposed-conv phase pair: taps [0, n_taps) = (ph, pw = 0), [n_taps, 2 n_taps) = (ph, 1)
   if (g.n_phases > 2) return DBS_ERR_UNSUPPORTED;   // all four phases merged: tile kernel only
   if (pairw && (fuse_res || stats || g.out_stride != 2 || g.n_taps != 4)) return DBS_ERR_UNSUPPORTED;
@@ -644,10 +772,13 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   // per pass (>= 2 stages: the alternative streams chunk_w bytes of weights with every a_pad-byte strip)
   static const int pass_env = [] { const char* e = getenv("DBS_STRIP_PASS"); return e ? atoi(e) : 1; }();
   const int sp_tiles = g.B * p.tiles_h;   // row blocks: the unit CTAs split in pass mode
-  if (p.n_tiles_n == 1 && all_w + 3 * a_pad <= kSmemBudget) {
+  // (the prologue variants carry 3 KB more static shared memory: the per-channel table and a third barrier set)
+  const uint32_t budget = pre ? kSmemBudget - 4096 : kSmemBudget;
+  const uint32_t strip_pad = pre && pre->res ? 2 * a_pad : a_pad;   // residual form: [raw strip | residual strip] per stage
+  if (p.n_tiles_n == 1 && all_w + 3 * strip_pad <= budget) {
     p.resident = 1;
     p.w_region_bytes = (all_w + 1023u) & ~1023u;
-    p.stage_bytes = a_pad;
+    p.stage_bytes = strip_pad;
   } else if (pass_env && p.n_tiles_n > 1 && all_w + (uint32_t)(pass_env >= 2 ? 2 : 3) * a_pad <= kSmemBudget &&
              sp_tiles >= num_sms()) {
     p.resident = 2;
@@ -661,7 +792,16 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   // space-to-depth stride-2 convs pay 78 % more MMA work for their zero taps: only worth it with resident weights
   // (64 channels: 45 vs 58 us; with streamed weights at 128 channels the tile kernel is faster, 37 vs 60 us)
   if (g.s2d && p.resident != 1) return DBS_ERR_UNSUPPORTED;
-  int stages = (int)((kSmemBudget - p.w_region_bytes) / p.stage_bytes);
+  if (pre) {
+    // GroupNorm prologue: layer weights resident (tile = image * tiles_h + row block)
+    if (p.resident != 1) return DBS_ERR_UNSUPPORTED;
+    p.pre_stats = pre_stats; p.pre_gamma = pre->gamma; p.pre_beta = pre->beta; p.pre_tb = pre->tb;
+    p.pre_tb_stride = pre->tb_stride;
+    p.pre_inv_cnt = 1.0f / (float)((int64_t)H * W * (g.C0 / 8));
+    p.pre_H = H; p.pre_rows = rows; p.pre_res = pre->res ? 1 : 0;
+    while ((1 << p.pre_cg_log2) < g.C0 / 8) ++p.pre_cg_log2;
+  }
+  int stages = (int)((budget - p.w_region_bytes) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return DBS_ERR_UNSUPPORTED;
   p.stages = stages;
@@ -680,6 +820,8 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   } else if ((rc = encode_act(enc, &m0, in0, g.C0, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
   if (g.C1 > 0) {
     if ((rc = encode_act(enc, &m1, in1, g.C1, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
+  } else if (pre && pre->res) {
+    if ((rc = encode_act(enc, &m1, pre->res, g.C0, H, W, g.B, 1, KC, W, rows, 1, sw))) return rc;
   } else {
     m1 = m0;
   }
@@ -702,6 +844,16 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   const bool wide = g.Cout > 64;
   if (wide && stats && (!is_pow2(p.Cg) || p.Cg < 16)) return DBS_ERR_UNSUPPORTED;
   Kern kern = table[stats ? 1 : 0][wide ? 3 : (nch == 1 ? 0 : (nch == 2 ? 1 : 2))];
+  // GroupNorm-prologue variants: [stats][NCH index], 8 epilogue warps + kXW transform warps
+  static const Kern pre_table[2][3] = {
+      {conv_strip_kernel<false, 1, false, kEpiWarpsPre, true>, conv_strip_kernel<false, 2, false, kEpiWarpsPre, true>,
+       conv_strip_kernel<false, 4, false, kEpiWarpsPre, true>},
+      {conv_strip_kernel<true, 1, false, kEpiWarpsPre, true>, conv_strip_kernel<true, 2, false, kEpiWarpsPre, true>,
+       conv_strip_kernel<true, 4, false, kEpiWarpsPre, true>}};
+  if (pre) {
+    if (wide || (nch != 1 && nch != 2 && nch != 4)) return DBS_ERR_UNSUPPORTED;
+    kern = pre_table[stats ? 1 : 0][nch == 1 ? 0 : (nch == 2 ? 1 : 2)];
+  }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -711,13 +863,20 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
                                                    (int)(kSmemBudget + 2048));
         if (e != cudaSuccess) attr_err = e;
       }
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 3; ++b) {
+        const cudaError_t e = cudaFuncSetAttribute(pre_table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(kSmemBudget - 4096 + 2048));
+        if (e != cudaSuccess) attr_err = e;
+      }
   });
   DBS_CUDA(attr_err);
   const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();   // resident == 2 has sp_tiles >= num_sms()
   prof_set_label("strip H%d W%d C%d+%d->%d taps%d os%d KC%d B%d res%d st%d%s%s", H, W, g.C0, g.C1, g.Cout, g.n_taps,
-                 g.out_stride, KC, g.B, p.resident, p.stages, fuse_res ? " +res1x1" : "", pairw ? " x2 phases" : "");
+                 g.out_stride, KC, g.B, p.resident, p.stages, fuse_res ? " +res1x1" : (pre ? (pre->res ? " gn+res>" : " gn>") : ""),
+                 pairw ? " x2 phases" : "");
   ProfScope prof(kProfConvTC, st);
-  kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, mwr, p);
+  kern<<<grid, strip_threads(pre ? kEpiWarpsPre : kEpiWarpsDefault, pre != nullptr), smem, st>>>(m0, m1, mw, mwr, p);
   DBS_LAUNCHED();
   return DBS_OK;
 }

@@ -1075,9 +1075,29 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     std::string nm = std::string(name) + ".conv1";
     if ((rc = maybe_tap<T>(c, nm.c_str(), ty, c.B, H, W, bw.cout))) return rc;
   }
-  if ((rc = run_gn<T>(c, ty, th, sd, bw.g1, bw.b1, bw.tb_off, true, (const T*)nullptr, H, W, bw.cout))) return rc;
-  if (c.use_tc && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
-  if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
+  // GroupNorm prologue: where the strip kernel keeps conv2's weights resident, conv2 reads conv1's RAW output and its
+  // transform warps normalise the strips in shared memory (SiLU(GN1) + time bias): the GN1 activation and its gn_apply
+  // launch vanish.  Needs a fresh statistics slice for conv2 while conv1's is still unread.
+  float* const stats1 = c.stats;
+  bool gn1_fused = false;
+  if (c.use_tc && sizeof(T) == 2 && sd && !c.tap && G == 8 && c.next_stats()) {
+    GnFuse pre{bw.g1, bw.b1, c.tbias + bw.tb_off, c.n_t == 1 ? 0 : (int64_t)c.plan->sumC, nullptr};
+    rc = conv_strip_launch(g2, (const __nv_bfloat16*)ty, nullptr, bw.conv2.w16, bw.conv2.bias, (__nv_bfloat16*)th, c.stats, G,
+                           c.st, nullptr, nullptr, nullptr, &pre, stats1);     // raw conv2 output -> th
+    if (rc == DBS_OK) { gn1_fused = true; sd = true; }
+    else if (rc != DBS_ERR_UNSUPPORTED) return rc;
+  }
+  T* const y2 = gn1_fused ? th : ty;       // raw conv2 output
+  if (!gn1_fused) {
+    // (a declined prologue attempt has already moved c.stats on to conv2's slice: GN1 reads conv1's)
+    float* const stats2 = c.stats;
+    c.stats = stats1;
+    rc = run_gn<T>(c, ty, th, sd, bw.g1, bw.b1, bw.tb_off, true, (const T*)nullptr, H, W, bw.cout);
+    c.stats = stats2;
+    if (rc) return rc;
+    if (c.use_tc && stats2 == stats1 && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+    if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
+  }
   const T* res = in0;
   if (bw.has_res) {
     if (!res_done) {
@@ -1087,11 +1107,11 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     res = tr;
   }
   if (c.defer && c.defer->want && sd && !c.tap) {
-    c.defer->done = true; c.defer->y = ty; c.defer->res = res; c.defer->gamma = bw.g2; c.defer->beta = bw.b2;
+    c.defer->done = true; c.defer->y = y2; c.defer->res = res; c.defer->gamma = bw.g2; c.defer->beta = bw.b2;
     c.defer->stats = c.stats;
     return DBS_OK;
   }
-  if ((rc = run_gn<T>(c, ty, out, sd, bw.g2, bw.b2, 0, false, res, H, W, bw.cout))) return rc;
+  if ((rc = run_gn<T>(c, y2, out, sd, bw.g2, bw.b2, 0, false, res, H, W, bw.cout))) return rc;
   return maybe_tap<T>(c, name, out, c.B, H, W, bw.cout);
 }
 

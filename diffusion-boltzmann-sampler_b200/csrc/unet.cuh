@@ -64,10 +64,14 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
 // when they fit.  Same contract as conv_tc_launch (DBS_ERR_UNSUPPORTED if not eligible).
 // With w_res != nullptr the ConvBlock's 1x1 residual conv of the SAME input (score_network.py:131,151) is
 // computed in the same pass (extra weight slab on the dh = 0 group, own accumulator, own output).
+// With pre != nullptr the input is the RAW output of a conv whose GroupNorm(8) sums are pre_stats [B][8][2]: dedicated
+// transform warps rewrite each landed strip in shared memory as SiLU(GN(.)) + time bias [+ pre->res] (pre->gamma / beta /
+// tb / res) before the MMAs read it — the GroupNorm prologue: the normalised activation never exists in HBM.
 int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloat16* in1,
                       const __nv_bfloat16* w, const float* bias, __nv_bfloat16* out, float* stats,
                       int groups, cudaStream_t st, const __nv_bfloat16* w_res = nullptr,
-                      const float* bias_res = nullptr, __nv_bfloat16* out_res = nullptr);
+                      const float* bias_res = nullptr, __nv_bfloat16* out_res = nullptr,
+                      const GnFuse* pre = nullptr, const float* pre_stats = nullptr);
 
 // geometry builders
 ConvGeom geom_conv(int B, int H, int W, int C0, int C1, int Cout, int ksize, int stride);

@@ -11,7 +11,7 @@ from dbs_b200 import abi
 import bench
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-Bs = [int(a) for a in sys.argv[2:]] or [1024, 128]
+Bs = [int(a) for a in sys.argv[2:] if int(a) > 0]
 torch.manual_seed(0)
 net = ScoreNetwork(1, 32, 64, 3).eval()
 t = torch.full((1,), 0.5, device="cuda")
@@ -47,6 +47,8 @@ print("=== graph-replayed sampler step (forward + EM), ms per EM step and whole-
 for B in [64, 128, 256, 512, 1024, 2048]:
     NS = 12
     smp = DiffusionSampler(net, num_steps=NS, device="cuda", precision="bf16")
+    if os.environ.get("SPLIT", "1") == "0":
+        smp.split_streams = False
     smp.sample((B, 1, L, L), seed=1)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

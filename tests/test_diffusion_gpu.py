@@ -431,6 +431,24 @@ def test_graph_cache_survives_shape_changes_and_weight_updates():
     assert len(smp._graphs) <= smp._MAX_PROGRAMS
 
 
+def test_two_stream_half_batch_split_equals_the_single_program():
+    """Opt-in (split_streams = True): large bf16 batches run as two half-batch programs on two streams (the memory-bound
+    kernels of one half under the convs of the other).  Samples are independent and carry global Philox indices, so the split changes nothing but the
+    summation order of the GroupNorm atomics: same samples to bf16 rounding, host and device x0 ports included."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net(16, 32, 2, seed=12)
+    shape = (81, 1, 64, 64)
+    a = DiffusionSampler(net, num_steps=4, device="cuda", precision="bf16")
+    a.split_streams = True
+    b = DiffusionSampler(net, num_steps=4, device="cuda", precision="bf16")
+    assert a._split_sizes(shape) == (41, 40) and b._split_sizes(shape) is None
+    for kw in (dict(seed=3, sample_offset=7), dict(seed=4, x0=torch.randn(shape)), dict(seed=5, x0=torch.randn(shape).cuda())):
+        xa, xb = a.sample(shape, **kw), b.sample(shape, **kw)
+        assert xa.shape == xb.shape and torch.isfinite(xa).all()
+        assert float((xa - xb).pow(2).mean().sqrt() / xb.pow(2).mean().sqrt()) <= 5e-3
+    assert len(a._graphs) == 2
+
+
 def test_spin_frame_stream_matches_the_trajectory():
     """stream_spin_frames (the consumer is api/websocket.py:163-211: sign, energy_per_spin, magnetization per frame):
     packed frames from the pinned ring equal sign(x) of sample_with_trajectory's states, observables those of the
