@@ -33,6 +33,15 @@ using namespace tc;
 using namespace tch;
 
 constexpr int kTileM = 128;
+// Timing experiments of round 2 (handshake toggles 128 / 256 / 512 / 1024 / 2048 of DBS_STRIP_DBG, epilogue-side stage
+// release DBS_STRIP_EPI_RELEASE) are compiled in only with -DDBS_STRIP_EXPERIMENTS: every extra kernel-parameter read in
+// the per-tile loops of the MMA issuer / epilogue is a constant-bank round trip on the critical path (measured: the
+// 64 -> 64 layer at 64x64 went from 204 to 247 us with the checks compiled in).
+#ifdef DBS_STRIP_EXPERIMENTS
+constexpr bool kExp = true;
+#else
+constexpr bool kExp = false;
+#endif
 // Epilogue warps: 8 (default) = two per TMEM lane quadrant with up to two 16-column chunks each; 16
 // (-DDBS_STRIP_EPI_WARPS=16) = four per quadrant, one chunk each.  Measured equal within 1-2 % in round 1 (conv 1.382 vs
 // 1.373 ms per forward at C2): the drain is a latency chain per tile, not issue-bound, so half the warps do the same
@@ -95,11 +104,19 @@ struct StripParams {
   int64_t pre_tb_stride;
   float pre_inv_cnt;
   int pre_H, pre_cg_log2, pre_rows, pre_res;
+  int epi_release;  // 1: the strip stage of a tile's LAST chunk is released by the epilogue (after the tile's TMEM-full
+                    // barrier, i.e. after its MMAs have read the operands) instead of by a second tcgen05.commit
   int s2d_cpp;  // > 0: input read through the space-to-depth view, chunks per row parity (= 2C / KC), see ConvGeom::s2d
   int dbg;  // diagnostics (env DBS_STRIP_DBG): 1 no MMA, 2 no epilogue body, 4 no stores, 8 no strip loads, 128 MMA issuer ignores
             // the TMEM-empty barrier, 512 epilogue ignores the TMEM-full barrier, 256 producer ignores the stage-empty barrier (timing experiments only: results are garbage)
 };
 
+
+// Pins a loop-invariant value in a register.  Without it the compiler re-reads kernel parameters from the constant bank
+// inside the per-tile loops of the single-thread roles, and every such read is a round trip on the role's critical path
+// (measured in round 2: five extra parameter checks in these loops cost 20 % of a layer's time).
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
 
 // MMA issuer role.  The taps of one vertical offset dh share their A rows, so their weight slabs
 // are stacked along N in shared memory ([dw = -1 | 0 | +1] x Nb couts) and ONE tcgen05.mma with
@@ -112,24 +129,26 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
                                                uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tfull,
                                                uint32_t bar_tempty, uint32_t bar_w, uint32_t bar_wfree, int n_it, int n_s,
                                                uint32_t bar_xfull) {
-  const int chunks = p.chunks0 + p.chunks1;
+  const int chunks = pin(p.chunks0 + p.chunks1);
   const uint32_t row_bytes = (uint32_t)p.KC * 2;
-  const uint32_t chunk_w_bytes = p.slab_bytes * p.n_slabs;
-  const int acc_cols = (p.nacc + p.has_res) * p.Nb;
-  const uint32_t lo_bits = (uint32_t)p.desc_hi;            // LBO field
-  const uint32_t hi32 = (uint32_t)(p.desc_hi >> 32);       // SBO, version, swizzle mode
+  const uint32_t chunk_w_bytes = pin(p.slab_bytes * p.n_slabs);
+  const int acc_cols = pin((p.nacc + p.has_res) * p.Nb);
+  const uint32_t lo_bits = pin((uint32_t)p.desc_hi);            // LBO field
+  const uint32_t hi32 = pin((uint32_t)(p.desc_hi >> 32));       // SBO, version, swizzle mode
+  const int resident = pin(p.resident), n_stages = pin(p.stages);
+  const uint32_t stage_bytes = pin(p.stage_bytes), b_in_stage = pin((p.a_bytes + 1023u) & ~1023u);
   uint32_t aoff[G], boff[G], idesc[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    aoff[g] = ((uint32_t)(p.grp_row[g] * p.W) * row_bytes) >> 4;
-    boff[g] = (p.slab_bytes * (uint32_t)p.grp_off[g]) >> 4;
-    idesc[g] = p.idesc_g[g];
+    aoff[g] = pin(((uint32_t)(p.grp_row[g] * p.W) * row_bytes) >> 4);
+    boff[g] = pin((p.slab_bytes * (uint32_t)p.grp_off[g]) >> 4);
+    idesc[g] = pin(p.idesc_g[g]);
   }
   // Zero-initialisation: the first MMA of a tile (chunk 0, group 0) overwrites the nacc tap slots.  With a
   // fused residual the widest group (dh = 0, nacc + 1 slabs) is issued FIRST so that the same overwrite also
   // covers the residual slot (the host orders the groups accordingly).
   auto acc_flag = [](int ch, int g, int k) -> uint32_t { return (ch == 0 && g == 0 && k == 0) ? 0u : 1u; };
-  if (p.resident == 1) {
+  if (resident == 1) {
     mbar_wait(bar_w, 0);
     tc_fence_after();
   }
@@ -138,7 +157,7 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
   int pass_left = 0;       // resident == 2: tiles left in the current pass
   uint32_t wphase = 0;
   for (int it = 0; it < n_it; ++it) {
-    if (p.resident == 2 && pass_left == 0) {   // a new pass: its n-tile's weights must have landed
+    if (resident == 2 && pass_left == 0) {   // a new pass: its n-tile's weights must have landed
       mbar_wait(bar_w, wphase);
       tc_fence_after();
       wphase ^= 1;
@@ -146,7 +165,7 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
     }
     const int as = it & 1;
     const uint32_t aphase = (it >> 1) & 1;
-    if (!(p.dbg & 128)) mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+    if (!(kExp && (kExp && (p.dbg & 128)))) mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + as * acc_cols;
     for (int ch = 0; ch < chunks; ++ch) {
@@ -155,11 +174,11 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
       // are made visible to the tensor core's async-proxy reads by the fence.proxy.async they execute before arriving)
       if (bar_xfull) mbar_wait(bar_xfull + 8 * stage, phase);
       tc_fence_after();
-      const uint32_t a_base = ring + stage * p.stage_bytes;
-      const uint32_t b_base = p.resident ? w_region + ch * chunk_w_bytes : a_base + ((p.a_bytes + 1023u) & ~1023u);
+      const uint32_t a_base = ring + stage * stage_bytes;
+      const uint32_t b_base = resident ? w_region + ch * chunk_w_bytes : a_base + b_in_stage;
       const uint32_t a_lo = lo_bits | ((a_base & 0x3FFFFu) >> 4);
       const uint32_t b_lo = lo_bits | ((b_base & 0x3FFFFu) >> 4);
-      if (!(p.dbg & 1)) {
+      if (!(kExp && (p.dbg & 1))) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
 #pragma unroll
@@ -167,11 +186,12 @@ __device__ __forceinline__ void strip_mma_role(const StripParams& p, uint32_t ri
             umma_bf16_lohi(d_tmem, a_lo + aoff[g] + 2 * k, b_lo + boff[g] + 2 * k, hi32, idesc[g], acc_flag(ch, g, k));
         }
       }
-      if (p.dbg & 1024) mbar_arrive(bar_empty + 8 * stage); else umma_commit(bar_empty + 8 * stage);
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      if (kExp && (kExp && (p.dbg & 1024))) mbar_arrive(bar_empty + 8 * stage);
+      else if (!(kExp && p.epi_release && ch == chunks - 1)) umma_commit(bar_empty + 8 * stage);
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
-    if (p.dbg & 2048) mbar_arrive(bar_tfull + 8 * as); else umma_commit(bar_tfull + 8 * as);
-    if (p.resident == 2 && --pass_left == 0) umma_commit(bar_wfree);   // the pass's MMAs no longer read the weights
+    if (kExp && (kExp && (p.dbg & 2048))) mbar_arrive(bar_tfull + 8 * as); else umma_commit(bar_tfull + 8 * as);
+    if (resident == 2 && --pass_left == 0) umma_commit(bar_wfree);   // the pass's MMAs no longer read the weights
   }
 }
 
@@ -265,55 +285,68 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             else tma_load_3d(dst, &map_wr, bar_w, ch * p.KC, co0, 0);
           }
       };
-      if (p.resident == 1) load_weights(0);  // n_tiles_n == 1 here
+      // loop invariants pinned in registers (see pin()): the producer's per-tile work is then address arithmetic only
+      const int resident = pin(p.resident), n_stages = pin(p.stages), tiles_h = pin(p.tiles_h), Ht = pin(p.Ht);
+      const int n_tiles_n = pin(p.n_tiles_n), Nb = pin(p.Nb), KC = pin(p.KC), chunks0 = pin(p.chunks0), dh_min = pin(p.dh_min);
+      const int s2d_cpp = pin(p.s2d_cpp), n_slabs = pin(p.n_slabs);
+      const uint32_t stage_bytes = pin(p.stage_bytes), b_in_stage = pin((p.a_bytes + 1023u) & ~1023u), slab_bytes = pin(p.slab_bytes);
+      const bool pre_res = kPre && p.pre_res;
+      const uint32_t tx_bytes = pin(p.a_bytes * (pre_res ? 2u : 1u) + (p.resident ? 0u : chunk_w_bytes));
+      if (resident == 1) load_weights(0);  // n_tiles_n == 1 here
       int stage = 0;
       uint32_t phase = 0;
-      const int per_img = p.n_tiles_n * p.tiles_h;
       int pass = 0, in_pass = 0;
+      // tile -> (image, n-tile, row block) kept incrementally: one division per CTA, none per tile
+      int n, nt, hb;
+      if (resident == 2) {
+        n = tile_lo / tiles_h; hb = tile_lo - n * tiles_h; nt = 0;
+      } else {
+        const int per_img = n_tiles_n * tiles_h;
+        n = tile_lo / per_img;
+        const int rem = tile_lo - n * per_img;
+        nt = rem / tiles_h;
+        hb = rem - nt * tiles_h;
+      }
+      const int n0 = n, hb0 = hb;
       for (int it = 0; it < n_it; ++it) {
-        int n, nt, h0;
-        if (p.resident == 2) {
-          if (in_pass == 0) {
-            // the previous pass's MMAs must be done with the weight region before it is overwritten
-            if (pass > 0) mbar_wait(bar_wfree, (uint32_t)(pass - 1) & 1u);
-            load_weights(pass * p.Nb);
-          }
-          const int sblk = tile_lo + in_pass;
-          n = sblk / p.tiles_h; h0 = (sblk - n * p.tiles_h) * p.Ht; nt = pass;
-          if (++in_pass == n_s) { in_pass = 0; ++pass; }
-        } else {
-          const int tile = tile_lo + it;
-          n = tile / per_img;
-          const int rem = tile - n * per_img;
-          nt = rem / p.tiles_h; h0 = (rem - nt * p.tiles_h) * p.Ht;
+        if (resident == 2 && in_pass == 0) {
+          // the previous pass's MMAs must be done with the weight region before it is overwritten
+          if (pass > 0) mbar_wait(bar_wfree, (uint32_t)(pass - 1) & 1u);
+          load_weights(pass * Nb);
         }
-        const int co0 = nt * p.Nb;
+        const int t_n = n, h0 = hb * Ht, co0 = nt * Nb;
+        if (resident == 2) {
+          if (++hb == tiles_h) { hb = 0; ++n; }
+          if (++in_pass == n_s) { in_pass = 0; ++pass; ++nt; n = n0; hb = hb0; }
+        } else {
+          if (++hb == tiles_h) { hb = 0; if (++nt == n_tiles_n) { nt = 0; ++n; } }
+        }
         for (int ch = 0; ch < chunks; ++ch) {
-          if (!(p.dbg & 256)) mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t a_dst = ring + stage * p.stage_bytes;
+          if (!(kExp && (p.dbg & 256))) mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t a_dst = ring + stage * stage_bytes;
           const uint32_t fb = bar_full + 8 * stage;
-          if (p.dbg & 8) {
+          if (kExp && (p.dbg & 8)) {
             mbar_arrive(fb);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
             continue;
           }
-          mbar_expect_tx(fb, p.a_bytes * (kPre && p.pre_res ? 2u : 1u) + (p.resident ? 0u : chunk_w_bytes));
-          if (kPre && p.pre_res)   // the block's residual for the same rows, [strip | residual strip] in one stage
-            tma_load_5d(a_dst + ((p.a_bytes + 1023u) & ~1023u), &map_in1, fb, ch * p.KC, 0, 0, h0 + p.dh_min, n);
-          if (p.s2d_cpp) {
+          mbar_expect_tx(fb, tx_bytes);
+          if (pre_res)   // the block's residual for the same rows, [strip | residual strip] in one stage
+            tma_load_5d(a_dst + b_in_stage, &map_in1, fb, ch * KC, 0, 0, h0 + dh_min, t_n);
+          if (s2d_cpp) {
             // chunk -> (row parity py, channel offset inside the 2C-wide pixel pair)
-            const int py = ch / p.s2d_cpp;
-            tma_load_5d(a_dst, &map_in0, fb, (ch - py * p.s2d_cpp) * p.KC, 0, py, h0 + p.dh_min, n);
-          } else if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, ch * p.KC, 0, 0, h0 + p.dh_min, n);
-          else tma_load_5d(a_dst, &map_in1, fb, (ch - p.chunks0) * p.KC, 0, 0, h0 + p.dh_min, n);
-          if (!p.resident) {
-            const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
-            for (int t = 0; t < p.n_slabs; ++t) {
-              if (p.slab_tap[t] >= 0) tma_load_3d(b_dst + t * p.slab_bytes, &map_w, fb, ch * p.KC, co0, p.slab_tap[t]);
-              else tma_load_3d(b_dst + t * p.slab_bytes, &map_wr, fb, ch * p.KC, co0, 0);
+            const int py = ch / s2d_cpp;
+            tma_load_5d(a_dst, &map_in0, fb, (ch - py * s2d_cpp) * KC, 0, py, h0 + dh_min, t_n);
+          } else if (ch < chunks0) tma_load_5d(a_dst, &map_in0, fb, ch * KC, 0, 0, h0 + dh_min, t_n);
+          else tma_load_5d(a_dst, &map_in1, fb, (ch - chunks0) * KC, 0, 0, h0 + dh_min, t_n);
+          if (!resident) {
+            const uint32_t b_dst = a_dst + b_in_stage;
+            for (int t = 0; t < n_slabs; ++t) {
+              if (p.slab_tap[t] >= 0) tma_load_3d(b_dst + t * slab_bytes, &map_w, fb, ch * KC, co0, p.slab_tap[t]);
+              else tma_load_3d(b_dst + t * slab_bytes, &map_wr, fb, ch * KC, co0, 0);
             }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -477,7 +510,12 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     }
     int in_pass = 0;
     int xb = 0;  // exchange-buffer parity, toggled per chunk (one named barrier per chunk suffices)
+    int rel_stage = -1;      // strip stage of the current tile's last chunk (epi_release)
     for (int it = 0; it < n_it; ++it) {
+      if (kExp && p.epi_release) {
+        rel_stage += chunks;
+        while (rel_stage >= p.stages) rel_stage -= p.stages;
+      }
       const int t_n = n, t_nt = nt, t_hb = hb;
       if (p.resident == 2) {
         if (++hb == p.tiles_h) { hb = 0; ++n; }
@@ -496,11 +534,13 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       __nv_bfloat16* optr =
           p.out + (((int64_t)t_n * p.Hout + (a * p.out_stride + p.oph)) * p.Wout + (wl * p.out_stride + p.opw)) * p.Cout + co0;
 
-      if (!(p.dbg & 512)) mbar_wait(bar_tfull + 8 * as, aphase);
+      if (!(kExp && (kExp && (p.dbg & 512)))) mbar_wait(bar_tfull + 8 * as, aphase);
       tc_fence_after();
+      // the tile's MMAs are complete: its last strip stage can be refilled (one elected thread of the warps on this tile)
+      if (kExp && p.epi_release && q == 0 && hsel == 0 && lane == 0) mbar_arrive(bar_empty + 8 * rel_stage);
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       // outputs of this tile: 1, or 2 for a transposed-conv phase pair (never with statistics); idle warps: 0
-      const int n_out = (p.dbg & 2) ? 0 : (kStats ? 1 : p.n_out);
+      const int n_out = (kExp && (p.dbg & 2)) ? 0 : (kStats ? 1 : p.n_out);
 #pragma unroll
       for (int mc = 0; mc < MYCH; ++mc) {
       const int chunk = hsel * MYCH + mc;
@@ -513,8 +553,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         __nv_bfloat16* const optr_o = optr + o * p.out2_off;
         uint32_t v0[16], vp[16], vm[16];
         tmem_ld16(tbase + slot_c * p.Nb + c, v0);
-        if (slot_p >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + slot_p * p.Nb + c, vp);
-        if (slot_m >= 0 && !(p.dbg & 64)) tmem_ld16(tbase + slot_m * p.Nb + c, vm);
+        if (slot_p >= 0 && !(kExp && (p.dbg & 64))) tmem_ld16(tbase + slot_p * p.Nb + c, vp);
+        if (slot_m >= 0 && !(kExp && (p.dbg & 64))) tmem_ld16(tbase + slot_m * p.Nb + c, vm);
         tmem_ld_wait();
         if (xchg) {
           // publish the edge lanes: my lane 0's P_{+1} is pixel m+1 of the previous warp's lane 31,
@@ -531,7 +571,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         }
         // neighbour columns: all shuffles of a side are issued back to back, in place (no shared temporary, so
         // the sixteen of them are in flight together instead of one SHFL -> FFMA round trip per column)
-        if (slot_p >= 0 && !(p.dbg & 16)) {
+        if (slot_p >= 0 && !(kExp && (p.dbg & 16))) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) vp[j] = __shfl_down_sync(0xffffffffu, vp[j], 1);
           if (xchg && lane == 31) {
@@ -539,7 +579,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             for (int j = 0; j < 16; ++j) vp[j] = __float_as_uint(s_x[xb][half][(q + 1) & 3][0][j]);
           }
         }
-        if (slot_m >= 0 && !(p.dbg & 16)) {
+        if (slot_m >= 0 && !(kExp && (p.dbg & 16))) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) vm[j] = __shfl_up_sync(0xffffffffu, vm[j], 1);
           if (xchg && lane == 0) {
@@ -557,15 +597,15 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           f[4 * j4 + 2] = __uint_as_float(v0[4 * j4 + 2]) + b4.z;
           f[4 * j4 + 3] = __uint_as_float(v0[4 * j4 + 3]) + b4.w;
         }
-        if (slot_p >= 0 && !(p.dbg & 16)) {
+        if (slot_p >= 0 && !(kExp && (p.dbg & 16))) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaf(m_right, __uint_as_float(vp[j]), f[j]);
         }
-        if (slot_m >= 0 && !(p.dbg & 16)) {
+        if (slot_m >= 0 && !(kExp && (p.dbg & 16))) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaf(m_left, __uint_as_float(vm[j]), f[j]);
         }
-        if (kStats && !(p.dbg & 32)) {
+        if (kStats && !(kExp && (p.dbg & 32))) {
 #pragma unroll
           for (int r = 0; r < GPC; ++r) {
 #pragma unroll
@@ -582,7 +622,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         uint4* dst = reinterpret_cast<uint4*>(optr_o + c);
-        if (!(p.dbg & 4)) {
+        if (!(kExp && (p.dbg & 4))) {
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
@@ -757,6 +797,7 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   }
   p.bias = bias; p.out = out; p.stats = stats;
   { const char* e = getenv("DBS_STRIP_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { static const int er = [] { const char* e = getenv("DBS_STRIP_EPI_RELEASE"); return e ? atoi(e) : 0; }(); p.epi_release = er; }
   p.a_bytes = (uint32_t)rows * W * KC * 2;
   p.slab_bytes = (uint32_t)Nb * KC * 2;
   uint32_t cols = 32;

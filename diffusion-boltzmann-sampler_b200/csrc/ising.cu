@@ -666,10 +666,13 @@ __device__ __forceinline__ uint64_t rot1_left_L(uint64_t v, int L, uint64_t mask
   return k64 ? ((v << 1) | (v >> 63)) : (((v << 1) & maskL) | (v >> (L - 1)));
 }
 
-template <bool k64>
+// kObs: the same launch also evaluates E and M of every chain (the lattice is in registers anyway) and adds
+// {1, E/N, (E/N)^2, |M|, M^2, M^4} to the fp64 observable block of the chain's group — one launch per measurement of the
+// temperature sweep instead of three (dbs_ising_measure).  E and M are formed exactly as ising_obs_packed_kernel does.
+template <bool k64, bool kObs>
 __global__ void __launch_bounds__(32 * kCorrWarps)
 ising_corr_warp2_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chains, const int32_t* __restrict__ group,
-                        long long* __restrict__ acc) {
+                        long long* __restrict__ acc, float negJ, float negh, double* __restrict__ block, int block_stride) {
   const int W = (L + 31) >> 5, R = L / 2;
   __shared__ unsigned char s_bin[32 * 32];   // radial bin of (di, |dj|), di, |dj| < R; 255 = outside 0 < r < R
   __shared__ int s_nd[32];                   // half-plane displacements per bin
@@ -705,6 +708,36 @@ ising_corr_warp2_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chai
     if (lane < L) lo = W == 2 ? ((uint64_t)b[lane * 2] | ((uint64_t)b[lane * 2 + 1] << 32)) : (uint64_t)b[lane];
     if (lane + 32 < L) hi = (uint64_t)b[(lane + 32) * 2] | ((uint64_t)b[(lane + 32) * 2 + 1] << 32);
     const bool v0 = lane < L, v1 = lane + 32 < L;
+    if (kObs) {
+      // bonds to the right neighbour (column rotation by one) and to the row below (row shift by one)
+      int r0 = lane + 1; if (r0 >= L) r0 -= L;
+      int r1 = lane + 33; while (r1 >= L) r1 -= L;
+      const uint64_t a_lo = __shfl_sync(0xffffffffu, lo, r0 & 31), a_hi = __shfl_sync(0xffffffffu, hi, r0 & 31);
+      const uint64_t b_lo = __shfl_sync(0xffffffffu, lo, r1 & 31), b_hi = __shfl_sync(0xffffffffu, hi, r1 & 31);
+      const uint64_t dn0 = v0 ? (r0 >= 32 ? a_hi : a_lo) : 0ull, dn1 = v1 ? (r1 >= 32 ? b_hi : b_lo) : 0ull;
+      int dis = __popcll(lo ^ dn0) + __popcll(hi ^ dn1);
+      if (v0) dis += __popcll(lo ^ rot1_right_L<k64>(lo, L));
+      if (v1) dis += __popcll(hi ^ rot1_right_L<k64>(hi, L));
+      int up = __popcll(lo) + __popcll(hi);
+      dis = __reduce_add_sync(0xffffffffu, dis);
+      up = __reduce_add_sync(0xffffffffu, up);
+      if (lane == 0) {
+        const int N = L * L;
+        const int agree = 2 * N - dis;
+        const float s_bond = (float)(2 * agree - 2 * N);
+        const float s_spin = (float)(2 * up - N);
+        const float energy = __fadd_rn(__fmul_rn(negJ, s_bond), __fmul_rn(negh, s_spin));
+        const float mag = __fdiv_rn(s_spin, (float)N);
+        const double e = (double)energy / (double)N, m = (double)mag, m2 = m * m;
+        double* a = block + (int64_t)g * block_stride;
+        atomicAdd(a + 0, 1.0);
+        atomicAdd(a + 1, e);
+        atomicAdd(a + 2, e * e);
+        atomicAdd(a + 3, fabs(m));
+        atomicAdd(a + 4, m2);
+        atomicAdd(a + 5, m2 * m2);
+      }
+    }
     int* part = &s_part[warp][0][lane];
     for (int di = 0; di < R; ++di) {
       int r0 = lane + di; if (r0 >= L) r0 -= L;
@@ -912,13 +945,26 @@ extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chai
       if (L == 64) ising_corr_warp_kernel<true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
       else ising_corr_warp_kernel<false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
     } else {
-      if (L == 64) ising_corr_warp2_kernel<true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
-      else ising_corr_warp2_kernel<false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc);
+      if (L == 64) ising_corr_warp2_kernel<true, false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc, 0.f, 0.f, nullptr, 0);
+      else ising_corr_warp2_kernel<false, false><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, acc, 0.f, 0.f, nullptr, 0);
     }
     DBS_LAUNCHED();
     return DBS_OK;
   }
   ising_corr_kernel<<<(unsigned)n_chains, kCorrThreads, smem, as_stream(stream)>>>(bits, L, ref_mask, group, acc);
+  DBS_LAUNCHED();
+  return DBS_OK;
+}
+
+extern "C" int dbs_ising_measure(const uint32_t* bits, int L, int64_t n_chains, float J, float h, const int32_t* group,
+                                 double* block, int block_stride, long long* corr_acc, void* stream) {
+  DBS_REQUIRE(supported_L(L) && !(L & 1) && L <= 64, "ising_measure: even lattice sizes 4..64 only (got %d)", L);
+  if (n_chains == 0) return DBS_OK;
+  DBS_REQUIRE(bits && block && corr_acc && n_chains >= 0 && block_stride >= 6, "ising_measure: bad arguments");
+  const unsigned grid = (unsigned)((n_chains + kCorrWarps - 1) / kCorrWarps);
+  ProfScope prof(kProfIsingObs, as_stream(stream));
+  if (L == 64) ising_corr_warp2_kernel<true, true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, corr_acc, -J, -h, block, block_stride);
+  else ising_corr_warp2_kernel<false, true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, corr_acc, -J, -h, block, block_stride);
   DBS_LAUNCHED();
   return DBS_OK;
 }

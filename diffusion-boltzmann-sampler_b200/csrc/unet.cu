@@ -455,26 +455,37 @@ int launch_init_fast(const std::vector<float>& w_host, const std::vector<float>&
 
 // Final conv C -> 1 (3x3, pad 1) on the bf16 path, optionally fused with the GroupNorm apply that produces its
 // input (the last decoder block's  SiLU(GN(conv2)) + residual, score_network.py:148-151, 259, 268).
-// A CTA owns TH full-width rows of one image: the rows (+ one halo row each side) are brought into shared
-// memory once with coalesced 16-byte loads — transformed on the way when fused, so the normalised tensor
-// never exists in HBM — then one thread per pixel forms the 9 x C dot product.  The weights arrive as a
-// __grid_constant__ kernel parameter, so every FFMA takes its weight straight from the constant bank.
-// Shared-memory layout: C*2 bytes per pixel, the 16-byte chunk index XOR-swizzled with the pixel index so
-// that the per-pixel LDS.128 of a quarter-warp touch all 32 banks.
-template <int C> struct FinalW { float w[9 * C]; float bias, scale; };
+// A CTA owns TH full-width rows of one image.
+//   phase 1: the rows (+ one halo row each side) are brought into shared memory once with coalesced 16-byte loads —
+//            transformed on the way when fused, so the normalised tensor never exists in HBM (bf16, C*2 bytes per pixel,
+//            the 16-byte chunk index XOR-swizzled with the pixel index: conflict-free for the loads below);
+//   phase 2: the nine per-tap dot products of every strip pixel, D[pixel][tap] = sum_c a[pixel][c] * w[tap][c], are a
+//            [pixels x C] x [C x 9] product: warps run it as mma.sync m16n8k16 bf16 tiles (16 pixels x 2 x 8 taps, operands
+//            by ldmatrix, the weight fragments built once per thread from the __grid_constant__ parameter) — 288 MACs per
+//            pixel are ~1.3 warp instructions instead of ~600 thread instructions of unpack + FFMA.  (tcgen05 needs
+//            M = 128 x N >= 16 tiles fed from UMMA-layout operands; for a 9-column product the warp-level MMA is the fit.)
+//   phase 3: out[p] = scale * (bias + sum_taps D[p + offset(tap)][tap]) — a nine-point stencil on fp32 scalars.
+// bfrag: the B-operand fragments of the weights, [C/16 k-steps][2 n-tiles][2 halves][32 lanes] packed bf16 pairs, built once
+// per plan (a lane-dependent index into the constant bank would serialise 32 ways)
+struct FinalW { const uint32_t* bfrag; float bias, scale; };
+constexpr int kFinalDStride = 10;   // floats per pixel of the D table (9 taps, padded to an even count for 8-byte stores)
 
 template <int C, bool kFuseGn>
 __global__ void __launch_bounds__(256)
 final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
                    const float* __restrict__ stats, float inv_cnt, float eps, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ out, int H, int W, int TH,
-                   const __grid_constant__ FinalW<C> fw) {
+                   const __grid_constant__ FinalW fw) {
   constexpr int NCK = C / 8;                 // 16-byte chunks per pixel
   constexpr int PPL = NCK >= 8 ? 1 : 8 / NCK;  // pixels per 128 bytes
+  constexpr int KS = C / 16;                 // k-steps of the m16n8k16 MMA
   extern __shared__ __align__(16) uint8_t sm_raw[];
   __shared__ float s_sc[C], s_sh[C];
   const int n = blockIdx.y, h0 = blockIdx.x * TH;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_pix = (TH + 2) * W;
+  const int n_pix16 = (n_pix + 15) & ~15;    // the MMA walks whole 16-pixel groups (the tail reads unused smem)
+  float* s_d = reinterpret_cast<float*>(sm_raw + (size_t)n_pix16 * (C * 2));
   if (kFuseGn) {
     if (tid < C) {
       const int gi = tid / (C / 8);
@@ -487,16 +498,17 @@ final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __r
     }
     __syncthreads();
   }
-  const int n_vec = (TH + 2) * W * NCK;
+  // ---- phase 1
+  const int n_vec = n_pix * NCK;
   for (int idx = tid; idx < n_vec; idx += blockDim.x) {
     const int ck = idx % NCK, pi = idx / NCK;
     const int r = pi / W, wl = pi - r * W, ih = h0 + r - 1;
-    if (ih < 0 || ih >= H) continue;         // never read: the taps below apply the same bounds
+    if (ih < 0 || ih >= H) continue;         // never used: phase 3 applies the same bounds
     const int64_t g = (((int64_t)n * H + ih) * W + wl) * C + ck * 8;
     uint4 raw = *reinterpret_cast<const uint4*>(y + g);
     if (kFuseGn) {
       float v[8], rr[8];
-      Vec16<__nv_bfloat16>::load(y + g, v);
+      Vec16<__nv_bfloat16>::unpack(raw, v);
       Vec16<__nv_bfloat16>::load(res + g, rr);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = fmaf(1.0f, rr[k], silu_fast(fmaf(v[k], s_sc[ck * 8 + k], s_sh[ck * 8 + k])));
@@ -511,51 +523,109 @@ final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __r
     const int swz = (pi / PPL) & (NCK - 1);
     *reinterpret_cast<uint4*>(sm_raw + (size_t)pi * (C * 2) + ((ck ^ swz) << 4)) = raw;
   }
+  // weight fragments of the B operand (K x N = channels x taps, "col" layout): b0 = (k = 2t, 2t+1; n = g), b1 = (k + 8)
+  const int fg = lane >> 2, ft = lane & 3;
+  uint32_t bfrag[KS][2][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) bfrag[ks][j][hh] = __ldg(fw.bfrag + ((ks * 2 + j) * 2 + hh) * 32 + lane);
   __syncthreads();
-  const int hl = tid / W, wl = tid - hl * W;
-  if (hl >= TH || h0 + hl >= H) return;
-  float acc = 0.f;
+  // ---- phase 2: D[pixel][tap] for every strip pixel
+  const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm_raw);
+  const int nwarps = blockDim.x >> 5;
+  for (int grp = warp; grp < n_pix16 / 16; grp += nwarps) {
+    // ldmatrix.x4: lane i addresses row (i % 8) of matrix i / 8; matrices = (pixels 0-7 | 8-15) x (k 0-7 | 8-15)
+    const int mid = lane >> 3;
+    const int pi = grp * 16 + (lane & 7) + 8 * (mid & 1);
+    const int swz = (pi / PPL) & (NCK - 1);
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int ih = h0 + hl + kh - 1;
-    if (ih < 0 || ih >= H) continue;
+    for (int ks = 0; ks < KS; ++ks) {
+      const int ck = 2 * ks + (mid >> 1);
+      const uint32_t addr = sm_base + (uint32_t)pi * (C * 2) + (uint32_t)((ck ^ swz) << 4);
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int iw = wl + kw - 1;
-      if (iw < 0 || iw >= W) continue;
-      const int pi = (hl + kh) * W + iw;
-      const uint8_t* base = sm_raw + (size_t)pi * (C * 2);
-      const int swz = (pi / PPL) & (NCK - 1);
+      for (int j = 0; j < 2; ++j)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                     "{%0, %1, %2, %3};"
+                     : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bfrag[ks][j][0]), "r"(bfrag[ks][j][1]));
+    }
+    // accumulator fragment: (row g, cols 2t, 2t+1), (row g + 8, same cols); col = tap inside the n-tile
+    float* d0 = s_d + (size_t)(grp * 16 + fg) * kFinalDStride;
+    float* d1 = d0 + 8 * kFinalDStride;
+    *reinterpret_cast<float2*>(d0 + 2 * ft) = make_float2(acc[0][0], acc[0][1]);
+    *reinterpret_cast<float2*>(d1 + 2 * ft) = make_float2(acc[0][2], acc[0][3]);
+    if (ft == 0) { d0[8] = acc[1][0]; d1[8] = acc[1][2]; }
+  }
+  __syncthreads();
+  // ---- phase 3: nine-point stencil on the scalar tables
+  for (int o = tid; o < TH * W; o += blockDim.x) {
+    const int hl = o / W, wl = o - hl * W;
+    if (h0 + hl >= H) break;
+    float acc = 0.f;
 #pragma unroll
-      for (int ck = 0; ck < NCK; ++ck) {
-        const uint4 q = *reinterpret_cast<const uint4*>(base + ((ck ^ swz) << 4));
-        const uint32_t wq[4] = {q.x, q.y, q.z, q.w};
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = h0 + hl + kh - 1;
+      if (ih < 0 || ih >= H) continue;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&wq[i]);
-          acc = fmaf(__low2float(h2), fw.w[(kh * 3 + kw) * C + ck * 8 + 2 * i], acc);
-          acc = fmaf(__high2float(h2), fw.w[(kh * 3 + kw) * C + ck * 8 + 2 * i + 1], acc);
-        }
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = wl + kw - 1;
+        if (iw < 0 || iw >= W) continue;
+        acc += s_d[(size_t)((hl + kh) * W + iw) * kFinalDStride + kh * 3 + kw];
       }
     }
+    out[((int64_t)n * H + h0 + hl) * W + wl] = fw.scale * (acc + fw.bias);
   }
-  out[((int64_t)n * H + h0 + hl) * W + wl] = fw.scale * (acc + fw.bias);
+}
+
+// host-side build of FinalW::bfrag from the [tap][C] fp32 weights (round-to-nearest-even bf16)
+static uint32_t bf16_bits(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0u;
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+std::vector<uint32_t> final_bfrag_host(const std::vector<float>& w, int C) {
+  std::vector<uint32_t> t((size_t)(C / 16) * 2 * 2 * 32);
+  for (int ks = 0; ks < C / 16; ++ks)
+    for (int j = 0; j < 2; ++j)
+      for (int hh = 0; hh < 2; ++hh)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int tap = 8 * j + (lane >> 2), c = 16 * ks + 2 * (lane & 3) + 8 * hh;
+          const float w0 = tap < 9 ? w[(size_t)tap * C + c] : 0.f, w1 = tap < 9 ? w[(size_t)tap * C + c + 1] : 0.f;
+          t[(size_t)(((ks * 2 + j) * 2 + hh) * 32 + lane)] = bf16_bits(w0) | (bf16_bits(w1) << 16);
+        }
+  return t;
 }
 
 template <int C>
-int launch_final_fused(const std::vector<float>& w_host, float bias, float scale, const __nv_bfloat16* y,
+int launch_final_fused(const uint32_t* bfrag_dev, float bias, float scale, const __nv_bfloat16* y,
                        const __nv_bfloat16* res, const float* stats, const float* gamma, const float* beta, float* out,
                        int64_t B, int H, int W, cudaStream_t st) {
-  FinalW<C> fw;
-  for (int i = 0; i < 9 * C; ++i) fw.w[i] = w_host[i];
-  fw.bias = bias; fw.scale = scale;
-  int TH = 256 / W;
+  FinalW fw;
+  fw.bfrag = bfrag_dev; fw.bias = bias; fw.scale = scale;
+  // rows per CTA: up to 512 output pixels while the strip + its D table stay within 72 KB (3 CTAs per SM)
+  int TH = 512 / W;
   if (TH > H) TH = H;
-  const size_t smem = (size_t)(TH + 2) * W * C * 2;
+  auto bytes = [&](int th) { return (size_t)((((th + 2) * W + 15) & ~15)) * (C * 2 + kFinalDStride * 4); };
+  while (TH > 1 && bytes(TH) > 72 * 1024) TH >>= 1;
+  const size_t smem = bytes(TH);
   const dim3 grid((unsigned)((H + TH - 1) / TH), (unsigned)B);
   const float inv_cnt = 1.0f / (float)((int64_t)H * W * (C / 8));
-  if (res) final_fused_kernel<C, true><<<grid, TH * W, smem, st>>>(y, res, stats, inv_cnt, 1e-5f, gamma, beta, out, H, W, TH, fw);
-  else final_fused_kernel<C, false><<<grid, TH * W, smem, st>>>(y, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, out, H, W, TH, fw);
+  static bool attr_done = false;
+  if (!attr_done) {
+    DBS_CUDA(cudaFuncSetAttribute(final_fused_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    DBS_CUDA(cudaFuncSetAttribute(final_fused_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    attr_done = true;
+  }
+  if (res) final_fused_kernel<C, true><<<grid, 256, smem, st>>>(y, res, stats, inv_cnt, 1e-5f, gamma, beta, out, H, W, TH, fw);
+  else final_fused_kernel<C, false><<<grid, 256, smem, st>>>(y, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, out, H, W, TH, fw);
   DBS_LAUNCHED();
   return DBS_OK;
 }
@@ -836,7 +906,8 @@ struct dbs_unet_plan {
   float *twt = nullptr, *tbt = nullptr;  // concatenated per-block time Linear [sumC][T], [sumC]
   int sumC = 0;
   float *init_w = nullptr, *init_b = nullptr, *final_w = nullptr, *final_b = nullptr;
-  std::vector<float> final_w_host;   // [tap][C], kernel-parameter copy for the fused final conv
+  std::vector<float> final_w_host;   // [tap][C] host copy of the final conv's weights
+  uint32_t* final_bfrag = nullptr;   // their mma.sync B fragments (final_bfrag_host), C a multiple of 16 only
   std::vector<float> init_w_host, init_b_host;   // [tap][C], [C]: kernel-parameter copies for the init conv
   float final_b_host = 0.f;
   std::vector<dbs::BlockW> enc, dec;
@@ -1179,8 +1250,8 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
     DBS_CUDA(cudaMemsetAsync(stats, 0, (size_t)n_stat_slices * B * 8 * 2 * 4, st));
   }
   // fused final conv (bf16 path): C in {16, 32, 64}, power-of-two width <= 128, tile within 48 KB of shared memory
-  const bool final_fused_ok = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && W <= 128 && (W & (W - 1)) == 0 &&
-                              (size_t)(std::min(256 / W, H) + 2) * W * C * 2 <= 48 * 1024 && !fixup;
+  const bool final_fused_ok = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && W <= 128 && W >= 4 && (W & (W - 1)) == 0 &&
+                              (size_t)((3 * W + 15) & ~15) * (C * 2 + 40) <= 72 * 1024 && !fixup;
   static const bool defer_off = [] { const char* e = getenv("DBS_FINAL_FUSE"); return e && e[0] == '0'; }();
   DeferredGn defer;
   defer.want = final_fused_ok && use_tc && !tap && !defer_off;
@@ -1385,9 +1456,9 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
       if (final_fused_ok) {
         const __nv_bfloat16* yin = defer.done ? (const __nv_bfloat16*)defer.y : (const __nv_bfloat16*)cur;
         const __nv_bfloat16* rin = defer.done ? (const __nv_bfloat16*)defer.res : nullptr;
-        if (C == 16) rc = launch_final_fused<16>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
-        else if (C == 32) rc = launch_final_fused<32>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
-        else rc = launch_final_fused<64>(plan->final_w_host, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
+        if (C == 16) rc = launch_final_fused<16>(plan->final_bfrag, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
+        else if (C == 32) rc = launch_final_fused<32>(plan->final_bfrag, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
+        else rc = launch_final_fused<64>(plan->final_bfrag, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
         if (rc) return rc;
       } else {
         final_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(cur, plan->final_w, plan->final_b, score, n_pix,
@@ -1473,6 +1544,16 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
         cudaMemcpy(&plan->final_b_host, plan->final_b, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
       set_error("unet_plan_create: reading back the final conv weights failed");
       return fail(DBS_ERR_CUDA);
+    }
+    if (C % 16 == 0) {
+      const std::vector<uint32_t> bf = final_bfrag_host(plan->final_w_host, C);
+      void* d = nullptr;
+      if ((rc = dev_alloc(plan, bf.size() * 4, &d))) return fail(rc);
+      if (cudaMemcpy(d, bf.data(), bf.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("unet_plan_create: final conv fragment upload failed");
+        return fail(DBS_ERR_CUDA);
+      }
+      plan->final_bfrag = (uint32_t*)d;
     }
   }
 

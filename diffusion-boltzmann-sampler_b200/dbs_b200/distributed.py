@@ -64,11 +64,15 @@ def allreduce_block(acc):
 
 
 def finalize_observables(acc):
-    """{count, sum E/N, sum |M|, sum M^2, sum M^4} per group -> means and the Binder cumulant."""
-    a = acc.detach().cpu().numpy().reshape(-1, 5)
+    """Per-group sums -> means and the Binder cumulant.  Six columns {count, sum E/N, sum (E/N)^2, sum |M|, sum M^2,
+    sum M^4} (the temperature sweep's block) or the five without the energy square."""
+    a = acc.detach().cpu().numpy()
+    a = a.reshape(-1, a.shape[-1]) if a.ndim > 1 else a.reshape(-1, 5)
+    if a.shape[1] == 5:
+        a = np.concatenate([a[:, :2], np.full((a.shape[0], 1), np.nan), a[:, 2:]], axis=1)
     n = np.maximum(a[:, 0], 1.0)
-    m2, m4 = a[:, 3] / n, a[:, 4] / n
+    m2, m4 = a[:, 4] / n, a[:, 5] / n
     with np.errstate(divide="ignore", invalid="ignore"):
         binder = 1.0 - m4 / (3.0 * m2 * m2)
-    return {"count": a[:, 0], "energy_per_spin": a[:, 1] / n, "abs_magnetization": a[:, 2] / n,
+    return {"count": a[:, 0], "energy_per_spin": a[:, 1] / n, "e2": a[:, 2] / n, "abs_magnetization": a[:, 3] / n,
             "m2": m2, "m4": m4, "binder": binder}

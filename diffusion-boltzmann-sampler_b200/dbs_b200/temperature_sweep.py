@@ -50,12 +50,19 @@ def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_tempera
                                                        index[lo:].data_ptr(), seed, gid, stride, offset, 0,
                                                        mh.zero_field, runtime.current_stream()), "ising_sweeps")
 
+    # ONE fp64 block per temperature: {count, sum E/N, sum (E/N)^2, sum |M|, sum M^2, sum M^4, C-sums r = 0 .. R-1}
+    #  -> one all-reduce.  C(r) sums are integers: accumulated exactly in int64 and appended at the end.
     nT = len(temps)
-    acc = torch.zeros((nT, 5), dtype=torch.float64, device=dev)
     R = L // 2
+    NOBS = 6
+    block = torch.zeros((nT, NOBS + R), dtype=torch.float64, device=dev)
     corr = torch.zeros((nT, R), dtype=torch.int64, device=dev)
-    e = torch.empty(n, dtype=torch.float32, device=dev)
-    m = torch.empty(n, dtype=torch.float32, device=dev)
+    fused = with_correlation and L % 2 == 0 and L <= 64        # one launch per measurement (dbs_ising_measure)
+    if not fused:
+        e = torch.empty(n, dtype=torch.float32, device=dev)
+        m = torch.empty(n, dtype=torch.float32, device=dev)
+        acc5 = torch.zeros((nT, 5), dtype=torch.float64, device=dev)
+        e2 = torch.zeros(nT, dtype=torch.float64, device=dev)
     done = 0
     if burn_in:
         sweeps(burn_in, done)
@@ -64,27 +71,41 @@ def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_tempera
     for _ in range(n_measure // measure_every):
         sweeps(measure_every, done)
         done += measure_every
-        abi.check(abi.lib.dbs_ising_observables(bits.data_ptr(), L, n, float(J), float(h), e.data_ptr(), m.data_ptr(),
-                                                runtime.current_stream()))
-        abi.check(abi.lib.dbs_observable_accumulate(e.data_ptr(), m.data_ptr(), L, n, group.data_ptr(), acc.data_ptr(),
+        if fused:
+            abi.check(abi.lib.dbs_ising_measure(bits.data_ptr(), L, n, float(J), float(h), group.data_ptr(), block.data_ptr(),
+                                                NOBS + R, corr.data_ptr(), runtime.current_stream()), "ising_measure")
+        else:
+            abi.check(abi.lib.dbs_ising_observables(bits.data_ptr(), L, n, float(J), float(h), e.data_ptr(), m.data_ptr(),
                                                     runtime.current_stream()))
-        if with_correlation:
-            abi.check(abi.lib.dbs_ising_correlation(bits.data_ptr(), L, n, 0, group.data_ptr(), corr.data_ptr(),
-                                                    runtime.current_stream()))
+            abi.check(abi.lib.dbs_observable_accumulate(e.data_ptr(), m.data_ptr(), L, n, group.data_ptr(), acc5.data_ptr(),
+                                                        runtime.current_stream()))
+            e2.index_add_(0, group.long(), (e.double() / (L * L)) ** 2)
+            if with_correlation:
+                abi.check(abi.lib.dbs_ising_correlation(bits.data_ptr(), L, n, 0, group.data_ptr(), corr.data_ptr(),
+                                                        runtime.current_stream()))
         n_meas += 1
-    corr_f = corr.to(torch.float64)
+    if not fused:
+        block[:, 0:2] = acc5[:, 0:2]
+        block[:, 2] = e2
+        block[:, 3:6] = acc5[:, 2:5]
+    block[:, NOBS:] = corr.to(torch.float64)
     if reduce:
-        allreduce_block(acc)
-        allreduce_block(corr_f)
-    out = finalize_observables(acc)
-    out["acc"] = acc
-    out["corr_sums"] = corr_f
+        allreduce_block(block)                      # the one collective of the path
+    out = finalize_observables(block[:, :NOBS])
+    out["acc"] = block[:, [0, 1, 3, 4, 5]]          # {count, sum E/N, sum |M|, sum M^2, sum M^4} (round-1 layout)
+    out["block"] = block
+    out["corr_sums"] = block[:, NOBS:]
     out["temperatures"] = temps
     out["sweeps"] = done
     out["flip_attempts_this_rank"] = float(n) * L * L * done
+    # specific heat and susceptibility per spin from the block (api/routes/sampling.py:522-527: var(E) / T^2, var(|M|) / T)
+    N = float(L * L)
+    e_mean, e2_mean = out["energy_per_spin"], out["e2"]
+    out["specific_heat"] = N * (e2_mean - e_mean ** 2) / np.maximum(temps, 1e-300) ** 2
+    out["susceptibility"] = N * (out["m2"] - out["abs_magnetization"] ** 2) / np.maximum(temps, 1e-300)
     if with_correlation:
         from backend.ml.analysis.correlation import _displacement_counts
         cnt = _displacement_counts(L).astype(np.float64) * (L * L) * chains_per_temperature * max(n_meas, 1)
-        c = corr_f.cpu().numpy()
+        c = out["corr_sums"].cpu().numpy()
         out["C_r"] = np.divide(c, cnt[None, :], where=cnt[None, :] > 0, out=np.zeros_like(c))
     return out

@@ -151,6 +151,14 @@ int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chains,
                           const uint32_t* ref_mask, const int32_t* group,
                           long long* acc, void* stream);
 
+/* One launch per measurement of a temperature sweep (even L <= 64): E and M of every chain
+ * (as dbs_ising_observables forms them), block[group][0..5] += {1, E/N, (E/N)^2, |M|, M^2, M^4} (fp64 atomics, the
+ * specific heat and susceptibility sums of api/routes/sampling.py:522-527 included) and the C(r) sums of
+ * dbs_ising_correlation with every site a reference site into corr_acc[group][r] (int64, exact).  block rows are
+ * block_stride doubles apart (>= 6): the caller appends the C(r) columns and all-reduces ONE block. */
+int dbs_ising_measure(const uint32_t* bits, int L, int64_t n_chains, float J, float h, const int32_t* group,
+                      double* block, int block_stride, long long* corr_acc, void* stream);
+
 /* Block accumulation of per-chain observables into the fp64 all-reduce block
  * (SURVEY.md §8e): acc[group][0..4] += {1, E/N, |M|, M^2, M^4}. */
 int dbs_observable_accumulate(const float* energy, const float* magnetization, int L,
