@@ -84,6 +84,11 @@ __device__ __forceinline__ float silu_fast(float x) {
 // per SM halves — the limiter of the 128/256-channel layers.  The leader CTA (cluster rank 0) issues the MMAs;
 // both CTAs' TMA loads signal the leader's full barrier, tcgen05.commit multicasts to both CTAs' empty / tfull
 // barriers, and the peer's epilogue warps hand the TMEM stage back on the leader's tempty barrier.
+// Pins a loop-invariant value in a register: without it the single-thread roles re-read kernel parameters from the
+// constant bank inside their per-k-block loops, a round trip on their critical path each (see conv_strip.cu).
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ int pin(int v) { asm volatile("" : "+r"(v)); return v; }
+
 template <int kRun, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
@@ -150,7 +155,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t b_rows_off = kPair ? (uint32_t)rank * (uint32_t)(p.Nb >> 1) : 0u;   // my half of the weight tile
-      const uint32_t ring_base = smem_base + p.w_region_bytes;
+      const uint32_t ring_base = pin(smem_base + p.w_region_bytes);
+      const int KC = pin(p.KC), chunks0 = pin(p.chunks0), n_stages = pin(p.stages), n_taps = pin(p.n_taps);
+      const int resident = pin(p.resident), Nb = pin(p.Nb);
+      const uint32_t stage_bytes = pin(p.stage_bytes), b_off = pin((p.a_bytes + 1023u) & ~1023u);
+      const uint32_t tx_bytes = pin(kPair ? 2u * (p.a_bytes + p.b_bytes) : p.a_bytes + (p.resident ? 0u : p.b_bytes));
       if (!kPair && p.resident) {
         // the layer's weights, once: k-block kb = tap * chunks + chunk at w_region + kb * b_pad
         mbar_expect_tx(bar_w, p.b_bytes * (uint32_t)n_kblocks);
@@ -163,29 +172,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
         const int ph4 = tile_ph / tiles_per_phase, tile = tile_ph - ph4 * tiles_per_phase;
         const int nt = tile / p.n_tiles_m, mt = tile - nt * p.n_tiles_m;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Nb + (int)b_rows_off;
-        for (int t = ph4 * p.n_taps; t < (ph4 + 1) * p.n_taps; ++t) {
+        const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * Nb + (int)b_rows_off;
+        for (int t = ph4 * n_taps; t < (ph4 + 1) * n_taps; ++t) {
           const int cw = w0 + p.tap_dw[t], chh = h0 + p.tap_dh[t], cp = p.tap_p[t];
+          const int tc0 = p.tap_c0[t], tc1 = p.tap_c1[t], tw_ = p.tap_w[t];     // per tap, not per k-block
           for (int ch = 0; ch < kblocks_per_tap; ++ch) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            const uint32_t a_dst = (kPair ? smem_base : ring_base) + stage * p.stage_bytes;
-            const uint32_t b_dst = a_dst + ((p.a_bytes + 1023u) & ~1023u);
+            const uint32_t a_dst = (kPair ? smem_base : ring_base) + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + b_off;
             const uint32_t fb = bar_full + 8 * stage;
             if (kPair) {
               // both CTAs' bytes land on the LEADER's barrier (peer bit of the address cleared); the leader posts the
               // expected total once
-              if (rank == 0) mbar_expect_tx(fb, 2u * (p.a_bytes + p.b_bytes));
+              if (rank == 0) mbar_expect_tx(fb, tx_bytes);
               const uint32_t fbl = fb & 0xFEFFFFFFu;
-              if (ch < p.chunks0) tma_load_5d_2sm(a_dst, &map_in0, fbl, p.tap_c0[t] + ch * p.KC, cw, cp, chh, n0);
-              else tma_load_5d_2sm(a_dst, &map_in1, fbl, p.tap_c1[t] + (ch - p.chunks0) * p.KC, cw, cp, chh, n0);
-              tma_load_3d_2sm(b_dst, &map_w, fbl, ch * p.KC, co0, p.tap_w[t]);
+              if (ch < chunks0) tma_load_5d_2sm(a_dst, &map_in0, fbl, tc0 + ch * KC, cw, cp, chh, n0);
+              else tma_load_5d_2sm(a_dst, &map_in1, fbl, tc1 + (ch - chunks0) * KC, cw, cp, chh, n0);
+              tma_load_3d_2sm(b_dst, &map_w, fbl, ch * KC, co0, tw_);
             } else {
-              mbar_expect_tx(fb, p.a_bytes + (p.resident ? 0u : p.b_bytes));
-              if (ch < p.chunks0) tma_load_5d(a_dst, &map_in0, fb, p.tap_c0[t] + ch * p.KC, cw, cp, chh, n0);
-              else tma_load_5d(a_dst, &map_in1, fb, p.tap_c1[t] + (ch - p.chunks0) * p.KC, cw, cp, chh, n0);
-              if (!p.resident) tma_load_3d(b_dst, &map_w, fb, ch * p.KC, co0, p.tap_w[t]);
+              mbar_expect_tx(fb, tx_bytes);
+              if (ch < chunks0) tma_load_5d(a_dst, &map_in0, fb, tc0 + ch * KC, cw, cp, chh, n0);
+              else tma_load_5d(a_dst, &map_in1, fb, tc1 + (ch - chunks0) * KC, cw, cp, chh, n0);
+              if (!resident) tma_load_3d(b_dst, &map_w, fb, ch * KC, co0, tw_);
             }
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -197,11 +207,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      const int mmas = p.KC / 16;
-      const uint32_t lo_bits = (uint32_t)p.desc_hi, hi32 = (uint32_t)(p.desc_hi >> 32), idesc = p.idesc;
-      const uint32_t b_off = (p.a_bytes + 1023u) & ~1023u;
-      const uint32_t ring_base = smem_base + (kPair ? 0u : p.w_region_bytes);
-      if (!kPair && p.resident) {
+      const int mmas = pin(p.KC / 16);
+      const uint32_t lo_bits = pin((uint32_t)p.desc_hi), hi32 = pin((uint32_t)(p.desc_hi >> 32)), idesc = pin(p.idesc);
+      const uint32_t b_off = pin((p.a_bytes + 1023u) & ~1023u);
+      const uint32_t ring_base = pin(smem_base + (kPair ? 0u : p.w_region_bytes));
+      const uint32_t stage_bytes = pin(p.stage_bytes), b_pad = pin(p.b_pad);
+      const int n_stages = pin(p.stages), acc_stride = pin(p.Nb), n_kb = pin(n_kblocks);
+      const bool w_resident = !kPair && p.resident;
+      if (w_resident) {
         mbar_wait(bar_w, 0);
         tc_fence_after();
       }
@@ -210,12 +223,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.Nb;
-        for (int kb = 0; kb < n_kblocks; ++kb) {
+        const uint32_t d_tmem = tmem_base + as * acc_stride;
+        for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = ring_base + stage * p.stage_bytes;
-          const uint32_t b_addr = (!kPair && p.resident) ? smem_base + (uint32_t)kb * p.b_pad : a_addr + b_off;
+          const uint32_t a_addr = ring_base + stage * stage_bytes;
+          const uint32_t b_addr = w_resident ? smem_base + (uint32_t)kb * b_pad : a_addr + b_off;
           const uint32_t a_lo = lo_bits | ((a_addr & 0x3FFFFu) >> 4);
           const uint32_t b_lo = lo_bits | ((b_addr & 0x3FFFFu) >> 4);
           const uint32_t acc0 = kb ? 1u : 0u;
@@ -239,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
             }
             umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         if (kPair) umma_commit_2sm(bar_tfull + 8 * as); else umma_commit(bar_tfull + 8 * as);   // accumulator complete -> epilogue
       }

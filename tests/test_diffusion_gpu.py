@@ -245,6 +245,21 @@ def test_sampler_default_net_vs_oracle_and_bf16_bound():
     assert (np.sign(got16) == np.sign(want)).mean() >= 0.995
 
 
+def test_bf16_bound_over_a_full_config4_trajectory():
+    """the bf16 tcgen05 path against the fp32 path at the configuration the headline is quoted on —
+    64x64, ALL 1000 Euler-Maruyama steps, batch 64, default network, identical in-kernel Philox noise.  Measured on a B200
+    (profiles/r2_bf16_long.py): relative rms error 7.7e-4 after the last step (it grows with the first ~400 steps and then
+    saturates), 99.977 % of the spins agree.  Stated bound: rms error <= 3e-3 of the rms, sign agreement >= 99.9 %."""
+    from backend.ml.samplers.diffusion import DiffusionSampler
+    net = _net()
+    shape, N = (64, 1, 64, 64), 1000
+    want = DiffusionSampler(net, num_steps=N, device="cuda", precision="fp32").sample(shape, seed=123)
+    got = DiffusionSampler(net, num_steps=N, device="cuda", precision="bf16").sample(shape, seed=123)
+    assert torch.isfinite(got).all()
+    assert float((got - want).pow(2).mean().sqrt() / want.pow(2).mean().sqrt()) <= 3e-3
+    assert float((torch.sign(got) == torch.sign(want)).float().mean()) >= 0.999
+
+
 def test_sampler_api_surface():
     """Shapes / types / contracts of backend/tests/test_diffusion_sampler.py (reference)."""
     from backend.ml.samplers.diffusion import DiffusionSampler, PretrainedDiffusionSampler
