@@ -306,7 +306,7 @@ def bench_ours(args, world, rank, local):
         "frac": round(achieved / peaks["bf16_sustained"], 4), "frac_of_burst": round(achieved / peaks["bf16_burst"], 4),
         "peak_source": peaks["source"] + ", sustained bf16 (kernels timed inside a long step)",
         "traffic": round(traffic * Bp, 0) if traffic else None,
-        "traffic_note": CONV_TRAFFIC_64.get("note"),
+        "traffic_note": CONV_TRAFFIC_64.get("note"), "traffic_source": CONV_TRAFFIC_64.get("source"),
         "per": f"one forward of {Bp} samples (the conv launches of one EM step on one GPU)",
         "algorithmic_flops": flops_sample * Bp, "flops_per_sample_step": flops_sample,
         "conv_launches_per_em_step": conv_n // PROF_STEPS, "conv_ms_per_em_step": round(conv_ms / PROF_STEPS, 4),
@@ -380,7 +380,12 @@ def bench_ours(args, world, rank, local):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one forward at 64x64, from the ncu --set full
 # capture named in "source" (per sample; bench scales it by the batch).  None until a capture of this build exists.
-CONV_TRAFFIC_64 = {"bytes_per_sample_forward": None, "source": None, "note": None}
+CONV_TRAFFIC_64 = {"bytes_per_sample_forward": 9.365e6, "source": "profiles/r2_conv_ncu_64.csv",
+                   "note": "dram__bytes_read.sum + dram__bytes_write.sum of the 22 conv launches of one forward (ncu --set full, "
+                           "batch 512, 64x64: 2.89 GB read + 1.90 GB written = 9.37 MB per sample, cold L2 per launch under ncu's "
+                           "cache control), scaled by the batch.  Algorithmic conv input + output bytes: 13.1 MB per sample "
+                           "(SURVEY 8d) -- the captured traffic is BELOW it because conv1 and the 1x1 residual conv of a block "
+                           "share one read of their input and the GroupNorm statistics come from the epilogue: no wasted re-reads"}
 
 
 def gn_apply_bytes_per_sample(L, prec):
@@ -642,7 +647,13 @@ def bench_lj():
     for _ in range(3):
         x1, _ = o_lang.mala_step(p, x1, 1.0, 1e-3, rng.standard_normal((N, 2)).astype(np.float32), 0.5)
     dtm = (time.time() - t0) / 3
+    ld2 = LangevinDynamics(s, temperature=1.0, dt=1e-4, seed=11)
+    st2 = _State(s, pos)
+    ld2._advance(st2, 50)
+    acc_small_dt = round(float(ld2.last_accepted.float().mean()), 3)
     out["mala"] = {"metric": "lj_mala_config_steps_per_s", "value": round(B * n_mala / (ms_m * 1e-3), 1),
+                   "note": "dt = 1e-3 is SURVEY 8d's specification; at rho* = 0.8 its proposals are almost never accepted "
+                           f"(the step cost does not depend on the outcome); dt = 1e-4 accepts {acc_small_dt}",
                    "ms_per_step": round(ms_m / n_mala, 4), "acceptance": round(float(ld.last_accepted.float().mean()), 3),
                    "sample": f"{B} chains x {n_mala} steps, dt=1e-3, T*=1.0",
                    "cpu_baseline": {"value": round(1.0 / dtm, 2), "unit": "config-steps/s", "cores": 1, "kind": "port",

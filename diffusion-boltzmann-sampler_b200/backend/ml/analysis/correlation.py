@@ -40,14 +40,23 @@ def pair_correlation(samples, ref_indices=None) -> Dict[str, List[float]]:
     ref_indices: None reproduces the reference — min(100, L*L) reference sites drawn once per
     call with np.random.choice (analysis/correlation.py:25-26); "all" uses every site (the same
     estimator with less noise); or an explicit list of flattened site indices.
+    +/-1 lattices (4 <= L <= 128) go through the bit-packed XOR / popcount kernel (integer-exact sums); lattices with any
+    other value are correlated as real numbers (_pair_correlation_real), as the reference's product does.
     """
     x = samples if isinstance(samples, torch.Tensor) else torch.as_tensor(np.asarray(samples))
     n, L, _ = x.shape
     R = L // 2
     if ref_indices is None:
         ref_indices = np.random.choice(L * L, min(100, L * L), replace=False)
+    xd = runtime.to_device(x)
+    if abi.lib.dbs_ising_words_per_chain(L) < 0 or not bool(((xd == 1) | (xd == -1)).all()):
+        # real-valued samples (undiscretised diffusion output, the (B, 1, L, L) sets of comprehensive_comparison) and
+        # lattice sizes the packed engine does not take: the
+        # reference multiplies the values themselves (analysis/correlation.py:42); the bit-packed kernel would
+        # binarise them.  Same sums on the GPU from the circular cross-correlation of the masked with the full lattice.
+        return _pair_correlation_real(xd, ref_indices)
     model = IsingModel(L)
-    bits = model.pack(x)
+    bits = model.pack(xd)
     W = bits.shape[2]
     mask_dev = None
     if isinstance(ref_indices, str):
@@ -68,6 +77,38 @@ def pair_correlation(samples, ref_indices=None) -> Dict[str, List[float]]:
     sums = acc.cpu().numpy().astype(np.float64)
     counts = (_displacement_counts(L) * n_ref * n).astype(np.float64)
     c = np.divide(sums, counts, where=counts > 0, out=np.zeros_like(sums))
+    return {"r": list(range(R)), "C_r": c.tolist()}
+
+
+def _pair_correlation_real(xd: torch.Tensor, ref_indices) -> Dict[str, List[float]]:
+    """pair_correlation for lattices of arbitrary real values, on the GPU in fp64:
+    sum over reference sites x and samples of s(x) s(x + d) = [corr(mask * s, s)](d), evaluated for every displacement at
+    once through the FFT of the periodic lattice, then binned by r = int(|d|) over the window [-R, R]^2 exactly as the
+    reference's loops do (a displacement and its negative are distinct entries of the window; at even L the offsets
+    -R and +R reach the same site and are both counted, as in the reference)."""
+    n, L, _ = xd.shape
+    R = L // 2
+    s = xd.to(torch.float64)
+    mask = torch.zeros(L * L, dtype=torch.float64, device=xd.device)
+    if isinstance(ref_indices, str):
+        if ref_indices != "all":
+            raise ValueError("ref_indices must be None, 'all' or a sequence of site indices")
+        mask[:] = 1.0
+    else:
+        mask[torch.as_tensor(np.unique(np.asarray(ref_indices, dtype=np.int64)), device=xd.device)] = 1.0
+    n_ref = int(mask.sum().item())
+    ms = s * mask.reshape(1, L, L)
+    # cc[d] = sum_x ms(x) s(x + d)  (circular), summed over the samples
+    cc = torch.fft.irfft2(torch.conj(torch.fft.rfft2(ms)) * torch.fft.rfft2(s), s=(L, L)).sum(0)
+    d = torch.arange(-R, R + 1, device=xd.device)
+    rr = torch.sqrt((d[:, None] ** 2 + d[None, :] ** 2).to(torch.float64)).to(torch.int64)
+    win = cc[(d % L)[:, None], (d % L)[None, :]]
+    sums = torch.zeros(R, dtype=torch.float64, device=xd.device)
+    keep = (rr > 0) & (rr < R)
+    sums.index_add_(0, rr[keep], win[keep])
+    counts = (_displacement_counts(L) * n_ref * n).astype(np.float64)
+    sm = sums.cpu().numpy()
+    c = np.divide(sm, counts, where=counts > 0, out=np.zeros_like(sm))
     return {"r": list(range(R)), "C_r": c.tolist()}
 
 

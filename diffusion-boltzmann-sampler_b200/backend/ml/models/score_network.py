@@ -164,8 +164,9 @@ class ScoreNetwork(nn.Module):
                              float(self.output_scale), 1 if self.normalize_output else 0)
         freqs = self.time_embed.frequencies().to(torch.float32).contiguous()
         handle = ctypes.c_void_p()
-        abi.check(abi.lib.dbs_unet_plan_create(ctypes.byref(cfg), arr, len(sd), freqs.data_ptr(),
-                                               ctypes.byref(handle)), "unet_plan_create")
+        with runtime.CAPTURE_LOCK:      # the build synchronises the device: never while another thread captures a graph
+            abi.check(abi.lib.dbs_unet_plan_create(ctypes.byref(cfg), arr, len(sd), freqs.data_ptr(),
+                                                   ctypes.byref(handle)), "unet_plan_create")
         self._plan = _Plan(handle, ver)
         return handle
 

@@ -157,8 +157,9 @@ class ContinuousScoreNetwork(nn.Module):
         pos_f = self.pos_embed.freqs.detach().to("cpu", torch.float32).contiguous()
         t_f = self.time_embed.frequencies().to(torch.float32).contiguous()
         handle = ctypes.c_void_p()
-        abi.check(abi.lib.dbs_csn_plan_create(ctypes.byref(cfg), arr, len(sd), pos_f.data_ptr(), t_f.data_ptr(),
-                                              ctypes.byref(handle)), "csn_plan_create")
+        with runtime.CAPTURE_LOCK:      # the build synchronises the device: never while another thread captures a graph
+            abi.check(abi.lib.dbs_csn_plan_create(ctypes.byref(cfg), arr, len(sd), pos_f.data_ptr(), t_f.data_ptr(),
+                                                  ctypes.byref(handle)), "csn_plan_create")
         self._plan = _Plan(handle, ver)
         return handle
 

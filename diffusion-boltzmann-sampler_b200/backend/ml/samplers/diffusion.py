@@ -22,7 +22,7 @@ import torch
 from dbs_b200 import abi, runtime
 from ..models.diffusion import DiffusionProcess
 
-_CAPTURE_LOCK = threading.Lock()   # CUDA-graph captures of different samplers never overlap (see _StepProgram)
+_CAPTURE_LOCK = runtime.CAPTURE_LOCK   # CUDA-graph captures of different samplers never overlap (see _StepProgram)
 
 
 def _f32(v: float) -> float:
@@ -68,18 +68,20 @@ class _StepProgram:
         self.ws = self.model.engine_workspace(shape, self.precision)
         self._stage = torch.empty((DiffusionSampler._TABLE_ROWS, self.STRIDE), dtype=torch.float32).pin_memory()
         self._seed_stage = torch.zeros(2, dtype=torch.int64).pin_memory()
-        self._issue()                      # warm-up: one-time function attributes, tensor-map encoder lookup
-        torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         # thread_local: the capture records kernel launches only (workspace and buffers exist already), so CUDA calls of
         # OTHER threads — an MCMC job on the server's thread pool allocating its lattices (routes/training.py:191) — must
         # neither fail nor invalidate it, as they would in "global" mode.  torch.cuda.graph captures on ONE process-wide
         # side stream by default: two samplers capturing from two threads would begin a capture on a stream that is
-        # already capturing, so captures are serialised and each gets a stream of its own.  The cyclic garbage collector
-        # may run finalisers (cudaFree of a dropped plan, ...) on whichever thread happens to allocate — also on this
-        # one in mid-capture, where they are not permitted: it is paused for the capture (plan finalisers additionally
-        # defer themselves, runtime.release_plan).
+        # already capturing, so captures are serialised and each gets a stream of its own.  The warm-up launch and its
+        # synchronisation are inside the same lock (a device-wide synchronise issued by one thread while another thread
+        # was in mid-capture failed intermittently with "operation not permitted when stream is capturing"), and wait on
+        # this thread's stream only.  The cyclic garbage collector may run finalisers (cudaFree of a dropped plan, ...) on
+        # whichever thread happens to allocate — also on this one in mid-capture, where they are not permitted: it is
+        # paused for the capture (plan finalisers additionally defer themselves, runtime.release_plan).
         with _CAPTURE_LOCK:
+            self._issue()                  # warm-up: one-time function attributes, tensor-map encoder lookup
+            torch.cuda.current_stream().synchronize()
             gc_was_on = gc.isenabled()
             gc.disable()
             try:

@@ -40,6 +40,7 @@ class MetropolisHastings:
         # from it so np.random.seed() keeps runs reproducible
         self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
         self._sweeps_done = 0
+        self._starts_drawn = 0
         # h == 0: the kernel's multi-spin path (agreement counts for 32 sites at once, two thresholds)
         self.zero_field = 0 if (model.h != 0 or model.J == 0) else (1 if model.J > 0 else -1)
 
@@ -75,9 +76,15 @@ class MetropolisHastings:
     def step(self, spins: torch.Tensor) -> torch.Tensor:
         """One random-site attempt (samplers/mcmc.py:26-50): mutates and returns `spins`, flips at
         most one spin.  Site and uniform come from NumPy's global RNG like the reference's."""
+        if self._per_chain:
+            raise NotImplementedError("MetropolisHastings.step: one random-site attempt uses one acceptance table; with a "
+                                      "per-chain temperature tensor use sweep() / sample() (tables are selected per chain there)")
         L = self.model.size
         i = int(np.random.randint(L))
         j = int(np.random.randint(L))
+        # (the reference draws its uniform only when dE > 0, which it learns from a host read of dE; here the draw is
+        # made unconditionally so that no device->host synchronisation is needed: same acceptance rule, a different
+        # position in NumPy's stream afterwards)
         r = int(np.random.randint(0, 2 ** 32, dtype=np.uint64))
         tables, _ = self._tables()
         x = runtime.to_device(spins)
@@ -100,8 +107,11 @@ class MetropolisHastings:
     def _initial_bits(self, initial, n_chains):
         L = self.model.size
         if initial is None:
-            # hot start (samplers/mcmc.py:82) from the engine's Philox INIT stream
-            return self.model.random_packed(n_chains, self.seed)
+            # hot start (samplers/mcmc.py:82) from the engine's Philox INIT stream; every call draws a fresh one, as the
+            # reference does (chain ids continue where the previous call's stopped)
+            off = self._starts_drawn
+            self._starts_drawn += n_chains
+            return self.model.random_packed(n_chains, self.seed, chain_offset=off)
         init = initial if isinstance(initial, torch.Tensor) else torch.as_tensor(initial)
         if init.dim() == 2:
             init = init.unsqueeze(0).expand(n_chains, L, L)

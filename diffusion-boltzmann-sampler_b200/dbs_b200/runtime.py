@@ -7,6 +7,11 @@ import torch
 
 from . import abi
 
+# CUDA-graph captures (samplers) and the device-wide synchronisations of plan builds never overlap: a thread-local capture
+# tolerates other threads' launches and allocations, but a cudaDeviceSynchronize issued elsewhere in mid-capture was seen
+# to fail one of the two intermittently ("operation not permitted when stream is capturing").  Re-entrant.
+CAPTURE_LOCK = threading.RLock()
+
 _parked = []                       # (destroy_fn, handle) of plans whose release had to wait for a stream capture to end
 _parked_lock = threading.Lock()
 
@@ -74,4 +79,5 @@ def release_plan(destroy_fn, handle):
     destroy_fn(handle)
 
 
-__all__ = ["abi", "require_cuda", "current_stream", "to_device", "like_input", "ptr", "release_plan", "flush_released"]
+__all__ = ["abi", "require_cuda", "current_stream", "to_device", "like_input", "ptr", "release_plan", "flush_released",
+           "CAPTURE_LOCK"]

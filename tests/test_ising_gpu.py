@@ -162,6 +162,42 @@ def test_odd_lattice_observables_and_correlation_equal_reference(L):
     assert mh.sweep(x) is x
 
 
+def test_pair_correlation_of_real_valued_lattices_follows_the_reference_product():
+    """Real-valued samples (undiscretised diffusion output) are correlated as numbers, as analysis/correlation.py:42 does
+    (`ref_spin * sample[ni, nj]`), not binarised: against a direct evaluation of the reference's loops in float64, for
+    given reference sites, every site, and a lattice size the packed engine does not take; and the real-valued route
+    agrees with the bit-packed kernel on +/-1 input."""
+    from backend.ml.analysis import correlation as corr
+    rng = np.random.RandomState(3)
+
+    def direct(x, ref):
+        n, L, _ = x.shape
+        R = L // 2
+        c, k = np.zeros(R), np.zeros(R)
+        for s in x.astype(np.float64):
+            for idx in ref:
+                i, j = divmod(int(idx), L)
+                for di in range(-R, R + 1):
+                    for dj in range(-R, R + 1):
+                        r = int(np.sqrt(di * di + dj * dj))
+                        if 0 < r < R:
+                            c[r] += s[i, j] * s[(i + di) % L, (j + dj) % L]
+                            k[r] += 1
+        return np.divide(c, k, where=k > 0, out=np.zeros_like(c))
+
+    for L in (8, 6, 3):
+        x = rng.randn(5, L, L).astype(np.float32)
+        ref = rng.choice(L * L, min(7, L * L), replace=False)
+        np.testing.assert_allclose(corr.pair_correlation(torch.tensor(x), ref_indices=ref)["C_r"], direct(x, ref), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(corr.pair_correlation(torch.tensor(x), ref_indices="all")["C_r"], direct(x, np.arange(L * L)),
+                                   rtol=1e-9, atol=1e-9)
+    s = torch.tensor(rng.choice([-1.0, 1.0], size=(6, 16, 16)).astype(np.float32))
+    ref = rng.choice(256, 30, replace=False)
+    packed = corr.pair_correlation(s, ref_indices=ref)["C_r"]
+    real = corr._pair_correlation_real(s.cuda(), ref)["C_r"]
+    np.testing.assert_allclose(real, packed, rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize("L", [12, 32, 64, 128])
 def test_pair_correlation_all_sites_vs_oracle(L):
     from backend.ml.analysis.correlation import pair_correlation
