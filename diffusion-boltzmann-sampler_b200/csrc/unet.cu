@@ -805,6 +805,105 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
   }
 }
 
+// GroupNorm apply of the FIRST encoder block's second conv with the block's residual recomputed from the network input.
+// The block's input is the init conv's output h = W_i * x + b_i (score_network.py:238, one input channel, no activation
+// in between), so its residual projection r = W_r h + b_r (score_network.py:131,151) is itself a 3x3 convolution of the
+// one-channel input: r[p][c] = bc[c] + sum_tap wc[tap][c] * x[p + tap], wc = W_r W_i composed once per plan in fp32.  Nine
+// FMAs per output element from a 16 KB-per-sample tensor replace writing r (by conv1's epilogue) and reading it back here:
+// 2 x the block's activation bytes, and conv1 runs without its fused 1x1 residual output.  A thread keeps one 8-channel
+// vector for UN pixels at a time, so each 32-byte weight row read from shared memory serves UN pixels.
+template <int UN>
+__global__ void __launch_bounds__(256, 2)
+gn_apply_xres_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, const float* __restrict__ stats,
+                     float inv_cnt, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ xin, const float* __restrict__ wc, const float* __restrict__ bc,
+                     int H, int W, int C, int TH) {
+  // A CTA owns TH full-width rows of one image; the rows of x (+ one halo row / column each side, zero outside the
+  // image: the init conv's padding) sit in shared memory, so a tap is one LDS shared by the eight threads of a pixel.
+  constexpr int V = 8;
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_w = s_dyn;                       // [9][C] composed weights, then [C] composed bias
+  float* s_x = s_dyn + 10 * C;              // [(TH + 2)][W + 2]
+  const int n = blockIdx.y, h0 = blockIdx.x * TH;
+  const int Cg = C / 8;
+  const int cv = C / V;
+  const int c = (threadIdx.x % cv) * V;
+  const int prow = threadIdx.x / cv;
+  const int ppb = blockDim.x / cv;
+  const int Wp = W + 2;
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wc[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[9 * C + i] = bc[i];
+  const float* xb = xin + (int64_t)n * H * W;
+  for (int i = threadIdx.x; i < (TH + 2) * Wp; i += blockDim.x) {
+    const int r = i / Wp, cc = i - r * Wp;
+    const int ih = h0 + r - 1, iw = cc - 1;
+    s_x[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.f;
+  }
+  const int rows = min(TH, H - h0);
+  const int n_pix = rows * W;
+  const __nv_bfloat16* yb = y + ((int64_t)n * H + h0) * W * C + c;
+  __nv_bfloat16* ob = out + ((int64_t)n * H + h0) * W * C + c;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int gi = (c + k) / Cg;
+    const float s0 = stats[((int64_t)n * 8 + gi) * 2 + 0], s1 = stats[((int64_t)n * 8 + gi) * 2 + 1];
+    const float mean = s0 * inv_cnt;
+    const float rstd = rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps);
+    const float a = rstd * gamma[c + k];
+    sc[k] = a;
+    sh[k] = beta[c + k] - mean * a;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int p0 = prow; p0 < n_pix; p0 += UN * ppb) {
+    uint4 q[UN];
+    float r[UN][V];
+    int xo[UN];                                // offset of the pixel's top-left tap in s_x
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * ppb;
+      const bool live = p < n_pix;
+      q[u] = live ? Vec16<__nv_bfloat16>::load_raw(yb + (int64_t)p * C) : make_uint4(0, 0, 0, 0);
+      const int pr = live ? p / W : 0, pc = live ? p - pr * W : 0;
+      xo[u] = pr * Wp + pc;
+    }
+    {
+      const float4 c0 = *reinterpret_cast<const float4*>(&s_w[9 * C + c]), c1 = *reinterpret_cast<const float4*>(&s_w[9 * C + c + 4]);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        r[u][0] = c0.x; r[u][1] = c0.y; r[u][2] = c0.z; r[u][3] = c0.w;
+        r[u][4] = c1.x; r[u][5] = c1.y; r[u][6] = c1.z; r[u][7] = c1.w;
+      }
+    }
+#pragma unroll 1
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[(kh * 3 + kw) * C + c]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[(kh * 3 + kw) * C + c + 4]);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const float xv = s_x[xo[u] + kh * Wp + kw];
+          r[u][0] = fmaf(xv, w0.x, r[u][0]); r[u][1] = fmaf(xv, w0.y, r[u][1]);
+          r[u][2] = fmaf(xv, w0.z, r[u][2]); r[u][3] = fmaf(xv, w0.w, r[u][3]);
+          r[u][4] = fmaf(xv, w1.x, r[u][4]); r[u][5] = fmaf(xv, w1.y, r[u][5]);
+          r[u][6] = fmaf(xv, w1.z, r[u][6]); r[u][7] = fmaf(xv, w1.w, r[u][7]);
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * ppb;
+      if (p >= n_pix) break;
+      float v[V];
+      Vec16<__nv_bfloat16>::unpack(q[u], v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = silu_fast(fmaf(v[k], sc[k], sh[k])) + r[u][k];
+      Vec16<__nv_bfloat16>::store(ob + (int64_t)p * C, v);
+    }
+  }
+}
+
 // stand-alone time path: gridDim.x = distinct t values, gridDim.y CTAs per value (see time_path above)
 __global__ void __launch_bounds__(256)
 time_kernel(const __grid_constant__ TimeArgs ta) {
@@ -908,6 +1007,8 @@ struct dbs_unet_plan {
   float *init_w = nullptr, *init_b = nullptr, *final_w = nullptr, *final_b = nullptr;
   std::vector<float> final_w_host;   // [tap][C] host copy of the final conv's weights
   uint32_t* final_bfrag = nullptr;   // their mma.sync B fragments (final_bfrag_host), C a multiple of 16 only
+  // first encoder block: residual projection composed with the init conv, [9][cout] + [cout] (gn_apply_xres_kernel)
+  float *enc0_wc = nullptr, *enc0_bc = nullptr;
   std::vector<float> init_w_host, init_b_host;   // [tap][C], [C]: kernel-parameter copies for the init conv
   float final_b_host = 0.f;
   std::vector<dbs::BlockW> enc, dec;
@@ -1010,6 +1111,7 @@ struct Ctx {
   bool use_tc;
   const char* tap; float* tap_out; int64_t tap_numel; bool tapped = false;
   DeferredGn* defer = nullptr;
+  const float* xin = nullptr;      // the network input (B, 1, H, W): set while the FIRST encoder block runs (residual from input)
   float* stats_base = nullptr; int64_t stats_stride = 0; int* stats_next = nullptr; int stats_slices = 0;
   // bf16 path: every conv+GroupNorm pair gets its own slice of one region zeroed by ONE memset per forward
   // (instead of a memset node in front of each conv); returns false when the region is used up
@@ -1133,8 +1235,16 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   }
 
   if (c.use_tc && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
+  // First encoder block on the tensor-core path (opt-in, DBS_XRES=1): its residual projection is recomputed from the
+  // one-channel network input inside the closing GroupNorm apply (gn_apply_xres_kernel), so conv1 runs WITHOUT the fused
+  // 1x1 residual output and the residual tensor is neither written nor read.  Measured at 64x64, B = 1024 (round 2):
+  // conv1 475 -> 346 us, but the apply kernel's 72 FMAs per 8-channel vector make it latency-bound at 396 us against
+  // 259 us for the HBM-bound GroupNorm apply it replaces: net zero, so the fused 1x1 stays the default.
+  static const bool xres_off = [] { const char* e = getenv("DBS_XRES"); return !(e && e[0] == '1'); }();
+  const bool xres = c.use_tc && sizeof(T) == 2 && bw.has_res && c.xin && c.plan->enc0_wc && &bw == &c.plan->enc[0] && !c.tap &&
+                    !xres_off && C1 == 0 && bw.cout % 8 == 0 && bw.cout <= 256 && G == 8;
   bool res_done = false;
-  if (c.use_tc && sizeof(T) == 2 && bw.has_res) {
+  if (c.use_tc && sizeof(T) == 2 && bw.has_res && !xres) {
     // conv1 and the 1x1 residual conv read the same input: one pass of the strip kernel does both
     rc = conv_strip_launch(g1, (const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, bw.conv1.w16, bw.conv1.bias,
                            (__nv_bfloat16*)ty, c.stats, G, c.st, bw.res.w16, bw.res.bias, (__nv_bfloat16*)tr);
@@ -1168,6 +1278,21 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     if (rc) return rc;
     if (c.use_tc && stats2 == stats1 && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
     if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
+  }
+  if (xres && sd) {
+    const int cv = bw.cout / 8;
+    const int threads = (256 / cv) * cv;
+    constexpr int UN = 4;
+    int TH = std::max(1, 512 / W);             // ~512 pixels per CTA
+    if (TH > H) TH = H;
+    const size_t smem = ((size_t)10 * bw.cout + (size_t)(TH + 2) * (W + 2)) * 4;
+    prof_set_label("HW%d C%d xres", H * W, bw.cout);
+    ProfScope prof(kProfGnApply, c.st);
+    gn_apply_xres_kernel<UN><<<dim3((unsigned)((H + TH - 1) / TH), (unsigned)c.B), threads, smem, c.st>>>(
+        (const __nv_bfloat16*)y2, (__nv_bfloat16*)out, c.stats, 1.0f / (float)((int64_t)H * W * (bw.cout / 8)), 1e-5f, bw.g2, bw.b2,
+        c.xin, c.plan->enc0_wc, c.plan->enc0_bc, H, W, bw.cout, TH);
+    DBS_LAUNCHED();
+    return DBS_OK;
   }
   const T* res = in0;
   if (bw.has_res) {
@@ -1330,6 +1455,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
       Ctx cc = sub_ctx(b0, nbc);
       const T* in_c = cur + b0 * h * w * ch;
       T* skip_c = skip[i] + b0 * h * w * co;
+      cc.xin = (i == 0 && !fixup) ? x + b0 * h * w : nullptr;    // block 0's input is the init conv of x
       if ((rc = run_block<T>(cc, plan->enc[i], name, in_c, ch, (const T*)nullptr, 0, h, w, ty, th, tr, skip_c))) return rc;
       ConvGeom gd = geom_conv((int)nbc, h, w, co, 0, co, 3, 2);
       static const bool s2d_off = [] { const char* e = getenv("DBS_STRIP_S2D"); return e && e[0] == '0'; }();
@@ -1577,6 +1703,40 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
       repack_s2d_kernel<<<(unsigned)((n4 + 255) / 256), 256>>>(plan->down[i].w16, plan->down[i].w16_s2d, co, co);
     }
     ch = co; enc_ch.push_back(co);
+  }
+  {
+    // encoder.0's residual projection composed with the init conv: wc[tap][co] = sum_ci Wr[co][ci] Wi[ci][tap],
+    // bc[co] = br[co] + sum_ci Wr[co][ci] bi[ci]  (fp32 on the host; see gn_apply_xres_kernel)
+    const int co0 = C << 1;
+    const dbs_param* wr = pt.find("encoder.0.residual.weight");
+    const dbs_param* br = pt.find("encoder.0.residual.bias");
+    if (wr && br && wr->numel == (int64_t)co0 * C && br->numel == co0) {
+      std::vector<float> hwr((size_t)co0 * C), hbr((size_t)co0), wc((size_t)9 * co0), bc((size_t)co0);
+      if (cudaMemcpy(hwr.data(), wr->data, hwr.size() * 4, wr->is_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess ||
+          cudaMemcpy(hbr.data(), br->data, hbr.size() * 4, br->is_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess) {
+        set_error("unet_plan_create: reading encoder.0.residual failed");
+        return fail(DBS_ERR_CUDA);
+      }
+      for (int o = 0; o < co0; ++o) {
+        double b = hbr[o];
+        for (int ci = 0; ci < C; ++ci) b += (double)hwr[(size_t)o * C + ci] * plan->init_b_host[ci];
+        bc[o] = (float)b;
+        for (int t = 0; t < 9; ++t) {
+          double a = 0.0;
+          for (int ci = 0; ci < C; ++ci) a += (double)hwr[(size_t)o * C + ci] * plan->init_w_host[(size_t)t * C + ci];
+          wc[(size_t)t * co0 + o] = (float)a;
+        }
+      }
+      void *dw = nullptr, *db = nullptr;
+      if ((rc = dev_alloc(plan, wc.size() * 4, &dw))) return fail(rc);
+      if ((rc = dev_alloc(plan, bc.size() * 4, &db))) return fail(rc);
+      if (cudaMemcpy(dw, wc.data(), wc.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(db, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("unet_plan_create: composed residual upload failed");
+        return fail(DBS_ERR_CUDA);
+      }
+      plan->enc0_wc = (float*)dw; plan->enc0_bc = (float*)db;
+    }
   }
   if ((rc = make_block(plan, pt, "middle.", ch, ch, &plan->mid))) return fail(rc);
   plan->mid.tb_off = off; off += ch; tls.push_back({"middle.", ch});
