@@ -748,24 +748,26 @@ ising_corr_warp2_kernel(const uint32_t* __restrict__ bits, int L, int64_t n_chai
       const uint64_t sa = v0 ? (r0 >= 32 ? a_hi : a_lo) : 0ull;
       const uint64_t sb = v1 ? (r1 >= 32 ? b_hi : b_lo) : 0ull;
       const unsigned char* brow = s_bin + di * R;
-      {   // dj = k >= 0: bit j of the shifted row = bit (j + k) mod L
+      // dj = +k (bit j of the shifted row = bit (j + k) mod L: right rotation) and dj = -k (left rotation) fall in the same
+      // radial bin, so one pass over k handles both with one bin lookup and one shared-memory add
+      {
         const int k0 = di == 0 ? 1 : 0;
         uint64_t ra = sa, rb = sb;
         if (k0) { ra = rot1_right_L<k64>(ra, L); rb = rot1_right_L<k64>(rb, L); }
-        for (int k = k0; k < R; ++k) {
-          const int bin = brow[k];
-          if (bin == 255) break;       // r >= R from here on (r = 0 only at di = dj = 0, which is never visited)
-          atomicAdd(part + bin * 32, __popcll(lo ^ ra) + __popcll(hi ^ rb));
+        uint64_t la = rot1_left_L<k64>(sa, L, maskL), lb = rot1_left_L<k64>(sb, L, maskL);   // k = 1 of the negative side
+        if (k0 == 0) {
+          const int bin = brow[0];     // dj = 0 (di > 0): counted once
+          if (bin != 255) atomicAdd(part + bin * 32, __popcll(lo ^ ra) + __popcll(hi ^ rb));
           ra = rot1_right_L<k64>(ra, L); rb = rot1_right_L<k64>(rb, L);
         }
-      }
-      if (di > 0) {   // dj = -k: a right rotation by L - k = a left rotation by k
-        uint64_t ra = rot1_left_L<k64>(sa, L, maskL), rb = rot1_left_L<k64>(sb, L, maskL);
         for (int k = 1; k < R; ++k) {
           const int bin = brow[k];
-          if (bin == 255) break;
-          atomicAdd(part + bin * 32, __popcll(lo ^ ra) + __popcll(hi ^ rb));
-          ra = rot1_left_L<k64>(ra, L, maskL); rb = rot1_left_L<k64>(rb, L, maskL);
+          if (bin == 255) break;       // r >= R from here on (r = 0 only at di = dj = 0, which is never visited)
+          int pc = __popcll(lo ^ ra) + __popcll(hi ^ rb);
+          if (di > 0) pc += __popcll(lo ^ la) + __popcll(hi ^ lb);
+          atomicAdd(part + bin * 32, pc);
+          ra = rot1_right_L<k64>(ra, L); rb = rot1_right_L<k64>(rb, L);
+          la = rot1_left_L<k64>(la, L, maskL); lb = rot1_left_L<k64>(lb, L, maskL);
         }
       }
     }
