@@ -35,7 +35,8 @@ int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const floa
                   const float* pre_b, const float* post_g, const float* post_b, int silu, const float* tbias,
                   int64_t tb_stride, int tokens_per_cfg, const float* res, void* out, int out_bf16, int64_t M,
                   cudaStream_t st, const float* pos_freqs = nullptr, const float* head_w2 = nullptr,
-                  const float* head_b2 = nullptr);
+                  const float* head_b2 = nullptr, const __nv_bfloat16* W2 = nullptr, const float* bias2 = nullptr,
+                  const float* post2_g = nullptr, const float* post2_b = nullptr);
 int csn_tc_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t B, int N, int heads, cudaStream_t st);
 }  // namespace dbs
 
@@ -468,8 +469,20 @@ int forward_impl(dbs_csn_plan* plan, const float* x, const float* t, int64_t n_t
       // kernels' prologue and epilogue; h (the residual stream) stays fp32, h1 / qkv / attention output are bf16
       const float* tb = tbias + (int64_t)i * H;
       const int64_t tbs = n_t == 1 ? 0 : (int64_t)nb * H;
-      if ((rc = csn_tc_linear(h, 0, b.fc1_h, b.fc1_b, H, nullptr, nullptr, b.n1_g, b.n1_b, 1, tb, tbs, N, nullptr, h1, 1, M, st))) return rc;
-      if ((rc = csn_tc_linear(h1, 1, b.fc2_h, b.fc2_b, H, nullptr, nullptr, b.n2_g, b.n2_b, 1, nullptr, 0, N, h, h, 0, M, st))) return rc;
+      // MLPBlock as ONE launch: fc1 -> norm1 -> SiLU -> + time bias -> fc2 -> norm2 -> SiLU -> + x, in place on the
+      // residual stream (a CTA reads and writes only its own token rows).  Parity-green but measured SLOWER than the two
+      // launches (4096 x 256: linears 9.89 vs 9.30 ms per forward): the CTA runs stage -> MMA -> drain -> MMA -> drain as
+      // serial phases and the third weight tile drops it from 3 to 2 CTAs per SM, so the saved HBM round trip of the bf16
+      // intermediate is paid back in latency.  Opt-in: DBS_CSN_FUSE_MLP=1.
+      static const bool fuse_mlp = [] { const char* e = getenv("DBS_CSN_FUSE_MLP"); return e && e[0] == '1'; }();
+      if (fuse_mlp) {
+        if ((rc = csn_tc_linear(h, 0, b.fc1_h, b.fc1_b, H, nullptr, nullptr, b.n1_g, b.n1_b, 1, tb, tbs, N, nullptr, h, 0, M, st,
+                                nullptr, nullptr, nullptr, b.fc2_h, b.fc2_b, b.n2_g, b.n2_b)))
+          return rc;
+      } else {
+        if ((rc = csn_tc_linear(h, 0, b.fc1_h, b.fc1_b, H, nullptr, nullptr, b.n1_g, b.n1_b, 1, tb, tbs, N, nullptr, h1, 1, M, st))) return rc;
+        if ((rc = csn_tc_linear(h1, 1, b.fc2_h, b.fc2_b, H, nullptr, nullptr, b.n2_g, b.n2_b, 1, nullptr, 0, N, h, h, 0, M, st))) return rc;
+      }
       if ((rc = csn_tc_linear(h, 0, b.qkv_h, b.qkv_b, 3 * H, b.an_g, b.an_b, nullptr, nullptr, 0, nullptr, 0, N, nullptr, qkv, 1, M, st))) return rc;
       if ((rc = csn_tc_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)h1, B, N, c.num_heads, st))) return rc;
       if ((rc = csn_tc_linear(h1, 1, b.proj_h, b.proj_b, H, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, N, h, h, 0, M, st))) return rc;

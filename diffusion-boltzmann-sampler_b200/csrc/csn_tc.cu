@@ -67,6 +67,11 @@ struct TcLinArgs {
   // applied to the thread's row in the epilogue; out = score fp32 [M][2]
   const float* head_w2;         // [2][64], null = no head
   const float* head_b2;         // [2]
+  // fused MLPBlock (:123-136): this launch is fc1 (post LayerNorm norm1, SiLU, + time bias) AND fc2 (LayerNorm norm2, SiLU)
+  // + the block's residual x.  The activated fc1 rows go straight from the TMEM drain into the bf16 A-operand tile of the
+  // second GEMM: the intermediate never reaches HBM and the residual stream is read once and written once per block.
+  const __nv_bfloat16* W2;      // [128][128] bf16, null = single layer
+  const float *bias2, *post2_g, *post2_b;
 };
 
 // a warp converts 128-wide rows to bf16 and stores them into the swizzled K-major operand tile; the loads of
@@ -156,6 +161,8 @@ csn_tc_linear_kernel(const TcLinArgs a) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* As = smem;                   // 2 slabs x 16 KB
   uint8_t* Ws = smem + 2 * kAtomBytes;  // 2 slabs x 16 KB
+  uint8_t* Ws2 = smem + 4 * kAtomBytes; // fused MLPBlock: fc2's weights, 2 slabs x 16 KB (allocated only then)
+  __shared__ __align__(16) float s_bias2[128], s_pg2[128], s_pb2[128];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_tmem;
   // per-column epilogue vectors of this CTA's 128 columns: warp-uniform reads, so they are served as
@@ -172,11 +179,13 @@ csn_tc_linear_kernel(const TcLinArgs a) {
     s_pb[c] = a.post_b ? a.post_b[c] : 0.f;
     s_tb[c] = tb_shared ? a.tbias[col0 + c] : 0.f;
     if (a.head_w2) s_w2[c >> 6][c & 63] = a.head_w2[c];
+    if (a.W2) { s_bias2[c] = a.bias2[c]; s_pg2[c] = a.post2_g[c]; s_pb2[c] = a.post2_b[c]; }
   }
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 128);
   // this CTA's 128 weight rows, once
   stage_tile<true>(Ws, a.W + (int64_t)col0 * 128, 128, warp, lane, nullptr, nullptr);
+  if (a.W2) stage_tile<true>(Ws2, a.W2, 128, warp, lane, nullptr, nullptr);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -184,6 +193,7 @@ csn_tc_linear_kernel(const TcLinArgs a) {
   const uint32_t tmem = s_tmem;
   const uint32_t a_lo = (uint32_t)kDesc128 | ((smem_u32(As) & 0x3FFFFu) >> 4);
   const uint32_t w_lo = (uint32_t)kDesc128 | ((smem_u32(Ws) & 0x3FFFFu) >> 4);
+  const uint32_t w2_lo = (uint32_t)kDesc128 | ((smem_u32(Ws2) & 0x3FFFFu) >> 4);
   const uint32_t hi32 = (uint32_t)(kDesc128 >> 32);
   const int64_t n_tiles = (a.M + 127) / 128;
   uint32_t phase = 0;
@@ -236,6 +246,91 @@ csn_tc_linear_kernel(const TcLinArgs a) {
       rstd = rsqrtf(fmaxf(ss * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
     }
     const float* tb = (a.tbias && !tb_shared) ? a.tbias + (live ? m / a.tokens_per_cfg : 0) * a.tb_stride : nullptr;
+    if (a.W2) {
+      // ---- fused MLPBlock, stage 1 drain: norm1 -> SiLU -> + time bias, written as the bf16 A operand of fc2
+#pragma unroll 1
+      for (int c = ch * 64; c < ch * 64 + 64; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j2 = 0; j2 < 8; ++j2) {
+          float y[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int j = 2 * j2 + k;
+            float x = (__uint_as_float(v[j]) + s_bias[c + j] - mean) * rstd * s_pg[c + j] + s_pb[c + j];
+            x = silu_fast(x) + s_tb[c + j];
+            if (tb) x += __ldg(tb + c + j);
+            y[k] = x;
+          }
+          pk[j2] = pack_bf16(y[0], y[1]);
+        }
+        // element k = c .. c + 15 of row `row`: slab k / 64, 16-byte chunks (k % 64) / 8 and + 1, XOR (row % 8)
+        uint8_t* rowp = As + (uint32_t)(c >> 6) * kAtomBytes + (uint32_t)row * 128u;
+        const int c8 = (c & 63) >> 3;
+        *reinterpret_cast<uint4*>(rowp + (((c8) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(rowp + (((c8 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();          // every row of the operand tile written, TMEM drained
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t o = (uint32_t)(k >> 2) * (kAtomBytes >> 4) + (uint32_t)(k & 3) * 2u;
+          umma_bf16_lohi(tmem, a_lo + o, w2_lo + o, hi32, idesc_bf16(128, 128), k ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar));
+      }
+      mbar_wait(smem_u32(&bar), phase);
+      phase ^= 1;
+      tc_fence_after();
+      // ---- stage 2 drain: norm2 -> SiLU -> + x (the block's residual, read back from L2) -> out
+      float s2 = 0.f, ss2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float f = __uint_as_float(v[j]) + s_bias2[c + j];
+          s2 += f;
+          ss2 = fmaf(f, f, ss2);
+        }
+      }
+      const float mean2 = s2 * (1.0f / 128.0f);
+      const float rstd2 = rsqrtf(fmaxf(ss2 * (1.0f / 128.0f) - mean2 * mean2, 0.f) + 1e-5f);
+#pragma unroll 1
+      for (int c = ch * 64; c < ch * 64 + 64; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (live) {
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.X) + m * 128 + c);
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + m * 128 + c);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 r4 = rp[j4];
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int j = 4 * j4 + k;
+              const float x = (__uint_as_float(v[j]) + s_bias2[c + j] - mean2) * rstd2 * s_pg2[c + j] + s_pb2[c + j];
+              o[k] = silu_fast(x) + rr[k];
+            }
+            dst[j4] = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+      continue;
+    }
     if (a.head_w2) {
       // output head: columns 0..63 hold Linear(128 -> 64) of the row (64..127 are zero padding); SiLU, then the
       // 64 -> 2 projection as two thread-local dot products
@@ -505,24 +600,28 @@ int csn_tc_convert_weights(const float* src, __nv_bfloat16* dst, int64_t n) {
 int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const float* bias, int N_total, const float* pre_g,
                   const float* pre_b, const float* post_g, const float* post_b, int silu, const float* tbias,
                   int64_t tb_stride, int tokens_per_cfg, const float* res, void* out, int out_bf16, int64_t M,
-                  cudaStream_t st, const float* pos_freqs, const float* head_w2, const float* head_b2) {
+                  cudaStream_t st, const float* pos_freqs, const float* head_w2, const float* head_b2,
+                  const __nv_bfloat16* W2, const float* bias2, const float* post2_g, const float* post2_b) {
   DBS_REQUIRE(N_total % 128 == 0 && (!post_g || N_total == 128), "csn_tc_linear: unsupported width %d", N_total);
+  DBS_REQUIRE(!W2 || (N_total == 128 && post_g && post2_g && bias2 && !in_bf16 && !out_bf16 && !res && !head_w2 && !pos_freqs),
+              "csn_tc_linear: the fused MLPBlock form needs fp32 in / out, both LayerNorms and no other fusion");
   TcLinArgs a;
   a.X = X; a.W = W; a.bias = bias; a.N_total = N_total; a.pre_g = pre_g; a.pre_b = pre_b; a.post_g = post_g; a.post_b = post_b;
   a.silu = silu; a.tbias = tbias; a.tb_stride = tb_stride; a.tokens_per_cfg = tokens_per_cfg; a.res = res; a.out = out;
   a.in_bf16 = in_bf16; a.out_bf16 = out_bf16; a.M = M;
   a.pos_freqs = pos_freqs; a.head_w2 = head_w2; a.head_b2 = head_b2;
-  const size_t smem = 4 * kAtomBytes + 1024;
+  a.W2 = W2; a.bias2 = bias2; a.post2_g = post2_g; a.post2_b = post2_b;
+  const size_t smem = (W2 ? 6 : 4) * kAtomBytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    DBS_CUDA(cudaFuncSetAttribute(csn_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DBS_CUDA(cudaFuncSetAttribute(csn_tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * kAtomBytes + 1024)));
     attr_done = true;
   }
   const int64_t n_tiles = (M + 127) / 128;
   const int by = N_total / 128;
   int64_t bx = (148 * 3 + by - 1) / by;
   if (bx > n_tiles) bx = n_tiles;
-  prof_set_label("tc linear N%d ln%d/%d", N_total, pre_g ? 1 : 0, post_g ? 1 : 0);
+  prof_set_label("tc linear N%d ln%d/%d%s", N_total, pre_g ? 1 : 0, post_g ? 1 : 0, W2 ? " +fc2 (MLPBlock)" : "");
   ProfScope prof(kProfCsnLinear, st);
   csn_tc_linear_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, smem, st>>>(a);
   DBS_LAUNCHED();
