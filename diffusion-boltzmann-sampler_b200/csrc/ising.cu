@@ -930,6 +930,24 @@ extern "C" int dbs_ising_observables_f32(const float* spins, int L, int64_t n, f
   return DBS_OK;
 }
 
+namespace dbs {
+// ising_corr_fft.cu: spectral evaluation of the same sums (64 x 64 only)
+int ising_corr_fft_launch(const uint32_t* bits, int64_t n_chains, const int32_t* group, long long* acc, float J, float h,
+                          double* block, int block_stride, cudaStream_t st);
+// 0 = automatic (spectral kernel at L = 64 with every site a reference site, XOR / POPC kernels otherwise),
+// 1 = always the XOR / POPC kernels, 2 = spectral where it applies (same as 0 today)
+static std::atomic<int> g_corr_method{0};
+static bool corr_use_fft(int L, const uint32_t* ref_mask) {
+  static const bool env_off = [] { const char* e = getenv("DBS_CORR_FFT"); return e && e[0] == '0'; }();
+  return L == 64 && !ref_mask && !env_off && g_corr_method.load(std::memory_order_relaxed) != 1;
+}
+}  // namespace dbs
+
+extern "C" int dbs_ising_set_correlation_method(int method) {
+  if (method < 0 || method > 2) { set_error("ising_set_correlation_method: method %d (0 automatic, 1 direct, 2 spectral)", method); return DBS_ERR_INVALID; }
+  return g_corr_method.exchange(method, std::memory_order_relaxed);
+}
+
 extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chains, const uint32_t* ref_mask,
                                      const int32_t* group, long long* acc, void* stream) {
   DBS_REQUIRE(supported_L(L), "ising: lattice size %d unsupported (4..%d, not 3)", L, kMaxL);
@@ -939,6 +957,7 @@ extern "C" int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chai
   const int W = (L + 31) / 32, tpc = L * W;
   const size_t smem = (size_t)(2 * tpc + L * (2 * W + 2)) * 4 + (size_t)(L / 2) * 4;
   ProfScope prof(kProfIsingObs, as_stream(stream));
+  if (corr_use_fft(L, ref_mask)) return ising_corr_fft_launch(bits, n_chains, group, acc, 0.f, 0.f, nullptr, 0, as_stream(stream));
   static const bool warp_off = [] { const char* e = getenv("DBS_CORR_WARP"); return e && e[0] == '0'; }();
   if (!ref_mask && L <= 64 && !warp_off) {
     const unsigned grid = (unsigned)((n_chains + kCorrWarps - 1) / kCorrWarps);
@@ -965,6 +984,7 @@ extern "C" int dbs_ising_measure(const uint32_t* bits, int L, int64_t n_chains, 
   DBS_REQUIRE(bits && block && corr_acc && n_chains >= 0 && block_stride >= 6, "ising_measure: bad arguments");
   const unsigned grid = (unsigned)((n_chains + kCorrWarps - 1) / kCorrWarps);
   ProfScope prof(kProfIsingObs, as_stream(stream));
+  if (corr_use_fft(L, nullptr)) return ising_corr_fft_launch(bits, n_chains, group, corr_acc, J, h, block, block_stride, as_stream(stream));
   if (L == 64) ising_corr_warp2_kernel<true, true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, corr_acc, -J, -h, block, block_stride);
   else ising_corr_warp2_kernel<false, true><<<grid, 32 * kCorrWarps, 0, as_stream(stream)>>>(bits, L, n_chains, group, corr_acc, -J, -h, block, block_stride);
   DBS_LAUNCHED();

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "dbs_ising_observables_f32": (i32, [vp, i32, i64, f32, f32, vp, vp, vp]),
     "dbs_ising_correlation": (i32, [vp, i32, i64, vp, vp, vp, vp]),
     "dbs_ising_measure": (i32, [vp, i32, i64, f32, f32, vp, vp, i32, vp, vp]),
+    "dbs_ising_set_correlation_method": (i32, [i32]),
     "dbs_observable_accumulate": (i32, [vp, vp, i32, i64, vp, vp, vp]),
     "dbs_em_step": (i32, [vp, vp, vp, i64, i64, f32, f32, f32, f32, i32, u64, i64, i64, vp]),
     "dbs_gaussian_fill": (i32, [vp, i64, i64, u64, i64, i64, vp]),

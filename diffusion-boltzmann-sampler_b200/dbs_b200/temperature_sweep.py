@@ -101,6 +101,10 @@ def run_temperature_sweep(lattice_size=64, temperatures=None, chains_per_tempera
         block[:, 2] = e2
         block[:, 3:6] = acc5[:, 2:5]
     block[:, NOBS:] = corr.to(torch.float64)
+    if with_correlation and int(corr[:, 0].abs().sum()) != 0:
+        # r = 0 is never a valid radius; the spectral C(r) kernel marks a lost exactness argument there (include/dbs_b200.h)
+        raise RuntimeError("C(r): the spectral kernel met a value that is not an integer; rerun with "
+                           "dbs_ising_set_correlation_method(1)")
     if reduce:
         allreduce_block(block)                      # the one collective of the path
     out = finalize_observables(block[:, :NOBS])

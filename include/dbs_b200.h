@@ -159,6 +159,14 @@ int dbs_ising_correlation(const uint32_t* bits, int L, int64_t n_chains,
 int dbs_ising_measure(const uint32_t* bits, int L, int64_t n_chains, float J, float h, const int32_t* group,
                       double* block, int block_stride, long long* corr_acc, void* stream);
 
+/* How dbs_ising_correlation (ref_mask == NULL) and dbs_ising_measure evaluate the C(r) sums.  0 (default) = automatic:
+ * at L = 64 the spectral kernel (|FFT2|^2 -> inverse FFT2 of four chains at a time, every value rounded to the integer it
+ * is; csrc/ising_corr_fft.cu), the XOR / POPC displacement kernels at every other size; 1 = always XOR / POPC; 2 = spectral
+ * where it applies.  Both produce the same int64 sums bit for bit.  The spectral kernel leaves acc[group][0] (r = 0 is
+ * never a valid radius) at zero unless a value was not within 1/4 of an integer — callers treat a non-zero bin 0 as an
+ * error.  Process-wide; returns the previous method, or DBS_ERR_INVALID. */
+int dbs_ising_set_correlation_method(int method);
+
 /* Block accumulation of per-chain observables into the fp64 all-reduce block
  * (SURVEY.md §8e): acc[group][0..4] += {1, E/N, |M|, M^2, M^4}. */
 int dbs_observable_accumulate(const float* energy, const float* magnetization, int L,

@@ -212,6 +212,78 @@ def test_pair_correlation_all_sites_vs_oracle(L):
                           np.array(o.pair_correlation(s, idx)["C_r"]))
 
 
+def _corr_sums(bits, group, n_groups, method, measure=False, J=1.0, h=0.0):
+    """C(r) sums (and, with measure, the fp64 observable block) of packed 64 x 64 chains with a chosen evaluation method."""
+    from dbs_b200 import abi, runtime
+    prev = abi.lib.dbs_ising_set_correlation_method(method)
+    try:
+        n = bits.shape[0]
+        acc = torch.zeros((n_groups, 32), dtype=torch.int64, device=bits.device)
+        gp = group.data_ptr() if group is not None else 0
+        if measure:
+            block = torch.zeros((n_groups, 6), dtype=torch.float64, device=bits.device)
+            abi.check(abi.lib.dbs_ising_measure(bits.data_ptr(), 64, n, J, h, gp, block.data_ptr(), 6, acc.data_ptr(),
+                                                runtime.current_stream()))
+            return acc.cpu(), block.cpu()
+        abi.check(abi.lib.dbs_ising_correlation(bits.data_ptr(), 64, n, 0, gp, acc.data_ptr(), runtime.current_stream()))
+        return acc.cpu(), None
+    finally:
+        abi.lib.dbs_ising_set_correlation_method(prev)
+
+
+@pytest.mark.parametrize("n_chains", [1, 2, 3, 4, 5, 7, 64, 1001])
+def test_spectral_correlation_equals_the_displacement_kernel_bit_for_bit(n_chains):
+    """The |FFT2|^2 -> inverse FFT2 evaluation of the C(r) sums at 64 x 64 (csrc/ising_corr_fft.cu) against the XOR / POPC
+    kernels: same int64 sums, bin 0 untouched — for hot, ordered, striped, strongly magnetised and equilibrated lattices,
+    with no group array, one group per chain, contiguous groups and groups that change inside a quad of chains."""
+    IsingModel, MetropolisHastings = _mods()
+    m = IsingModel(64)
+    rng = np.random.RandomState(n_chains)
+    s = rng.choice([-1.0, 1.0], size=(n_chains, 64, 64)).astype(np.float32)
+    s[0] = 1.0
+    if n_chains > 2:
+        s[2] = np.where((np.arange(64)[:, None] // 8 + np.arange(64)[None, :] // 4) % 2, 1.0, -1.0)
+    if n_chains > 4:
+        s[4] = np.where(rng.rand(64, 64) < 0.93, 1.0, -1.0)
+    bits = m.pack(torch.tensor(s)).cuda()
+    if n_chains >= 64:
+        MetropolisHastings(m, 2.269, seed=9).sweeps_packed(bits[8:], 30, sweep_offset=0)
+    for name, group, ng in (("none", None, 1),
+                            ("per chain", torch.arange(n_chains, dtype=torch.int32), n_chains),
+                            ("runs of 6", (torch.arange(n_chains) // 6).to(torch.int32), (n_chains + 5) // 6),
+                            ("alternating", (torch.arange(n_chains) % 3).to(torch.int32), 3)):
+        gd = group.cuda() if group is not None else None
+        want, _ = _corr_sums(bits, gd, ng, 1)
+        got, _ = _corr_sums(bits, gd, ng, 2)
+        assert torch.equal(got, want), name
+        assert int(got[:, 0].abs().sum()) == 0
+    # against the oracle's direct loops on a few chains
+    k = min(n_chains, 3)
+    want = o.pair_correlation(s[:k], None)
+    got, _ = _corr_sums(bits[:k], None, 1, 2)
+    from backend.ml.analysis.correlation import _displacement_counts
+    cnt = _displacement_counts(64).astype(np.float64) * 4096 * k
+    c = np.divide(got[0].numpy().astype(np.float64), cnt, where=cnt > 0, out=np.zeros(32))
+    assert np.array_equal(c, np.array(want["C_r"]))
+
+
+def test_spectral_measure_block_equals_the_displacement_kernel():
+    """dbs_ising_measure through the spectral kernel: identical C(r) sums and the same fp64 observable block (same
+    per-chain E and M; the block is a sum of fp64 atomics, compared to rounding of the summation order)."""
+    IsingModel, MetropolisHastings = _mods()
+    m = IsingModel(64, J=0.8, h=0.0)
+    n = 515
+    bits = m.random_packed(n, seed=5)
+    temps = np.repeat(np.array([1.8, 2.269, 3.1]), 172)[:n]
+    MetropolisHastings(m, temps, seed=5).sweeps_packed(bits, 40, sweep_offset=0)
+    group = torch.tensor(np.repeat(np.arange(3), 172)[:n].astype(np.int32)).cuda()
+    want, wb = _corr_sums(bits, group, 3, 1, measure=True, J=0.8)
+    got, gb = _corr_sums(bits, group, 3, 2, measure=True, J=0.8)
+    assert torch.equal(got, want)
+    assert torch.allclose(gb, wb, rtol=1e-12, atol=1e-12)
+    assert torch.equal(gb[:, 0], torch.tensor([172.0, 172.0, 171.0], dtype=torch.float64))
+
+
 def test_mcmc_api_contract():
     """Reference contract tests (backend/tests/test_mcmc.py:22-71, 256-349): beta, step flips at
     most one spin and mutates/returns its argument, sample/trajectory shapes."""
