@@ -3,14 +3,15 @@
 // displacement.  Same integer sums (see ising_corr_fft.cuh for why they are exact); pair_correlation of the reference:
 // backend/ml/analysis/correlation.py:8-47.
 //
-// Work decomposition: a CTA of 64 threads owns four chains at a time.  Thread t holds one 64-point line in registers in
-// every pass (row t / column t), lines meet in a padded shared-memory buffer between passes:
-//   rows fwd (z1) -> cols fwd -> P1 parked in shared memory (thread-private column)
-//   rows fwd (z2) -> cols fwd -> P2 in registers -> q = P1 + i P2 -> cols inv -> rows inv -> round -> radial bins
+// Work decomposition: a set of 64 threads owns four chains at a time; a CTA is four independent sets (their own named
+// barriers), one CTA per SM.  Thread t holds one 64-point line in registers in every pass (row t / column t), lines meet in
+// a padded shared-memory buffer between passes; the six passes of a round run through ONE transform body in a loop
+// (first cut: six inlined bodies = 206 KB of straight-line code per kernel, ncu: 3.9 of 4.9 stall samples per issue were
+// "no instruction" — the kernel was instruction-fetch bound at 25 % issue utilisation).
 // Per-thread bin partials live in a [bin][thread] fp32 table (exact small integers), reduced to int64 and added to the
-// group's accumulator when the CTA's temperature group changes (chains of a group are contiguous, so almost never).
+// group's accumulator when the set's temperature group changes (chains of a group are contiguous, so almost never).
 // Four chains of different groups are processed as two rounds of single (real-only) lattices, re -> one group, im -> another.
-// ~60 KB of shared memory per CTA, three CTAs per SM.
+// ~57 KB of shared memory per set.
 #include "common.cuh"
 #include "ising_corr_fft.cuh"
 
@@ -19,37 +20,41 @@ namespace {
 
 using namespace cfft;
 
-constexpr int kFftThreads = 64;
+constexpr int kSets = 4;             // independent 64-thread sets per CTA, four chains each per iteration
+constexpr int kSetThreads = 64;
 constexpr int kFlushRounds = 24;     // |q| <= 16384, <= ~20 displacements of a bin per row: 24 rounds stay below 2^24
 
-struct __align__(16) FftSmem {
-  cpx buf[64 * kStride];
-  float pw[64 * 64];
-  float part[32 * 64];
-  uint64_t rows[4][64];
-  unsigned char bin[32 * 32];
+__device__ const BinTable g_bin_table = make_bin_table();
+
+struct __align__(16) SetSmem {
+  cpx buf[64 * kStride];             // lines meet here between passes; its head doubles as the row staging of the E / M step
+  float pw[64 * 64];                 // P1, a thread-private column per thread
+  float part[32 * 64];               // [bin][thread] partial sums, exact integers in fp32
 };
 
+__device__ __forceinline__ void set_barrier(int set) { asm volatile("bar.sync %0, 64;" ::"r"(set + 1) : "memory"); }
+
 template <bool kObs>
-__global__ void __launch_bounds__(kFftThreads, 3)
+__global__ void __launch_bounds__(kSets * kSetThreads, 1)
 ising_corr_fft_kernel(const uint32_t* __restrict__ bits, int64_t n_chains, const int32_t* __restrict__ group,
                       long long* __restrict__ acc, float negJ, float negh, double* __restrict__ block, int block_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FftSmem& sm = *reinterpret_cast<FftSmem*>(smem_raw);
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  for (int q = t; q < 32 * 32; q += kFftThreads) sm.bin[q] = radial_bin(q >> 5, q & 31);
+  const int set = threadIdx.x >> 6, t = threadIdx.x & 63, lane = t & 31, warp = t >> 5;
+  SetSmem& sm = reinterpret_cast<SetSmem*>(smem_raw)[set];
+  const unsigned char* bin_tab = g_bin_table.v;
 #pragma unroll
   for (int b = 0; b < 32; ++b) sm.part[b * 64 + t] = 0.f;
-  __syncthreads();
 
+  // contiguous quads of chains per set: chains of a temperature group are contiguous, so a set rarely changes group
   const int64_t n_quads = (n_chains + 3) >> 2;
-  const int64_t q_lo = n_quads * blockIdx.x / gridDim.x, q_hi = n_quads * (blockIdx.x + 1) / gridDim.x;
+  const int64_t unit = (int64_t)blockIdx.x * kSets + set, n_units = (int64_t)gridDim.x * kSets;
+  const int64_t q_lo = n_quads * unit / n_units, q_hi = n_quads * (unit + 1) / n_units;
   int cur_g = -1, acc_rounds = 0;
   bool dirty = false;              // the bin table holds sums that belong to cur_g
   float maxdev = 0.f;
 
   auto flush = [&]() {
-    __syncthreads();
+    set_barrier(set);
     if (cur_g >= 0 && dirty) {
       if (t > 0 && t < 32) {
         long long s = 0;
@@ -62,7 +67,7 @@ ising_corr_fft_kernel(const uint32_t* __restrict__ bits, int64_t n_chains, const
       if (maxdev > 0.25f) atomicAdd(reinterpret_cast<unsigned long long*>(acc + (int64_t)cur_g * 32), 1ull);
     }
     maxdev = 0.f;
-    __syncthreads();
+    set_barrier(set);
 #pragma unroll
     for (int b = 0; b < 32; ++b) sm.part[b * 64 + t] = 0.f;
     acc_rounds = 0;
@@ -94,14 +99,15 @@ ising_corr_fft_kernel(const uint32_t* __restrict__ bits, int64_t n_chains, const
     if (kObs) {
       // E and M of the four chains, formed exactly as ising_obs_packed_kernel / ising_corr_warp2_kernel do: bonds to the
       // right neighbour (column rotation by one) and to the row below; a warp takes chains warp and warp + 2
-      sm.rows[0][t] = r0; sm.rows[1][t] = r1; sm.rows[2][t] = r2; sm.rows[3][t] = r3;
-      __syncthreads();
+      uint64_t (*rows)[64] = reinterpret_cast<uint64_t (*)[64]>(sm.buf);
+      rows[0][t] = r0; rows[1][t] = r1; rows[2][t] = r2; rows[3][t] = r3;
+      set_barrier(set);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = warp + 2 * cc;
         if (c < nv) {
-          const uint64_t lo = sm.rows[c][lane], hi = sm.rows[c][lane + 32];
-          const uint64_t dn0 = sm.rows[c][(lane + 1) & 63], dn1 = sm.rows[c][(lane + 33) & 63];
+          const uint64_t lo = rows[c][lane], hi = rows[c][lane + 32];
+          const uint64_t dn0 = rows[c][(lane + 1) & 63], dn1 = rows[c][(lane + 33) & 63];
           int dis = __popcll(lo ^ dn0) + __popcll(hi ^ dn1);
           dis += __popcll(lo ^ ((lo >> 1) | (lo << 63))) + __popcll(hi ^ ((hi >> 1) | (hi << 63)));
           int up = __popcll(lo) + __popcll(hi);
@@ -126,7 +132,7 @@ ising_corr_fft_kernel(const uint32_t* __restrict__ bits, int64_t n_chains, const
           }
         }
       }
-      // sm.rows is rewritten only after the barriers of the transform passes below
+      set_barrier(set);            // the staging rows live in buf, which pass 0 overwrites
     }
     const int n_rounds = same ? 1 : 2;
 #pragma unroll 1
@@ -141,42 +147,36 @@ ising_corr_fft_kernel(const uint32_t* __restrict__ bits, int64_t n_chains, const
       if (aa == 0.f && ac == 0.f) continue;
       const int g_re = same ? g0 : (rd ? g2 : g0), g_im = same ? g0 : (rd ? g3 : g1);
 
-      phase_rows_fwd(t, ra, aa, rb, ab, sm.buf);
-      __syncthreads();
-      {
-        cpx v[64];
-        float p[64];
-        phase_cols_load(t, sm.buf, v);
-        phase_cols_power(v, p);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) sm.pw[j * 64 + t] = p[j];     // thread-private column: no barrier needed for pw
-      }
-      __syncthreads();                                             // every column of buf has been read
-      phase_rows_fwd(t, rc, ac, rdd, ad, sm.buf);
-      __syncthreads();
-      {
-        cpx v[64];
-        float p1[64], p2[64];
-        phase_cols_load(t, sm.buf, v);
-        __syncthreads();                                           // buf is overwritten by the inverse column pass
-        phase_cols_power(v, p2);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) p1[j] = sm.pw[j * 64 + t];
-        phase_cols_inv(t, p1, p2, sm.buf);
-      }
-      __syncthreads();
-      {
-        cpx v[64];
-        phase_rows_inv(t, sm.buf, v);                              // row t again: no hazard with the next round's row pass
-        if (same) {
-          ensure_group(g_re);
-          phase_bin(t, v, 1.f, 1.f, sm.bin, sm.part, maxdev);
+      // six passes through ONE transform body (see ising_corr_fft.cuh); v stays in registers from pass 3 to pass 4
+      cpx v[64];
+#pragma unroll 1
+      for (int pass = 0; pass < 6; ++pass) {
+        if (pass == 0 || pass == 2) {
+          const bool first = pass == 0;
+          load_bits(v, first ? ra : rc, first ? aa : ac, first ? rb : rdd, first ? ab : ad);
+        } else if (pass == 1 || pass == 3) load_col(t, sm.buf, v);
+        else if (pass == 5) load_row(t, sm.buf, v);
+        if (pass == 3) set_barrier(set);        // every column of buf has been read before pass 4 overwrites it
+        fft64<false>(v);
+        if (pass == 0 || pass == 2) {
+          store_row(t, v, sm.buf);
+          set_barrier(set);
+        } else if (pass == 1) {
+          store_power(t, v, sm.pw);             // thread-private column: no barrier needed for pw
+          set_barrier(set);                     // every column of buf has been read before pass 2 overwrites it
+        } else if (pass == 3) {
+          build_q(t, v, sm.pw);
+        } else if (pass == 4) {
+          store_col(t, v, sm.buf);
+          set_barrier(set);
         } else {
-          ensure_group(g_re);
-          phase_bin(t, v, 1.f, 0.f, sm.bin, sm.part, maxdev);
-          if (ac != 0.f) {
-            ensure_group(g_im);
-            phase_bin(t, v, 0.f, 1.f, sm.bin, sm.part, maxdev);
+          // row t of buf was read by this thread only: no hazard with the next round's pass 0.  One binning pass when
+          // the four chains share their group, else Re q -> the first chain's group and Im q -> the second's
+          const int n_bp = same ? 1 : (ac != 0.f ? 2 : 1);
+#pragma unroll 1
+          for (int bp = 0; bp < n_bp; ++bp) {
+            ensure_group(bp ? g_im : g_re);
+            bin_row(t, v, (same || bp == 0) ? 1.f : 0.f, (same || bp == 1) ? 1.f : 0.f, bin_tab, sm.part, maxdev);
           }
         }
       }
@@ -193,21 +193,22 @@ int ising_corr_fft_launch(const uint32_t* bits, int64_t n_chains, const int32_t*
                           double* block, int block_stride, cudaStream_t st) {
   static int n_sm = 0;
   static bool attr_done = false;
+  constexpr int smem = (int)(kSets * sizeof(SetSmem));
   if (!attr_done) {
     int dev = 0;
     DBS_CUDA(cudaGetDevice(&dev));
     DBS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    DBS_CUDA(cudaFuncSetAttribute(ising_corr_fft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FftSmem)));
-    DBS_CUDA(cudaFuncSetAttribute(ising_corr_fft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FftSmem)));
+    DBS_CUDA(cudaFuncSetAttribute(ising_corr_fft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DBS_CUDA(cudaFuncSetAttribute(ising_corr_fft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   const int64_t n_quads = (n_chains + 3) / 4;
-  int64_t grid = (int64_t)n_sm * 3;
-  if (grid > n_quads) grid = n_quads;
+  int64_t grid = (n_quads + kSets - 1) / kSets;
+  if (grid > n_sm) grid = n_sm;
   if (block)
-    ising_corr_fft_kernel<true><<<(unsigned)grid, kFftThreads, sizeof(FftSmem), st>>>(bits, n_chains, group, acc, -J, -h, block, block_stride);
+    ising_corr_fft_kernel<true><<<(unsigned)grid, kSets * kSetThreads, smem, st>>>(bits, n_chains, group, acc, -J, -h, block, block_stride);
   else
-    ising_corr_fft_kernel<false><<<(unsigned)grid, kFftThreads, sizeof(FftSmem), st>>>(bits, n_chains, group, acc, 0.f, 0.f, nullptr, 0);
+    ising_corr_fft_kernel<false><<<(unsigned)grid, kSets * kSetThreads, smem, st>>>(bits, n_chains, group, acc, 0.f, 0.f, nullptr, 0);
   DBS_LAUNCHED();
   return DBS_OK;
 }
