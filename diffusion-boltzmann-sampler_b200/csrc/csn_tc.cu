@@ -666,49 +666,55 @@ constexpr uint32_t kQBytes = 256 * 64;         // Q (two 128-row tiles), K: 64-b
 constexpr uint32_t kVtSlab = 32 * 128;         // V^T: 32 rows x 64 keys per slab, SWIZZLE_128B
 constexpr uint32_t kPTile = 4 * kAtomBytes;    // P tile: 128 rows x 256 keys
 
-__global__ void __launch_bounds__(256, 1)
-csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int64_t n_pairs, int N,
-                        int heads, float scale_log2e) {
+// One CTA = one (configuration, head, 128-query tile) unit at a time, 128 threads (thread = query row = TMEM lane), 104 KB of
+// shared memory and 256 TMEM columns, so TWO CTAs share an SM and their phases interleave: while one is in its softmax
+// (MUFU / TMEM-read work) the other loads, transposes or runs its MMAs.  The first cut (one 256-thread CTA per SM working
+// on both query tiles of a pair in lock step) ran every phase serially: 1.23 ms per layer at 4096 x 256.  K and V of a
+// pair are fetched once per query tile (L2 hits the second time).
+__global__ void __launch_bounds__(128, 2)
+csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int64_t n_units, int N,
+                        int heads, int n_qt, float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Qs = smem;                       // 16 KB
-  uint8_t* Ks = Qs + kQBytes;               // 16 KB
-  uint8_t* Vt = Ks + kQBytes;               // 4 slabs x 4 KB
-  uint8_t* Ps = Vt + 4 * kVtSlab;           // 2 tiles x 64 KB
+  uint8_t* Ks = smem;                       // 256 keys x 64 B, SWIZZLE_64B                 16 KB
+  uint8_t* Qs = Ks + kQBytes;               // 128 queries x 64 B                             8 KB
+  uint8_t* Vt = Qs + kQBytes / 2;           // V^T: 4 slabs of 32 rows x 64 keys             16 KB
+  uint8_t* Ps = Vt + 4 * kVtSlab;           // P: 128 rows x 256 keys, 4 K-slabs             64 KB
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   const int H = heads * kHD;
-  const int n_qt = (N + 127) / 128;         // query tiles (1 or 2)
-  const int t_mine = warp >> 2, qd = warp & 3;
-  const int row = qd * 32 + lane;           // my query row inside my tile
-  const int qi = t_mine * 128 + row;        // my query
+  const int row = threadIdx.x;              // my query row inside the tile (= warp * 32 + lane: the warp's TMEM lane quadrant)
   uint32_t phase = 0;
-  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int64_t pair = unit / n_qt;
+    const int t_mine = (int)(unit - pair * n_qt);
     const int64_t b = pair / heads;
     const int h = (int)(pair - b * heads);
+    const int qi = t_mine * 128 + row;      // my query
     const __nv_bfloat16* base = qkv + b * N * 3 * H + h * kHD;
-    // ---- phase 1: Q, K rows (64 B each) into the SWIZZLE_64B K-major layout; V transposed into V^T slabs
-    for (int idx = threadIdx.x; idx < 256 * 4; idx += 256) {
+    // ---- phase 1: K rows and my tile's Q rows (64 B each) into the SWIZZLE_64B K-major layout; V transposed into V^T slabs
+    for (int idx = threadIdx.x; idx < 256 * 4; idx += 128) {
       const int r = idx >> 2, c = idx & 3;
-      uint4 qv = make_uint4(0, 0, 0, 0), kv = make_uint4(0, 0, 0, 0);
-      if (r < N) {
-        const __nv_bfloat16* tok = base + (int64_t)r * 3 * H;
-        qv = *reinterpret_cast<const uint4*>(tok + c * 8);
-        kv = *reinterpret_cast<const uint4*>(tok + H + c * 8);
-      }
-      const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
-      *reinterpret_cast<uint4*>(Qs + off) = qv;
-      *reinterpret_cast<uint4*>(Ks + off) = kv;
+      uint4 kv = make_uint4(0, 0, 0, 0);
+      if (r < N) kv = *reinterpret_cast<const uint4*>(base + (int64_t)r * 3 * H + H + c * 8);
+      *reinterpret_cast<uint4*>(Ks + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4)) = kv;
     }
-    {
-      const int k = threadIdx.x;            // key
+    for (int idx = threadIdx.x; idx < 128 * 4; idx += 128) {
+      const int r = idx >> 2, c = idx & 3, qr = t_mine * 128 + r;
+      uint4 qv = make_uint4(0, 0, 0, 0);
+      if (qr < N) qv = *reinterpret_cast<const uint4*>(base + (int64_t)qr * 3 * H + c * 8);
+      *reinterpret_cast<uint4*>(Qs + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4)) = qv;
+    }
+#pragma unroll 1
+    for (int kk = 0; kk < 2; ++kk) {
+      const int k = threadIdx.x + 128 * kk;     // key
       uint32_t w[16];
       if (k < N) {
         const uint4* vp = reinterpret_cast<const uint4*>(base + (int64_t)k * 3 * H + 2 * H);
@@ -729,17 +735,15 @@ csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
     }
     fence_async_smem();
     __syncthreads();
-    // ---- phase 2: S = Q K^T, one N-column accumulator per query tile
+    // ---- phase 2: S = Q K^T into an N-column accumulator
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t q_lo = (uint32_t)kDesc64 | ((smem_u32(Qs) & 0x3FFFFu) >> 4);
       const uint32_t k_lo = (uint32_t)kDesc64 | ((smem_u32(Ks) & 0x3FFFFu) >> 4);
       const uint32_t hi = (uint32_t)(kDesc64 >> 32);
       const uint32_t idesc = idesc_bf16(128, N);
-      for (int t = 0; t < n_qt; ++t)
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          umma_bf16_lohi(tmem + t * 256, q_lo + (uint32_t)t * ((128u * 64u) >> 4) + ks * 2u, k_lo + ks * 2u, hi, idesc, ks ? 1u : 0u);
+      for (int ks = 0; ks < 2; ++ks) umma_bf16_lohi(tmem, q_lo + ks * 2u, k_lo + ks * 2u, hi, idesc, ks ? 1u : 0u);
       umma_commit(smem_u32(&bar));
     }
     mbar_wait(smem_u32(&bar), phase);
@@ -747,8 +751,9 @@ csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
     tc_fence_after();
     // ---- phase 3: softmax of my query row, P -> shared memory (bf16, A operand of P V)
     float l = 0.f;
-    if (t_mine < n_qt) {
-      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + t_mine * 256;
+    {
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      // (two chunks in flight with four partial maxima / sums per thread was measured: 1.25 vs 1.19 ms per layer, no gain)
       float mx = -INFINITY;
       for (int c = 0; c < N; c += 16) {
         uint32_t v[16];
@@ -758,7 +763,7 @@ csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
         for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
       const float mxs = mx * scale_log2e;
-      uint8_t* prow = Ps + (uint32_t)t_mine * kPTile + (uint32_t)row * 128u;
+      uint8_t* prow = Ps + (uint32_t)row * 128u;
       for (int c = 0; c < N; c += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c, v);
@@ -783,27 +788,26 @@ csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    // ---- phase 4: O = P V (N = 32 columns per tile, over the S columns just consumed)
+    // ---- phase 4: O = P V (32 columns, over the S columns just consumed)
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t p_lo = (uint32_t)kDesc128 | ((smem_u32(Ps) & 0x3FFFFu) >> 4);
       const uint32_t v_lo = (uint32_t)kDesc128 | ((smem_u32(Vt) & 0x3FFFFu) >> 4);
       const uint32_t hi = (uint32_t)(kDesc128 >> 32);
       const uint32_t idesc = idesc_bf16(128, kHD);
-      for (int t = 0; t < n_qt; ++t)
-        for (int ks = 0; ks < N / 16; ++ks) {
-          const uint32_t po = (uint32_t)t * (kPTile >> 4) + (uint32_t)(ks >> 2) * (kAtomBytes >> 4) + (uint32_t)(ks & 3) * 2u;
-          const uint32_t vo = (uint32_t)(ks >> 2) * (kVtSlab >> 4) + (uint32_t)(ks & 3) * 2u;
-          umma_bf16_lohi(tmem + t * 256, p_lo + po, v_lo + vo, hi, idesc, ks ? 1u : 0u);
-        }
+      for (int ks = 0; ks < N / 16; ++ks) {
+        const uint32_t po = (uint32_t)(ks >> 2) * (kAtomBytes >> 4) + (uint32_t)(ks & 3) * 2u;
+        const uint32_t vo = (uint32_t)(ks >> 2) * (kVtSlab >> 4) + (uint32_t)(ks & 3) * 2u;
+        umma_bf16_lohi(tmem, p_lo + po, v_lo + vo, hi, idesc, ks ? 1u : 0u);
+      }
       umma_commit(smem_u32(&bar));
     }
     mbar_wait(smem_u32(&bar), phase);
     phase ^= 1;
     tc_fence_after();
     // ---- phase 5: normalise and store my query's head slice
-    if (t_mine < n_qt) {
-      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + t_mine * 256;
+    {
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
       uint32_t v0[16], v1[16];
       tmem_ld16(taddr, v0);
       tmem_ld16(taddr + 16, v1);
@@ -826,7 +830,7 @@ csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   }
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, 256);
   }
 }
 
@@ -899,17 +903,22 @@ int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const floa
 
 int csn_tc_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t B, int N, int heads, cudaStream_t st) {
   DBS_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "csn_tc_attention: N = %d not in {16, 32, ..., 256}", N);
-  const size_t smem = 2 * kQBytes + 4 * kVtSlab + 2 * kPTile + 1024;
+  const size_t smem = kQBytes + kQBytes / 2 + 4 * kVtSlab + kPTile + 1024;
   static bool attr_done = false;
+  static int n_sm = 148;
   if (!attr_done) {
+    int dev = 0;
+    DBS_CUDA(cudaGetDevice(&dev));
+    DBS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     DBS_CUDA(cudaFuncSetAttribute(csn_tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int64_t n_pairs = B * heads;
-  const int grid = (int)(n_pairs < 148 ? n_pairs : 148);
+  const int n_qt = (N + 127) / 128;
+  const int64_t n_units = B * heads * n_qt;
+  const int grid = (int)(n_units < 2 * n_sm ? n_units : 2 * n_sm);
   prof_set_label("tc attention N%d heads%d", N, heads);
   ProfScope prof(kProfCsnAttention, st);
-  csn_tc_attention_kernel<<<grid, 256, smem, st>>>(qkv, out, n_pairs, N, heads, (1.0f / sqrtf((float)kHD)) * 1.4426950408889634f);
+  csn_tc_attention_kernel<<<grid, 128, smem, st>>>(qkv, out, n_units, N, heads, n_qt, (1.0f / sqrtf((float)kHD)) * 1.4426950408889634f);
   DBS_LAUNCHED();
   return DBS_OK;
 }
