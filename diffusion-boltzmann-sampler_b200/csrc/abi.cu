@@ -1,4 +1,5 @@
 // abi.cu — the parts of the C ABI that are not kernels: error text, version, launch counter.
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -23,6 +24,14 @@ void set_error(const char* fmt, ...) {
 
 namespace dbs {
 bool g_prof_on = false;
+bool pdl_enabled() {
+  // Measured at 64x64, graph-replayed EM steps (profiles/README.md): 0.611 -> 0.583 ms per step at B = 64 and 0.914 -> 0.898 at
+  // B = 128, but 1.55 -> 1.58 ms at B = 256 and 11.9 -> 12.2 ms at B = 2048 — CTAs of the next grid parked on the SMs cost the
+  // running persistent kernels more than the hidden prologues save once a kernel lasts longer than a few waves.  Off unless
+  // DBS_PDL=1 (small-batch serving).
+  static const bool on = [] { const char* e = getenv("DBS_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
 namespace {
 struct ProfPair { cudaEvent_t a, b; int cls; std::string label; };
 std::vector<std::pair<std::string, float>> g_detail;

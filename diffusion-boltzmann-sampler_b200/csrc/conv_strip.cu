@@ -220,6 +220,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   __shared__ float s_x[2][4][4][2][16];           // [parity][sub][quadrant][side][col]: cross-warp neighbours (W > 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();          // the next kernel of the step may begin its prologue as SMs free up (common.cuh)
   const uint32_t w_region = smem_u32(smem);                       // resident weights (may be empty)
   const uint32_t ring = w_region + p.w_region_bytes;              // strip (+ streamed weight) stages
   const uint32_t bar_full = smem_u32(&bars[0]);
@@ -259,6 +260,20 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  // Everything so far touches only this layer's constants and on-chip state.  The layer's resident weights are constants
+  // too: their TMA loads are issued before the wait, so that they travel behind the previous kernel's tail.
+  if (warp == 0 && lane == 0 && p.resident == 1) {
+    const uint32_t cwb = p.slab_bytes * p.n_slabs;
+    const int n_ch = p.chunks0 + p.chunks1;
+    mbar_expect_tx(bar_w, cwb * n_ch);
+    for (int ch = 0; ch < n_ch; ++ch)
+      for (int t = 0; t < p.n_slabs; ++t) {
+        const uint32_t dst = w_region + (ch * p.n_slabs + t) * p.slab_bytes;
+        if (p.slab_tap[t] >= 0) tma_load_3d(dst, &map_w, bar_w, ch * p.KC, 0, p.slab_tap[t]);
+        else tma_load_3d(dst, &map_wr, bar_w, ch * p.KC, 0, 0);
+      }
+  }
+  pdl_wait();                       // from here on: activations / statistics written by the previous kernel of the stream
 
   // contiguous tile range per CTA: consecutive tiles are rows of the same image, which lets the
   // epilogue keep GroupNorm partial sums in registers until the image changes.  resident == 2: the range is
@@ -292,7 +307,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       const uint32_t stage_bytes = pin(p.stage_bytes), b_in_stage = pin((p.a_bytes + 1023u) & ~1023u), slab_bytes = pin(p.slab_bytes);
       const bool pre_res = kPre && p.pre_res;
       const uint32_t tx_bytes = pin(p.a_bytes * (pre_res ? 2u : 1u) + (p.resident ? 0u : chunk_w_bytes));
-      if (resident == 1) load_weights(0);  // n_tiles_n == 1 here
+      // (resident == 1: the weights were requested before pdl_wait above; n_tiles_n == 1 there)
       int stage = 0;
       uint32_t phase = 0;
       int pass = 0, in_pass = 0;
@@ -917,7 +932,8 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
                  g.out_stride, KC, g.B, p.resident, p.stages, fuse_res ? " +res1x1" : (pre ? (pre->res ? " gn+res>" : " gn>") : ""),
                  pairw ? " x2 phases" : "");
   ProfScope prof(kProfConvTC, st);
-  kern<<<grid, strip_threads(pre ? kEpiWarpsPre : kEpiWarpsDefault, pre != nullptr), smem, st>>>(m0, m1, mw, mwr, p);
+  DBS_CUDA(launch_chained(kern, dim3((unsigned)grid), dim3(strip_threads(pre ? kEpiWarpsPre : kEpiWarpsDefault, pre != nullptr)), smem, st,
+                          m0, m1, mw, mwr, p));
   DBS_LAUNCHED();
   return DBS_OK;
 }

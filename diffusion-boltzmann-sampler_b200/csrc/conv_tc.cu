@@ -103,6 +103,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   __shared__ __align__(16) float s_gamma[kRun == 16 ? kMaxCout : 4], s_beta[kRun == 16 ? kMaxCout : 4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();          // the next kernel of the step may begin its prologue as SMs free up (common.cuh)
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_full = smem_u32(&bars[0]);
   const uint32_t bar_empty = smem_u32(&bars[kMaxStages]);
@@ -138,6 +139,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
   if (kPair) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  // everything above touches only this layer's constants (bias, gamma / beta, tensor maps) and on-chip state; from here on the
+  // kernel reads activations and statistics buffers that the previous kernel of the stream writes
+  pdl_wait();
 
   // work units: tiles, or pairs of M-adjacent tiles (this CTA takes tile 2k + rank of the pair)
   const int half_m = p.n_tiles_m >> 1;
@@ -692,14 +696,16 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     DBS_CUDA(cudaLaunchKernelEx(&cfg, kern, m0, m1, mw, p));
   } else {
     const int grid = total_units < sms ? total_units : sms;
-    kern<<<grid, kThreads, smem, st>>>(m0, m1, mw, p);
+    DBS_CUDA(launch_chained(kern, dim3((unsigned)grid), dim3(kThreads), smem, st, m0, m1, mw, p));
   }
   DBS_LAUNCHED();
   return DBS_OK;

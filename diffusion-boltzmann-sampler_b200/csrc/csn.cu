@@ -42,7 +42,7 @@ int csn_tc_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t B, in
 
 struct dbs_csn_plan {
   dbs_csn_config cfg;
-  std::vector<void*> allocs;
+  dbs::DevArena arena;
   float *pos_freqs = nullptr, *t_freqs = nullptr;
   float *tw0 = nullptr, *tb0 = nullptr, *tw2 = nullptr, *tb2 = nullptr;
   float *twt = nullptr, *tbt = nullptr;   // every block's time Linear, concatenated: [nb*H][T], [nb*H]
@@ -352,8 +352,7 @@ int upload(dbs_csn_plan* plan, const ParamTable& pt, const std::string& name, in
   DBS_REQUIRE(q->numel == numel, "csn plan: parameter '%s' has %lld elements, expected %lld", name.c_str(),
               (long long)q->numel, (long long)numel);
   void* d = nullptr;
-  DBS_CUDA(cudaMalloc(&d, (size_t)(numel ? numel : 4) * 4));
-  plan->allocs.push_back(d);
+  DBS_CUDA(plan->arena.take((size_t)(numel ? numel : 4) * 4, &d));
   DBS_CUDA(cudaMemcpy(d, q->data, (size_t)numel * 4, q->is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
   *out = (float*)d;
   return DBS_OK;
@@ -361,8 +360,7 @@ int upload(dbs_csn_plan* plan, const ParamTable& pt, const std::string& name, in
 
 int upload_host(dbs_csn_plan* plan, const float* src, int64_t numel, float** out) {
   void* d = nullptr;
-  DBS_CUDA(cudaMalloc(&d, (size_t)(numel ? numel : 4) * 4));
-  plan->allocs.push_back(d);
+  DBS_CUDA(plan->arena.take((size_t)(numel ? numel : 4) * 4, &d));
   DBS_CUDA(cudaMemcpy(d, src, (size_t)numel * 4, cudaMemcpyHostToDevice));
   *out = (float*)d;
   return DBS_OK;
@@ -596,8 +594,7 @@ extern "C" int dbs_csn_plan_create(const dbs_csn_config* cfg, const dbs_param* p
           {b.qkv_w, &b.qkv_h, (int64_t)3 * H * H}, {b.proj_w, &b.proj_h, (int64_t)H * H}};
       for (auto& e : cv) {
         void* d = nullptr;
-        if (cudaMalloc(&d, (size_t)e.n * 2) != cudaSuccess) { set_error("csn plan: cudaMalloc failed"); rc = DBS_ERR_CUDA; break; }
-        plan->allocs.push_back(d);
+        if (plan->arena.take((size_t)e.n * 2, &d) != cudaSuccess) { set_error("csn plan: cudaMalloc failed"); rc = DBS_ERR_CUDA; break; }
         *e.dst = (__nv_bfloat16*)d;
         if ((rc = csn_tc_convert_weights(e.src, *e.dst, e.n))) break;
       }
@@ -617,8 +614,7 @@ extern "C" int dbs_csn_plan_create(const dbs_csn_config* cfg, const dbs_param* p
     auto to_bf16 = [&](const std::vector<float>& src, __nv_bfloat16** dst) {
       if (rc) return;
       void* d = nullptr;
-      if (cudaMalloc(&d, src.size() * 2) != cudaSuccess || cudaMalloc((void**)&tmp, src.size() * 4) != cudaSuccess) { set_error("csn plan: cudaMalloc failed"); rc = DBS_ERR_CUDA; return; }
-      plan->allocs.push_back(d); plan->allocs.push_back(tmp);
+      if (plan->arena.take(src.size() * 2, &d) != cudaSuccess || plan->arena.take(src.size() * 4, (void**)&tmp) != cudaSuccess) { set_error("csn plan: cudaMalloc failed"); rc = DBS_ERR_CUDA; return; }
       if (cudaMemcpy(tmp, src.data(), src.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("csn plan: upload failed"); rc = DBS_ERR_CUDA; return; }
       *dst = (__nv_bfloat16*)d;
       rc = csn_tc_convert_weights(tmp, *dst, (int64_t)src.size());
@@ -647,7 +643,7 @@ extern "C" int dbs_csn_plan_create(const dbs_csn_config* cfg, const dbs_param* p
 
 extern "C" void dbs_csn_plan_destroy(dbs_csn_plan* plan) {
   if (!plan) return;
-  for (void* p : plan->allocs) cudaFree(p);
+  plan->arena.release();
   delete plan;
 }
 

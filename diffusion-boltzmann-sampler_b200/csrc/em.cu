@@ -53,6 +53,8 @@ struct EmArgs {
 
 template <bool kVec, bool kFill>
 __global__ void __launch_bounds__(256) em_kernel(EmArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (a.coef2) {          // Langevin corrector step (samplers/diffusion.py:441-447): (x + ss * s) + ((sqrt(2 ss) * z) * T)
     if (a.coef[1] == 0.f) return;      // inactive at the final predictor step
     a.c1 = a.coef2[0]; a.dt = 1.0f; a.c2 = a.coef2[1]; a.temperature = a.coef[0]; a.add_noise = 1;
@@ -125,8 +127,8 @@ int launch_em(const EmArgs& a, cudaStream_t st) {
                    (kFill || ((reinterpret_cast<uintptr_t>(a.score) & 15) == 0 &&
                               (!a.noise || (reinterpret_cast<uintptr_t>(a.noise) & 15) == 0)));
   ProfScope prof(kProfEm, st);
-  if (vec) em_kernel<true, kFill><<<(unsigned)blocks, 256, 0, st>>>(a);
-  else em_kernel<false, kFill><<<(unsigned)blocks, 256, 0, st>>>(a);
+  if (vec) DBS_CUDA(launch_chained(em_kernel<true, kFill>, dim3((unsigned)blocks), dim3(256), 0, st, a));
+  else DBS_CUDA(launch_chained(em_kernel<false, kFill>, dim3((unsigned)blocks), dim3(256), 0, st, a));
   DBS_LAUNCHED();
   return DBS_OK;
 }
@@ -292,6 +294,8 @@ namespace dbs {
 namespace {
 __global__ void table_next_kernel(float* __restrict__ cur, const float* __restrict__ table, int* __restrict__ counter,
                                   int stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int k = *counter;
   for (int i = threadIdx.x; i < stride; i += blockDim.x) cur[i] = table[(int64_t)k * stride + i];
   __syncthreads();
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(256) corrector_coef_kernel(const float* __rest
 
 extern "C" int dbs_step_table_next(float* cur, const float* table, int* counter, int stride, void* stream) {
   DBS_REQUIRE(cur && table && counter && stride >= 1 && stride <= 4096, "step_table_next: bad arguments");
-  dbs::table_next_kernel<<<1, 64, 0, dbs::as_stream(stream)>>>(cur, table, counter, stride);
+  DBS_CUDA(dbs::launch_chained(dbs::table_next_kernel, dim3(1), dim3(64), 0, dbs::as_stream(stream), cur, table, counter, stride));
   DBS_LAUNCHED();
   return DBS_OK;
 }

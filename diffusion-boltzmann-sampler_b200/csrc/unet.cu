@@ -410,6 +410,8 @@ init_conv_fast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ o
   // horizontal fusion: when all samples share t (the sampler's case) the first ta.n_ctas CTAs compute the time
   // biases of every ConvBlock while the others run the init conv — the time MLP's ~20 us of dependent L2 round
   // trips disappear behind the conv instead of preceding it as a launch of their own
+  pdl_launch_dependents();
+  pdl_wait();
   if ((int)blockIdx.x < ta.n_ctas) {
     extern __shared__ float sm_time[];
     time_path(ta, 0, blockIdx.x, ta.n_ctas, sm_time);
@@ -447,8 +449,8 @@ int launch_init_fast(const std::vector<float>& w_host, const std::vector<float>&
   InitW<C> iw;
   for (int i = 0; i < 9 * C; ++i) iw.w[i] = w_host[i];
   for (int i = 0; i < C; ++i) iw.b[i] = b_host[i];
-  init_conv_fast_kernel<C><<<(unsigned)((n_pix + 255) / 256) + (unsigned)ta.n_ctas, 256,
-                             ta.n_ctas ? (size_t)4 * ta.T * 4 : 0, st>>>(x, out, n_pix, H, W, iw, ta);
+  DBS_CUDA(launch_chained(init_conv_fast_kernel<C>, dim3((unsigned)((n_pix + 255) / 256) + (unsigned)ta.n_ctas), dim3(256),
+                          ta.n_ctas ? (size_t)4 * ta.T * 4 : 0, st, x, out, n_pix, H, W, iw, ta));
   DBS_LAUNCHED();
   return DBS_OK;
 }
@@ -481,6 +483,8 @@ final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __r
   constexpr int KS = C / 16;                 // k-steps of the m16n8k16 MMA
   extern __shared__ __align__(16) uint8_t sm_raw[];
   __shared__ float s_sc[C], s_sh[C];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y, h0 = blockIdx.x * TH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_pix = (TH + 2) * W;
@@ -644,8 +648,9 @@ int launch_final_fused(const uint32_t* bfrag_dev, float bias, float scale, const
     DBS_CUDA(cudaFuncSetAttribute(final_fused_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     attr_done = true;
   }
-  if (res) final_fused_kernel<C, true><<<grid, 256, smem, st>>>(y, res, stats, inv_cnt, 1e-5f, gamma, beta, out, H, W, TH, fw);
-  else final_fused_kernel<C, false><<<grid, 256, smem, st>>>(y, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, out, H, W, TH, fw);
+  if (res) DBS_CUDA(launch_chained(final_fused_kernel<C, true>, grid, dim3(256), smem, st, y, res, stats, inv_cnt, 1e-5f, gamma, beta, out, H, W, TH, fw));
+  else DBS_CUDA(launch_chained(final_fused_kernel<C, false>, grid, dim3(256), smem, st, y, (const __nv_bfloat16*)nullptr, (const float*)nullptr, 0.f, 0.f,
+                               (const float*)nullptr, (const float*)nullptr, out, H, W, TH, fw));
   DBS_LAUNCHED();
   return DBS_OK;
 }
@@ -742,6 +747,8 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
                 const float* __restrict__ tbias, int t_stride, const T* __restrict__ res, float res_scale,
                 int HW, int C, int G) {
   constexpr int V = Vec16<T>::N;
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y;
   const int Cg = C / G;
   const int cv = C / V;                       // 16-byte vectors per pixel (divides blockDim.x, see launch)
@@ -1020,7 +1027,7 @@ struct BlockW {
 
 struct dbs_unet_plan {
   dbs_unet_config cfg;
-  std::vector<void*> allocs;
+  dbs::DevArena arena;
   float *freqs = nullptr, *tw0 = nullptr, *tb0 = nullptr, *tw2 = nullptr, *tb2 = nullptr;
   float *twt = nullptr, *tbt = nullptr;  // concatenated per-block time Linear [sumC][T], [sumC]
   int sumC = 0;
@@ -1050,8 +1057,7 @@ struct ParamTable {
 };
 
 int dev_alloc(dbs_unet_plan* plan, size_t bytes, void** out) {
-  DBS_CUDA(cudaMalloc(out, bytes ? bytes : 16));
-  plan->allocs.push_back(*out);
+  DBS_CUDA(plan->arena.take(bytes, out));
   return DBS_OK;
 }
 
@@ -1203,9 +1209,9 @@ int run_gn(Ctx& c, const T* y, T* out, bool have_raw_stats, const float* gamma, 
   ProfScope prof(kProfGnApply, c.st);
   const dim3 grid((unsigned)bx, (unsigned)c.B);
 #define DBS_GN_LAUNCH(UN)                                                                                   \
-  gn_apply_kernel<T, UN><<<grid, threads, 0, c.st>>>(y, out, c.stats, have_raw_stats ? 1 : 0, inv_cnt, 1e-5f, gamma, beta, \
-                                                     add_time ? c.tbias + tb_off : nullptr,                 \
-                                                     c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, HW, C, G)
+  DBS_CUDA(launch_chained(gn_apply_kernel<T, UN>, grid, dim3(threads), 0, c.st, y, out, c.stats, have_raw_stats ? 1 : 0,     \
+                          inv_cnt, 1e-5f, gamma, beta, add_time ? c.tbias + tb_off : (const float*)nullptr,          \
+                          c.n_t == 1 ? 0 : c.plan->sumC, res, 1.0f, HW, C, G))
   if (tune_un >= 4) DBS_GN_LAUNCH(4);
   else if (tune_un == 2) DBS_GN_LAUNCH(2);
   else DBS_GN_LAUNCH(1);
@@ -1800,7 +1806,7 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
 
 extern "C" void dbs_unet_plan_destroy(dbs_unet_plan* plan) {
   if (!plan) return;
-  for (void* p : plan->allocs) cudaFree(p);
+  plan->arena.release();
   delete plan;
 }
 
