@@ -699,38 +699,55 @@ csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
     const int h = (int)(pair - b * heads);
     const int qi = t_mine * 128 + row;      // my query
     const __nv_bfloat16* base = qkv + b * N * 3 * H + h * kHD;
-    // ---- phase 1: K rows and my tile's Q rows (64 B each) into the SWIZZLE_64B K-major layout; V transposed into V^T slabs
-    for (int idx = threadIdx.x; idx < 256 * 4; idx += 128) {
-      const int r = idx >> 2, c = idx & 3;
-      uint4 kv = make_uint4(0, 0, 0, 0);
-      if (r < N) kv = *reinterpret_cast<const uint4*>(base + (int64_t)r * 3 * H + H + c * 8);
-      *reinterpret_cast<uint4*>(Ks + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4)) = kv;
-    }
-    for (int idx = threadIdx.x; idx < 128 * 4; idx += 128) {
-      const int r = idx >> 2, c = idx & 3, qr = t_mine * 128 + r;
-      uint4 qv = make_uint4(0, 0, 0, 0);
-      if (qr < N) qv = *reinterpret_cast<const uint4*>(base + (int64_t)qr * 3 * H + c * 8);
-      *reinterpret_cast<uint4*>(Qs + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4)) = qv;
-    }
-#pragma unroll 1
-    for (int kk = 0; kk < 2; ++kk) {
-      const int k = threadIdx.x + 128 * kk;     // key
-      uint32_t w[16];
-      if (k < N) {
-        const uint4* vp = reinterpret_cast<const uint4*>(base + (int64_t)k * 3 * H + 2 * H);
+    // ---- phase 1: K rows and my tile's Q rows (64 B each) into the SWIZZLE_64B K-major layout; V transposed into V^T slabs.
+    // All of a thread's global loads (8 K chunks, 4 Q chunks, the V rows of two keys: 20 x 16 B) are issued before the first
+    // shared-memory store, so the unit pays one global round trip instead of one per loop iteration.
+    {
+      uint4 kq[8], qq[4], vq[2][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const uint4 v4 = vp[i]; w[4 * i] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w; }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = 0u;
+      for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + 128 * i, r = idx >> 2, c = idx & 3;
+        kq[i] = make_uint4(0, 0, 0, 0);
+        if (r < N) kq[i] = *reinterpret_cast<const uint4*>(base + (int64_t)r * 3 * H + H + c * 8);
       }
-      uint8_t* slab = Vt + (uint32_t)(k >> 6) * kVtSlab + (uint32_t)(k & 7) * 2u;
-      const int kc = (k & 63) >> 3;
 #pragma unroll
-      for (int n2 = 0; n2 < 16; ++n2) {
-        const int n0 = 2 * n2, n1 = 2 * n2 + 1;
-        *reinterpret_cast<uint16_t*>(slab + n0 * 128 + ((kc ^ (n0 & 7)) << 4)) = (uint16_t)(w[n2] & 0xFFFFu);
-        *reinterpret_cast<uint16_t*>(slab + n1 * 128 + ((kc ^ (n1 & 7)) << 4)) = (uint16_t)(w[n2] >> 16);
+      for (int i = 0; i < 4; ++i) {
+        const int idx = threadIdx.x + 128 * i, r = idx >> 2, c = idx & 3, qr = t_mine * 128 + r;
+        qq[i] = make_uint4(0, 0, 0, 0);
+        if (qr < N) qq[i] = *reinterpret_cast<const uint4*>(base + (int64_t)qr * 3 * H + c * 8);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = threadIdx.x + 128 * kk;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vq[kk][i] = make_uint4(0, 0, 0, 0);
+          if (k < N) vq[kk][i] = reinterpret_cast<const uint4*>(base + (int64_t)k * 3 * H + 2 * H)[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + 128 * i, r = idx >> 2, c = idx & 3;
+        *reinterpret_cast<uint4*>(Ks + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4)) = kq[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = threadIdx.x + 128 * i, r = idx >> 2, c = idx & 3;
+        *reinterpret_cast<uint4*>(Qs + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4)) = qq[i];
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = threadIdx.x + 128 * kk;     // key
+        const uint32_t w[16] = {vq[kk][0].x, vq[kk][0].y, vq[kk][0].z, vq[kk][0].w, vq[kk][1].x, vq[kk][1].y, vq[kk][1].z, vq[kk][1].w,
+                                vq[kk][2].x, vq[kk][2].y, vq[kk][2].z, vq[kk][2].w, vq[kk][3].x, vq[kk][3].y, vq[kk][3].z, vq[kk][3].w};
+        uint8_t* slab = Vt + (uint32_t)(k >> 6) * kVtSlab + (uint32_t)(k & 7) * 2u;
+        const int kc = (k & 63) >> 3;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+          const int n0 = 2 * n2, n1 = 2 * n2 + 1;
+          *reinterpret_cast<uint16_t*>(slab + n0 * 128 + ((kc ^ (n0 & 7)) << 4)) = (uint16_t)(w[n2] & 0xFFFFu);
+          *reinterpret_cast<uint16_t*>(slab + n1 * 128 + ((kc ^ (n1 & 7)) << 4)) = (uint16_t)(w[n2] >> 16);
+        }
       }
     }
     fence_async_smem();

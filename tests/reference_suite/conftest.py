@@ -30,6 +30,24 @@ def _reference_seed():
     np.random.seed(SEED)
 
 
+# Two tests of test_models.py::TestMemoryAndPerformance compare wall-clock times taken with time.time() around single
+# calls (a first forward of a fresh network against sixteen later ones).  On a shared box one scheduling hiccup, or a Python
+# garbage-collection pass that releases earlier tests' device memory inside the timed call, flips them (observed once in
+# about six runs of the suite: 31 ms against a 21 ms bound, 5-8 ms normally).  They get ONE retry; every other test runs once.
+_WALL_CLOCK = ("test_batch_processing_efficient", "test_inference_completes_quickly")
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_call(item):
+    outcome = yield
+    if item.name in _WALL_CLOCK and outcome.excinfo is not None:
+        try:
+            item.runtest()
+        except Exception:
+            return
+        outcome.force_result(None)
+
+
 def pytest_collection_modifyitems(config, items):
     here = __file__.rsplit("/", 1)[0]
     for item in items:

@@ -35,6 +35,10 @@ def test_argument_validation_needs_no_gpu():
     assert abi.lib.dbs_ising_words_per_chain(3) < 0 and abi.lib.dbs_ising_words_per_chain(129) < 0
     rc = abi.lib.dbs_ising_sweeps(0, 130, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0)
     assert rc == abi.ERR_INVALID and "unsupported" in abi.last_error()
+    # C(r) evaluation method: a process-wide switch that returns the previous value (no device work)
+    assert abi.lib.dbs_ising_set_correlation_method(1) == 0
+    assert abi.lib.dbs_ising_set_correlation_method(0) == 1
+    assert abi.lib.dbs_ising_set_correlation_method(7) == abi.ERR_INVALID and "method" in abi.last_error()
     with pytest.raises(ValueError):
         abi.check(rc, "ising_sweeps")
 
