@@ -267,6 +267,30 @@ def test_spectral_correlation_equals_the_displacement_kernel_bit_for_bit(n_chain
     assert np.array_equal(c, np.array(want["C_r"]))
 
 
+def test_spectral_correlation_at_the_full_config3_ensemble():
+    """BASELINE config 3 at full size: 65 536 chains 64 x 64, 64 temperatures in [1.5, 3.5] x 1024 chains, equilibrated for
+    50 sweeps — the spectral and the displacement kernels return the same int64 C(r) sums for every temperature, bin 0 stays
+    zero, and the sums obey the size-independent properties of a correlation function of +/-1 spins: |C(r)| <= 1 and
+    C(1) of the coldest ensemble close to 1, of the hottest well below it."""
+    IsingModel, MetropolisHastings = _mods()
+    from backend.ml.analysis.correlation import _displacement_counts
+    m = IsingModel(64)
+    n = 65536
+    temps = np.repeat(np.linspace(1.5, 3.5, 64), 1024)
+    group = torch.tensor(np.repeat(np.arange(64), 1024).astype(np.int32)).cuda()
+    bits = m.random_packed(n, seed=11)
+    MetropolisHastings(m, temps, seed=11).sweeps_packed(bits, 50, sweep_offset=0)
+    want, wb = _corr_sums(bits, group, 64, 1, measure=True)
+    got, gb = _corr_sums(bits, group, 64, 2, measure=True)
+    assert torch.equal(got, want)
+    assert int(got[:, 0].abs().sum()) == 0
+    assert torch.allclose(gb, wb, rtol=1e-12, atol=1e-12)
+    cnt = _displacement_counts(64).astype(np.float64) * 4096 * 1024
+    c = got.numpy().astype(np.float64)[:, 1:] / cnt[None, 1:]
+    assert np.all(np.abs(c) <= 1.0 + 1e-12)
+    assert c[0, 0] > 0.9 and c[-1, 0] < 0.5 and c[0, 0] > c[-1, 0]
+
+
 def test_spectral_measure_block_equals_the_displacement_kernel():
     """dbs_ising_measure through the spectral kernel: identical C(r) sums and the same fp64 observable block (same
     per-chain E and M; the block is a sum of fp64 atomics, compared to rounding of the summation order)."""
