@@ -204,7 +204,11 @@ __device__ __forceinline__ float strip_silu(float x) {   // same form as gn_appl
   return fmaf(0.5f, t, 0.5f);       // sigmoid(x); the caller multiplies by x (and adds the time bias in the same FMA)
 }
 
-template <bool kStats, int NCH, bool kWide, int kEpiWarps = kEpiWarpsDefault, bool kPre = false>
+// kSpec: the epilogue's per-chunk parameters as compile-time constants for the standard 3x3 layer (one output, accumulator slots
+// dw = -1 | 0 | +1 = 0 | 1 | 2): 1 = without, 2 = with the fused 1x1 residual conv; kXchgT = an image row spans several warps
+// (W > 32).  0 = every case, parameters read at run time.  The epilogue's instruction stream is latency-critical: with these
+// few values folded the 64 -> 64 layer at 64x64 went from 200.8 to 192.2 us (profiles/README.md).
+template <bool kStats, int NCH, bool kWide, int kEpiWarps = kEpiWarpsDefault, bool kPre = false, int kSpec = 0, bool kXchgT = false>
 __global__ void __launch_bounds__(strip_threads(kEpiWarps, kPre), (kEpiWarps <= 8 && !kPre) ? 2 : 1)   // <= 8 warps: cap at 96 registers
 conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constant__ CUtensorMap map_in1,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wr,
@@ -490,7 +494,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     const int hl = row / p.W, wl = row - hl * p.W;
     const float m_right = wl < p.W - 1 ? 1.f : 0.f;   // pixel m+1 is in the same image row
     const float m_left = wl > 0 ? 1.f : 0.f;
-    const bool xchg = p.W > 32;             // an image row spans several warps
+    const bool xchg = kSpec ? kXchgT : (p.W > 32);   // an image row spans several warps
     constexpr int CG = kWide ? 16 : 2 * NCH;  // channels of a group inside one chunk
     constexpr int GPC = 16 / CG;              // groups per 16-column chunk (1 when kWide)
     float st_s[MYCH * GPC], st_ss[MYCH * GPC];
@@ -555,7 +559,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       if (kExp && p.epi_release && q == 0 && hsel == 0 && lane == 0) mbar_arrive(bar_empty + 8 * rel_stage);
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       // outputs of this tile: 1, or 2 for a transposed-conv phase pair (never with statistics); idle warps: 0
-      const int n_out = (kExp && (p.dbg & 2)) ? 0 : (kStats ? 1 : p.n_out);
+      const int n_out = (kExp && (p.dbg & 2)) ? 0 : ((kStats || kSpec) ? 1 : p.n_out);
 #pragma unroll
       for (int mc = 0; mc < MYCH; ++mc) {
       const int chunk = hsel * MYCH + mc;
@@ -564,12 +568,14 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       for (int o = 0; o < n_out; ++o) {
         // (with MYCH = 2, requesting both chunks from TMEM before using the first was measured: no gain)
         const int c = chunk * 16;
-        const int slot_c = o ? p.slot2_c : p.slot_c, slot_p = o ? p.slot2_p : p.slot_p, slot_m = o ? p.slot2_m : p.slot_m;
-        __nv_bfloat16* const optr_o = optr + o * p.out2_off;
+        constexpr int kNb = NCH * 16;          // = p.Nb (Nb is Cout up to 64 couts, 64 beyond)
+        const int slot_c = kSpec ? 1 : (o ? p.slot2_c : p.slot_c), slot_p = kSpec ? 2 : (o ? p.slot2_p : p.slot_p),
+                  slot_m = kSpec ? 0 : (o ? p.slot2_m : p.slot_m);
+        __nv_bfloat16* const optr_o = kSpec ? optr : optr + o * p.out2_off;
         uint32_t v0[16], vp[16], vm[16];
-        tmem_ld16(tbase + slot_c * p.Nb + c, v0);
-        if (slot_p >= 0 && !(kExp && (p.dbg & 64))) tmem_ld16(tbase + slot_p * p.Nb + c, vp);
-        if (slot_m >= 0 && !(kExp && (p.dbg & 64))) tmem_ld16(tbase + slot_m * p.Nb + c, vm);
+        tmem_ld16(tbase + slot_c * kNb + c, v0);
+        if (slot_p >= 0 && !(kExp && (p.dbg & 64))) tmem_ld16(tbase + slot_p * kNb + c, vp);
+        if (slot_m >= 0 && !(kExp && (p.dbg & 64))) tmem_ld16(tbase + slot_m * kNb + c, vm);
         tmem_ld_wait();
         if (xchg) {
           // publish the edge lanes: my lane 0's P_{+1} is pixel m+1 of the previous warp's lane 31,
@@ -641,10 +647,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        if (p.has_res) {
+        if (kSpec == 2 || (kSpec == 0 && p.has_res)) {
           // fused 1x1 residual conv of the same input (score_network.py:131,151): own slot, own bias, no GN
           uint32_t vr[16];
-          tmem_ld16(tbase + p.nacc * p.Nb + c, vr);
+          tmem_ld16(tbase + (kSpec ? 3 : p.nacc) * kNb + c, vr);
           tmem_ld_wait();
           const float4* br = reinterpret_cast<const float4*>(s_bias_r + co0 + c);
           uint32_t pr[8];
@@ -896,10 +902,22 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
        conv_strip_kernel<false, 4, true>},
       {conv_strip_kernel<true, 1, false>, conv_strip_kernel<true, 2, false>, conv_strip_kernel<true, 4, false>,
        conv_strip_kernel<true, 4, true>}};
+  // specialised epilogues (kSpec) for the standard 3x3 layers with statistics: [NCH 2 | 4 | 4 wide][res][xchg]
+  static const Kern spec_table[3][2][2] = {
+      {{conv_strip_kernel<true, 2, false, kEpiWarpsDefault, false, 1, false>, conv_strip_kernel<true, 2, false, kEpiWarpsDefault, false, 1, true>},
+       {conv_strip_kernel<true, 2, false, kEpiWarpsDefault, false, 2, false>, conv_strip_kernel<true, 2, false, kEpiWarpsDefault, false, 2, true>}},
+      {{conv_strip_kernel<true, 4, false, kEpiWarpsDefault, false, 1, false>, conv_strip_kernel<true, 4, false, kEpiWarpsDefault, false, 1, true>},
+       {conv_strip_kernel<true, 4, false, kEpiWarpsDefault, false, 2, false>, conv_strip_kernel<true, 4, false, kEpiWarpsDefault, false, 2, true>}},
+      {{conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 1, false>, conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 1, true>},
+       {conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 2, false>, conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 2, true>}}};
   const int nch = Nb / 16;
   const bool wide = g.Cout > 64;
   if (wide && stats && (!is_pow2(p.Cg) || p.Cg < 16)) return DBS_ERR_UNSUPPORTED;
   Kern kern = table[stats ? 1 : 0][wide ? 3 : (nch == 1 ? 0 : (nch == 2 ? 1 : 2))];
+  static const bool spec_off = [] { const char* e = getenv("DBS_STRIP_SPEC"); return e && e[0] == '0'; }();
+  const bool standard3x3 = stats && !pairw && !pre && !g.s2d && g.n_taps == 9 && nacc == 3 && p.n_out == 1 && p.slot_m == 0 &&
+                           p.slot_c == 1 && p.slot_p == 2 && (!fuse_res || p.nacc == 3) && (nch == 2 || nch == 4);
+  if (standard3x3 && !spec_off) kern = spec_table[wide ? 2 : (nch == 2 ? 0 : 1)][fuse_res ? 1 : 0][W > 32 ? 1 : 0];
   // GroupNorm-prologue variants: [stats][NCH index], 8 epilogue warps + kXW transform warps
   static const Kern pre_table[2][3] = {
       {conv_strip_kernel<false, 1, false, kEpiWarpsPre, true>, conv_strip_kernel<false, 2, false, kEpiWarpsPre, true>,
@@ -919,6 +937,13 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
                                                    (int)(kSmemBudget + 2048));
         if (e != cudaSuccess) attr_err = e;
       }
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) {
+          const cudaError_t e = cudaFuncSetAttribute(spec_table[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)(kSmemBudget + 2048));
+          if (e != cudaSuccess) attr_err = e;
+        }
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 3; ++b) {
         const cudaError_t e = cudaFuncSetAttribute(pre_table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
