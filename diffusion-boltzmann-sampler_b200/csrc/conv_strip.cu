@@ -559,19 +559,22 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       if (kExp && p.epi_release && q == 0 && hsel == 0 && lane == 0) mbar_arrive(bar_empty + 8 * rel_stage);
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       // outputs of this tile: 1, or 2 for a transposed-conv phase pair (never with statistics); idle warps: 0
-      const int n_out = (kExp && (p.dbg & 2)) ? 0 : ((kStats || kSpec) ? 1 : p.n_out);
+      const int n_out = (kExp && (p.dbg & 2)) ? 0 : (kSpec == 3 ? 2 : ((kStats || kSpec) ? 1 : p.n_out));
 #pragma unroll
       for (int mc = 0; mc < MYCH; ++mc) {
       const int chunk = hsel * MYCH + mc;
       if (chunk >= NCH) break;                 // idle warps / chunks beyond the tile's columns
-#pragma unroll 1
+#pragma unroll(kSpec == 3 ? 2 : 1)
       for (int o = 0; o < n_out; ++o) {
         // (with MYCH = 2, requesting both chunks from TMEM before using the first was measured: no gain)
         const int c = chunk * 16;
         constexpr int kNb = NCH * 16;          // = p.Nb (Nb is Cout up to 64 couts, 64 beyond)
-        const int slot_c = kSpec ? 1 : (o ? p.slot2_c : p.slot_c), slot_p = kSpec ? 2 : (o ? p.slot2_p : p.slot_p),
-                  slot_m = kSpec ? 0 : (o ? p.slot2_m : p.slot_m);
-        __nv_bfloat16* const optr_o = kSpec ? optr : optr + o * p.out2_off;
+        // kSpec 1 / 2: slots dw = -1 | 0 | +1 = 0 | 1 | 2.  kSpec 3 (transposed-conv phase pair): output 0 from slots
+        // (dw = -1, 0) = (0, 1), output 1 from (dw = 0, +1) = (2, 3); the loop is unrolled so that the slots fold per output
+        const int slot_c = kSpec == 3 ? (o ? 2 : 1) : (kSpec ? 1 : (o ? p.slot2_c : p.slot_c));
+        const int slot_p = kSpec == 3 ? (o ? 3 : -1) : (kSpec ? 2 : (o ? p.slot2_p : p.slot_p));
+        const int slot_m = kSpec == 3 ? (o ? -1 : 0) : (kSpec ? 0 : (o ? p.slot2_m : p.slot_m));
+        __nv_bfloat16* const optr_o = (kSpec == 1 || kSpec == 2) ? optr : optr + o * p.out2_off;
         uint32_t v0[16], vp[16], vm[16];
         tmem_ld16(tbase + slot_c * kNb + c, v0);
         if (slot_p >= 0 && !(kExp && (p.dbg & 64))) tmem_ld16(tbase + slot_p * kNb + c, vp);
@@ -647,7 +650,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        if (kSpec == 2 || (kSpec == 0 && p.has_res)) {
+        if (kSpec == 2 || (kSpec == 0 && p.has_res)) {   // (never with kSpec 1 / 3)
           // fused 1x1 residual conv of the same input (score_network.py:131,151): own slot, own bias, no GN
           uint32_t vr[16];
           tmem_ld16(tbase + (kSpec ? 3 : p.nacc) * kNb + c, vr);
@@ -910,6 +913,11 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
        {conv_strip_kernel<true, 4, false, kEpiWarpsDefault, false, 2, false>, conv_strip_kernel<true, 4, false, kEpiWarpsDefault, false, 2, true>}},
       {{conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 1, false>, conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 1, true>},
        {conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 2, false>, conv_strip_kernel<true, 4, true, kEpiWarpsDefault, false, 2, true>}}};
+  // transposed-conv phase pairs (kSpec 3): [NCH 2 | 4 | 4 wide][xchg]
+  static const Kern pair_table[3][2] = {
+      {conv_strip_kernel<false, 2, false, kEpiWarpsDefault, false, 3, false>, conv_strip_kernel<false, 2, false, kEpiWarpsDefault, false, 3, true>},
+      {conv_strip_kernel<false, 4, false, kEpiWarpsDefault, false, 3, false>, conv_strip_kernel<false, 4, false, kEpiWarpsDefault, false, 3, true>},
+      {conv_strip_kernel<false, 4, true, kEpiWarpsDefault, false, 3, false>, conv_strip_kernel<false, 4, true, kEpiWarpsDefault, false, 3, true>}};
   const int nch = Nb / 16;
   const bool wide = g.Cout > 64;
   if (wide && stats && (!is_pow2(p.Cg) || p.Cg < 16)) return DBS_ERR_UNSUPPORTED;
@@ -918,6 +926,9 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   const bool standard3x3 = stats && !pairw && !pre && !g.s2d && g.n_taps == 9 && nacc == 3 && p.n_out == 1 && p.slot_m == 0 &&
                            p.slot_c == 1 && p.slot_p == 2 && (!fuse_res || p.nacc == 3) && (nch == 2 || nch == 4);
   if (standard3x3 && !spec_off) kern = spec_table[wide ? 2 : (nch == 2 ? 0 : 1)][fuse_res ? 1 : 0][W > 32 ? 1 : 0];
+  const bool standard_pair = pairw && !stats && !pre && !fuse_res && p.n_out == 2 && p.slot_m == 0 && p.slot_c == 1 && p.slot_p == -1 &&
+                             p.slot2_c == 2 && p.slot2_p == 3 && p.slot2_m == -1 && (nch == 2 || nch == 4);
+  if (standard_pair && !spec_off) kern = pair_table[wide ? 2 : (nch == 2 ? 0 : 1)][W > 32 ? 1 : 0];
   // GroupNorm-prologue variants: [stats][NCH index], 8 epilogue warps + kXW transform warps
   static const Kern pre_table[2][3] = {
       {conv_strip_kernel<false, 1, false, kEpiWarpsPre, true>, conv_strip_kernel<false, 2, false, kEpiWarpsPre, true>,
@@ -934,6 +945,12 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 4; ++b) {
         const cudaError_t e = cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(kSmemBudget + 2048));
+        if (e != cudaSuccess) attr_err = e;
+      }
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const cudaError_t e = cudaFuncSetAttribute(pair_table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)(kSmemBudget + 2048));
         if (e != cudaSuccess) attr_err = e;
       }
