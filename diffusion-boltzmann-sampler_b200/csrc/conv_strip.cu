@@ -221,7 +221,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_bias[kMaxCout];
   __shared__ __align__(16) float s_bias_r[kMaxCout];
-  __shared__ float s_x[2][4][4][2][16];           // [parity][sub][quadrant][side][col]: cross-warp neighbours (W > 32)
+  __shared__ __align__(16) float s_x[2][4][4][2][16];   // [parity][sub][quadrant][side][col]: cross-warp neighbours (W > 32)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();          // the next kernel of the step may begin its prologue as SMs free up (common.cuh)
@@ -583,13 +583,17 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         if (xchg) {
           // publish the edge lanes: my lane 0's P_{+1} is pixel m+1 of the previous warp's lane 31,
           // my lane 31's P_{-1} is pixel m-1 of the next warp's lane 0
+          // (as four 16-byte accesses per side: the exchange used to be 64 scalar shared-memory instructions per chunk on
+          // top of the 32 shuffles, all through the same MIO queue)
           if (lane == 0 && slot_p >= 0) {
+            uint4* d = reinterpret_cast<uint4*>(&s_x[xb][half][q][0][0]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s_x[xb][half][q][0][j] = __uint_as_float(vp[j]);
+            for (int j4 = 0; j4 < 4; ++j4) d[j4] = make_uint4(vp[4 * j4], vp[4 * j4 + 1], vp[4 * j4 + 2], vp[4 * j4 + 3]);
           }
           if (lane == 31 && slot_m >= 0) {
+            uint4* d = reinterpret_cast<uint4*>(&s_x[xb][half][q][1][0]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s_x[xb][half][q][1][j] = __uint_as_float(vm[j]);
+            for (int j4 = 0; j4 < 4; ++j4) d[j4] = make_uint4(vm[4 * j4], vm[4 * j4 + 1], vm[4 * j4 + 2], vm[4 * j4 + 3]);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
         }
@@ -599,16 +603,24 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 16; ++j) vp[j] = __shfl_down_sync(0xffffffffu, vp[j], 1);
           if (xchg && lane == 31) {
+            const uint4* sp = reinterpret_cast<const uint4*>(&s_x[xb][half][(q + 1) & 3][0][0]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) vp[j] = __float_as_uint(s_x[xb][half][(q + 1) & 3][0][j]);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 t4 = sp[j4];
+              vp[4 * j4] = t4.x; vp[4 * j4 + 1] = t4.y; vp[4 * j4 + 2] = t4.z; vp[4 * j4 + 3] = t4.w;
+            }
           }
         }
         if (slot_m >= 0 && !(kExp && (p.dbg & 16))) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) vm[j] = __shfl_up_sync(0xffffffffu, vm[j], 1);
           if (xchg && lane == 0) {
+            const uint4* sp = reinterpret_cast<const uint4*>(&s_x[xb][half][(q + 3) & 3][1][0]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) vm[j] = __float_as_uint(s_x[xb][half][(q + 3) & 3][1][j]);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 t4 = sp[j4];
+              vm[4 * j4] = t4.x; vm[4 * j4 + 1] = t4.y; vm[4 * j4 + 2] = t4.z; vm[4 * j4 + 3] = t4.w;
+            }
           }
         }
         float f[16];
