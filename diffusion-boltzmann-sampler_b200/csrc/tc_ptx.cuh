@@ -35,13 +35,13 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug traps after ~4 s instead of hanging the GPU.
+// Bounded wait: a protocol bug traps instead of hanging the GPU.  The bound is a count of failed polls (2^26: seconds at
+// the hardware's try_wait suspend time, far beyond any legitimate wait); the earlier form read the global timer inside the
+// loop, and the compiler issued that read on EVERY failed poll of every role's wait loop.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 14)) t0 = global_timer_ns();
-    if (spins > (1u << 14) && (spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+    if (++spins == (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
