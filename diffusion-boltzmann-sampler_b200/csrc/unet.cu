@@ -840,7 +840,7 @@ gn_apply_kernel(const T* __restrict__ y, T* __restrict__ out, const float* __res
 // 2 x the block's activation bytes, and conv1 runs without its fused 1x1 residual output.  A thread keeps one 8-channel
 // vector for UN pixels at a time, so each 32-byte weight row read from shared memory serves UN pixels.
 template <int UN>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, UN <= 2 ? 4 : 2)
 gn_apply_xres_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, const float* __restrict__ stats,
                      float inv_cnt, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ xin, const float* __restrict__ wc, const float* __restrict__ bc,
@@ -927,6 +927,121 @@ gn_apply_xres_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
 #pragma unroll
       for (int k = 0; k < V; ++k) v[k] = silu_fast(fmaf(v[k], sc[k], sh[k])) + r[u][k];
       Vec16<__nv_bfloat16>::store(ob + (int64_t)p * C, v);
+    }
+  }
+}
+
+// The same kernel with the nine-tap residual on warp-level tensor-core MMAs (C = 64, W % 16 == 0): per 16 consecutive pixels of
+// a row a warp forms  r[16 px][64 ch] = patch[16 px][16 taps (9 used)] x wc[16][64]  as eight mma.sync m16n8k16 (bf16 operands,
+// fp32 accumulate, the composed bias as the accumulators' initial value) instead of 16 x 64 x 9 FFMAs — the CUDA-core form
+// above spends more than half of its issue slots there and runs at 360-390 us for 1.09 GB (B = 1024, 64x64), i.e. compute
+// bound.  The A fragment comes straight from the fp32 x tile in shared memory (thread (g, t) of the warp holds taps 2t, 2t+1
+// and, for t = 0, tap 8 of pixels g and g + 8), the B fragments (the weights) are loop-invariant registers.  The
+// accumulator fragments (pixel rows g / g + 8, channel pairs) go through a per-warp 4 KB shared-memory tile to reach the
+// (pixel, 8-channel vector) layout in which the raw conv output is loaded, normalised and stored with 16-byte accesses.
+// Rounding: x and wc enter the MMA as bf16 (the two-launch path stores the residual itself as bf16).
+__global__ void __launch_bounds__(256, 2)
+gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, const float* __restrict__ stats,
+                         float inv_cnt, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ xin, const float* __restrict__ wc, const float* __restrict__ bc,
+                         int H, int W, int TH) {
+  constexpr int C = 64, V = 8;
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_r = s_dyn;                       // [8 warps][16 px][72]: residual tile of a warp (row stride 72 floats: conflict-free)
+  float* s_x = s_dyn + 8 * 16 * 72;         // [(TH + 2)][W + 2]
+  const int n = blockIdx.y, h0 = blockIdx.x * TH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Wp = W + 2;
+  const float* xb = xin + (int64_t)n * H * W;
+  for (int i = threadIdx.x; i < (TH + 2) * Wp; i += blockDim.x) {
+    const int r = i / Wp, cc = i - r * Wp;
+    const int ih = h0 + r - 1, iw = cc - 1;
+    s_x[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.f;
+  }
+  // B fragments: b0 = (k = 2t, 2t+1; n = g), b1 = (k = 2t+8, 2t+9; n = g) of n-tile j  <->  wc[tap = k][channel 8j + g]
+  uint32_t bf[8][2];
+  float bias0[8], bias1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = 8 * j + g;
+    const float w0 = __ldg(wc + (2 * t) * C + ch), w1 = __ldg(wc + (2 * t + 1) * C + ch);
+    const float w8 = t == 0 ? __ldg(wc + 8 * C + ch) : 0.f;
+    __nv_bfloat162 h = __floats2bfloat162_rn(w0, w1);
+    bf[j][0] = *reinterpret_cast<const uint32_t*>(&h);
+    h = __floats2bfloat162_rn(w8, 0.f);
+    bf[j][1] = *reinterpret_cast<const uint32_t*>(&h);
+    bias0[j] = __ldg(bc + 8 * j + 2 * t);
+    bias1[j] = __ldg(bc + 8 * j + 2 * t + 1);
+  }
+  // GroupNorm scale / shift of my 8-channel vector (vector index lane % 8: fixed for the thread's whole life)
+  const int c = (lane & 7) * V;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int gi = (c + k) / (C / 8);
+    const float s0 = stats[((int64_t)n * 8 + gi) * 2 + 0], s1 = stats[((int64_t)n * 8 + gi) * 2 + 1];
+    const float mean = s0 * inv_cnt;
+    const float rstd = rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps);
+    const float a = rstd * gamma[c + k];
+    sc[k] = a;
+    sh[k] = beta[c + k] - mean * a;
+  }
+  __syncthreads();
+  const int rows = min(TH, H - h0);
+  const int n_tiles = rows * W / 16;                      // W % 16 == 0: a tile is 16 consecutive pixels of one row
+  const __nv_bfloat16* yb = y + ((int64_t)n * H + h0) * W * C;
+  __nv_bfloat16* ob = out + ((int64_t)n * H + h0) * W * C;
+  float* rt = s_r + warp * 16 * 72;
+  // taps of this thread: k0 = 2t -> (kh, kw), k1 = 2t + 1
+  const int k0 = 2 * t, k1 = 2 * t + 1;
+  const int o0 = (k0 / 3) * Wp + (k0 % 3), o1 = (k1 / 3) * Wp + (k1 % 3), o8 = 2 * Wp + 2;
+#pragma unroll 1
+  for (int tile = warp; tile < n_tiles; tile += 8) {
+    const int p0 = tile * 16;
+    const int pr = p0 / W, pc = p0 - pr * W;
+    // the raw conv output of my four (pixel, vector) slots, requested before the MMA work
+    uint4 q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const uint4*>(yb + (int64_t)(p0 + (lane >> 3) + 4 * i) * C + c);
+    // A fragments: rows g and g + 8 of the tile
+    const float* xa = s_x + pr * Wp + pc + g;
+    const float* xc = xa + 8;
+    uint32_t a0, a1, a2, a3;
+    {
+      __nv_bfloat162 h = __floats2bfloat162_rn(xa[o0], xa[o1]);
+      a0 = *reinterpret_cast<const uint32_t*>(&h);
+      h = __floats2bfloat162_rn(xc[o0], xc[o1]);
+      a1 = *reinterpret_cast<const uint32_t*>(&h);
+      h = __floats2bfloat162_rn(t == 0 ? xa[o8] : 0.f, 0.f);
+      a2 = *reinterpret_cast<const uint32_t*>(&h);
+      h = __floats2bfloat162_rn(t == 0 ? xc[o8] : 0.f, 0.f);
+      a3 = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    __syncwarp();                                         // the previous tile's reads of rt are done
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d0 = bias0[j], d1 = bias1[j], d2 = bias0[j], d3 = bias1[j];
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                   "{%0, %1, %2, %3};"
+                   : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[j][0]), "r"(bf[j][1]));
+      // accumulator fragment: (row g, channels 8j + 2t, + 1), (row g + 8, same channels)
+      *reinterpret_cast<float2*>(rt + g * 72 + 8 * j + 2 * t) = make_float2(d0, d1);
+      *reinterpret_cast<float2*>(rt + (g + 8) * 72 + 8 * j + 2 * t) = make_float2(d2, d3);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pl = (lane >> 3) + 4 * i;                 // pixel inside the tile
+      const float4 r0 = *reinterpret_cast<const float4*>(rt + pl * 72 + c);
+      const float4 r1 = *reinterpret_cast<const float4*>(rt + pl * 72 + c + 4);
+      const float rr[V] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      float v[V];
+      Vec16<__nv_bfloat16>::unpack(q[i], v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = silu_fast(fmaf(v[k], sc[k], sh[k])) + rr[k];
+      Vec16<__nv_bfloat16>::store(ob + (int64_t)(p0 + pl) * C + c, v);
     }
   }
 }
@@ -1261,14 +1376,18 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   }
 
   if (c.use_tc && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
-  // First encoder block on the tensor-core path (opt-in, DBS_XRES=1): its residual projection is recomputed from the
-  // one-channel network input inside the closing GroupNorm apply (gn_apply_xres_kernel), so conv1 runs WITHOUT the fused
-  // 1x1 residual output and the residual tensor is neither written nor read.  Measured at 64x64, B = 1024 (round 2):
-  // conv1 475 -> 346 us, but the apply kernel's 72 FMAs per 8-channel vector make it latency-bound at 396 us against
-  // 259 us for the HBM-bound GroupNorm apply it replaces: net zero, so the fused 1x1 stays the default.
-  static const bool xres_off = [] { const char* e = getenv("DBS_XRES"); return !(e && e[0] == '1'); }();
+  // First encoder block on the tensor-core path: its residual projection is recomputed from the one-channel network input
+  // inside the closing GroupNorm apply, so conv1 runs WITHOUT the fused 1x1 residual output and the residual tensor is
+  // neither written nor read.  Measured at 64x64, B = 1024: conv1 474 -> 329 us.  With the residual as 72 FMAs per
+  // 8-channel vector (gn_apply_xres_kernel) the apply kernel was compute-bound at 360-396 us against 259 us for the
+  // HBM-bound apply it replaces — net zero; with the residual on warp-level MMAs (gn_apply_xres_mma_kernel, 64 channels,
+  // W % 16 == 0) it takes 249 us: 733 -> 578 us for the pair, which is why the path is ON where the MMA kernel applies.
+  // DBS_XRES=0 keeps the fused 1x1, DBS_XRES=1 forces the recomputation (CUDA-core kernel where the MMA one does not apply).
+  static const int xres_env = [] { const char* e = getenv("DBS_XRES"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  static const bool xres_mma_off = [] { const char* e = getenv("DBS_XRES_MMA"); return e && e[0] == '0'; }();
+  const bool xres_mma_ok = bw.cout == 64 && W % 16 == 0 && !xres_mma_off;
   const bool xres = c.use_tc && sizeof(T) == 2 && bw.has_res && c.xin && c.plan->enc0_wc && &bw == &c.plan->enc[0] && !c.tap &&
-                    !xres_off && C1 == 0 && bw.cout % 8 == 0 && bw.cout <= 256 && G == 8;
+                    (xres_env == 1 || (xres_env == -1 && xres_mma_ok)) && C1 == 0 && bw.cout % 8 == 0 && bw.cout <= 256 && G == 8;
   bool res_done = false;
   if (c.use_tc && sizeof(T) == 2 && bw.has_res && !xres) {
     // conv1 and the 1x1 residual conv read the same input: one pass of the strip kernel does both
@@ -1308,15 +1427,39 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
   if (xres && sd) {
     const int cv = bw.cout / 8;
     const int threads = (256 / cv) * cv;
-    constexpr int UN = 4;
-    int TH = std::max(1, 512 / W);             // ~512 pixels per CTA
+    static const int un_env = [] { const char* e = getenv("DBS_XRES_UN"); return e ? atoi(e) : 4; }();
+    static const int px_env = [] { const char* e = getenv("DBS_XRES_PX"); return e ? atoi(e) : 2048; }();   // 512: 273 us, 2048: 249 us
+    int TH = std::max(1, px_env / W);          // ~512 pixels per CTA
     if (TH > H) TH = H;
     const size_t smem = ((size_t)10 * bw.cout + (size_t)(TH + 2) * (W + 2)) * 4;
     prof_set_label("HW%d C%d xres", H * W, bw.cout);
     ProfScope prof(kProfGnApply, c.st);
-    gn_apply_xres_kernel<UN><<<dim3((unsigned)((H + TH - 1) / TH), (unsigned)c.B), threads, smem, c.st>>>(
-        (const __nv_bfloat16*)y2, (__nv_bfloat16*)out, c.stats, 1.0f / (float)((int64_t)H * W * (bw.cout / 8)), 1e-5f, bw.g2, bw.b2,
-        c.xin, c.plan->enc0_wc, c.plan->enc0_bc, H, W, bw.cout, TH);
+    const dim3 xgrid((unsigned)((H + TH - 1) / TH), (unsigned)c.B);
+    const float xinv = 1.0f / (float)((int64_t)H * W * (bw.cout / 8));
+    static const bool mma_off = [] { const char* e = getenv("DBS_XRES_MMA"); return e && e[0] == '0'; }();
+    if (bw.cout == 64 && W % 16 == 0 && !mma_off) {
+      const size_t smem_m = ((size_t)8 * 16 * 72 + (size_t)(TH + 2) * (W + 2)) * 4;
+      static bool attr_done = false;
+      if (!attr_done) {
+        DBS_CUDA(cudaFuncSetAttribute(gn_apply_xres_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done = true;
+      }
+      if (smem_m <= 64 * 1024) {
+        gn_apply_xres_mma_kernel<<<xgrid, 256, smem_m, c.st>>>((const __nv_bfloat16*)y2, (__nv_bfloat16*)out, c.stats, xinv, 1e-5f, bw.g2,
+                                                              bw.b2, c.xin, c.plan->enc0_wc, c.plan->enc0_bc, H, W, TH);
+        DBS_LAUNCHED();
+        return DBS_OK;
+      }
+    }
+    if (un_env <= 1)
+      gn_apply_xres_kernel<1><<<xgrid, threads, smem, c.st>>>((const __nv_bfloat16*)y2, (__nv_bfloat16*)out, c.stats, xinv, 1e-5f, bw.g2,
+                                                             bw.b2, c.xin, c.plan->enc0_wc, c.plan->enc0_bc, H, W, bw.cout, TH);
+    else if (un_env == 2)
+      gn_apply_xres_kernel<2><<<xgrid, threads, smem, c.st>>>((const __nv_bfloat16*)y2, (__nv_bfloat16*)out, c.stats, xinv, 1e-5f, bw.g2,
+                                                             bw.b2, c.xin, c.plan->enc0_wc, c.plan->enc0_bc, H, W, bw.cout, TH);
+    else
+      gn_apply_xres_kernel<4><<<xgrid, threads, smem, c.st>>>((const __nv_bfloat16*)y2, (__nv_bfloat16*)out, c.stats, xinv, 1e-5f, bw.g2,
+                                                             bw.b2, c.xin, c.plan->enc0_wc, c.plan->enc0_bc, H, W, bw.cout, TH);
     DBS_LAUNCHED();
     return DBS_OK;
   }

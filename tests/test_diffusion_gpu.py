@@ -260,14 +260,16 @@ def test_bf16_bound_over_a_full_config4_trajectory():
     assert float((torch.sign(got) == torch.sign(want)).float().mean()) >= 0.999
 
 
-def test_opt_in_fusion_paths_stay_parity_green():
-    """The measured-but-not-default fusion paths: the GroupNorm prologue on the strip kernel's transform
-    warps (DBS_GN_PROLOGUE=1) and the first encoder block's residual recomputed from the network input (DBS_XRES=1) are
-    selected by environment variables read once per process, so they are exercised in a child process: bf16 forward of the
-    default network against the oracle within the bf16 bound, at 32x32 and 64x64."""
+def test_switchable_fusion_paths_stay_parity_green():
+    """The switchable fusion paths of the U-Net executor: the GroupNorm prologue on the strip kernel's
+    transform warps (DBS_GN_PROLOGUE=1, off by default), the first encoder block's residual recomputed from the network
+    input inside the GroupNorm apply (on by default through the MMA kernel; DBS_XRES_MMA=0 selects the CUDA-core kernel,
+    DBS_XRES=0 the fused 1x1 residual conv).  The switches are read once per process, so each combination runs in a child
+    process: bf16 forward of the default network against the oracle within the bf16 bound, at 32x32 and 64x64, and the
+    per-layer labels show that the intended kernels really ran."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent("""
-        import sys, numpy as np, torch
+        import sys, os, numpy as np, torch, tempfile
         sys.path[:0] = [%r, %r]
         from backend.ml.models.score_network import ScoreNetwork
         from oracle import unet as o_unet
@@ -275,7 +277,7 @@ def test_opt_in_fusion_paths_stay_parity_green():
         net = ScoreNetwork(1, 32, 64, 3).eval()
         sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
         from dbs_b200 import abi
-        import tempfile, os
+        want_labels, forbid_labels = sys.argv[1].split(","), [w for w in sys.argv[2].split(",") if w]
         for L, B in ((32, 6), (64, 3)):
             x, t = torch.randn(B, 1, L, L), torch.full((B,), 0.37)
             want = o_unet.unet_forward(sd, x, t).numpy()
@@ -286,16 +288,20 @@ def test_opt_in_fusion_paths_stay_parity_green():
             path = os.path.join(tempfile.mkdtemp(), "labels.tsv")
             abi.check(abi.lib.dbs_profile_dump(path.encode()))
             labels = open(path).read()
-            assert " gn>" in labels and "xres" in labels, labels      # both paths were really taken
+            assert all(w in labels for w in want_labels) and not any(w in labels for w in forbid_labels), labels
             err = float(np.sqrt(((got - want) ** 2).mean()) / np.sqrt((want ** 2).mean()))
             assert np.isfinite(got).all() and err <= 2e-2, (L, err)
             print("ok", L, err)
     """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
             os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffusion-boltzmann-sampler_b200"))
-    env = dict(os.environ, DBS_GN_PROLOGUE="1", DBS_XRES="1")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("ok") == 2
+    for env, want, forbid in ((dict(DBS_GN_PROLOGUE="1", DBS_XRES="1"), " gn>,xres", ""),
+                              (dict(DBS_XRES_MMA="0", DBS_XRES="1"), "xres", " gn>"),
+                              (dict(), "xres", " gn>"),
+                              (dict(DBS_XRES="0"), "+res1x1", "xres")):
+        r = subprocess.run([sys.executable, "-c", code, want, forbid], env=dict(os.environ, **env), capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, (env, r.stdout + r.stderr)
+        assert r.stdout.count("ok") == 2
 
 
 def test_programmatic_dependent_launch_gives_the_same_samples():
