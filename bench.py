@@ -419,7 +419,10 @@ def gn_apply_bytes_per_sample(L, prec):
         if prec == "bf16" and r_ * r_ <= 128 and 128 <= c_ <= 256:
             continue
         by += r_ * r_ * c_ * 2 * esz                                     # GN1: in + out
-        if not (prec == "bf16" and li == len(levels) - 1):
+        xres = (prec == "bf16" and li == 0 and c_ == 64 and r_ % 16 == 0 and os.environ.get("DBS_XRES", "") != "0")
+        if xres:
+            by += r_ * r_ * c_ * 2 * esz + r_ * r_ * 4                   # first block's GN2: in + out + the fp32 network input
+        elif not (prec == "bf16" and li == len(levels) - 1):
             by += r_ * r_ * c_ * 3 * esz                                 # GN2: in + residual + out
     return by
 
