@@ -1046,6 +1046,160 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
   }
 }
 
+// First encoder block, conv1 composed with the init conv (C = 32 -> 64 channels, bf16 path).  The init conv's 32-channel
+// output has ONE consumer left once the block's residual is recomputed from the network input (above): conv1.  Both are
+// linear, so  y1 = conv1(init_conv(x))  is a function of the one-channel input alone:
+//   y1[p][co] = b1[co] + sum_t in(p + t) * ( Bc[co][t] + sum_s Wc[co][t][s] * x~[p + t + s] )        t, s over the 3x3 offsets
+//   Wc[co][t][s] = sum_ci W1[co][ci][t] Wi[ci][s],   Bc[co][t] = sum_ci W1[co][ci][t] bi[ci]
+// x~ is the zero-padded input and in(q) says whether pixel q lies inside the image: conv1 pads the init conv's OUTPUT with
+// zeros, so a tap t that leaves the image contributes neither its weights nor its share of the init bias — which is why
+// the 81 (t, s) products are kept apart instead of being summed into one 5x5 kernel.  Per 16 consecutive pixels of a row a
+// warp forms  [16 px][96] x [96][64]  (81 products, 9 bias taps, 6 zero columns) as 6 x 8 mma.sync m16n8k16 with bf16
+// operands and fp32 accumulators: 2 x 96 x 64 MACs per pixel instead of conv1's 2 x 288 x 64 + the init conv's 2 x 9 x 32,
+// no 32-channel activation in HBM (268 MB written and read at B = 1024, 64x64), one launch instead of two.  The A
+// fragments come straight from the fp32 x tile in shared memory (two-pixel halo), masked per pixel by in(p + t); the B
+// fragments are built once per plan; GroupNorm sums are taken on the fp32 accumulators, an n-tile being exactly one group.
+__global__ void __launch_bounds__(256, 2)
+enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
+                     const uint2* __restrict__ bfrag, const float* __restrict__ b1, int H, int W, int TH) {
+  constexpr int C = 64;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  uint2* s_b = reinterpret_cast<uint2*>(sm_raw);                                   // [6][8][32] B fragments
+  __nv_bfloat16* s_y = reinterpret_cast<__nv_bfloat16*>(sm_raw + 6 * 8 * 32 * 8);  // [8 warps][16 px][72]
+  float* s_x = reinterpret_cast<float*>(sm_raw + 6 * 8 * 32 * 8 + 8 * 16 * 72 * 2); // [(TH + 4)][W + 4]
+  __shared__ float s_stat[16];
+  const int n = blockIdx.y, h0 = blockIdx.x * TH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int Wp = W + 4;
+  for (int i = threadIdx.x; i < 6 * 8 * 32; i += blockDim.x) s_b[i] = bfrag[i];
+  if (threadIdx.x < 16) s_stat[threadIdx.x] = 0.f;
+  const float* xb = xin + (int64_t)n * H * W;
+  for (int i = threadIdx.x; i < (TH + 4) * Wp; i += blockDim.x) {
+    const int r = i / Wp, cc = i - r * Wp;
+    const int ih = h0 + r - 2, iw = cc - 2;
+    s_x[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.f;
+  }
+  // my 20 regular k-indices (k-steps 0..4: k = 16 kk + 2 t4 + {0, 1, 8, 9} = 9 t + s < 80): offset of x~[p + t + s] relative
+  // to the pixel and the tap t whose in() bit gates it, packed as (offset + 1024) << 4 | t
+  uint32_t ktab[20];
+#pragma unroll
+  for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 16 * kk + 2 * t4 + (q & 1) + 8 * (q >> 1);
+      const int t = k / 9, sI = k - 9 * t;
+      const int off = (t / 3 - 1 + sI / 3 - 1) * Wp + (t % 3 - 1 + sI % 3 - 1);
+      ktab[kk * 4 + q] = ((uint32_t)(off + 1024) << 4) | (uint32_t)t;
+    }
+  float bia0[8], bia1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { bia0[j] = __ldg(b1 + 8 * j + 2 * t4); bia1[j] = __ldg(b1 + 8 * j + 2 * t4 + 1); }
+  float st_s[8], st_ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_ss[j] = 0.f; }
+  __syncthreads();
+  const int rows = min(TH, H - h0);
+  const int n_tiles = rows * W / 16;
+  __nv_bfloat16* ob = y + ((int64_t)n * H + h0) * W * C;
+  __nv_bfloat16* yt = s_y + warp * 16 * 72;
+#pragma unroll 1
+  for (int tile = warp; tile < n_tiles; tile += 8) {
+    const int p0 = tile * 16;
+    const int pr = p0 / W, pc = p0 - pr * W;
+    // in(p + t) for my two pixels (rows g and g + 8 of the tile): bit t = 3 (th + 1) + (tw + 1); bit 9 = 0 (zero columns)
+    const int ih = h0 + pr;
+    const uint32_t rowok = (ih > 0 ? 1u : 0u) | 2u | (ih < H - 1 ? 4u : 0u);
+    uint32_t inm[2];
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      const int iw = pc + g + 8 * r2;
+      const uint32_t colok = (iw > 0 ? 1u : 0u) | 2u | (iw < W - 1 ? 4u : 0u);
+      uint32_t m = 0;
+#pragma unroll
+      for (int th = 0; th < 3; ++th)
+        if ((rowok >> th) & 1u) m |= colok << (3 * th);
+      inm[r2] = m;
+    }
+    const float* xc0 = s_x + (pr + 2) * Wp + (pc + g + 2);
+    const float* xc1 = xc0 + 8;
+    float d[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { d[j][0] = bia0[j]; d[j][1] = bia1[j]; d[j][2] = bia0[j]; d[j][3] = bia1[j]; }
+#pragma unroll
+    for (int kk = 0; kk < 6; ++kk) {
+      float av[2][4];                                   // [pixel row][q]: k = 16 kk + 2 t4 + {0, 1, 8, 9}
+      if (kk < 5) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t e = ktab[kk * 4 + q];
+          const int off = (int)(e >> 4) - 1024;
+          const uint32_t tb = e & 15u;
+          av[0][q] = ((inm[0] >> tb) & 1u) ? xc0[off] : 0.f;
+          av[1][q] = ((inm[1] >> tb) & 1u) ? xc1[off] : 0.f;
+        }
+      } else {
+        // k = 80: the last product (t = 8, s = 8); k = 81 .. 89: the bias taps (value 1 where the tap is inside); 90 ..: zero
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = 80 + 2 * t4 + (q & 1) + 8 * (q >> 1);
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2) {
+            float v = 0.f;
+            if (k == 80) v = ((inm[r2] >> 8) & 1u) ? (r2 ? xc1 : xc0)[2 * Wp + 2] : 0.f;
+            else if (k < 90) v = ((inm[r2] >> (k - 81)) & 1u) ? 1.f : 0.f;
+            av[r2][q] = v;
+          }
+        }
+      }
+      uint32_t a0, a1, a2, a3;
+      {
+        __nv_bfloat162 h = __floats2bfloat162_rn(av[0][0], av[0][1]);
+        a0 = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2bfloat162_rn(av[1][0], av[1][1]);
+        a1 = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2bfloat162_rn(av[0][2], av[0][3]);
+        a2 = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2bfloat162_rn(av[1][2], av[1][3]);
+        a3 = *reinterpret_cast<const uint32_t*>(&h);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint2 b = s_b[(kk * 8 + j) * 32 + lane];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                     "{%0, %1, %2, %3};"
+                     : "+f"(d[j][0]), "+f"(d[j][1]), "+f"(d[j][2]), "+f"(d[j][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+      }
+    }
+    __syncwarp();                                         // the previous tile's reads of yt are done
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st_s[j] += (d[j][0] + d[j][1]) + (d[j][2] + d[j][3]);
+      st_ss[j] = fmaf(d[j][0], d[j][0], fmaf(d[j][1], d[j][1], fmaf(d[j][2], d[j][2], fmaf(d[j][3], d[j][3], st_ss[j]))));
+      __nv_bfloat162 h = __floats2bfloat162_rn(d[j][0], d[j][1]);
+      *reinterpret_cast<__nv_bfloat162*>(yt + g * 72 + 8 * j + 2 * t4) = h;
+      h = __floats2bfloat162_rn(d[j][2], d[j][3]);
+      *reinterpret_cast<__nv_bfloat162*>(yt + (g + 8) * 72 + 8 * j + 2 * t4) = h;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pl = (lane >> 3) + 4 * i;
+      *reinterpret_cast<uint4*>(ob + (int64_t)(p0 + pl) * C + (lane & 7) * 8) =
+          *reinterpret_cast<const uint4*>(yt + pl * 72 + (lane & 7) * 8);
+    }
+  }
+  // GroupNorm sums of this CTA's rows: group j = channels 8 j .. 8 j + 7 = n-tile j
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a = warp_sum(st_s[j]), b = warp_sum(st_ss[j]);
+    if (lane == 0) { atomicAdd(&s_stat[2 * j], a); atomicAdd(&s_stat[2 * j + 1], b); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) atomicAdd(stats + (int64_t)n * 16 + threadIdx.x, s_stat[threadIdx.x]);
+}
+
 // stand-alone time path: gridDim.x = distinct t values, gridDim.y CTAs per value (see time_path above)
 __global__ void __launch_bounds__(256)
 time_kernel(const __grid_constant__ TimeArgs ta) {
@@ -1151,6 +1305,8 @@ struct dbs_unet_plan {
   uint32_t* final_bfrag = nullptr;   // their mma.sync B fragments (final_bfrag_host), C a multiple of 16 only
   // first encoder block: residual projection composed with the init conv, [9][cout] + [cout] (gn_apply_xres_kernel)
   float *enc0_wc = nullptr, *enc0_bc = nullptr;
+  uint2* enc0_bfrag = nullptr;       // enc0_composed_kernel: B fragments of conv1 composed with the init conv, [6][8][32]
+  float* enc0_b1 = nullptr;          // conv1's bias
   std::vector<float> init_w_host, init_b_host;   // [tap][C], [C]: kernel-parameter copies for the init conv
   float final_b_host = 0.f;
   std::vector<dbs::BlockW> enc, dec;
@@ -1253,6 +1409,7 @@ struct Ctx {
   const char* tap; float* tap_out; int64_t tap_numel; bool tapped = false;
   DeferredGn* defer = nullptr;
   const float* xin = nullptr;      // the network input (B, 1, H, W): set while the FIRST encoder block runs (residual from input)
+  bool compose0 = false;           // the first block's conv1 runs composed with the init conv (no init-conv activation exists)
   float* stats_base = nullptr; int64_t stats_stride = 0; int* stats_next = nullptr; int stats_slices = 0;
   // bf16 path: every conv+GroupNorm pair gets its own slice of one region zeroed by ONE memset per forward
   // (instead of a memset node in front of each conv); returns false when the region is used up
@@ -1395,6 +1552,26 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
                            (__nv_bfloat16*)ty, c.stats, G, c.st, bw.res.w16, bw.res.bias, (__nv_bfloat16*)tr);
     if (rc == DBS_OK) { res_done = true; sd = true; }
     else if (rc != DBS_ERR_UNSUPPORTED) return rc;
+  }
+  if (c.compose0 && &bw == &c.plan->enc[0]) {
+    DBS_REQUIRE(xres && sizeof(T) == 2 && bw.cout == 64 && W % 16 == 0 && c.plan->enc0_bfrag,
+                "unet_forward: composed first layer without its preconditions");
+    int TH = 2048 / W;
+    if (TH > H) TH = H;
+    if (TH < 1) TH = 1;
+    const size_t smem = (size_t)6 * 8 * 32 * 8 + (size_t)8 * 16 * 72 * 2 + (size_t)(TH + 4) * (W + 4) * 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+      DBS_CUDA(cudaFuncSetAttribute(enc0_composed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_done = true;
+    }
+    DBS_REQUIRE(smem <= 96 * 1024, "unet_forward: composed first layer: x tile of %d rows does not fit", TH);
+    prof_set_label("enc0 conv1 composed with init conv H%d W%d", H, W);
+    ProfScope prof(kProfConvTC, c.st);
+    enc0_composed_kernel<<<dim3((unsigned)((H + TH - 1) / TH), (unsigned)c.B), 256, smem, c.st>>>(
+        c.xin, (__nv_bfloat16*)ty, c.stats, c.plan->enc0_bfrag, c.plan->enc0_b1, H, W, TH);
+    DBS_LAUNCHED();
+    res_done = true; sd = true;
   }
   if (!res_done && (rc = run_conv<T>(c, g1, in0, in1, bw.conv1, ty, c.stats, G, &sd))) return rc;
   {
@@ -1553,7 +1730,15 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   // ---- time path: its own launch, unless the bf16 init conv below can carry it (all samples share t)
   TimeArgs ta{t, plan->freqs, plan->tw0, plan->tb0, plan->tw2, plan->tb2, plan->twt, plan->tbt, tbias, Td, plan->sumC, 0};
   static const bool tfuse_off = [] { const char* e = getenv("DBS_TIME_FUSE"); return e && e[0] == '0'; }();
-  const bool time_fused = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && n_t == 1 && !tfuse_off && !fixup;
+  // First block's conv1 composed with the init conv (enc0_composed_kernel): the same preconditions as the recomputed
+  // residual of that block (run_block: xres through the MMA kernel), so that nothing reads the init conv's activation.
+  // DBS_ENC0_COMPOSED=0 keeps the two launches.
+  static const bool compose_off = [] { const char* e = getenv("DBS_ENC0_COMPOSED"); return e && e[0] == '0'; }();
+  static const bool xres_env_off = [] { const char* e = getenv("DBS_XRES"); return e && e[0] == '0'; }();
+  static const bool xres_mma_env_off = [] { const char* e = getenv("DBS_XRES_MMA"); return e && e[0] == '0'; }();
+  const bool compose0 = use_tc && sizeof(T) == 2 && !tap && !fixup && !compose_off && !xres_env_off && !xres_mma_env_off && C == 32 &&
+                        nb >= 1 && plan->enc0_bfrag && plan->enc0_wc && plan->enc[0].has_res && W % 16 == 0 && getenv("DBS_L2_CHUNK_MB") == nullptr;
+  const bool time_fused = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && n_t == 1 && !tfuse_off && !fixup && !compose0;
   if (!time_fused) {
     prof_set_label("time");
     ProfScope prof(kProfUnetMisc, st);
@@ -1564,7 +1749,8 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   }
 
   // ---- init conv
-  {
+  c.compose0 = compose0;
+  if (!compose0) {
     const int64_t n_pix = B * H * W;
     prof_set_label(time_fused ? "time+init_conv" : "init_conv");
     ProfScope prof(kProfUnetMisc, st);
@@ -1905,6 +2091,48 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
         return fail(DBS_ERR_CUDA);
       }
       plan->enc0_wc = (float*)dw; plan->enc0_bc = (float*)db;
+    }
+    // conv1 of the first block composed with the init conv (enc0_composed_kernel): Wk[k][co], k = 9 t + s products, then
+    // the nine bias taps, laid out as mma.sync B fragments (lane = 4 g + t4: b0 = k 2 t4, 2 t4 + 1; b1 = k + 8; n = g)
+    const dbs_param* w1 = pt.find("encoder.0.conv1.weight");
+    const dbs_param* bb1 = pt.find("encoder.0.conv1.bias");
+    if (C == 32 && w1 && bb1 && w1->numel == (int64_t)co0 * C * 9 && bb1->numel == co0) {
+      std::vector<float> hw1((size_t)co0 * C * 9), hb1((size_t)co0), wk((size_t)96 * co0, 0.f);
+      if (cudaMemcpy(hw1.data(), w1->data, hw1.size() * 4, w1->is_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess ||
+          cudaMemcpy(hb1.data(), bb1->data, hb1.size() * 4, bb1->is_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess) {
+        set_error("unet_plan_create: reading encoder.0.conv1 failed");
+        return fail(DBS_ERR_CUDA);
+      }
+      for (int o = 0; o < co0; ++o)
+        for (int t = 0; t < 9; ++t) {
+          double bsum = 0.0;
+          for (int ci = 0; ci < C; ++ci) bsum += (double)hw1[((size_t)o * C + ci) * 9 + t] * plan->init_b_host[ci];
+          wk[(size_t)(81 + t) * co0 + o] = (float)bsum;
+          for (int s2 = 0; s2 < 9; ++s2) {
+            double a = 0.0;
+            for (int ci = 0; ci < C; ++ci) a += (double)hw1[((size_t)o * C + ci) * 9 + t] * plan->init_w_host[(size_t)s2 * C + ci];
+            wk[(size_t)(9 * t + s2) * co0 + o] = (float)a;
+          }
+        }
+      std::vector<uint32_t> frag((size_t)6 * 8 * 32 * 2);
+      for (int kk = 0; kk < 6; ++kk)
+        for (int j = 0; j < 8; ++j)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int gg = lane >> 2, tt = lane & 3, ch = 8 * j + gg, k0 = 16 * kk + 2 * tt;
+            auto W_ = [&](int k) { return wk[(size_t)k * co0 + ch]; };
+            const size_t idx = ((size_t)(kk * 8 + j) * 32 + lane) * 2;
+            frag[idx] = bf16_bits(W_(k0)) | (bf16_bits(W_(k0 + 1)) << 16);
+            frag[idx + 1] = bf16_bits(W_(k0 + 8)) | (bf16_bits(W_(k0 + 9)) << 16);
+          }
+      void *df = nullptr, *d1 = nullptr;
+      if ((rc = dev_alloc(plan, frag.size() * 4, &df))) return fail(rc);
+      if ((rc = dev_alloc(plan, hb1.size() * 4, &d1))) return fail(rc);
+      if (cudaMemcpy(df, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(d1, hb1.data(), hb1.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("unet_plan_create: composed conv1 upload failed");
+        return fail(DBS_ERR_CUDA);
+      }
+      plan->enc0_bfrag = (uint2*)df; plan->enc0_b1 = (float*)d1;
     }
   }
   if ((rc = make_block(plan, pt, "middle.", ch, ch, &plan->mid))) return fail(rc);

@@ -264,7 +264,8 @@ def test_switchable_fusion_paths_stay_parity_green():
     """The switchable fusion paths of the U-Net executor: the GroupNorm prologue on the strip kernel's
     transform warps (DBS_GN_PROLOGUE=1, off by default), the first encoder block's residual recomputed from the network
     input inside the GroupNorm apply (on by default through the MMA kernel; DBS_XRES_MMA=0 selects the CUDA-core kernel,
-    DBS_XRES=0 the fused 1x1 residual conv).  The switches are read once per process, so each combination runs in a child
+    DBS_XRES=0 the fused 1x1 residual conv), the first block's conv1 composed with the init conv (on by default with it;
+    DBS_ENC0_COMPOSED=0 keeps the init conv and conv1 as two launches).  The switches are read once per process, so each combination runs in a child
     process: bf16 forward of the default network against the oracle within the bf16 bound, at 32x32 and 64x64, and the
     per-layer labels show that the intended kernels really ran."""
     import os, subprocess, sys, textwrap
@@ -295,9 +296,10 @@ def test_switchable_fusion_paths_stay_parity_green():
     """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
             os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffusion-boltzmann-sampler_b200"))
     for env, want, forbid in ((dict(DBS_GN_PROLOGUE="1", DBS_XRES="1"), " gn>,xres", ""),
-                              (dict(DBS_XRES_MMA="0", DBS_XRES="1"), "xres", " gn>"),
-                              (dict(), "xres", " gn>"),
-                              (dict(DBS_XRES="0"), "+res1x1", "xres")):
+                              (dict(DBS_XRES_MMA="0", DBS_XRES="1"), "xres", " gn>,composed"),
+                              (dict(), "xres,composed with init conv", " gn>,init_conv"),
+                              (dict(DBS_ENC0_COMPOSED="0"), "xres,init_conv", "composed"),
+                              (dict(DBS_XRES="0"), "+res1x1,init_conv", "xres,composed")):
         r = subprocess.run([sys.executable, "-c", code, want, forbid], env=dict(os.environ, **env), capture_output=True,
                            text=True, timeout=300)
         assert r.returncode == 0, (env, r.stdout + r.stderr)
