@@ -875,8 +875,9 @@ gn_apply_xres_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
   for (int k = 0; k < V; ++k) {
     const int gi = (c + k) / Cg;
     const float s0 = stats[((int64_t)n * 8 + gi) * 2 + 0], s1 = stats[((int64_t)n * 8 + gi) * 2 + 1];
-    const float mean = s0 * inv_cnt;
-    const float rstd = rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps);
+    // inv_cnt > 0: raw (sum, sum of squares) from a conv epilogue; inv_cnt == 0: (mean, rstd) from gn_stats_kernel
+    const float mean = inv_cnt > 0.f ? s0 * inv_cnt : s0;
+    const float rstd = inv_cnt > 0.f ? rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps) : s1;
     const float a = rstd * gamma[c + k];
     sc[k] = a;
     sh[k] = beta[c + k] - mean * a;
@@ -981,8 +982,9 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
   for (int k = 0; k < V; ++k) {
     const int gi = (c + k) / (C / 8);
     const float s0 = stats[((int64_t)n * 8 + gi) * 2 + 0], s1 = stats[((int64_t)n * 8 + gi) * 2 + 1];
-    const float mean = s0 * inv_cnt;
-    const float rstd = rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps);
+    // inv_cnt > 0: raw (sum, sum of squares) from a conv epilogue; inv_cnt == 0: (mean, rstd) from gn_stats_kernel
+    const float mean = inv_cnt > 0.f ? s0 * inv_cnt : s0;
+    const float rstd = inv_cnt > 0.f ? rsqrtf(fmaxf(s1 * inv_cnt - mean * mean, 0.f) + eps) : s1;
     const float a = rstd * gamma[c + k];
     sc[k] = a;
     sh[k] = beta[c + k] - mean * a;
@@ -996,14 +998,24 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
   // taps of this thread: k0 = 2t -> (kh, kw), k1 = 2t + 1
   const int k0 = 2 * t, k1 = 2 * t + 1;
   const int o0 = (k0 / 3) * Wp + (k0 % 3), o1 = (k1 / 3) * Wp + (k1 % 3), o8 = 2 * Wp + 2;
+  // the raw conv output of my four (pixel, vector) slots is requested one tile ahead: with the loads issued only at the top
+  // of the tile they serve, a warp has bytes in flight for about half of its time and sixteen warps per SM do not cover
+  // the HBM latency (249 us for 1.07 GB at B = 1024, 64x64)
+  uint4 q[4];
+  if (warp < n_tiles) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const uint4*>(yb + (int64_t)(warp * 16 + (lane >> 3) + 4 * i) * C + c);
+  }
 #pragma unroll 1
   for (int tile = warp; tile < n_tiles; tile += 8) {
     const int p0 = tile * 16;
     const int pr = p0 / W, pc = p0 - pr * W;
-    // the raw conv output of my four (pixel, vector) slots, requested before the MMA work
-    uint4 q[4];
+    uint4 qn[4];
+    {
+      const int pn = tile + 8 < n_tiles ? p0 + 128 : p0;   // last round: a harmless re-read of the current slots
 #pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const uint4*>(yb + (int64_t)(p0 + (lane >> 3) + 4 * i) * C + c);
+      for (int i = 0; i < 4; ++i) qn[i] = *reinterpret_cast<const uint4*>(yb + (int64_t)(pn + (lane >> 3) + 4 * i) * C + c);
+    }
     // A fragments: rows g and g + 8 of the tile
     const float* xa = s_x + pr * Wp + pc + g;
     const float* xc = xa + 8;
@@ -1043,6 +1055,8 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
       for (int k = 0; k < V; ++k) v[k] = silu_fast(fmaf(v[k], sc[k], sh[k])) + rr[k];
       Vec16<__nv_bfloat16>::store(ob + (int64_t)(p0 + pl) * C + c, v);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = qn[i];
   }
 }
 
@@ -1052,46 +1066,64 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
 //   y1[p][co] = b1[co] + sum_t in(p + t) * ( Bc[co][t] + sum_s Wc[co][t][s] * x~[p + t + s] )        t, s over the 3x3 offsets
 //   Wc[co][t][s] = sum_ci W1[co][ci][t] Wi[ci][s],   Bc[co][t] = sum_ci W1[co][ci][t] bi[ci]
 // x~ is the zero-padded input and in(q) says whether pixel q lies inside the image: conv1 pads the init conv's OUTPUT with
-// zeros, so a tap t that leaves the image contributes neither its weights nor its share of the init bias — which is why
-// the 81 (t, s) products are kept apart instead of being summed into one 5x5 kernel.  Per 16 consecutive pixels of a row a
-// warp forms  [16 px][96] x [96][64]  (81 products, 9 bias taps, 6 zero columns) as 6 x 8 mma.sync m16n8k16 with bf16
-// operands and fp32 accumulators: 2 x 96 x 64 MACs per pixel instead of conv1's 2 x 288 x 64 + the init conv's 2 x 9 x 32,
-// no 32-channel activation in HBM (268 MB written and read at B = 1024, 64x64), one launch instead of two.  The A
-// fragments come straight from the fp32 x tile in shared memory (two-pixel halo), masked per pixel by in(p + t); the B
-// fragments are built once per plan; GroupNorm sums are taken on the fp32 accumulators, an n-tile being exactly one group.
+// zeros, so a tap t that leaves the image contributes neither its weights nor its share of the init bias.
+// A warp works on 4 x 4-pixel tiles (16 MMA rows), fetched from a CTA-wide counter, in one of two forms:
+//   * interior tile (no pixel on the image's outer ring, 77 % of the tiles at 64x64): every in() is 1 and the 81 (t, s)
+//     products collapse to ONE 5x5 kernel  W5[co][u] = sum_{t + s = u} Wc[co][t][s]  plus the summed bias taps:
+//     [16 px][32] x [32][64] (25 products, the bias column, 6 zero columns) = 2 x 8 mma.sync m16n8k16;
+//   * border tile: the products are kept apart and masked per pixel by in(p + t):  [16 px][96] x [96][64]  (81 products,
+//     9 bias taps, 6 zero columns) = 6 x 8 MMAs.
+// bf16 operands, fp32 accumulators, 2 x 32 (or 96) x 64 MACs per pixel instead of conv1's 2 x 288 x 64 + the init conv's
+// 2 x 9 x 32, no 32-channel activation in HBM (268 MB written and read at B = 1024, 64x64), one launch instead of two.
+// The first form of this kernel ran every tile (16 pixels of a row) through the masked 96-wide form and was bound by
+// shared-memory wavefronts (~290 per tile: 160 masked A loads, 96 for the B fragments): 255 us at B = 1024 against 82 us
+// for its 537 MB of stores; an interior tile costs ~80.  The A fragments come straight from the fp32 x tile in shared
+// memory (two-pixel halo); the B fragments are built once per plan; GroupNorm sums are taken on the fp32 accumulators, an
+// n-tile being exactly one group.
 __global__ void __launch_bounds__(256, 2)
 enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
                      const uint2* __restrict__ bfrag, const float* __restrict__ b1, int H, int W, int TH) {
   constexpr int C = 64;
+  constexpr int kFragMasked = 6 * 8 * 32, kFragInner = 2 * 8 * 32;
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  uint2* s_b = reinterpret_cast<uint2*>(sm_raw);                                   // [6][8][32] B fragments
-  __nv_bfloat16* s_y = reinterpret_cast<__nv_bfloat16*>(sm_raw + 6 * 8 * 32 * 8);  // [8 warps][16 px][72]
-  float* s_x = reinterpret_cast<float*>(sm_raw + 6 * 8 * 32 * 8 + 8 * 16 * 72 * 2); // [(TH + 4)][W + 4]
+  uint2* s_b = reinterpret_cast<uint2*>(sm_raw);                                   // [6][8][32] masked + [2][8][32] interior
+  const uint2* s_b5 = s_b + kFragMasked;
+  __nv_bfloat16* s_y = reinterpret_cast<__nv_bfloat16*>(sm_raw + (kFragMasked + kFragInner) * 8);   // [8 warps][16 px][72]
+  float* s_x = reinterpret_cast<float*>(sm_raw + (kFragMasked + kFragInner) * 8 + 8 * 16 * 72 * 2); // [(TH + 4)][W + 4]
   __shared__ float s_stat[16];
+  __shared__ uint32_t s_ktab[20 * 4];
+  __shared__ int s_next;
   const int n = blockIdx.y, h0 = blockIdx.x * TH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int Wp = W + 4;
-  for (int i = threadIdx.x; i < 6 * 8 * 32; i += blockDim.x) s_b[i] = bfrag[i];
+  for (int i = threadIdx.x; i < kFragMasked + kFragInner; i += blockDim.x) s_b[i] = bfrag[i];
   if (threadIdx.x < 16) s_stat[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) s_next = 0;
+  // masked form: the 20 regular k-indices of a lane (k-steps 0..4: k = 16 kk + 2 t4 + {0, 1, 8, 9} = 9 t + s < 80): offset of
+  // x~[p + t + s] relative to the pixel and the tap t whose in() bit gates it, packed as (offset + 1024) << 4 | t
+  if (threadIdx.x < 80) {
+    const int tq = threadIdx.x & 3, e = threadIdx.x >> 2, kk = e >> 2, q = e & 3;
+    const int k = 16 * kk + 2 * tq + (q & 1) + 8 * (q >> 1);
+    const int t = k / 9, sI = k - 9 * t;
+    const int off = (t / 3 - 1 + sI / 3 - 1) * Wp + (t % 3 - 1 + sI % 3 - 1);
+    s_ktab[threadIdx.x] = ((uint32_t)(off + 1024) << 4) | (uint32_t)t;
+  }
   const float* xb = xin + (int64_t)n * H * W;
   for (int i = threadIdx.x; i < (TH + 4) * Wp; i += blockDim.x) {
     const int r = i / Wp, cc = i - r * Wp;
     const int ih = h0 + r - 2, iw = cc - 2;
     s_x[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + ih * W + iw) : 0.f;
   }
-  // my 20 regular k-indices (k-steps 0..4: k = 16 kk + 2 t4 + {0, 1, 8, 9} = 9 t + s < 80): offset of x~[p + t + s] relative
-  // to the pixel and the tap t whose in() bit gates it, packed as (offset + 1024) << 4 | t
-  uint32_t ktab[20];
+  // interior form: k = 5 (uy + 2) + (ux + 2) < 25; my k-indices 2 t4 + {0, 1, 8, 9} (k-step 0), 16 + 2 t4 + {0, 1} (k-step 1);
+  // k = 24 (the last product) and k = 25 (the bias column) sit in lane t4 = 0's upper pair of k-step 1, the rest is zero
+  int o5[6];
 #pragma unroll
-  for (int kk = 0; kk < 5; ++kk)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = 16 * kk + 2 * t4 + (q & 1) + 8 * (q >> 1);
-      const int t = k / 9, sI = k - 9 * t;
-      const int off = (t / 3 - 1 + sI / 3 - 1) * Wp + (t % 3 - 1 + sI % 3 - 1);
-      ktab[kk * 4 + q] = ((uint32_t)(off + 1024) << 4) | (uint32_t)t;
-    }
+  for (int q = 0; q < 6; ++q) {
+    const int k = q < 4 ? 2 * t4 + (q & 1) + 8 * (q >> 1) : 16 + 2 * t4 + (q & 1);
+    o5[q] = (k / 5 - 2) * Wp + (k % 5 - 2);
+  }
+  const int o24 = 2 * Wp + 2;
   float bia0[8], bia1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { bia0[j] = __ldg(b1 + 8 * j + 2 * t4); bia1[j] = __ldg(b1 + 8 * j + 2 * t4 + 1); }
@@ -1100,76 +1132,104 @@ enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ 
   for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_ss[j] = 0.f; }
   __syncthreads();
   const int rows = min(TH, H - h0);
-  const int n_tiles = rows * W / 16;
+  const int tiles_x = W >> 2;
+  const int n_tiles = (rows >> 2) * tiles_x;                // H % 4 == 0, TH % 4 == 0 (host)
   __nv_bfloat16* ob = y + ((int64_t)n * H + h0) * W * C;
   __nv_bfloat16* yt = s_y + warp * 16 * 72;
+  auto pack2 = [](float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  };
 #pragma unroll 1
-  for (int tile = warp; tile < n_tiles; tile += 8) {
-    const int p0 = tile * 16;
-    const int pr = p0 / W, pc = p0 - pr * W;
-    // in(p + t) for my two pixels (rows g and g + 8 of the tile): bit t = 3 (th + 1) + (tw + 1); bit 9 = 0 (zero columns)
-    const int ih = h0 + pr;
-    const uint32_t rowok = (ih > 0 ? 1u : 0u) | 2u | (ih < H - 1 ? 4u : 0u);
-    uint32_t inm[2];
-#pragma unroll
-    for (int r2 = 0; r2 < 2; ++r2) {
-      const int iw = pc + g + 8 * r2;
-      const uint32_t colok = (iw > 0 ? 1u : 0u) | 2u | (iw < W - 1 ? 4u : 0u);
-      uint32_t m = 0;
-#pragma unroll
-      for (int th = 0; th < 3; ++th)
-        if ((rowok >> th) & 1u) m |= colok << (3 * th);
-      inm[r2] = m;
-    }
-    const float* xc0 = s_x + (pr + 2) * Wp + (pc + g + 2);
-    const float* xc1 = xc0 + 8;
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(&s_next, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_tiles) break;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int r0 = 4 * ty, c0 = 4 * tx;                   // tile origin: row inside the CTA's rows, image column
+    const int ih0 = h0 + r0;
+    // MMA rows g and g + 8 of the tile are the pixels (g >> 2, g & 3) and two rows below
+    const float* xc0 = s_x + (r0 + (g >> 2) + 2) * Wp + (c0 + (g & 3) + 2);
+    const float* xc1 = xc0 + 2 * Wp;
     float d[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { d[j][0] = bia0[j]; d[j][1] = bia1[j]; d[j][2] = bia0[j]; d[j][3] = bia1[j]; }
+    if (ih0 > 0 && ih0 + 4 < H && c0 > 0 && c0 + 4 < W) {
 #pragma unroll
-    for (int kk = 0; kk < 6; ++kk) {
-      float av[2][4];                                   // [pixel row][q]: k = 16 kk + 2 t4 + {0, 1, 8, 9}
-      if (kk < 5) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t e = ktab[kk * 4 + q];
-          const int off = (int)(e >> 4) - 1024;
-          const uint32_t tb = e & 15u;
-          av[0][q] = ((inm[0] >> tb) & 1u) ? xc0[off] : 0.f;
-          av[1][q] = ((inm[1] >> tb) & 1u) ? xc1[off] : 0.f;
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t a0, a1, a2, a3;
+        if (kk == 0) {
+          a0 = pack2(xc0[o5[0]], xc0[o5[1]]);
+          a1 = pack2(xc1[o5[0]], xc1[o5[1]]);
+          a2 = pack2(xc0[o5[2]], xc0[o5[3]]);
+          a3 = pack2(xc1[o5[2]], xc1[o5[3]]);
+        } else {
+          a0 = pack2(xc0[o5[4]], xc0[o5[5]]);
+          a1 = pack2(xc1[o5[4]], xc1[o5[5]]);
+          a2 = t4 == 0 ? pack2(xc0[o24], 1.f) : 0u;
+          a3 = t4 == 0 ? pack2(xc1[o24], 1.f) : 0u;
         }
-      } else {
-        // k = 80: the last product (t = 8, s = 8); k = 81 .. 89: the bias taps (value 1 where the tap is inside); 90 ..: zero
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = 80 + 2 * t4 + (q & 1) + 8 * (q >> 1);
+        for (int j = 0; j < 8; ++j) {
+          const uint2 b = s_b5[(kk * 8 + j) * 32 + lane];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                       "{%0, %1, %2, %3};"
+                       : "+f"(d[j][0]), "+f"(d[j][1]), "+f"(d[j][2]), "+f"(d[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+        }
+      }
+    } else {
+      // in(p + t) for my two pixels: bit t = 3 (th + 1) + (tw + 1); bit 9 = 0 (zero columns)
+      const int iw = c0 + (g & 3);
+      const uint32_t colok = (iw > 0 ? 1u : 0u) | 2u | (iw < W - 1 ? 4u : 0u);
+      uint32_t inm[2];
 #pragma unroll
-          for (int r2 = 0; r2 < 2; ++r2) {
-            float v = 0.f;
-            if (k == 80) v = ((inm[r2] >> 8) & 1u) ? (r2 ? xc1 : xc0)[2 * Wp + 2] : 0.f;
-            else if (k < 90) v = ((inm[r2] >> (k - 81)) & 1u) ? 1.f : 0.f;
-            av[r2][q] = v;
+      for (int r2 = 0; r2 < 2; ++r2) {
+        const int ih = ih0 + (g >> 2) + 2 * r2;
+        const uint32_t rowok = (ih > 0 ? 1u : 0u) | 2u | (ih < H - 1 ? 4u : 0u);
+        uint32_t m = 0;
+#pragma unroll
+        for (int th = 0; th < 3; ++th)
+          if ((rowok >> th) & 1u) m |= colok << (3 * th);
+        inm[r2] = m;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 6; ++kk) {
+        float av[2][4];                                   // [pixel row][q]: k = 16 kk + 2 t4 + {0, 1, 8, 9}
+        if (kk < 5) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t e = s_ktab[(kk * 4 + q) * 4 + t4];
+            const int off = (int)(e >> 4) - 1024;
+            const uint32_t tb = e & 15u;
+            av[0][q] = ((inm[0] >> tb) & 1u) ? xc0[off] : 0.f;
+            av[1][q] = ((inm[1] >> tb) & 1u) ? xc1[off] : 0.f;
+          }
+        } else {
+          // k = 80: the last product (t = 8, s = 8); k = 81 .. 89: the bias taps (value 1 where the tap is inside); 90 ..: zero
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = 80 + 2 * t4 + (q & 1) + 8 * (q >> 1);
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+              float v = 0.f;
+              if (k == 80) v = ((inm[r2] >> 8) & 1u) ? (r2 ? xc1 : xc0)[2 * Wp + 2] : 0.f;
+              else if (k < 90) v = ((inm[r2] >> (k - 81)) & 1u) ? 1.f : 0.f;
+              av[r2][q] = v;
+            }
           }
         }
-      }
-      uint32_t a0, a1, a2, a3;
-      {
-        __nv_bfloat162 h = __floats2bfloat162_rn(av[0][0], av[0][1]);
-        a0 = *reinterpret_cast<const uint32_t*>(&h);
-        h = __floats2bfloat162_rn(av[1][0], av[1][1]);
-        a1 = *reinterpret_cast<const uint32_t*>(&h);
-        h = __floats2bfloat162_rn(av[0][2], av[0][3]);
-        a2 = *reinterpret_cast<const uint32_t*>(&h);
-        h = __floats2bfloat162_rn(av[1][2], av[1][3]);
-        a3 = *reinterpret_cast<const uint32_t*>(&h);
-      }
+        const uint32_t a0 = pack2(av[0][0], av[0][1]), a1 = pack2(av[1][0], av[1][1]);
+        const uint32_t a2 = pack2(av[0][2], av[0][3]), a3 = pack2(av[1][2], av[1][3]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint2 b = s_b[(kk * 8 + j) * 32 + lane];
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-                     "{%0, %1, %2, %3};"
-                     : "+f"(d[j][0]), "+f"(d[j][1]), "+f"(d[j][2]), "+f"(d[j][3])
-                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+        for (int j = 0; j < 8; ++j) {
+          const uint2 b = s_b[(kk * 8 + j) * 32 + lane];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                       "{%0, %1, %2, %3};"
+                       : "+f"(d[j][0]), "+f"(d[j][1]), "+f"(d[j][2]), "+f"(d[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+        }
       }
     }
     __syncwarp();                                         // the previous tile's reads of yt are done
@@ -1183,10 +1243,11 @@ enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ 
       *reinterpret_cast<__nv_bfloat162*>(yt + (g + 8) * 72 + 8 * j + 2 * t4) = h;
     }
     __syncwarp();
+    // staged row pl = 4 i + (lane >> 3) is pixel (i, lane >> 3) of the tile: four pixels x 128 B contiguous per store
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pl = (lane >> 3) + 4 * i;
-      *reinterpret_cast<uint4*>(ob + (int64_t)(p0 + pl) * C + (lane & 7) * 8) =
+      *reinterpret_cast<uint4*>(ob + ((int64_t)(r0 + i) * W + c0 + (lane >> 3)) * C + (lane & 7) * 8) =
           *reinterpret_cast<const uint4*>(yt + pl * 72 + (lane & 7) * 8);
     }
   }
@@ -1554,12 +1615,12 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     else if (rc != DBS_ERR_UNSUPPORTED) return rc;
   }
   if (c.compose0 && &bw == &c.plan->enc[0]) {
-    DBS_REQUIRE(xres && sizeof(T) == 2 && bw.cout == 64 && W % 16 == 0 && c.plan->enc0_bfrag,
+    DBS_REQUIRE(xres && sizeof(T) == 2 && bw.cout == 64 && W % 16 == 0 && H % 4 == 0 && c.plan->enc0_bfrag,
                 "unet_forward: composed first layer without its preconditions");
-    int TH = 2048 / W;
+    int TH = 2048 / W / 4 * 4;         // rows per CTA: whole 4 x 4-pixel tiles
     if (TH > H) TH = H;
-    if (TH < 1) TH = 1;
-    const size_t smem = (size_t)6 * 8 * 32 * 8 + (size_t)8 * 16 * 72 * 2 + (size_t)(TH + 4) * (W + 4) * 4;
+    if (TH < 4) TH = 4;
+    const size_t smem = (size_t)(6 + 2) * 8 * 32 * 8 + (size_t)8 * 16 * 72 * 2 + (size_t)(TH + 4) * (W + 4) * 4;
     static bool attr_done = false;
     if (!attr_done) {
       DBS_CUDA(cudaFuncSetAttribute(enc0_composed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1601,7 +1662,15 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     if (c.use_tc && stats2 == stats1 && !c.next_stats()) DBS_CUDA(cudaMemsetAsync(c.stats, 0, stat_bytes, c.st));
     if ((rc = run_conv<T>(c, g2, th, (const T*)nullptr, bw.conv2, ty, c.stats, G, &sd))) return rc;
   }
-  if (xres && sd) {
+  if (xres) {
+    // conv2 ran on a kernel without the statistics epilogue (a lattice the strip / tile kernels do not tile, e.g. 24x48): a
+    // stand-alone pass delivers (mean, rstd) and the apply kernels are told so through inv_cnt = 0.  Falling through to
+    // the generic tail instead would read a residual tensor this path never writes.
+    if (!sd) {
+      ProfScope prof(kProfGnStats, c.st);
+      gn_stats_kernel<T><<<(unsigned)(c.B * G), 256, 0, c.st>>>(y2, c.stats, H * W, bw.cout, G, 1e-5f);
+      DBS_LAUNCHED();
+    }
     const int cv = bw.cout / 8;
     const int threads = (256 / cv) * cv;
     static const int un_env = [] { const char* e = getenv("DBS_XRES_UN"); return e ? atoi(e) : 4; }();
@@ -1612,7 +1681,7 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     prof_set_label("HW%d C%d xres", H * W, bw.cout);
     ProfScope prof(kProfGnApply, c.st);
     const dim3 xgrid((unsigned)((H + TH - 1) / TH), (unsigned)c.B);
-    const float xinv = 1.0f / (float)((int64_t)H * W * (bw.cout / 8));
+    const float xinv = sd ? 1.0f / (float)((int64_t)H * W * (bw.cout / 8)) : 0.f;
     static const bool mma_off = [] { const char* e = getenv("DBS_XRES_MMA"); return e && e[0] == '0'; }();
     if (bw.cout == 64 && W % 16 == 0 && !mma_off) {
       const size_t smem_m = ((size_t)8 * 16 * 72 + (size_t)(TH + 2) * (W + 2)) * 4;
@@ -1737,7 +1806,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
   static const bool xres_env_off = [] { const char* e = getenv("DBS_XRES"); return e && e[0] == '0'; }();
   static const bool xres_mma_env_off = [] { const char* e = getenv("DBS_XRES_MMA"); return e && e[0] == '0'; }();
   const bool compose0 = use_tc && sizeof(T) == 2 && !tap && !fixup && !compose_off && !xres_env_off && !xres_mma_env_off && C == 32 &&
-                        nb >= 1 && plan->enc0_bfrag && plan->enc0_wc && plan->enc[0].has_res && W % 16 == 0 && getenv("DBS_L2_CHUNK_MB") == nullptr;
+                        nb >= 1 && plan->enc0_bfrag && plan->enc0_wc && plan->enc[0].has_res && W % 16 == 0 && H % 4 == 0 && getenv("DBS_L2_CHUNK_MB") == nullptr;
   const bool time_fused = sizeof(T) == 2 && (C == 16 || C == 32 || C == 64) && n_t == 1 && !tfuse_off && !fixup && !compose0;
   if (!time_fused) {
     prof_set_label("time");
@@ -2114,12 +2183,21 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
             wk[(size_t)(9 * t + s2) * co0 + o] = (float)a;
           }
         }
-      std::vector<uint32_t> frag((size_t)6 * 8 * 32 * 2);
-      for (int kk = 0; kk < 6; ++kk)
+      // interior tiles: the products of one input offset u = t + s summed into a 5x5 kernel (k = 5 uy + ux < 25), k = 25 the
+      // summed bias taps, 26 .. 31 zero
+      std::vector<double> w5d((size_t)32 * co0, 0.0);
+      for (int o = 0; o < co0; ++o)
+        for (int t = 0; t < 9; ++t) {
+          w5d[(size_t)25 * co0 + o] += (double)wk[(size_t)(81 + t) * co0 + o];
+          for (int s2 = 0; s2 < 9; ++s2)
+            w5d[(size_t)(5 * (t / 3 + s2 / 3) + (t % 3 + s2 % 3)) * co0 + o] += (double)wk[(size_t)(9 * t + s2) * co0 + o];
+        }
+      std::vector<uint32_t> frag((size_t)(6 + 2) * 8 * 32 * 2);
+      for (int kk = 0; kk < 8; ++kk)
         for (int j = 0; j < 8; ++j)
           for (int lane = 0; lane < 32; ++lane) {
-            const int gg = lane >> 2, tt = lane & 3, ch = 8 * j + gg, k0 = 16 * kk + 2 * tt;
-            auto W_ = [&](int k) { return wk[(size_t)k * co0 + ch]; };
+            const int gg = lane >> 2, tt = lane & 3, ch = 8 * j + gg, k0 = 16 * (kk < 6 ? kk : kk - 6) + 2 * tt;
+            auto W_ = [&](int k) { return kk < 6 ? wk[(size_t)k * co0 + ch] : (float)w5d[(size_t)k * co0 + ch]; };
             const size_t idx = ((size_t)(kk * 8 + j) * 32 + lane) * 2;
             frag[idx] = bf16_bits(W_(k0)) | (bf16_bits(W_(k0 + 1)) << 16);
             frag[idx + 1] = bf16_bits(W_(k0 + 8)) | (bf16_bits(W_(k0 + 9)) << 16);

@@ -306,6 +306,55 @@ def test_switchable_fusion_paths_stay_parity_green():
         assert r.stdout.count("ok") == 2
 
 
+def test_composed_first_layer_tile_forms_match_the_two_launch_path():
+    """enc0_composed_kernel (csrc/unet.cu) runs 4x4-pixel tiles in two forms: interior tiles through the collapsed 5x5
+    kernel, tiles on the image's outer ring through the 81 masked products.  Shapes where every tile is a border tile (8x16),
+    where both forms mix (16x16, 24x48: rectangular, so a swapped row / column index would show) and the config-4 lattice:
+    the bf16 forward must agree with the fp32 oracle within the bf16 bound (2e-2 of the output rms; measured 8e-3, the same
+    as the two-launch path) and with the two-launch path (DBS_ENC0_COMPOSED=0: init conv + tcgen05 conv1, read once per
+    process, hence the child processes) within the same bound (measured 9e-3: two independent bf16 roundings; two runs of
+    ONE path differ by up to 4e-3 through the fp32 atomics of the GroupNorm sums).  24x48 is also the lattice on which
+    conv2 runs without a statistics epilogue: the recomputed-residual apply then takes (mean, rstd) from the stand-alone
+    pass (the first form of this path fell through to a residual tensor that the composed path never writes)."""
+    import os, subprocess, sys, tempfile, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path[:0] = [%r, %r]
+        from backend.ml.models.score_network import ScoreNetwork
+        torch.manual_seed(0)
+        net = ScoreNetwork(1, 32, 64, 3).eval()
+        outs = {}
+        for H, W, B in ((8, 16, 5), (16, 16, 4), (24, 48, 3), (64, 64, 2)):
+            g = torch.Generator().manual_seed(H * 100 + W)
+            x, t = torch.randn(B, 1, H, W, generator=g), torch.full((B,), 0.61)
+            outs[f"{H}x{W}"] = net.engine_forward(x, t, precision="bf16").cpu().numpy()
+        np.savez(sys.argv[1], **outs)
+    """) % (root, os.path.join(root, "diffusion-boltzmann-sampler_b200"))
+    res = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for flag in ("1", "0"):
+            path = os.path.join(tmp, f"c{flag}.npz")
+            r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, DBS_ENC0_COMPOSED=flag),
+                               capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            with np.load(path) as z:
+                res.append({k: z[k] for k in z.files})
+    net = _net()
+    sd = _sd(net)
+    for k in res[0]:
+        a, b = res[0][k].astype(np.float64), res[1][k].astype(np.float64)
+        assert np.isfinite(a).all()
+        err = float(np.sqrt(((a - b) ** 2).mean()) / np.sqrt((b ** 2).mean()))
+        assert err <= 2e-2, (k, err)
+        H, W = (int(v) for v in k.split("x"))
+        B = a.shape[0]
+        g = torch.Generator().manual_seed(H * 100 + W)
+        x, t = torch.randn(B, 1, H, W, generator=g), torch.full((B,), 0.61)
+        want = o_unet.unet_forward(sd, x, t).numpy().astype(np.float64)
+        assert float(np.sqrt(((a - want) ** 2).mean()) / np.sqrt((want ** 2).mean())) <= 2e-2, k
+
+
 def test_programmatic_dependent_launch_gives_the_same_samples():
     """DBS_PDL=1 launches the kernels of a sampler step with programmatic stream serialisation (the next kernel's prologue
     overlaps the previous kernel's tail; csrc/common.cuh).  Every kernel waits for its predecessor before it touches data, so
