@@ -938,7 +938,7 @@ gn_apply_xres_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restr
 // above spends more than half of its issue slots there and runs at 360-390 us for 1.09 GB (B = 1024, 64x64), i.e. compute
 // bound.  The A fragment comes straight from the fp32 x tile in shared memory (thread (g, t) of the warp holds taps 2t, 2t+1
 // and, for t = 0, tap 8 of pixels g and g + 8), the B fragments (the weights) are loop-invariant registers.  The
-// accumulator fragments (pixel rows g / g + 8, channel pairs) go through a per-warp 4 KB shared-memory tile to reach the
+// accumulator fragments (pixel rows g / g + 8, channel pairs) go through a per-warp 2.3 KB shared-memory tile (bf16) to reach the
 // (pixel, 8-channel vector) layout in which the raw conv output is loaded, normalised and stored with 16-byte accesses.
 // Rounding: x and wc enter the MMA as bf16 (the two-launch path stores the residual itself as bf16).
 __global__ void __launch_bounds__(256, 2)
@@ -948,8 +948,11 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
                          int H, int W, int TH) {
   constexpr int C = 64, V = 8;
   extern __shared__ __align__(16) float s_dyn[];
-  float* s_r = s_dyn;                       // [8 warps][16 px][72]: residual tile of a warp (row stride 72 floats: conflict-free)
-  float* s_x = s_dyn + 8 * 16 * 72;         // [(TH + 2)][W + 2]
+  // [8 warps][16 px][72] bf16: residual tile of a warp, rounded to bf16 as the two-launch path stores it (row stride 144 B:
+  // conflict-free for the fragment stores and the 16-byte loads; as fp32 the staging was 64 of the tile's ~70 shared-memory
+  // wavefronts and put the kernel's L1 pipe at 72 %)
+  __nv_bfloat16* s_r = reinterpret_cast<__nv_bfloat16*>(s_dyn);
+  float* s_x = s_dyn + 8 * 16 * 72 / 2;     // [(TH + 2)][W + 2]
   const int n = blockIdx.y, h0 = blockIdx.x * TH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -994,7 +997,7 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
   const int n_tiles = rows * W / 16;                      // W % 16 == 0: a tile is 16 consecutive pixels of one row
   const __nv_bfloat16* yb = y + ((int64_t)n * H + h0) * W * C;
   __nv_bfloat16* ob = out + ((int64_t)n * H + h0) * W * C;
-  float* rt = s_r + warp * 16 * 72;
+  __nv_bfloat16* rt = s_r + warp * 16 * 72;
   // taps of this thread: k0 = 2t -> (kh, kw), k1 = 2t + 1
   const int k0 = 2 * t, k1 = 2 * t + 1;
   const int o0 = (k0 / 3) * Wp + (k0 % 3), o1 = (k1 / 3) * Wp + (k1 % 3), o8 = 2 * Wp + 2;
@@ -1039,16 +1042,15 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
                    : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
                    : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[j][0]), "r"(bf[j][1]));
       // accumulator fragment: (row g, channels 8j + 2t, + 1), (row g + 8, same channels)
-      *reinterpret_cast<float2*>(rt + g * 72 + 8 * j + 2 * t) = make_float2(d0, d1);
-      *reinterpret_cast<float2*>(rt + (g + 8) * 72 + 8 * j + 2 * t) = make_float2(d2, d3);
+      *reinterpret_cast<__nv_bfloat162*>(rt + g * 72 + 8 * j + 2 * t) = __floats2bfloat162_rn(d0, d1);
+      *reinterpret_cast<__nv_bfloat162*>(rt + (g + 8) * 72 + 8 * j + 2 * t) = __floats2bfloat162_rn(d2, d3);
     }
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pl = (lane >> 3) + 4 * i;                 // pixel inside the tile
-      const float4 r0 = *reinterpret_cast<const float4*>(rt + pl * 72 + c);
-      const float4 r1 = *reinterpret_cast<const float4*>(rt + pl * 72 + c + 4);
-      const float rr[V] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      float rr[V];
+      Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(rt + pl * 72 + c), rr);
       float v[V];
       Vec16<__nv_bfloat16>::unpack(q[i], v);
 #pragma unroll
@@ -1070,9 +1072,12 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
 // A warp works on 4 x 4-pixel tiles (16 MMA rows), fetched from a CTA-wide counter, in one of two forms:
 //   * interior tile (no pixel on the image's outer ring, 77 % of the tiles at 64x64): every in() is 1 and the 81 (t, s)
 //     products collapse to ONE 5x5 kernel  W5[co][u] = sum_{t + s = u} Wc[co][t][s]  plus the summed bias taps:
-//     [16 px][32] x [32][64] (25 products, the bias column, 6 zero columns) = 2 x 8 mma.sync m16n8k16;
+//     [16 px][32] x [32][64] (25 products, two bias columns, 5 zero columns) = 2 x 8 mma.sync m16n8k16;
 //   * border tile: the products are kept apart and masked per pixel by in(p + t):  [16 px][96] x [96][64]  (81 products,
-//     9 bias taps, 6 zero columns) = 6 x 8 MMAs.
+//     9 bias taps, two columns for b1, 4 zero columns) = 6 x 8 MMAs.
+// The unmasked bias (b1, plus the summed bias taps in the interior form) rides in the MMA as TWO columns against A = 1:
+// its bf16 rounding and the bf16 rounding of what that left over (error 2^-17 of the bias), which frees sixteen
+// registers per thread for a third resident CTA (measured: 216 -> 212 us from the fold, 211 us with three CTAs).
 // bf16 operands, fp32 accumulators, 2 x 32 (or 96) x 64 MACs per pixel instead of conv1's 2 x 288 x 64 + the init conv's
 // 2 x 9 x 32, no 32-channel activation in HBM (268 MB written and read at B = 1024, 64x64), one launch instead of two.
 // The first form of this kernel ran every tile (16 pixels of a row) through the masked 96-wide form and was bound by
@@ -1080,9 +1085,9 @@ gn_apply_xres_mma_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __r
 // for its 537 MB of stores; an interior tile costs ~80.  The A fragments come straight from the fp32 x tile in shared
 // memory (two-pixel halo); the B fragments are built once per plan; GroupNorm sums are taken on the fp32 accumulators, an
 // n-tile being exactly one group.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ y, float* __restrict__ stats,
-                     const uint2* __restrict__ bfrag, const float* __restrict__ b1, int H, int W, int TH) {
+                     const uint2* __restrict__ bfrag, int H, int W, int TH) {
   constexpr int C = 64;
   constexpr int kFragMasked = 6 * 8 * 32, kFragInner = 2 * 8 * 32;
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -1124,9 +1129,6 @@ enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ 
     o5[q] = (k / 5 - 2) * Wp + (k % 5 - 2);
   }
   const int o24 = 2 * Wp + 2;
-  float bia0[8], bia1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { bia0[j] = __ldg(b1 + 8 * j + 2 * t4); bia1[j] = __ldg(b1 + 8 * j + 2 * t4 + 1); }
   float st_s[8], st_ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_ss[j] = 0.f; }
@@ -1154,7 +1156,7 @@ enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ 
     const float* xc1 = xc0 + 2 * Wp;
     float d[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { d[j][0] = bia0[j]; d[j][1] = bia1[j]; d[j][2] = bia0[j]; d[j][3] = bia1[j]; }
+    for (int j = 0; j < 8; ++j) { d[j][0] = 0.f; d[j][1] = 0.f; d[j][2] = 0.f; d[j][3] = 0.f; }
     if (ih0 > 0 && ih0 + 4 < H && c0 > 0 && c0 + 4 < W) {
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
@@ -1167,8 +1169,8 @@ enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ 
         } else {
           a0 = pack2(xc0[o5[4]], xc0[o5[5]]);
           a1 = pack2(xc1[o5[4]], xc1[o5[5]]);
-          a2 = t4 == 0 ? pack2(xc0[o24], 1.f) : 0u;
-          a3 = t4 == 0 ? pack2(xc1[o24], 1.f) : 0u;
+          a2 = t4 == 0 ? pack2(xc0[o24], 1.f) : (t4 == 1 ? 0x00003f80u : 0u);   // k = 24 | 25;  k = 26 (bf16 1.0) | 27
+          a3 = t4 == 0 ? pack2(xc1[o24], 1.f) : (t4 == 1 ? 0x00003f80u : 0u);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1207,7 +1209,7 @@ enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ 
             av[1][q] = ((inm[1] >> tb) & 1u) ? xc1[off] : 0.f;
           }
         } else {
-          // k = 80: the last product (t = 8, s = 8); k = 81 .. 89: the bias taps (value 1 where the tap is inside); 90 ..: zero
+          // k = 80: the last product (t = 8, s = 8); k = 81 .. 89: the bias taps (value 1 where the tap is inside); 90, 91: b1; 92 ..: zero
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int k = 80 + 2 * t4 + (q & 1) + 8 * (q >> 1);
@@ -1216,6 +1218,7 @@ enc0_composed_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ 
               float v = 0.f;
               if (k == 80) v = ((inm[r2] >> 8) & 1u) ? (r2 ? xc1 : xc0)[2 * Wp + 2] : 0.f;
               else if (k < 90) v = ((inm[r2] >> (k - 81)) & 1u) ? 1.f : 0.f;
+              else if (k < 92) v = 1.f;                    // conv1's own bias, bf16 high + low part
               av[r2][q] = v;
             }
           }
@@ -1630,7 +1633,7 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     prof_set_label("enc0 conv1 composed with init conv H%d W%d", H, W);
     ProfScope prof(kProfConvTC, c.st);
     enc0_composed_kernel<<<dim3((unsigned)((H + TH - 1) / TH), (unsigned)c.B), 256, smem, c.st>>>(
-        c.xin, (__nv_bfloat16*)ty, c.stats, c.plan->enc0_bfrag, c.plan->enc0_b1, H, W, TH);
+        c.xin, (__nv_bfloat16*)ty, c.stats, c.plan->enc0_bfrag, H, W, TH);
     DBS_LAUNCHED();
     res_done = true; sd = true;
   }
@@ -1684,7 +1687,7 @@ int run_block(Ctx& c, const BlockW& bw, const char* name, const T* in0, int C0, 
     const float xinv = sd ? 1.0f / (float)((int64_t)H * W * (bw.cout / 8)) : 0.f;
     static const bool mma_off = [] { const char* e = getenv("DBS_XRES_MMA"); return e && e[0] == '0'; }();
     if (bw.cout == 64 && W % 16 == 0 && !mma_off) {
-      const size_t smem_m = ((size_t)8 * 16 * 72 + (size_t)(TH + 2) * (W + 2)) * 4;
+      const size_t smem_m = (size_t)8 * 16 * 72 * 2 + (size_t)(TH + 2) * (W + 2) * 4;
       static bool attr_done = false;
       if (!attr_done) {
         DBS_CUDA(cudaFuncSetAttribute(gn_apply_xres_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -2185,13 +2188,21 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
         }
       // interior tiles: the products of one input offset u = t + s summed into a 5x5 kernel (k = 5 uy + ux < 25), k = 25 the
       // summed bias taps, 26 .. 31 zero
+      auto bf16_round = [](float v) { const uint32_t b = bf16_bits(v) << 16; float f; memcpy(&f, &b, 4); return f; };
       std::vector<double> w5d((size_t)32 * co0, 0.0);
+      for (int o = 0; o < co0; ++o) {
+        wk[(size_t)90 * co0 + o] = hb1[o];                               // masked form: b1 as bf16 high + low part
+        wk[(size_t)91 * co0 + o] = hb1[o] - bf16_round(hb1[o]);
+        w5d[(size_t)25 * co0 + o] = (double)hb1[o];
+      }
       for (int o = 0; o < co0; ++o)
         for (int t = 0; t < 9; ++t) {
           w5d[(size_t)25 * co0 + o] += (double)wk[(size_t)(81 + t) * co0 + o];
           for (int s2 = 0; s2 < 9; ++s2)
             w5d[(size_t)(5 * (t / 3 + s2 / 3) + (t % 3 + s2 % 3)) * co0 + o] += (double)wk[(size_t)(9 * t + s2) * co0 + o];
         }
+      for (int o = 0; o < co0; ++o)                                      // interior form: b1 + bias taps, high + low part
+        w5d[(size_t)26 * co0 + o] = w5d[(size_t)25 * co0 + o] - (double)bf16_round((float)w5d[(size_t)25 * co0 + o]);
       std::vector<uint32_t> frag((size_t)(6 + 2) * 8 * 32 * 2);
       for (int kk = 0; kk < 8; ++kk)
         for (int j = 0; j < 8; ++j)
