@@ -356,6 +356,28 @@ final_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const f
   if (live && c == 0) out[p] = scale * (acc + bias[0]);
 }
 
+// the same conv for channel counts whose vector count is not a power of two (base_channels 24, 48, ...: checkpoints the
+// reference's constructor accepts, not BASELINE configurations): one thread per pixel, plain loops
+template <typename T>
+__global__ void __launch_bounds__(256)
+final_conv_generic_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                          float* __restrict__ out, int64_t n_pix, int H, int W, int C, float scale) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  const int ww = (int)(p % W);
+  const int hh = (int)((p / W) % H);
+  float acc = 0.f;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ih = hh + kh - 1, iw = ww + kw - 1;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const T* src = in + (p + (int64_t)(kh - 1) * W + (kw - 1)) * C;
+      const float* wk = w + (kh * 3 + kw) * C;
+      for (int c = 0; c < C; ++c) acc = fmaf(to_f<T>(src[c]), __ldg(wk + c), acc);
+    }
+  out[p] = scale * (acc + bias[0]);
+}
+
 // Init conv 1 -> C on the bf16 path: one thread per pixel produces all C channels.  The 9 x C weights and
 // the bias arrive as a __grid_constant__ kernel parameter, so every FFMA reads its weight from the constant
 // bank (warp-uniform index) and the only memory instructions are 9 coalesced x loads and C/8 16-byte stores.
@@ -2001,9 +2023,7 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
     prof_set_label("final_conv");
     {
       const int cvf = C / (16 / (int)sizeof(T));
-      DBS_REQUIRE(cvf >= 1 && cvf <= 32 && (cvf & (cvf - 1)) == 0,
-                  "unet: base_channels %d unsupported by the final conv kernel (C/%d must be a power of two <= 32)", C,
-                  16 / (int)sizeof(T));
+      const bool cv_pow2 = C % (16 / (int)sizeof(T)) == 0 && cvf >= 1 && cvf <= 32 && (cvf & (cvf - 1)) == 0;
       ProfScope prof(kProfUnetMisc, st);
       const int64_t nthr = n_pix * cvf;
       if (final_fused_ok) {
@@ -2013,9 +2033,13 @@ int forward_impl(dbs_unet_plan* plan, const float* x, const float* t, int64_t n_
         else if (C == 32) rc = launch_final_fused<32>(plan->final_bfrag, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
         else rc = launch_final_fused<64>(plan->final_bfrag, plan->final_b_host, cfg.output_scale, yin, rin, defer.stats, defer.gamma, defer.beta, score, B, H, W, st);
         if (rc) return rc;
-      } else {
+      } else if (cv_pow2) {
         final_conv_kernel<T><<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(cur, plan->final_w, plan->final_b, score, n_pix,
                                                                             H, W, C, cfg.output_scale);
+        DBS_LAUNCHED();
+      } else {
+        final_conv_generic_kernel<T><<<(unsigned)((n_pix + 255) / 256), 256, 0, st>>>(cur, plan->final_w, plan->final_b, score,
+                                                                                     n_pix, H, W, C, cfg.output_scale);
         DBS_LAUNCHED();
       }
     }

@@ -233,6 +233,27 @@ def test_sampler_on_a_non_divisible_lattice_matches_oracle():
     assert _rel(got.cpu().numpy(), want) <= 1e-4
 
 
+@pytest.mark.parametrize("base,tdim,nb,H,W", [(8, 16, 1, 16, 16), (8, 32, 2, 32, 16), (16, 32, 2, 32, 32), (16, 64, 4, 32, 32),
+                                              (64, 64, 2, 16, 32), (64, 128, 3, 32, 32), (32, 64, 1, 16, 48), (32, 64, 2, 24, 48),
+                                              (32, 32, 4, 64, 64), (48, 64, 2, 16, 16), (24, 64, 2, 16, 32), (32, 128, 3, 40, 24)])
+def test_unet_other_architectures_vs_oracle(base, tdim, nb, H, W):
+    """ScoreNetwork(1, base, time_embed_dim, num_blocks) away from the default (32, 64, 3) — the API lets a checkpoint carry
+    any of these (models/score_network.py:153-200): fp32 path <= 1e-4 of the oracle, bf16 request (tcgen05 kernels where the
+    channel counts allow them, CUDA-core kernels with bf16 storage elsewhere) within the stated bf16 bound, per-sample t."""
+    net = _net(base, tdim, nb, seed=base + nb)
+    torch.manual_seed(H * 3 + W)
+    B = 3
+    x, t = torch.randn(B, 1, H, W), torch.rand(B)
+    want = o_unet.unet_forward(_sd(net), x, t).numpy()
+    got = net.engine_forward(x, t, precision="fp32").cpu().numpy()
+    assert _rel(got, want) <= 1e-4
+    if base % 8 == 0:
+        lo = net.engine_forward(x, t, precision="bf16").cpu().numpy()
+        assert np.isfinite(lo).all()
+        per = np.sqrt(((lo - want) ** 2).reshape(B, -1).mean(1)) / np.sqrt((want ** 2).reshape(B, -1).mean(1))
+        assert per.max() <= 4e-2, (int(per.argmax()), float(per.max()))
+
+
 def test_unet_rejects_unsupported_configurations_loudly():
     from backend.ml.models.score_network import ScoreNetwork
     net = ScoreNetwork(2, 16, 32, 2).eval()
