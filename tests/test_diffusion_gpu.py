@@ -254,6 +254,27 @@ def test_unet_other_architectures_vs_oracle(base, tdim, nb, H, W):
         assert per.max() <= 4e-2, (int(per.argmax()), float(per.max()))
 
 
+def test_unet_one_forward_past_two_gib_per_activation():
+    """DiffusionSampler.sample does not chunk its batch, so config 4 on one GPU can arrive as ONE forward of thousands of
+    64x64 samples: at B = 4096 a 64-channel bf16 activation is 2^31 bytes (B = 8192, 2^31 elements, was checked by hand:
+    profiles/r2_large_batch_probe.py).  Every sample of the big forward must match the same sample run 1024 at a time to
+    within the run-to-run spread of the bf16 path (fp32 atomics of the GroupNorm sums: measured 5e-3, bound 2e-2)."""
+    net = _net()
+    B, L = 4096, 64
+    g = torch.Generator(device="cuda").manual_seed(B)
+    x = torch.randn(B, 1, L, L, device="cuda", generator=g)
+    t = torch.rand(B, device="cuda", generator=g)
+    full = net.engine_forward(x, t, precision="bf16").float()
+    parts = torch.cat([net.engine_forward(x[i:i + 1024].contiguous(), t[i:i + 1024].contiguous(), precision="bf16").float()
+                       for i in range(0, B, 1024)])
+    assert bool(torch.isfinite(full).all())
+    per = ((full - parts) ** 2).flatten(1).mean(1).sqrt() / (parts ** 2).flatten(1).mean(1).sqrt()
+    assert per.max().item() <= 2e-2, (int(per.argmax()), float(per.max()))
+    del full, parts, x
+    net._workspace = None
+    torch.cuda.empty_cache()
+
+
 def test_unet_rejects_unsupported_configurations_loudly():
     from backend.ml.models.score_network import ScoreNetwork
     net = ScoreNetwork(2, 16, 32, 2).eval()
