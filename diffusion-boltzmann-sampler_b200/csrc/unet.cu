@@ -509,8 +509,11 @@ final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __r
   pdl_wait();
   const int n = blockIdx.y, h0 = blockIdx.x * TH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wshift = 31 - __clz(W);          // W is a power of two (launch_final_fused): no integer division per chunk / pixel
   const int n_pix = (TH + 2) * W;
   const int n_pix16 = (n_pix + 15) & ~15;    // the MMA walks whole 16-pixel groups (the tail reads unused smem)
+  const __nv_bfloat16* const yimg = y + (int64_t)n * H * W * C;      // 32-bit offsets inside the image from here on
+  const __nv_bfloat16* const rimg = kFuseGn ? res + (int64_t)n * H * W * C : nullptr;
   float* s_d = reinterpret_cast<float*>(sm_raw + (size_t)n_pix16 * (C * 2));
   if (kFuseGn) {
     if (tid < C) {
@@ -537,13 +540,13 @@ final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __r
     for (int u = 0; u < kU; ++u) {
       const int idx = base + u * (int)blockDim.x;
       const int ck = idx % NCK, pi = idx / NCK;
-      const int r = pi / W, wl = pi - r * W, ih = h0 + r - 1;
+      const int r = pi >> wshift, wl = pi & (W - 1), ih = h0 + r - 1;
       ok[u] = idx < n_vec && ih >= 0 && ih < H;   // rows outside the image are never used: phase 3 applies the same bounds
       pis[u] = pi; cks[u] = ck;
       if (ok[u]) {
-        const int64_t g = (((int64_t)n * H + ih) * W + wl) * C + ck * 8;
-        raw[u] = *reinterpret_cast<const uint4*>(y + g);
-        if (kFuseGn) rq[u] = *reinterpret_cast<const uint4*>(res + g);
+        const int g = ((ih << wshift) + wl) * C + ck * 8;
+        raw[u] = *reinterpret_cast<const uint4*>(yimg + g);
+        if (kFuseGn) rq[u] = *reinterpret_cast<const uint4*>(rimg + g);
       }
     }
 #pragma unroll
@@ -612,7 +615,7 @@ final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __r
   __syncthreads();
   // ---- phase 3: nine-point stencil on the scalar tables
   for (int o = tid; o < TH * W; o += blockDim.x) {
-    const int hl = o / W, wl = o - hl * W;
+    const int hl = o >> wshift, wl = o & (W - 1);
     if (h0 + hl >= H) break;
     float acc = 0.f;
 #pragma unroll
@@ -623,7 +626,7 @@ final_fused_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __r
       for (int kw = 0; kw < 3; ++kw) {
         const int iw = wl + kw - 1;
         if (iw < 0 || iw >= W) continue;
-        acc += s_d[(size_t)((hl + kh) * W + iw) * kFinalDStride + kh * 3 + kw];
+        acc += s_d[(((hl + kh) << wshift) + iw) * kFinalDStride + kh * 3 + kw];
       }
     }
     out[((int64_t)n * H + h0 + hl) * W + wl] = fw.scale * (acc + fw.bias);
