@@ -657,11 +657,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        uint4* dst = reinterpret_cast<uint4*>(optr_o + c);
-        if (!(kExp && (p.dbg & 4))) {
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        if (!(kExp && (p.dbg & 4))) st_global_256(optr_o + c, pk);   // the pixel's sixteen couts of this chunk: one 32-byte sector
         if (kSpec == 2 || (kSpec == 0 && p.has_res)) {   // (never with kSpec 1 / 3)
           // fused 1x1 residual conv of the same input (score_network.py:131,151): own slot, own bias, no GN
           uint32_t vr[16];
@@ -679,9 +675,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             pr[2 * j4] = *reinterpret_cast<const uint32_t*>(&h0);
             pr[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
           }
-          uint4* dr = reinterpret_cast<uint4*>(p.out_res + (optr - p.out) + c);
-          dr[0] = make_uint4(pr[0], pr[1], pr[2], pr[3]);
-          dr[1] = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+          st_global_256(p.out_res + (optr - p.out) + c, pr);
         }
         xb ^= 1;
       }
@@ -736,8 +730,9 @@ int conv_strip_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bf
   if (!KC) return DBS_ERR_UNSUPPORTED;
   if (stats && groups != 8) return DBS_ERR_UNSUPPORTED;     // GroupNorm(8): Cg = Cout / 8 = 2 * (Cout / 16)
   if (g.Cout == 48) return DBS_ERR_UNSUPPORTED;             // 3 chunks: group width 6 straddles no chunk, not built
-  if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w) |
-       reinterpret_cast<uintptr_t>(out)) & 15)
+  if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w)) & 15)
+    return DBS_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_res)) & 31)   // 32-byte epilogue stores
     return DBS_ERR_UNSUPPORTED;
   int dh_min = 0, dh_max = 0;
   for (int t = 0; t < n_taps_all; ++t) {

@@ -163,4 +163,13 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 }
 
 }  // namespace tc
+
+// One 32-byte global store per thread (st.global.v8.b32 -> STG.E.ENL2.256, sm_100+): an epilogue thread's sixteen bf16
+// outputs of a pixel are a whole 32-byte sector; as two 16-byte stores the L2 saw two half-sector writes per sector and
+// the MIO queue two instructions.  The address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 }  // namespace dbs
