@@ -349,9 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
             pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
           }
-          uint4* dst = reinterpret_cast<uint4*>(optr + c);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          st_global_256(optr + c, pk);   // sixteen couts of the pixel: one 32-byte sector (tc_ptx.cuh)
         }
       }
       if (kRun == 16 && p.fuse) {
@@ -407,9 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_constan
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
               pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
             }
-            uint4* dst = reinterpret_cast<uint4*>(optr + c);
-            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            st_global_256(optr + c, pk);
           }
         }
         tc_fence_before();
@@ -565,9 +561,9 @@ int conv_tc_launch(const ConvGeom& g, const __nv_bfloat16* in0, const __nv_bfloa
   if (groups > 8 || (stats && (groups < 1 || g.Cout % groups))) return DBS_ERR_UNSUPPORTED;
   if (g.Cout > kMaxCout) return DBS_ERR_UNSUPPORTED;
   if (stats && (!is_pow2(g.Cout / groups) || g.Cout / groups < 2)) return DBS_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w) |
-       reinterpret_cast<uintptr_t>(out)) & 15)
+  if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(w)) & 15)
     return DBS_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(out) & 31) || g.Cout % 16) return DBS_ERR_UNSUPPORTED;   // 32-byte epilogue stores
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return DBS_ERR_CUDA; }
 

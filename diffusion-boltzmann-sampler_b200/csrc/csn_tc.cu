@@ -310,20 +310,20 @@ csn_tc_linear_kernel(const TcLinArgs a) {
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
         if (live) {
-          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.X) + m * 128 + c);
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + m * 128 + c);
+          // a thread's sixteen fp32 columns are two 32-byte sectors of its row: 32-byte loads / stores (tc_ptx.cuh)
+          const float* rp = reinterpret_cast<const float*>(a.X) + m * 128 + c;
+          float* dst = reinterpret_cast<float*>(a.out) + m * 128 + c;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 r4 = rp[j4];
-            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-            float o[4];
+          for (int j8 = 0; j8 < 2; ++j8) {
+            float rr[8], o[8];
+            ld_global_256f(rp + 8 * j8, rr);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int j = 4 * j4 + k;
+            for (int k = 0; k < 8; ++k) {
+              const int j = 8 * j8 + k;
               const float x = (__uint_as_float(v[j]) + s_bias2[c + j] - mean2) * rstd2 * s_pg2[c + j] + s_pb2[c + j];
               o[k] = silu_fast(x) + rr[k];
             }
-            dst[j4] = make_float4(o[0], o[1], o[2], o[3]);
+            st_global_256f(dst + 8 * j8, o);
           }
         }
       }
@@ -384,22 +384,28 @@ csn_tc_linear_kernel(const TcLinArgs a) {
         }
       }
       if (live) {
+        // 32-byte loads / stores: a thread's chunk is one (bf16) or two (fp32) whole sectors of its row
         if (a.res) {
-          const float4* rp = reinterpret_cast<const float4*>(a.res + m * N + col0 + c);
+          const float* rp = a.res + m * N + col0 + c;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 r4 = rp[j4];
-            f[4 * j4] += r4.x; f[4 * j4 + 1] += r4.y; f[4 * j4 + 2] += r4.z; f[4 * j4 + 3] += r4.w;
+          for (int j8 = 0; j8 < 2; ++j8) {
+            float rr[8];
+            ld_global_256f(rp + 8 * j8, rr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[8 * j8 + k] += rr[k];
           }
         }
         if (a.out_bf16) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * N + col0 + c);
-          dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+          const uint32_t pk[8] = {pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]),
+                                  pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15])};
+          st_global_256(reinterpret_cast<__nv_bfloat16*>(a.out) + m * N + col0 + c, pk);
         } else {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + m * N + col0 + c);
+          float* dst = reinterpret_cast<float*>(a.out) + m * N + col0 + c;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+          for (int j8 = 0; j8 < 2; ++j8) {
+            const float o[8] = {f[8 * j8], f[8 * j8 + 1], f[8 * j8 + 2], f[8 * j8 + 3], f[8 * j8 + 4], f[8 * j8 + 5], f[8 * j8 + 6], f[8 * j8 + 7]};
+            st_global_256f(dst + 8 * j8, o);
+          }
         }
       }
     }
@@ -871,6 +877,8 @@ int csn_tc_linear(const void* X, int in_bf16, const __nv_bfloat16* W, const floa
                   cudaStream_t st, const float* pos_freqs, const float* head_w2, const float* head_b2,
                   const __nv_bfloat16* W2, const float* bias2, const float* post2_g, const float* post2_b) {
   DBS_REQUIRE(N_total % 128 == 0 && (!post_g || N_total == 128), "csn_tc_linear: unsupported width %d", N_total);
+  DBS_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(X)) & 31) == 0,
+              "csn_tc_linear: tensors must be 32-byte aligned");
   DBS_REQUIRE(!W2 || (N_total == 128 && post_g && post2_g && bias2 && !in_bf16 && !out_bf16 && !res && !head_w2 && !pos_freqs),
               "csn_tc_linear: the fused MLPBlock form needs fp32 in / out, both LayerNorms and no other fusion");
   TcLinArgs a;
