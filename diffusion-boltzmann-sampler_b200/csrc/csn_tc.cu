@@ -837,15 +837,15 @@ csn_tc_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
       tmem_ld_wait();
       if (qi < N) {
         const float inv = 1.0f / l;
-        uint4* dst = reinterpret_cast<uint4*>(out + (b * N + qi) * H + h * kHD);
-        uint32_t pk[16];
+        __nv_bfloat16* dst = out + (b * N + qi) * H + h * kHD;
+        uint32_t pa[8], pb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          pk[j] = pack_bf16(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv);
-          pk[8 + j] = pack_bf16(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv);
+          pa[j] = pack_bf16(__uint_as_float(v0[2 * j]) * inv, __uint_as_float(v0[2 * j + 1]) * inv);
+          pb[j] = pack_bf16(__uint_as_float(v1[2 * j]) * inv, __uint_as_float(v1[2 * j + 1]) * inv);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        st_global_256(dst, pa);          // the head slice of a query row: two 32-byte sectors
+        st_global_256(dst + 16, pb);
       }
     }
     tc_fence_before();
