@@ -1,12 +1,12 @@
 """Per-kernel counts of the Blackwell-specific SASS mnemonics in lib/libdbs_b200.so (cuobjdump -sass):
 UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor load), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit), SYNCS (mbarrier),
-HMMA (warp-level mma.sync).  usage: python profiles/sass_summary.py > profiles/sass_summary.txt"""
+HMMA (warp-level mma.sync), ENL2.256 (32-byte global loads / stores).  usage: python profiles/sass_summary.py > profiles/sass_summary.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "diffusion-boltzmann-sampler_b200", "lib", "libdbs_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip() or n
-MN = ["UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "HMMA", "LDSM", "MUFU", "POPC", "REDUX", "IMAD.WIDE"]
+MN = ["UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS", "UTCATOMSWS", "HMMA", "LDSM", "MUFU", "POPC", "REDUX", "IMAD.WIDE", "ENL2.256"]
 counts, cur, n_instr = collections.OrderedDict(), None, collections.Counter()
 for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
