@@ -657,7 +657,17 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
           pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        if (!(kExp && (p.dbg & 4))) st_global_256(optr_o + c, pk);   // the pixel's sixteen couts of this chunk: one 32-byte sector
+        if (!(kExp && (p.dbg & 4))) {
+          if (kSpec == 1 && NCH <= 2) {
+            // the plain 3x3 layer with <= 32 couts is the one place where the 32-byte store measured slower (191 -> 197 us
+            // at B = 1024, 64x64: two warp sets at the register cap); it keeps the two 16-byte stores
+            uint4* dst = reinterpret_cast<uint4*>(optr_o + c);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+            st_global_256(optr_o + c, pk);   // the pixel's sixteen couts of this chunk: one 32-byte sector
+          }
+        }
         if (kSpec == 2 || (kSpec == 0 && p.has_res)) {   // (never with kSpec 1 / 3)
           // fused 1x1 residual conv of the same input (score_network.py:131,151): own slot, own bias, no GN
           uint32_t vr[16];

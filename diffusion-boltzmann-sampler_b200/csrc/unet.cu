@@ -1395,7 +1395,6 @@ struct dbs_unet_plan {
   // first encoder block: residual projection composed with the init conv, [9][cout] + [cout] (gn_apply_xres_kernel)
   float *enc0_wc = nullptr, *enc0_bc = nullptr;
   uint2* enc0_bfrag = nullptr;       // enc0_composed_kernel: B fragments of conv1 composed with the init conv, [6][8][32]
-  float* enc0_b1 = nullptr;          // conv1's bias
   std::vector<float> init_w_host, init_b_host;   // [tap][C], [C]: kernel-parameter copies for the init conv
   float final_b_host = 0.f;
   std::vector<dbs::BlockW> enc, dec;
@@ -2240,15 +2239,13 @@ extern "C" int dbs_unet_plan_create(const dbs_unet_config* cfg, const dbs_param*
             frag[idx] = bf16_bits(W_(k0)) | (bf16_bits(W_(k0 + 1)) << 16);
             frag[idx + 1] = bf16_bits(W_(k0 + 8)) | (bf16_bits(W_(k0 + 9)) << 16);
           }
-      void *df = nullptr, *d1 = nullptr;
+      void* df = nullptr;                                                // (conv1's bias rides in the fragments)
       if ((rc = dev_alloc(plan, frag.size() * 4, &df))) return fail(rc);
-      if ((rc = dev_alloc(plan, hb1.size() * 4, &d1))) return fail(rc);
-      if (cudaMemcpy(df, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-          cudaMemcpy(d1, hb1.data(), hb1.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (cudaMemcpy(df, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("unet_plan_create: composed conv1 upload failed");
         return fail(DBS_ERR_CUDA);
       }
-      plan->enc0_bfrag = (uint2*)df; plan->enc0_b1 = (float*)d1;
+      plan->enc0_bfrag = (uint2*)df;
     }
   }
   if ((rc = make_block(plan, pt, "middle.", ch, ch, &plan->mid))) return fail(rc);
