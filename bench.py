@@ -399,9 +399,9 @@ def bench_ours(args, world, rank, local):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the conv launches of one forward at 64x64, from the ncu --set full
 # capture named in "source" (per sample; bench scales it by the batch).  None until a capture of this build exists.
-CONV_TRAFFIC_64 = {"bytes_per_sample_forward": 8.566e6, "source": "profiles/r2_ncu_64_head.csv",
+CONV_TRAFFIC_64 = {"bytes_per_sample_forward": 8.692e6, "source": "profiles/r2_conv_ncu_64_final_build.csv",
                    "note": "dram__bytes_read.sum + dram__bytes_write.sum of the 22 conv launches of one forward (ncu --set full, "
-                           "batch 512, 64x64, head build: 2.77 GB read + 1.62 GB written = 8.57 MB per sample, ncu's cache control "
+                           "batch 512, 64x64, final build: 2.77 GB read + 1.68 GB written = 8.69 MB per sample, ncu's cache control "
                            "between launches), scaled by the batch.  Algorithmic conv input + output bytes: 13.1 MB per sample "
                            "(SURVEY 8d) -- the captured traffic is BELOW it because conv1 and the 1x1 residual conv of a block "
                            "share one read of their input, the first block reads the one-channel network input instead of a "
